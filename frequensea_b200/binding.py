@@ -1,0 +1,185 @@
+"""ctypes binding of include/fsea.h (libfsea.so)."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libfsea.so")
+
+IN_U8, IN_S8, IN_F32C, IN_F64C = 0, 1, 2, 3
+WIN_NONE, WIN_HANN = 0, 1
+OUT_MAG, OUT_LOGMAG, OUT_PIX = 0, 1, 2
+FLAG_DC_PATCH = 1
+ARITH_AUTO, ARITH_F32, ARITH_F32X2 = 0, 1, 2
+
+OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM = 0, -1, -2, -3, -4, -5
+
+
+class FseaConfig(C.Structure):
+    _fields_ = [("fft_size", C.c_int), ("hop", C.c_int), ("in_format", C.c_int),
+                ("window", C.c_int), ("out_mode", C.c_int), ("flags", C.c_int),
+                ("pix_scale", C.c_float), ("device", C.c_int), ("arith", C.c_int),
+                ("reserved", C.c_int * 7)]
+
+
+class FseaError(RuntimeError):
+    def __init__(self, code: int, what: str, detail: str = ""):
+        self.code = code
+        super().__init__(f"{what}: fsea error {code}" + (f" ({detail})" if detail else ""))
+
+
+def lib_path() -> str:
+    return _LIB_PATH
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libfsea.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j", str(os.cpu_count() or 4)]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0 or verbose:
+        print(res.stdout)
+    if res.returncode != 0:
+        raise RuntimeError("building libfsea.so failed")
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libfsea.so.  Fails loudly when the extension is missing: there is
+    no Python / CPU implementation of the hot path behind this package."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise FileNotFoundError(
+            f"{_LIB_PATH} not built -- run `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(the CUDA extension is required; there is no CPU fallback)")
+    L = C.CDLL(_LIB_PATH)
+    vp, i, l = C.c_void_p, C.c_int, C.c_long
+    P = C.POINTER(FseaConfig)
+    L.fsea_device_count.restype = i
+    L.fsea_strerror.argtypes = [i]; L.fsea_strerror.restype = C.c_char_p
+    L.fsea_last_cuda_error.restype = C.c_char_p
+    L.fsea_config_default.argtypes = [P, i]; L.fsea_config_default.restype = None
+    L.fsea_plan_create.argtypes = [P, C.POINTER(vp)]; L.fsea_plan_create.restype = i
+    L.fsea_plan_destroy.argtypes = [vp]; L.fsea_plan_destroy.restype = i
+    L.fsea_input_bytes.argtypes = [vp, l]; L.fsea_input_bytes.restype = C.c_size_t
+    L.fsea_output_bytes.argtypes = [vp, l]; L.fsea_output_bytes.restype = C.c_size_t
+    L.fsea_frames_in.argtypes = [vp, C.c_size_t]; L.fsea_frames_in.restype = l
+    L.fsea_exec_device.argtypes = [vp, vp, vp, l, vp]; L.fsea_exec_device.restype = i
+    L.fsea_exec_host.argtypes = [vp, vp, vp, l]; L.fsea_exec_host.restype = i
+    L.fsea_plan_launch_count.argtypes = [vp]; L.fsea_plan_launch_count.restype = l
+    L.fsea_plan_kernel_name.argtypes = [vp]; L.fsea_plan_kernel_name.restype = C.c_char_p
+    L.fsea_gate_mean_host.argtypes = [vp, vp, l, C.POINTER(C.c_double)]; L.fsea_gate_mean_host.restype = i
+    _lib = L
+    return L
+
+
+def device_count() -> int:
+    return int(lib().fsea_device_count())
+
+
+def _check(rc: int, what: str) -> None:
+    if rc != OK:
+        L = lib()
+        detail = L.fsea_strerror(rc).decode()
+        if rc == ERR_CUDA:
+            detail += ": " + L.fsea_last_cuda_error().decode()
+        raise FseaError(rc, what, detail)
+
+
+_IN_NP = {IN_U8: np.uint8, IN_S8: np.uint8, IN_F32C: np.float32, IN_F64C: np.float64}
+
+
+class Plan:
+    """A batched IQ -> spectrum transform of fixed geometry (fsea_plan)."""
+
+    def __init__(self, fft_size: int, hop: int = 0, in_format: int = IN_U8, window: int = WIN_NONE,
+                 out_mode: int = OUT_MAG, flags: int = 0, pix_scale: float = 10.0, device: int = 0,
+                 arith: int = ARITH_AUTO):
+        L = lib()
+        cfg = FseaConfig()
+        L.fsea_config_default(C.byref(cfg), fft_size)
+        cfg.hop = hop or fft_size
+        cfg.in_format, cfg.window, cfg.out_mode, cfg.flags = in_format, window, out_mode, flags
+        cfg.pix_scale, cfg.device, cfg.arith = pix_scale, device, arith
+        self.cfg = cfg
+        self.n = fft_size
+        self.hop = cfg.hop
+        self.in_format, self.out_mode = in_format, out_mode
+        self._h = C.c_void_p()
+        _check(L.fsea_plan_create(C.byref(cfg), C.byref(self._h)), "fsea_plan_create")
+
+    # -- geometry
+    def input_bytes(self, n_frames: int) -> int:
+        return int(lib().fsea_input_bytes(self._h, n_frames))
+
+    def output_bytes(self, n_frames: int) -> int:
+        return int(lib().fsea_output_bytes(self._h, n_frames))
+
+    def frames_in(self, n_samples: int) -> int:
+        return int(lib().fsea_frames_in(self._h, n_samples))
+
+    @property
+    def out_dtype(self):
+        if self.out_mode == OUT_PIX:
+            return np.uint8
+        return np.float64 if self.in_format == IN_F64C else np.float32
+
+    @property
+    def kernel_name(self) -> str:
+        return lib().fsea_plan_kernel_name(self._h).decode()
+
+    @property
+    def launches(self) -> int:
+        return int(lib().fsea_plan_launch_count(self._h))
+
+    # -- execution
+    def exec_device(self, d_in: int, d_out: int, n_frames: int, stream: int = 0) -> None:
+        """Device pointers (ints); asynchronous on `stream` (a cudaStream_t handle)."""
+        _check(lib().fsea_exec_device(self._h, C.c_void_p(d_in), C.c_void_p(d_out), n_frames,
+                                      C.c_void_p(stream)), "fsea_exec_device")
+
+    def exec_host(self, data: np.ndarray, n_frames: int | None = None, out: np.ndarray | None = None) -> np.ndarray:
+        """Host buffers through the pinned H2D -> kernel -> D2H pipeline."""
+        data = np.ascontiguousarray(data, dtype=_IN_NP[self.in_format]).ravel()
+        per = 2
+        if n_frames is None:
+            n_frames = self.frames_in(data.size // per)
+        need = self.input_bytes(n_frames)
+        if data.nbytes < need:
+            raise ValueError(f"input too short: {data.nbytes} < {need} bytes for {n_frames} frames")
+        if out is None:
+            out = np.empty((n_frames, self.n), dtype=self.out_dtype)
+        assert out.flags.c_contiguous and out.nbytes >= self.output_bytes(n_frames)
+        _check(lib().fsea_exec_host(self._h, data.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
+                                    n_frames), "fsea_exec_host")
+        return out
+
+    def exec_host_ptr(self, h_in: int, h_out: int, n_frames: int) -> None:
+        """Raw host pointers (e.g. pinned torch tensors: copied from / to directly)."""
+        _check(lib().fsea_exec_host(self._h, C.c_void_p(h_in), C.c_void_p(h_out), n_frames), "fsea_exec_host")
+
+    def gate_mean(self, data: np.ndarray, rows: int) -> float:
+        data = np.ascontiguousarray(data, dtype=_IN_NP[self.in_format]).ravel()
+        m = C.c_double()
+        _check(lib().fsea_gate_mean_host(self._h, data.ctypes.data_as(C.c_void_p), rows, C.byref(m)),
+               "fsea_gate_mean_host")
+        return float(m.value)
+
+    def close(self) -> None:
+        if self._h:
+            lib().fsea_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

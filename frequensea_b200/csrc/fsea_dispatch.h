@@ -1,0 +1,40 @@
+// fsea_dispatch.h -- how the engine finds the kernel instantiation for a plan.
+// Each fsea_k_<N>.cu translation unit instantiates fsea_fft_kernel for one
+// transform length and registers its variants through fsea_get_kernel_<N>().
+#pragma once
+#include <stddef.h>
+
+enum {
+    FSEA_VAR_F32 = 0,    // 8-bit IQ, one frame per group, scalar fp32
+    FSEA_VAR_F32X2 = 1,  // 8-bit IQ, frame PAIR per group, packed FADD2/FMUL2/FFMA2
+    FSEA_VAR_F32C = 2,   // float2 samples, scalar fp32
+    FSEA_VAR_F64 = 3,    // double2 samples, fp64
+    FSEA_VAR_COUNT = 4
+};
+
+struct fsea_kernel_info {
+    const void* fn;      // __global__ entry (cudaLaunchKernel)
+    int threads;         // block size = T * G
+    int groups;          // G
+    int lanes;           // sequences per unit (1 or 2)
+    size_t smem;         // dynamic shared memory per block
+    int n, r0, r1, r2;   // shape
+    int tw1, tw2;        // twiddle table entries
+    int scalar_bytes;    // 4 or 8
+    const char* name;
+};
+
+typedef bool (*fsea_get_kernel_fn)(int variant, fsea_kernel_info* out);
+
+#define FSEA_DECL_SIZE(N) bool fsea_get_kernel_##N(int variant, fsea_kernel_info* out);
+FSEA_DECL_SIZE(16)
+FSEA_DECL_SIZE(32)
+FSEA_DECL_SIZE(64)
+FSEA_DECL_SIZE(128)
+FSEA_DECL_SIZE(256)
+FSEA_DECL_SIZE(512)
+FSEA_DECL_SIZE(1024)
+FSEA_DECL_SIZE(2048)
+FSEA_DECL_SIZE(4096)
+FSEA_DECL_SIZE(8192)
+#undef FSEA_DECL_SIZE

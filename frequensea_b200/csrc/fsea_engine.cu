@@ -1,0 +1,407 @@
+// fsea_engine.cu -- C ABI of the B200 IQ -> spectrum engine (include/fsea.h).
+//
+// Host side of the hot path: plans (twiddle / window tables in HBM, kernel
+// selection, launch geometry), the device-resident batch call and the
+// host-buffer call with a pinned, double-buffered H2D -> kernel -> D2H
+// pipeline.  No CPU fallback: every compute entry point needs a CUDA device.
+#include <cuda_runtime.h>
+
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/fsea.h"
+#include "fsea_dispatch.h"
+#include "fsea_kparams.h"
+
+// ------------------------------------------------------------------ errors
+static thread_local char g_cuda_err[256] = "";
+
+static int cuda_fail(cudaError_t e, const char* what) {
+    snprintf(g_cuda_err, sizeof(g_cuda_err), "%s: %s", what, cudaGetErrorString(e));
+    return FSEA_ERR_CUDA;
+}
+#define CU(call)                                        \
+    do {                                                \
+        cudaError_t e__ = (call);                       \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call); \
+    } while (0)
+
+extern "C" const char* fsea_last_cuda_error(void) { return g_cuda_err; }
+
+extern "C" const char* fsea_strerror(int code) {
+    switch (code) {
+        case FSEA_OK: return "ok";
+        case FSEA_ERR_INVALID: return "invalid argument";
+        case FSEA_ERR_UNSUPPORTED: return "unsupported fft size (power of two, 16..65536)";
+        case FSEA_ERR_NO_DEVICE: return "no CUDA device (this engine has no CPU fallback)";
+        case FSEA_ERR_CUDA: return "CUDA runtime error";
+        case FSEA_ERR_NOMEM: return "out of memory";
+    }
+    return "unknown error";
+}
+
+extern "C" int fsea_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+// ------------------------------------------------------------------ plan
+struct fsea_stage {                 // one pinned staging slot of the host pipeline
+    void* h_in = nullptr;
+    void* h_out = nullptr;
+    void* d_in = nullptr;
+    void* d_out = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    long frames = 0;                // frames in flight in this slot
+    long first = 0;
+};
+
+struct fsea_plan {
+    fsea_config cfg;
+    int hop;
+    int variant;
+    fsea_kernel_info ki;
+    int sample_bytes;               // bytes per complex input sample
+    int out_elem_bytes;
+    void* d_tw1 = nullptr;
+    void* d_tw2 = nullptr;
+    float* d_window = nullptr;
+    int max_blocks = 0;             // resident blocks on the device
+    long launches = 0;
+    // host pipeline
+    static const int NSTAGE = 3;
+    fsea_stage stage[NSTAGE];
+    long stage_frames = 0;
+    double* d_gate = nullptr;
+};
+
+static fsea_get_kernel_fn size_table(int n) {
+    switch (n) {
+        case 16: return fsea_get_kernel_16;
+        case 32: return fsea_get_kernel_32;
+        case 64: return fsea_get_kernel_64;
+        case 128: return fsea_get_kernel_128;
+        case 256: return fsea_get_kernel_256;
+        case 512: return fsea_get_kernel_512;
+        case 1024: return fsea_get_kernel_1024;
+        case 2048: return fsea_get_kernel_2048;
+        case 4096: return fsea_get_kernel_4096;
+        case 8192: return fsea_get_kernel_8192;
+    }
+    return nullptr;
+}
+
+extern "C" void fsea_config_default(fsea_config* cfg, int fft_size) {
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->fft_size = fft_size;
+    cfg->hop = fft_size;
+    cfg->in_format = FSEA_IN_U8;
+    cfg->window = FSEA_WIN_NONE;
+    cfg->out_mode = FSEA_OUT_MAG;
+    cfg->flags = 0;
+    cfg->pix_scale = 10.0f;
+    cfg->device = 0;
+    cfg->arith = FSEA_ARITH_AUTO;
+}
+
+template <typename S2>
+static void fill_twiddles(std::vector<S2>& t1, std::vector<S2>& t2, const fsea_kernel_info& ki) {
+    const long double PI2 = 6.283185307179586476925286766559005768L;
+    const int R0 = ki.r0, R1 = ki.r1, R2 = ki.r2;
+    t1.resize(std::max(ki.tw1, 1));
+    t2.resize(std::max(ki.tw2, 1));
+    for (int j = 1; j < R1; j++)
+        for (int k = 0; k < R0; k++) {
+            long double a = -PI2 * (long double)(j * k) / (long double)(R0 * R1);
+            t1[(j - 1) * R0 + k].x = cosl(a);
+            t1[(j - 1) * R0 + k].y = sinl(a);
+        }
+    const int M = R0 * R1;
+    for (int j = 1; j < R2; j++)
+        for (int i = 0; i < M; i++) {
+            long double a = -PI2 * (long double)((long)j * i) / (long double)ki.n;
+            t2[(j - 1) * M + i].x = cosl(a);
+            t2[(j - 1) * M + i].y = sinl(a);
+        }
+}
+
+extern "C" int fsea_plan_destroy(fsea_plan* p) {
+    if (!p) return FSEA_OK;
+    cudaSetDevice(p->cfg.device);
+    for (int s = 0; s < fsea_plan::NSTAGE; s++) {
+        fsea_stage& st = p->stage[s];
+        if (st.stream) cudaStreamSynchronize(st.stream);
+        if (st.h_in) cudaFreeHost(st.h_in);
+        if (st.h_out) cudaFreeHost(st.h_out);
+        if (st.d_in) cudaFree(st.d_in);
+        if (st.d_out) cudaFree(st.d_out);
+        if (st.done) cudaEventDestroy(st.done);
+        if (st.stream) cudaStreamDestroy(st.stream);
+    }
+    if (p->d_tw1) cudaFree(p->d_tw1);
+    if (p->d_tw2) cudaFree(p->d_tw2);
+    if (p->d_window) cudaFree(p->d_window);
+    if (p->d_gate) cudaFree(p->d_gate);
+    delete p;
+    return FSEA_OK;
+}
+
+extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
+    if (!cfg || !out) return FSEA_ERR_INVALID;
+    *out = nullptr;
+    const int n = cfg->fft_size;
+    if (n < 16 || n > 65536 || (n & (n - 1))) return FSEA_ERR_UNSUPPORTED;
+    fsea_get_kernel_fn get = size_table(n);
+    if (!get) return FSEA_ERR_UNSUPPORTED;
+    if (cfg->in_format < FSEA_IN_U8 || cfg->in_format > FSEA_IN_F64C) return FSEA_ERR_INVALID;
+    if (cfg->window != FSEA_WIN_NONE && cfg->window != FSEA_WIN_HANN) return FSEA_ERR_INVALID;
+    if (cfg->out_mode < FSEA_OUT_MAG || cfg->out_mode > FSEA_OUT_PIX) return FSEA_ERR_INVALID;
+    if (cfg->hop < 0) return FSEA_ERR_INVALID;
+    if (fsea_device_count() <= 0) return FSEA_ERR_NO_DEVICE;
+    if (cfg->device < 0 || cfg->device >= fsea_device_count()) return FSEA_ERR_INVALID;
+    CU(cudaSetDevice(cfg->device));
+
+    fsea_plan* p = new (std::nothrow) fsea_plan();
+    if (!p) return FSEA_ERR_NOMEM;
+    p->cfg = *cfg;
+    p->hop = cfg->hop > 0 ? cfg->hop : n;
+    switch (cfg->in_format) {
+        case FSEA_IN_U8:
+        case FSEA_IN_S8:
+            p->variant = (cfg->arith == FSEA_ARITH_F32) ? FSEA_VAR_F32 : FSEA_VAR_F32X2;
+            p->sample_bytes = 2;
+            break;
+        case FSEA_IN_F32C: p->variant = FSEA_VAR_F32C; p->sample_bytes = 8; break;
+        default: p->variant = FSEA_VAR_F64; p->sample_bytes = 16; break;
+    }
+    if (!get(p->variant, &p->ki)) { delete p; return FSEA_ERR_UNSUPPORTED; }
+    p->out_elem_bytes = (cfg->out_mode == FSEA_OUT_PIX) ? 1 : p->ki.scalar_bytes;
+
+    int rc = FSEA_OK;
+    do {
+        cudaError_t e;
+        if ((e = cudaFuncSetAttribute(p->ki.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ki.smem)) != cudaSuccess) {
+            rc = cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"); break;
+        }
+        int per_sm = 0, sms = 0;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p->ki.fn, p->ki.threads, p->ki.smem)) != cudaSuccess) {
+            rc = cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor"); break;
+        }
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
+        if (per_sm < 1) per_sm = 1;
+        p->max_blocks = per_sm * sms;
+
+        // twiddle tables, evaluated in long double, stored in the kernel's precision
+        if (p->ki.scalar_bytes == 4) {
+            std::vector<float2> t1, t2;
+            fill_twiddles(t1, t2, p->ki);
+            if ((e = cudaMalloc(&p->d_tw1, t1.size() * sizeof(float2))) != cudaSuccess ||
+                (e = cudaMalloc(&p->d_tw2, t2.size() * sizeof(float2))) != cudaSuccess ||
+                (e = cudaMemcpy(p->d_tw1, t1.data(), t1.size() * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess ||
+                (e = cudaMemcpy(p->d_tw2, t2.data(), t2.size() * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess) {
+                rc = cuda_fail(e, "twiddle upload"); break;
+            }
+        } else {
+            std::vector<double2> t1, t2;
+            fill_twiddles(t1, t2, p->ki);
+            if ((e = cudaMalloc(&p->d_tw1, t1.size() * sizeof(double2))) != cudaSuccess ||
+                (e = cudaMalloc(&p->d_tw2, t2.size() * sizeof(double2))) != cudaSuccess ||
+                (e = cudaMemcpy(p->d_tw1, t1.data(), t1.size() * sizeof(double2), cudaMemcpyHostToDevice)) != cudaSuccess ||
+                (e = cudaMemcpy(p->d_tw2, t2.data(), t2.size() * sizeof(double2), cudaMemcpyHostToDevice)) != cudaSuccess) {
+                rc = cuda_fail(e, "twiddle upload"); break;
+            }
+        }
+        if (cfg->window == FSEA_WIN_HANN) {
+            std::vector<float> w(n);
+            const long double PI2 = 6.283185307179586476925286766559005768L;
+            for (int i = 0; i < n; i++) w[i] = (float)(0.5L * (1.0L - cosl(PI2 * i / n)));
+            if ((e = cudaMalloc(&p->d_window, n * sizeof(float))) != cudaSuccess ||
+                (e = cudaMemcpy(p->d_window, w.data(), n * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) {
+                rc = cuda_fail(e, "window upload"); break;
+            }
+        }
+    } while (0);
+    if (rc != FSEA_OK) { fsea_plan_destroy(p); return rc; }
+    *out = p;
+    return FSEA_OK;
+}
+
+extern "C" size_t fsea_input_bytes(const fsea_plan* p, long n_frames) {
+    if (!p || n_frames <= 0) return 0;
+    return ((size_t)(n_frames - 1) * p->hop + p->cfg.fft_size) * p->sample_bytes;
+}
+extern "C" size_t fsea_output_bytes(const fsea_plan* p, long n_frames) {
+    if (!p || n_frames <= 0) return 0;
+    return (size_t)n_frames * p->cfg.fft_size * p->out_elem_bytes;
+}
+extern "C" long fsea_frames_in(const fsea_plan* p, size_t n_samples) {
+    if (!p || n_samples < (size_t)p->cfg.fft_size) return 0;
+    return (long)((n_samples - p->cfg.fft_size) / p->hop) + 1;
+}
+extern "C" long fsea_plan_launch_count(const fsea_plan* p) { return p ? p->launches : 0; }
+extern "C" const char* fsea_plan_kernel_name(const fsea_plan* p) { return p ? p->ki.name : ""; }
+
+
+static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cudaStream_t stream) {
+    if (n_frames <= 0) return FSEA_OK;
+    fsea_kparams kp;
+    kp.in = d_in;
+    kp.out = d_out;
+    kp.n_seq = n_frames;
+    kp.seq_stride = p->hop;
+    kp.tw1 = p->d_tw1;
+    kp.tw2 = p->d_tw2;
+    kp.window = p->d_window;
+    kp.pix_scale = p->cfg.pix_scale;
+    kp.flags = p->cfg.flags;
+    const bool eight_bit = p->cfg.in_format == FSEA_IN_U8 || p->cfg.in_format == FSEA_IN_S8;
+    kp.dc_term = (eight_bit && p->cfg.window == FSEA_WIN_NONE && !(p->cfg.flags & FSEA_FLAG_DC_PATCH)) ? 1 : 0;
+    kp.out_mode = p->cfg.out_mode;
+    kp.xor_mask = p->cfg.in_format == FSEA_IN_S8 ? 0x8080u : 0u;
+    const long units = (n_frames + p->ki.lanes - 1) / p->ki.lanes;
+    long blocks = (units + p->ki.groups - 1) / p->ki.groups;
+    if (blocks > p->max_blocks) blocks = p->max_blocks;
+    void* args[] = {&kp};
+    CU(cudaLaunchKernel(p->ki.fn, dim3((unsigned)blocks), dim3((unsigned)p->ki.threads), args, p->ki.smem, stream));
+    p->launches++;
+    return FSEA_OK;
+}
+
+extern "C" int fsea_exec_device(fsea_plan* p, const void* d_in, void* d_out, long n_frames, void* stream) {
+    if (!p || n_frames < 0 || (n_frames > 0 && (!d_in || !d_out))) return FSEA_ERR_INVALID;
+    CU(cudaSetDevice(p->cfg.device));
+    return launch(p, d_in, d_out, n_frames, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ host pipeline
+// Three slots, each with its own stream: while slot k computes, slot k+1's
+// input crosses PCIe and slot k-1's spectra return.  Caller memory that is
+// already page-locked (cudaHostAlloc / cudaHostRegister, e.g. a pinned torch
+// tensor) is copied from / to directly; pageable memory goes through the
+// plan's pinned staging buffers.
+static bool is_pinned_host(const void* ptr) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+static int ensure_stages(fsea_plan* p, long want_frames, bool staging) {
+    // slot size: ~32 MiB of output or the whole job if smaller
+    const size_t out_per = (size_t)p->cfg.fft_size * p->out_elem_bytes;
+    long sf = (long)std::max<size_t>(2, (32u << 20) / out_per);
+    if (sf > want_frames) sf = want_frames;
+    if (sf & 1) sf++;                                   // keep frame pairs together
+    const bool have_staging = p->stage[0].h_in != nullptr;
+    if (p->stage_frames >= sf && (!staging || have_staging)) return FSEA_OK;
+    if (sf < p->stage_frames) sf = p->stage_frames;
+    for (int s = 0; s < fsea_plan::NSTAGE; s++) {
+        fsea_stage& st = p->stage[s];
+        if (st.stream) CU(cudaStreamSynchronize(st.stream));
+        if (st.h_in) cudaFreeHost(st.h_in);
+        if (st.h_out) cudaFreeHost(st.h_out);
+        if (st.d_in) cudaFree(st.d_in);
+        if (st.d_out) cudaFree(st.d_out);
+        st.h_in = st.h_out = st.d_in = st.d_out = nullptr;
+        const size_t ib = fsea_input_bytes(p, sf), ob = fsea_output_bytes(p, sf);
+        if (staging || have_staging) {
+            CU(cudaMallocHost(&st.h_in, ib));
+            CU(cudaMallocHost(&st.h_out, ob));
+        }
+        CU(cudaMalloc(&st.d_in, ib));
+        CU(cudaMalloc(&st.d_out, ob));
+        if (!st.stream) CU(cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking));
+        if (!st.done) CU(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming));
+    }
+    p->stage_frames = sf;
+    return FSEA_OK;
+}
+
+extern "C" int fsea_exec_host(fsea_plan* p, const void* h_in, void* h_out, long n_frames) {
+    if (!p || n_frames < 0 || (n_frames > 0 && (!h_in || !h_out))) return FSEA_ERR_INVALID;
+    if (n_frames == 0) return FSEA_OK;
+    CU(cudaSetDevice(p->cfg.device));
+    const bool direct = is_pinned_host(h_in) && is_pinned_host(h_out);
+    int rc = ensure_stages(p, n_frames, !direct);
+    if (rc != FSEA_OK) return rc;
+    const size_t in_frame_stride = (size_t)p->hop * p->sample_bytes;
+    const size_t out_per = (size_t)p->cfg.fft_size * p->out_elem_bytes;
+    const long sf = p->stage_frames;
+    long issued = 0;
+    int slot = 0;
+    long pending[fsea_plan::NSTAGE] = {0, 0, 0};
+    long pending_first[fsea_plan::NSTAGE] = {0, 0, 0};
+    auto drain = [&](int s) -> int {
+        if (!pending[s]) return FSEA_OK;
+        fsea_stage& st = p->stage[s];
+        CU(cudaEventSynchronize(st.done));
+        if (!direct)
+            memcpy((uint8_t*)h_out + (size_t)pending_first[s] * out_per, st.h_out, (size_t)pending[s] * out_per);
+        pending[s] = 0;
+        return FSEA_OK;
+    };
+    while (issued < n_frames) {
+        fsea_stage& st = p->stage[slot];
+        if ((rc = drain(slot)) != FSEA_OK) return rc;
+        const long nf = std::min(sf, n_frames - issued);
+        const size_t ib = fsea_input_bytes(p, nf);
+        const uint8_t* src = (const uint8_t*)h_in + (size_t)issued * in_frame_stride;
+        uint8_t* dst = (uint8_t*)h_out + (size_t)issued * out_per;
+        if (!direct) { memcpy(st.h_in, src, ib); src = (const uint8_t*)st.h_in; dst = (uint8_t*)st.h_out; }
+        CU(cudaMemcpyAsync(st.d_in, src, ib, cudaMemcpyHostToDevice, st.stream));
+        if ((rc = launch(p, st.d_in, st.d_out, nf, st.stream)) != FSEA_OK) return rc;
+        CU(cudaMemcpyAsync(dst, st.d_out, (size_t)nf * out_per, cudaMemcpyDeviceToHost, st.stream));
+        CU(cudaEventRecord(st.done, st.stream));
+        pending[slot] = nf;
+        pending_first[slot] = issued;
+        issued += nf;
+        slot = (slot + 1) % fsea_plan::NSTAGE;
+    }
+    for (int s = 0; s < fsea_plan::NSTAGE; s++) {
+        if ((rc = drain((slot + s) % fsea_plan::NSTAGE)) != FSEA_OK) return rc;
+    }
+    return FSEA_OK;
+}
+
+// ------------------------------------------------------------------ sweep gate
+// c/fft-batch-broad.c:80-98: mean |X| over the first `rows` rows.  The rows'
+// magnitudes are produced by the MAG kernel and summed in fp64 on the device.
+__global__ void fsea_sum_kernel(const float* __restrict__ x, long n, double* __restrict__ acc) {
+    double s = 0.0;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) s += (double)x[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(acc, s);
+}
+
+extern "C" int fsea_gate_mean_host(fsea_plan* p, const void* h_in, long rows, double* mean_out) {
+    if (!p || !h_in || !mean_out || rows <= 0) return FSEA_ERR_INVALID;
+    if (p->cfg.out_mode != FSEA_OUT_MAG || p->ki.scalar_bytes != 4) return FSEA_ERR_INVALID;
+    CU(cudaSetDevice(p->cfg.device));
+    const size_t ib = fsea_input_bytes(p, rows), ob = fsea_output_bytes(p, rows);
+    void *d_in = nullptr, *d_out = nullptr;
+    if (!p->d_gate) CU(cudaMalloc(&p->d_gate, sizeof(double)));
+    CU(cudaMalloc(&d_in, ib));
+    cudaError_t e = cudaMalloc(&d_out, ob);
+    if (e != cudaSuccess) { cudaFree(d_in); return cuda_fail(e, "cudaMalloc"); }
+    int rc = FSEA_OK;
+    do {
+        if ((e = cudaMemcpy(d_in, h_in, ib, cudaMemcpyHostToDevice)) != cudaSuccess) { rc = cuda_fail(e, "H2D"); break; }
+        if ((e = cudaMemset(p->d_gate, 0, sizeof(double))) != cudaSuccess) { rc = cuda_fail(e, "memset"); break; }
+        if ((rc = launch(p, d_in, d_out, rows, 0)) != FSEA_OK) break;
+        const long n = rows * p->cfg.fft_size;
+        fsea_sum_kernel<<<256, 256>>>((const float*)d_out, n, p->d_gate);
+        p->launches++;
+        double total = 0;
+        if ((e = cudaMemcpy(&total, p->d_gate, sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess) { rc = cuda_fail(e, "D2H"); break; }
+        *mean_out = total / (double)n;
+    } while (0);
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return rc;
+}

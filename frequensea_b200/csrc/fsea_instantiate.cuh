@@ -1,0 +1,51 @@
+// fsea_instantiate.cuh -- per-length instantiation helper (included by fsea_k_<N>.cu).
+#pragma once
+#include "fsea_kernels.cuh"
+#include "fsea_dispatch.h"
+
+template <class SH, typename V>
+struct fsea_cfg {
+    static const int UNIT_BYTES = 2 * (int)sizeof(V);
+    static const int SB = (int)sizeof(typename fsea_vt<V>::scalar);
+    static const int XBYTES = SH::NPASS > 1 ? SH::UNITS * UNIT_BYTES : 0;      // exchange per group
+    static const int TWBYTES = (SH::TW1 + SH::TW2) * 2 * SB;
+    static const bool TWS = SH::NPASS > 1 && TWBYTES <= 16384;
+    static const int G_T = (128 / SH::T) > 1 ? (128 / SH::T) : 1;                // ~128 threads per block
+    static const int G_S = XBYTES ? ((96 * 1024) / XBYTES > 1 ? (96 * 1024) / XBYTES : 1) : 1024;
+    static const int G_0 = G_T < G_S ? G_T : G_S;
+    static const int G = (SH::T > 32 && G_0 > 15) ? 15 : G_0;                   // named barriers 1..15
+    static const size_t SMEM = (size_t)G * XBYTES + (TWS ? TWBYTES : 0);
+};
+
+template <class SH, typename V, int FMT>
+static bool fsea_fill(fsea_kernel_info* o, const char* name) {
+    typedef fsea_cfg<SH, V> C;
+    o->fn = (const void*)&fsea_fft_kernel<SH, V, FMT, C::G, C::TWS>;
+    o->threads = SH::T * C::G;
+    o->groups = C::G;
+    o->lanes = fsea_vt<V>::lanes;
+    o->smem = C::SMEM;
+    o->n = SH::N; o->r0 = SH::R0; o->r1 = SH::R1; o->r2 = SH::R2;
+    o->tw1 = SH::TW1; o->tw2 = SH::TW2;
+    o->scalar_bytes = C::SB;
+    o->name = name;
+    return true;
+}
+
+#define FSEA_STR2(x) #x
+#define FSEA_STR(x) FSEA_STR2(x)
+#define FSEA_DEFINE_SIZE(N, R0, R1, R2)                                                                  \
+    bool fsea_get_kernel_##N(int variant, fsea_kernel_info* out) {                                       \
+        typedef fsea_shape<N, R0, R1, R2> SH;                                                            \
+        switch (variant) {                                                                               \
+            case FSEA_VAR_F32:                                                                           \
+                return fsea_fill<SH, float, FSEA_IN_U8>(out, "fft<" FSEA_STR(N) ":" FSEA_STR(R0) "x" FSEA_STR(R1) "x" FSEA_STR(R2) ",f32>");      \
+            case FSEA_VAR_F32X2:                                                                         \
+                return fsea_fill<SH, f2, FSEA_IN_U8>(out, "fft<" FSEA_STR(N) ":" FSEA_STR(R0) "x" FSEA_STR(R1) "x" FSEA_STR(R2) ",f32x2>");       \
+            case FSEA_VAR_F32C:                                                                          \
+                return fsea_fill<SH, float, FSEA_IN_F32C>(out, "fft<" FSEA_STR(N) ":" FSEA_STR(R0) "x" FSEA_STR(R1) "x" FSEA_STR(R2) ",f32c>");   \
+            case FSEA_VAR_F64:                                                                           \
+                return fsea_fill<SH, double, FSEA_IN_F64C>(out, "fft<" FSEA_STR(N) ":" FSEA_STR(R0) "x" FSEA_STR(R1) "x" FSEA_STR(R2) ",f64>");   \
+        }                                                                                                \
+        return false;                                                                                    \
+    }

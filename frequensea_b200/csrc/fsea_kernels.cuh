@@ -1,0 +1,376 @@
+// fsea_kernels.cuh -- the sm_100a IQ -> spectrum kernels.
+//
+// One kernel template serves every transform length: a mixed-radix Stockham
+// FFT whose butterflies are the straight-line register codelets of
+// fsea_codelets.cuh (radix 8/16/32, 6-op "tangent" butterflies) and whose
+// only inter-thread traffic is one shared-memory exchange per pass boundary.
+//
+//   N = R0 * R1 * R2   (R2 = 1: two passes, R1 = R2 = 1: one pass)
+//   P = max radix      points a thread holds in registers
+//   T = N / P          threads that cooperate on one sequence ("a group")
+//
+// A "unit" of work is one sequence (V = float / double) or a PAIR of
+// independent sequences (V = f2: two frames, or two neighbouring columns /
+// rows of a four-step transform) whose fp32 arithmetic is issued as packed
+// FADD2 / FMUL2 / FFMA2.  Pass p (radix R, p_prev = product of earlier
+// radices, M = N / R butterflies, butterfly i, k = i mod p_prev):
+//     u_j  = x[i + j M] * W_{p_prev R}^{j k}        j = 0..R-1
+//     v    = DFT_R(u)
+//     y[(i - k) R + k + m p_prev] = v_m              m = 0..R-1
+// (autosort: the last pass leaves natural order).  The exchange buffer is
+// addressed through a' = a + (a >> log2 R0), which makes every STS/LDS of
+// every pass bank-conflict free while keeping all per-element offsets
+// compile-time immediates.
+//
+// What replaces what: the unpack + (-1)^n + fftw_execute + magnitude + DC
+// patch of src/nrf.c:598-631 and the per-row work of c/fft-batch.c:61-92 /
+// c/fft-batch-broad.c:63-118.  The (-1)^n pre-multiply of the reference is
+// realised as the equivalent output rotation by N/2 (store index), and its
+// uncentred u8/256 scaling as centred samples plus the analytic DC term
+// N/2 (1+i) in bin N/2 (exact by linearity, keeps fp32 error at 1e-7).
+#pragma once
+#include <stdint.h>
+#include "fsea_codelets.cuh"
+#include "../../include/fsea.h"
+#include "fsea_kparams.h"
+
+
+template <int X> struct fsea_log2 { static const int v = 1 + fsea_log2<X / 2>::v; };
+template <> struct fsea_log2<1> { static const int v = 0; };
+
+template <int N_, int R0_, int R1_, int R2_>
+struct fsea_shape {
+    static const int N = N_, R0 = R0_, R1 = R1_, R2 = R2_;
+    static const int P = (R0 > R1 ? (R0 > R2 ? R0 : R2) : (R1 > R2 ? R1 : R2));
+    static const int T = N / P;
+    static const int NPASS = (R1 == 1 ? 1 : (R2 == 1 ? 2 : 3));
+    static const int L0 = fsea_log2<R0>::v;
+    static const int UNITS = N + (N >> L0);          // padded exchange length
+    static const int TW1 = (R1 - 1) * R0;            // pass-1 table entries
+    static const int TW2 = (R2 - 1) * R0 * R1;       // pass-2 table entries
+    static_assert(R0 * R1 * R2 == N, "radices must multiply to N");
+    static_assert(R0 >= 8 || N < 8, "first radix >= 8 keeps the exchange conflict-free");
+};
+
+// ---- scalar helpers ---------------------------------------------------------
+__device__ __forceinline__ float fsea_sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float fsea_db(float pwr) {          // 10 log10(pwr + 1e-20)
+    return 3.010299956639812f * __log2f(pwr + 1.0e-20f);
+}
+__device__ __forceinline__ uint8_t fsea_pix(float db, float scale) {   // c/fft-batch.c:33-35,90-91
+    int v = __float2int_rz(db * scale);
+    v = max(0, min(255, v));
+    return (uint8_t)v;
+}
+
+template <typename V> struct fsea_cplx;
+template <> struct fsea_cplx<float>  { typedef float2 t; };
+template <> struct fsea_cplx<f2>     { typedef float2 t; };
+template <> struct fsea_cplx<double> { typedef double2 t; };
+
+// lane accessors: sequence `l` of the unit
+__device__ __forceinline__ float fsea_lane(float v, int) { return v; }
+__device__ __forceinline__ double fsea_lane(double v, int) { return v; }
+__device__ __forceinline__ float fsea_lane(f2 v, int l) { return l ? v.v.y : v.v.x; }
+
+// ---- input side: element e of the unit's sequence(s) -> (re, im) ------------
+// 8-bit IQ -> fp32 without cvt: PRMT drops the byte into the mantissa of
+// 2^15 (0x47000000 | b = 32768 + b/256), one FADD removes 32768.5:
+// (b - 128)/256 exactly.  Two's-complement input is flipped to offset binary
+// first (b ^ 0x80 == (b + 128) mod 256, src/nrf.c:102-105).
+// FMT here is FSEA_IN_U8 for both 8-bit conventions (the XOR mask is a kernel
+// argument) or FSEA_IN_F32C.
+template <int FMT, typename V> struct fsea_in;
+
+template <int FMT> struct fsea_in<FMT, float> {
+    const uint8_t* p;
+    uint32_t xm;
+    __device__ __forceinline__ void init(const fsea_kparams& kp, long unit, bool& live) {
+        long s = unit < kp.n_seq ? unit : kp.n_seq - 1;
+        live = unit < kp.n_seq;
+        xm = kp.xor_mask;
+        p = (const uint8_t*)kp.in + s * kp.seq_stride * (FMT == FSEA_IN_F32C ? 8 : 2);
+    }
+    __device__ __forceinline__ void load(int e, float& re, float& im) const {
+        if (FMT == FSEA_IN_F32C) {
+            float2 v = __ldg((const float2*)p + e);
+            re = v.x; im = v.y;
+        } else {
+            const uint32_t w = (uint32_t)__ldg((const unsigned short*)p + e) ^ xm;
+            re = __uint_as_float(__byte_perm(w, 0x47000000u, 0x7650)) - 32768.5f;
+            im = __uint_as_float(__byte_perm(w, 0x47000000u, 0x7651)) - 32768.5f;
+        }
+    }
+};
+
+template <int FMT> struct fsea_in<FMT, f2> {
+    const uint8_t *pa, *pb;
+    uint32_t xm;
+    __device__ __forceinline__ void init(const fsea_kparams& kp, long unit, bool& live) {
+        long s0 = 2 * unit, s1 = 2 * unit + 1;
+        live = s0 < kp.n_seq;
+        if (s0 >= kp.n_seq) s0 = kp.n_seq - 1;
+        if (s1 >= kp.n_seq) s1 = kp.n_seq - 1;
+        xm = kp.xor_mask;
+        const long b = (FMT == FSEA_IN_F32C ? 8 : 2);
+        pa = (const uint8_t*)kp.in + s0 * kp.seq_stride * b;
+        pb = (const uint8_t*)kp.in + s1 * kp.seq_stride * b;
+    }
+    __device__ __forceinline__ void load(int e, f2& re, f2& im) const {
+        if (FMT == FSEA_IN_F32C) {
+            float2 a = __ldg((const float2*)pa + e), b = __ldg((const float2*)pb + e);
+            re = mk2(a.x, b.x); im = mk2(a.y, b.y);
+        } else {
+            const uint32_t wa = (uint32_t)__ldg((const unsigned short*)pa + e) ^ xm;
+            const uint32_t wb = (uint32_t)__ldg((const unsigned short*)pb + e) ^ xm;
+            f2 r = mk2(__uint_as_float(__byte_perm(wa, 0x47000000u, 0x7650)),
+                       __uint_as_float(__byte_perm(wb, 0x47000000u, 0x7650)));
+            f2 i = mk2(__uint_as_float(__byte_perm(wa, 0x47000000u, 0x7651)),
+                       __uint_as_float(__byte_perm(wb, 0x47000000u, 0x7651)));
+            const f2 off = mk2(32768.5f, 32768.5f);
+            re = vsub(r, off); im = vsub(i, off);
+        }
+    }
+};
+
+template <> struct fsea_in<FSEA_IN_F64C, double> {
+    const double2* p;
+    __device__ __forceinline__ void init(const fsea_kparams& kp, long unit, bool& live) {
+        long s = unit < kp.n_seq ? unit : kp.n_seq - 1;
+        live = unit < kp.n_seq;
+        p = (const double2*)kp.in + s * kp.seq_stride;
+    }
+    __device__ __forceinline__ void load(int e, double& re, double& im) const {
+        double2 v = __ldg(p + e);
+        re = v.x; im = v.y;
+    }
+};
+
+// ---- output side: bin k of the unit's sequence(s) ---------------------------
+// The reference's (-1)^n input modulation (src/nrf.c:611-612) is the output
+// rotation by N/2: FFT bin k is stored at position (k + N/2) mod N.  In the
+// last pass a thread owns bins i + m*M (i < M), so the position is
+// i + ((m*M + N/2) mod N): a per-thread base pointer plus an immediate.
+template <int N, typename V> struct fsea_out {
+    typedef typename fsea_vt<V>::scalar S;
+    static const int LANES = fsea_vt<V>::lanes;
+    uint8_t* row[LANES];
+    bool live[LANES];
+    float pix_scale;
+    __device__ __forceinline__ void init(const fsea_kparams& kp, long unit, bool unit_live, int esz) {
+        pix_scale = kp.pix_scale;
+#pragma unroll
+        for (int l = 0; l < LANES; l++) {
+            long s = unit * LANES + l;
+            live[l] = unit_live && s < kp.n_seq;
+            row[l] = (uint8_t*)kp.out + (size_t)(live[l] ? s : 0) * N * esz;
+        }
+    }
+    template <int OUT> __device__ __forceinline__ void put(int l, int pos, S pwr) const {
+        if (!live[l]) return;
+        if (OUT == FSEA_OUT_MAG) {
+            if (sizeof(S) == 8) ((double*)row[l])[pos] = sqrt((double)pwr);
+            else ((float*)row[l])[pos] = fsea_sqrt_approx((float)pwr);
+        } else if (OUT == FSEA_OUT_LOGMAG) {
+            if (sizeof(S) == 8) ((double*)row[l])[pos] = 10.0 * log10((double)pwr + 1.0e-20);
+            else ((float*)row[l])[pos] = fsea_db((float)pwr);
+        } else {
+            if (sizeof(S) == 8) {
+                int v = (int)(10.0 * log10((double)pwr + 1.0e-20) * (double)pix_scale);
+                row[l][pos] = (uint8_t)max(0, min(255, v));
+            } else {
+                row[l][pos] = fsea_pix(fsea_db((float)pwr), pix_scale);
+            }
+        }
+    }
+    // bins i + m*M, m = 0..R-1, of one butterfly; dc_patch: bin N-1 also fills
+    // the DC slot N/2 and bin 0 is not stored (src/nrf.c:621-622).
+    template <int OUT, int R, int M>
+    __device__ __forceinline__ void store_bfly(int i, const V* re, const V* im, bool dc_patch) const {
+#pragma unroll
+        for (int m = 0; m < R; m++) {
+            constexpr int NN = N;
+            const int off = (m * M + NN / 2) & (NN - 1);
+            if (m == 0 && dc_patch && i == 0) continue;
+            const V pw = vfma2(re[m], re[m], vmul(im[m], im[m]));
+#pragma unroll
+            for (int l = 0; l < LANES; l++) {
+                put<OUT>(l, i + off, fsea_lane(pw, l));
+                if (m == R - 1 && dc_patch && i == M - 1) put<OUT>(l, NN / 2, fsea_lane(pw, l));
+            }
+        }
+    }
+    template <int R, int M>
+    __device__ __forceinline__ void store_sel(int mode, int i, const V* re, const V* im, bool dc_patch) const {
+        if (mode == FSEA_OUT_MAG) store_bfly<FSEA_OUT_MAG, R, M>(i, re, im, dc_patch);
+        else if (mode == FSEA_OUT_LOGMAG) store_bfly<FSEA_OUT_LOGMAG, R, M>(i, re, im, dc_patch);
+        else store_bfly<FSEA_OUT_PIX, R, M>(i, re, im, dc_patch);
+    }
+};
+
+// ---- group barrier ----------------------------------------------------------
+template <int T> __device__ __forceinline__ void fsea_group_sync(int group) {
+    if (T <= 32) {
+        __syncwarp();
+    } else {
+        asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(T) : "memory");
+    }
+}
+
+// ---- the kernel -------------------------------------------------------------
+// block = G groups of T threads; grid-stride over units; dynamic smem =
+// G * UNITS * sizeof(unit) [+ twiddle tables when TWS].
+template <class SH, typename V, int FMT, int G, bool TWS>
+__global__ void __launch_bounds__(SH::T* G)
+fsea_fft_kernel(const fsea_kparams kp) {
+    typedef typename fsea_vt<V>::scalar S;
+    typedef typename fsea_cplx<V>::t S2;
+    constexpr int N = SH::N, R0 = SH::R0, R1 = SH::R1, R2 = SH::R2, P = SH::P, T = SH::T;
+    constexpr int L0 = SH::L0, NPASS = SH::NPASS;
+    struct alignas(16) unit_t { V re, im; };
+
+    extern __shared__ __align__(16) unsigned char fsea_smem[];
+    unit_t* xbuf_all = reinterpret_cast<unit_t*>(fsea_smem);
+    const int tid = threadIdx.x;
+    const int g = tid / T;
+    const int t = tid - g * T;
+    unit_t* xb = xbuf_all + (size_t)g * SH::UNITS;
+
+    const S2* tw1 = (const S2*)kp.tw1;
+    const S2* tw2 = (const S2*)kp.tw2;
+    if (TWS && NPASS > 1) {
+        S2* stw = reinterpret_cast<S2*>(xbuf_all + (size_t)G * SH::UNITS);
+        for (int q = tid; q < SH::TW1 + SH::TW2; q += T * G)
+            stw[q] = (q < SH::TW1) ? tw1[q] : tw2[q - SH::TW1];
+        __syncthreads();
+        tw1 = stw;
+        tw2 = stw + SH::TW1;
+    }
+
+    const bool dc_patch = (kp.flags & FSEA_FLAG_DC_PATCH) != 0;
+    const int out_mode = kp.out_mode;
+    const int out_esz = (out_mode == FSEA_OUT_PIX) ? 1 : (int)sizeof(S);
+    const long n_units = (kp.n_seq + fsea_vt<V>::lanes - 1) / fsea_vt<V>::lanes;
+
+    for (long base = (long)blockIdx.x * G; base < n_units; base += (long)gridDim.x * G) {
+        const long unit = base + g;
+        bool live;
+        fsea_in<FMT, V> in;
+        in.init(kp, unit, live);
+        fsea_out<N, V> out;
+        out.init(kp, live ? unit : 0, live, out_esz);
+
+        V re[P], im[P];
+
+        // ---------------- pass 0: radix R0, p_prev = 1 ----------------
+        {
+            constexpr int M = N / R0, B = P / R0;
+            if (kp.window) {
+#pragma unroll
+                for (int b = 0; b < B; b++) {
+                    const int i = t + b * T;
+#pragma unroll
+                    for (int j = 0; j < R0; j++) {
+                        in.load(i + j * M, re[b * R0 + j], im[b * R0 + j]);
+                        const S w = (S)__ldg(kp.window + i + j * M);
+                        re[b * R0 + j] = vmuls(re[b * R0 + j], w);
+                        im[b * R0 + j] = vmuls(im[b * R0 + j], w);
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int b = 0; b < B; b++) {
+                    const int i = t + b * T;
+#pragma unroll
+                    for (int j = 0; j < R0; j++) in.load(i + j * M, re[b * R0 + j], im[b * R0 + j]);
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < B; b++) fsea_dft<R0, V>::run(re + b * R0, im + b * R0);
+            if (NPASS == 1) {
+                // N = R0, T = 1: bins m
+                if (kp.dc_term) { re[0] = vadd(re[0], vsplat((S)(N / 2), re[0])); im[0] = vadd(im[0], vsplat((S)(N / 2), im[0])); }
+                out.template store_sel<R0, 1>(out_mode, 0, re, im, dc_patch);
+            } else {
+#pragma unroll
+                for (int b = 0; b < B; b++) {
+                    const int i = t + b * T;
+                    unit_t* w = xb + i * (R0 + 1);                 // a' = i (R0 + 1) + m
+#pragma unroll
+                    for (int m = 0; m < R0; m++) { w[m].re = re[b * R0 + m]; w[m].im = im[b * R0 + m]; }
+                }
+            }
+        }
+        if (NPASS == 1) continue;
+        fsea_group_sync<T>(g);
+
+        // ---------------- pass 1: radix R1, p_prev = R0 ----------------
+        {
+            constexpr int M = N / R1, B = P / R1;
+            constexpr int JSTR = M + (M >> L0);                    // padded stride of j
+#pragma unroll
+            for (int b = 0; b < B; b++) {
+                const int i = t + b * T;
+                const int k = i & (R0 - 1);
+                const unit_t* r = xb + i + (i >> L0);
+#pragma unroll
+                for (int j = 0; j < R1; j++) { re[b * R1 + j] = r[j * JSTR].re; im[b * R1 + j] = r[j * JSTR].im; }
+#pragma unroll
+                for (int j = 1; j < R1; j++) {
+                    const S2 w = tw1[(j - 1) * R0 + k];
+                    vcmul(re[b * R1 + j], im[b * R1 + j], w.x, w.y);
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < B; b++) fsea_dft<R1, V>::run(re + b * R1, im + b * R1);
+            if (NPASS == 2) {
+                // N = R0 R1: i < R0 = M, k = i, bins i + m R0
+                if (kp.dc_term && t == 0) { re[0] = vadd(re[0], vsplat((S)(N / 2), re[0])); im[0] = vadd(im[0], vsplat((S)(N / 2), im[0])); }
+#pragma unroll
+                for (int b = 0; b < B; b++)
+                    out.template store_sel<R1, M>(out_mode, t + b * T, re + b * R1, im + b * R1, dc_patch);
+            } else {
+                fsea_group_sync<T>(g);                             // all pass-1 reads done (WAR)
+#pragma unroll
+                for (int b = 0; b < B; b++) {
+                    const int i = t + b * T;
+                    const int k = i & (R0 - 1), hi = i >> L0;
+                    unit_t* w = xb + hi * (R0 * R1 + R1) + k;      // a' = hi (R0 R1 + R1) + k + m (R0 + 1)
+#pragma unroll
+                    for (int m = 0; m < R1; m++) { w[m * (R0 + 1)].re = re[b * R1 + m]; w[m * (R0 + 1)].im = im[b * R1 + m]; }
+                }
+            }
+        }
+        if (NPASS == 2) { fsea_group_sync<T>(g); continue; }      // the next unit rewrites the exchange
+        fsea_group_sync<T>(g);
+
+        // ---------------- pass 2: radix R2, p_prev = R0 R1 ----------------
+        {
+            constexpr int M = N / R2, B = P / R2;
+            constexpr int JSTR = M + (M >> L0);
+#pragma unroll
+            for (int b = 0; b < B; b++) {
+                const int i = t + b * T;                           // k = i
+                const unit_t* r = xb + i + (i >> L0);
+#pragma unroll
+                for (int j = 0; j < R2; j++) { re[b * R2 + j] = r[j * JSTR].re; im[b * R2 + j] = r[j * JSTR].im; }
+#pragma unroll
+                for (int j = 1; j < R2; j++) {
+                    const S2 w = tw2[(j - 1) * M + i];
+                    vcmul(re[b * R2 + j], im[b * R2 + j], w.x, w.y);
+                }
+            }
+#pragma unroll
+            for (int b = 0; b < B; b++) fsea_dft<R2, V>::run(re + b * R2, im + b * R2);
+            if (kp.dc_term && t == 0) { re[0] = vadd(re[0], vsplat((S)(N / 2), re[0])); im[0] = vadd(im[0], vsplat((S)(N / 2), im[0])); }
+#pragma unroll
+            for (int b = 0; b < B; b++)
+                out.template store_sel<R2, M>(out_mode, t + b * T, re + b * R2, im + b * R2, dc_patch);
+        }
+        fsea_group_sync<T>(g);
+    }
+}

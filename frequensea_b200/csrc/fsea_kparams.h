@@ -1,0 +1,19 @@
+// fsea_kparams.h -- the kernel argument block, shared by the launch code
+// (fsea_engine.cu) and the kernels (fsea_kernels.cuh).
+#pragma once
+#include <stdint.h>
+
+struct fsea_kparams {
+    const void* in;        // raw IQ (8-bit pairs), float2 or double2 samples
+    void* out;             // float / uint8 / double rows of N
+    long n_seq;            // sequences (frames) in the batch
+    long seq_stride;       // complex samples between sequence starts (hop)
+    const void* tw1;       // pass-1 twiddles [j-1][k], k < R0            (S2 = float2/double2)
+    const void* tw2;       // pass-2 twiddles [j-1][k], k < R0*R1
+    const float* window;   // N floats or nullptr
+    float pix_scale;       // S * 10/log2(10) folded on the host? no: plain S
+    int flags;             // FSEA_FLAG_*
+    int dc_term;           // 1: add N/2 (1+i) to bin k=0 (uncentred 8-bit input, no patch)
+    int out_mode;          // FSEA_OUT_*
+    uint32_t xor_mask;     // 0x8080 for two's-complement input (FSEA_IN_S8), else 0
+};

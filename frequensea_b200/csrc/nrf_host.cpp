@@ -1,0 +1,313 @@
+// nrf_host.cpp -- the reference's nrf_* operator API for the IQ -> spectrum
+// path (include/nrf.h), as a one-frame client of the B200 engine.
+//
+// What is kept from the reference (behaviour, not code): the push-style block
+// graph (src/nrf.c:24-50), the file-replay device with its 60 Hz producer
+// thread and (b+128)%256 byte convention (src/nrf.c:95-131,162-170,256-357),
+// nrf_fft's observable semantics -- first N samples of the buffer, x = u8/256
+// or raw f64, (-1)^n shift, linear magnitude, row[N/2] = row[N/2-1], N x H
+// float64 history with row 0 newest, nrf_fft_shift (src/nrf.c:557-642) -- and
+// fail-stop errors (message on stderr + exit, src/nrf.c:54-78).
+//
+// What is replaced: fftw_plan_dft_1d / fftw_execute (src/nrf.c:564,615) and
+// the per-sample powf loop (src/nrf.c:601-614) by fsea_exec_host(), i.e. the
+// sm_100a kernels.  There is no CPU FFT here: without a CUDA device
+// nrf_fft_new() fails loudly.
+#include "nrf.h"
+
+#include <assert.h>
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "fsea.h"
+
+// ---------------------------------------------------------------- fail-stop
+static void nrf_die(const char* what, int code) {
+    fprintf(stderr, "NRF fatal error: %s: %s", what, fsea_strerror(code));
+    if (code == FSEA_ERR_CUDA) fprintf(stderr, " (%s)", fsea_last_cuda_error());
+    fprintf(stderr, "\n");
+    exit(EXIT_FAILURE);
+}
+
+// ---------------------------------------------------------------- block graph
+extern "C" void nrf_block_init(nrf_block* block, nrf_block_type type,
+                               nrf_block_process_fn process_fn, nrf_block_result_fn result_fn) {
+    assert(block->n_outputs == 0);          // objects are calloc'ed (src/nrf.c:28)
+    block->type = type;
+    block->process_fn = process_fn;
+    block->result_fn = result_fn;
+}
+
+extern "C" void nrf_block_connect(nrf_block* input, nrf_block* output) {
+    assert(input->n_outputs < NRF_BLOCK_MAX_OUTPUTS);
+    input->outputs[input->n_outputs++] = output;
+}
+
+// process this block, then hand its result to every connected output; the
+// intermediate result belongs to this call and is released here (src/nrf.c:37-50)
+extern "C" void nrf_block_process(nrf_block* block, nut_buffer* buffer) {
+    if (block->process_fn) block->process_fn(block, buffer);
+    if (block->n_outputs <= 0) return;
+    nut_buffer* result = block->result_fn(block);
+    for (int o = 0; o < block->n_outputs; o++) nrf_block_process((nrf_block*)block->outputs[o], result);
+    nut_buffer_free(result);
+}
+
+// ---------------------------------------------------------------- device (file replay)
+static const int kReplaySampleRate = 5000000;     // what the reference reports for replay, src/nrf.c:254
+
+// One device block arrives: convert two's-complement capture bytes to the
+// offset-binary u8 convention of nut buffers, publish, run the graph (src/nrf.c:95-131).
+static void device_ingest_block(nrf_device* dev, const uint8_t* raw) {
+    if (!dev->receiving) return;
+    pthread_mutex_lock(&dev->data_mutex);
+    const bool flip = dev->device_type != NRF_DEVICE_RTLSDR;
+    for (int i = 0; i < NRF_BUFFER_SIZE_BYTES; i++) dev->samples[i] = flip ? (uint8_t)(raw[i] ^ 0x80u) : raw[i];
+    pthread_mutex_unlock(&dev->data_mutex);
+    if (dev->decode_cb_fn) dev->decode_cb_fn(dev, dev->decode_cb_ctx);
+    if (!dev->receiving) return;
+    nrf_block_process(&dev->block, NULL);
+}
+
+static void* device_replay_thread(void* arg) {
+    nrf_device* dev = (nrf_device*)arg;
+    while (dev->receiving) {
+        device_ingest_block(dev, dev->receive_buffer + (size_t)dev->dummy_block_index * NRF_BUFFER_SIZE_BYTES);
+        if (!dev->paused) {                       // src/nrf.c:153-160
+            if (++dev->dummy_block_index >= dev->dummy_block_length) dev->dummy_block_index = 0;
+        }
+        nut_sleep_milliseconds(1000 / 60);
+    }
+    return NULL;
+}
+
+extern "C" nrf_device* nrf_device_new_with_config(const nrf_device_config config) {
+    nrf_device* dev = (nrf_device*)calloc(1, sizeof(nrf_device));
+    nrf_block_init(&dev->block, NRF_BLOCK_SOURCE, NULL, (nrf_block_result_fn)nrf_device_get_samples_buffer);
+    pthread_mutex_init(&dev->data_mutex, NULL);
+    dev->device_type = NRF_DEVICE_DUMMY;          // no USB SDR drivers in this build
+    dev->sample_rate = kReplaySampleRate;
+    const char* path = config.data_file;
+    fprintf(stderr, "WARN nrf_device_new: no SDR driver in this build. Replaying data file %s\n", path ? path : "(none)");
+    FILE* fp = path ? fopen(path, "rb") : NULL;
+    long size = 0;
+    if (fp) {
+        fseek(fp, 0L, SEEK_END);
+        size = ftell(fp);
+        rewind(fp);
+    }
+    if (fp && size >= NRF_BUFFER_SIZE_BYTES) {
+        dev->receive_buffer = (uint8_t*)calloc((size_t)size, 1);
+        dev->dummy_block_length = (int)(size / NRF_BUFFER_SIZE_BYTES);
+        if (fread(dev->receive_buffer, (size_t)size, 1, fp) != 1) fprintf(stderr, "WARN nrf_device_new: short read on %s\n", path);
+    } else {
+        // Missing file -> one silent block, as the reference (src/nrf.c:273-277).  A file
+        // shorter than one block would give the reference a zero-length ring and an
+        // out-of-bounds read (src/nrf.c:268); it is padded to one block here instead.
+        if (path && !fp) fprintf(stderr, "WARN nrf_device_new: Couldn't open %s. Using empty buffer.\n", path);
+        dev->receive_buffer = (uint8_t*)calloc(NRF_BUFFER_SIZE_BYTES, 1);
+        dev->dummy_block_length = 1;
+        if (fp && size > 0 && fread(dev->receive_buffer, (size_t)size, 1, fp) != 1) { /* keep zeros */ }
+    }
+    if (fp) fclose(fp);
+    dev->dummy_block_index = 0;
+    dev->receiving = 1;
+    pthread_create(&dev->receive_thread, NULL, device_replay_thread, dev);
+    return dev;
+}
+
+extern "C" nrf_device* nrf_device_new(double freq_mhz, const char* data_file) {
+    nrf_device_config config;
+    memset(&config, 0, sizeof(config));
+    config.freq_mhz = freq_mhz;
+    config.data_file = data_file;
+    return nrf_device_new_with_config(config);
+}
+
+// replay has no tuner: the value is returned unclamped (src/nrf.c:81-90,324-334)
+extern "C" double nrf_device_set_frequency(nrf_device* device, double freq_mhz) {
+    (void)device;
+    return freq_mhz;
+}
+
+extern "C" void nrf_device_set_decode_handler(nrf_device* device, nrf_device_decode_cb_fn fn, void* ctx) {
+    device->decode_cb_fn = fn;
+    device->decode_cb_ctx = ctx;
+}
+
+extern "C" void nrf_device_set_paused(nrf_device* device, int paused) { device->paused = paused; }
+
+extern "C" void nrf_device_step(nrf_device* device) {
+    if (++device->dummy_block_index >= device->dummy_block_length) device->dummy_block_index = 0;
+}
+
+extern "C" nut_buffer* nrf_device_get_samples_buffer(nrf_device* device) {
+    pthread_mutex_lock(&device->data_mutex);
+    nut_buffer* snapshot = nut_buffer_new_u8(NRF_SAMPLES_LENGTH, 2, device->samples);
+    pthread_mutex_unlock(&device->data_mutex);
+    return snapshot;
+}
+
+extern "C" void nrf_device_free(nrf_device* device) {
+    device->receiving = 0;
+    pthread_join(device->receive_thread, NULL);
+    free(device->receive_buffer);
+    pthread_mutex_destroy(&device->data_mutex);
+    free(device);
+}
+
+// ---------------------------------------------------------------- FFT block
+// Engine state behind nrf_fft::engine.  The staging arrays play the role of
+// the reference's persistent fft_in: a buffer shorter than N samples leaves
+// the tail of the previous call in place (src/nrf.c:599-614 only writes
+// size/2 entries); buffers longer than the reference's 131072-sample fft_in
+// (lua/fft-shifted.lua produces one) are clamped instead of overflowing.
+struct nrf_fft_engine {
+    fsea_plan* plan_u8 = nullptr;
+    fsea_plan* plan_f64 = nullptr;
+    uint8_t* stage_u8 = nullptr;     // 2N bytes
+    double* stage_f64 = nullptr;     // 2N doubles
+    float* row_f32 = nullptr;        // N
+    double* row_f64 = nullptr;       // N
+};
+
+static fsea_plan* make_plan(int n, int in_format) {
+    fsea_config cfg;
+    fsea_config_default(&cfg, n);
+    cfg.in_format = in_format;
+    cfg.out_mode = FSEA_OUT_MAG;
+    cfg.flags = FSEA_FLAG_DC_PATCH;              // row[N/2] = row[N/2-1], src/nrf.c:621-622
+    fsea_plan* plan = nullptr;
+    int rc = fsea_plan_create(&cfg, &plan);
+    if (rc != FSEA_OK) nrf_die("nrf_fft: fsea_plan_create", rc);
+    return plan;
+}
+
+extern "C" nrf_fft* nrf_fft_new(int fft_size, int fft_history_size) {
+    nrf_fft* fft = (nrf_fft*)calloc(1, sizeof(nrf_fft));
+    nrf_block_init(&fft->block, NRF_BLOCK_GENERIC, (nrf_block_process_fn)nrf_fft_process,
+                   (nrf_block_result_fn)nrf_fft_get_buffer);
+    fft->fft_size = fft_size;
+    fft->fft_history_size = fft_history_size;
+    fft->buffer = (double*)calloc((size_t)fft_size * (size_t)fft_history_size, sizeof(double));
+    nrf_fft_engine* eng = new nrf_fft_engine();
+    eng->plan_u8 = make_plan(fft_size, FSEA_IN_U8);
+    eng->stage_u8 = (uint8_t*)calloc(2 * (size_t)fft_size, 1);
+    eng->row_f32 = (float*)calloc((size_t)fft_size, sizeof(float));
+    fft->engine = eng;
+    return fft;
+}
+
+extern "C" void nrf_fft_process(nrf_fft* fft, nut_buffer* buffer) {
+    nrf_fft_engine* eng = (nrf_fft_engine*)fft->engine;
+    const int n = fft->fft_size;
+    const size_t have = (size_t)buffer->length * (size_t)buffer->channels / 2;   // complex samples offered
+    const size_t take = have < (size_t)n ? have : (size_t)n;                      // only the first N matter
+    double* row0 = fft->buffer;
+    const size_t hist = (size_t)n * (size_t)(fft->fft_history_size - 1);
+    int rc;
+    if (buffer->type == NUT_BUFFER_U8) {
+        memcpy(eng->stage_u8, buffer->data.u8, 2 * take);
+        rc = fsea_exec_host(eng->plan_u8, eng->stage_u8, eng->row_f32, 1);
+        if (rc != FSEA_OK) nrf_die("nrf_fft_process", rc);
+        if (fft->fft_history_size > 1) memmove(row0 + n, row0, hist * sizeof(double));   // src/nrf.c:617
+        for (int i = 0; i < n; i++) row0[i] = (double)eng->row_f32[i];
+    } else {
+        if (!eng->plan_f64) {
+            eng->plan_f64 = make_plan(n, FSEA_IN_F64C);
+            eng->stage_f64 = (double*)calloc(2 * (size_t)n, sizeof(double));
+            eng->row_f64 = (double*)calloc((size_t)n, sizeof(double));
+        }
+        memcpy(eng->stage_f64, buffer->data.f64, 2 * take * sizeof(double));
+        rc = fsea_exec_host(eng->plan_f64, eng->stage_f64, eng->row_f64, 1);
+        if (rc != FSEA_OK) nrf_die("nrf_fft_process", rc);
+        if (fft->fft_history_size > 1) memmove(row0 + n, row0, hist * sizeof(double));
+        memcpy(row0, eng->row_f64, (size_t)n * sizeof(double));
+    }
+}
+
+// horizontal scroll of every history row after a retune (src/nrf.c:569-596)
+extern "C" void nrf_fft_shift(nrf_fft* fft, double d) {
+    const int n = fft->fft_size, rows = fft->fft_history_size;
+    const int s = (int)round(n / d);
+    if (s == 0) return;
+    if (abs(s) >= n) {
+        memset(fft->buffer, 0, (size_t)n * rows * sizeof(double));
+        return;
+    }
+    for (int y = 0; y < rows; y++) {
+        double* row = fft->buffer + (size_t)y * n;
+        if (s > 0) {
+            memmove(row, row + s, (size_t)(n - s) * sizeof(double));
+            memset(row + (n - s), 0, (size_t)s * sizeof(double));
+        } else {
+            memmove(row - s, row, (size_t)(n + s) * sizeof(double));
+            memset(row, 0, (size_t)(-s) * sizeof(double));
+        }
+    }
+}
+
+extern "C" nut_buffer* nrf_fft_get_buffer(nrf_fft* fft) {
+    return nut_buffer_new_f64(fft->fft_size * fft->fft_history_size, 1, fft->buffer);
+}
+
+extern "C" void nrf_fft_free(nrf_fft* fft) {
+    nrf_fft_engine* eng = (nrf_fft_engine*)fft->engine;
+    if (eng) {
+        fsea_plan_destroy(eng->plan_u8);
+        fsea_plan_destroy(eng->plan_f64);
+        free(eng->stage_u8);
+        free(eng->stage_f64);
+        free(eng->row_f32);
+        free(eng->row_f64);
+        delete eng;
+    }
+    free(fft->buffer);          // the reference leaks this (src/nrf.c:637-642)
+    free(fft);
+}
+
+// ---------------------------------------------------------------- frequency shifter
+// Complex rotator in front of the FFT in lua/fft-shifted.lua (src/nrf.c:814-874):
+// out = in * e^{i phi_n} + 0.5, phase advanced by recurrence, state kept across calls.
+extern "C" nrf_freq_shifter* nrf_freq_shifter_new(int freq_offset, int sample_rate) {
+    nrf_freq_shifter* sh = (nrf_freq_shifter*)calloc(1, sizeof(nrf_freq_shifter));
+    nrf_block_init(&sh->block, NRF_BLOCK_GENERIC, (nrf_block_process_fn)nrf_freq_shifter_process,
+                   (nrf_block_result_fn)nrf_freq_shifter_get_buffer);
+    sh->freq_offset = freq_offset;
+    sh->sample_rate = sample_rate;
+    sh->cosine = 1.0;
+    sh->sine = 0.0;
+    return sh;
+}
+
+extern "C" void nrf_freq_shifter_process(nrf_freq_shifter* sh, nut_buffer* buffer) {
+    assert(buffer->channels == 2);
+    const double step = 2.0 * M_PI * sh->freq_offset / (double)sh->sample_rate;
+    const double dc = cos(step), ds = sin(step);
+    const int count = buffer->length * buffer->channels;
+    // The reference sizes its result as (count, 2), i.e. twice the payload, and
+    // fills only the first `count` values (src/nrf.c:849-852); kept, because
+    // nrf_fft_process() clamps what it reads.
+    if (!sh->buffer) sh->buffer = nut_buffer_new_f64(count, 2, NULL);
+    double* out = sh->buffer->data.f64;
+    double c = sh->cosine, s = sh->sine;
+    for (int i = 0; i + 1 < count; i += 2) {
+        const double vi = nut_buffer_get_f64(buffer, i), vq = nut_buffer_get_f64(buffer, i + 1);
+        out[i] = vi * c - vq * s + 0.5;
+        out[i + 1] = vi * s + vq * c + 0.5;
+        const double ns = c * ds + s * dc, nc = c * dc - s * ds;
+        s = ns;
+        c = nc;
+    }
+    sh->cosine = c;
+    sh->sine = s;
+}
+
+extern "C" nut_buffer* nrf_freq_shifter_get_buffer(nrf_freq_shifter* sh) { return nut_buffer_copy(sh->buffer); }
+
+extern "C" void nrf_freq_shifter_free(nrf_freq_shifter* sh) {
+    if (sh->buffer) nut_buffer_free(sh->buffer);
+    free(sh);
+}

@@ -1,0 +1,121 @@
+/*
+ * fsea.h -- C ABI of the B200 IQ -> spectrum engine (libfsea.so).
+ *
+ * This is the drop-in boundary below the reference's operator API: the
+ * reference's nrf_fft_* block (src/nrf.h:128-142, src/nrf.c:557-642) and its
+ * stand-alone sweep tools (c/fft-batch.c:54-102, c/fft-batch-broad.c:56-129,
+ * c/fft.c:45-56,181-197) call FFTW3 once per frame on the CPU
+ * (fftw_plan_dft_1d src/nrf.c:564, fftw_execute src/nrf.c:615); here the same
+ * per-frame work -- 8-bit IQ unpack, optional Hann window, power-of-two
+ * forward C2C FFT, fftshift, magnitude / log-magnitude / u8 pixel -- runs for
+ * a whole batch of frames in hand-written sm_100a kernels.  include/nrf.h
+ * (the reference's own operator names) is a one-frame client of this API.
+ *
+ * Plain C: pointers and sizes only.  Every function returns FSEA_OK (0) or a
+ * negative FSEA_ERR_* code; fsea_strerror() names it.  There is NO CPU
+ * fallback: without a CUDA device every compute entry point fails with
+ * FSEA_ERR_NO_DEVICE.
+ *
+ * Per-frame definition (frame f starts at complex sample f*hop; b = raw bytes):
+ *   t(b)   = b                     FSEA_IN_U8  (offset-binary: RTL-SDR, nut_buffer u8)
+ *          = (b + 128) mod 256     FSEA_IN_S8  (two's-complement HackRF / rfdata raw files;
+ *                                               fuses src/nrf.c:102-105)
+ *   x[n]   = (-1)^n * (t(b[2n]) + i t(b[2n+1])) / 256           window NONE  (src/nrf.c:605-612)
+ *          = (-1)^n * w[n] * ((t(b[2n])-128) + i (t(b[2n+1])-128)) / 256     window HANN,
+ *            w[n] = 0.5 (1 - cos(2 pi n / N))   (extension; no reference pin)
+ *          = (-1)^n * w[n] * sample[n]                          FSEA_IN_F32C / FSEA_IN_F64C
+ *   X[k]   = sum_n x[n] exp(-2 pi i n k / N)                    (k = N/2 is DC)
+ *   out[k] = |X[k]|                                             FSEA_OUT_MAG    (src/nrf.c:624-628)
+ *          = 10 log10(|X[k]|^2 + 1e-20)                         FSEA_OUT_LOGMAG (c/fft-batch.c:88-89)
+ *          = clamp_u8(trunc(pix_scale * 10 log10(|X[k]|^2 + 1e-20)))   FSEA_OUT_PIX (c/fft-batch.c:89-92)
+ *   FSEA_FLAG_DC_PATCH:  out[N/2] = out[N/2-1]   (src/nrf.c:621-622, c/fft-batch-broad.c:115-117)
+ * Output element type: float32 (MAG/LOGMAG), uint8 (PIX), float64 for
+ * FSEA_IN_F64C (computed in fp64).  Output row f holds N bins.
+ */
+#ifndef FSEA_H
+#define FSEA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSEA_VERSION 1
+
+enum { FSEA_IN_U8 = 0, FSEA_IN_S8 = 1, FSEA_IN_F32C = 2, FSEA_IN_F64C = 3 };
+enum { FSEA_WIN_NONE = 0, FSEA_WIN_HANN = 1 };
+enum { FSEA_OUT_MAG = 0, FSEA_OUT_LOGMAG = 1, FSEA_OUT_PIX = 2 };
+enum { FSEA_FLAG_DC_PATCH = 1 };
+/* arithmetic variant of the fp32 kernels (results agree to fp32 rounding) */
+enum { FSEA_ARITH_AUTO = 0, FSEA_ARITH_F32 = 1, FSEA_ARITH_F32X2 = 2 };
+
+enum {
+    FSEA_OK = 0,
+    FSEA_ERR_INVALID = -1,      /* bad argument / unsupported combination */
+    FSEA_ERR_UNSUPPORTED = -2,  /* fft_size not a power of two in [16, 65536] */
+    FSEA_ERR_NO_DEVICE = -3,    /* no CUDA device: there is no CPU fallback */
+    FSEA_ERR_CUDA = -4,         /* CUDA runtime error, see fsea_last_cuda_error() */
+    FSEA_ERR_NOMEM = -5
+};
+
+typedef struct {
+    int fft_size;      /* N: power of two, 16..65536 */
+    int hop;           /* complex samples between frame starts; 0 = N (no overlap); multiple of 8 */
+    int in_format;     /* FSEA_IN_* */
+    int window;        /* FSEA_WIN_* */
+    int out_mode;      /* FSEA_OUT_* */
+    int flags;         /* FSEA_FLAG_* */
+    float pix_scale;   /* S for FSEA_OUT_PIX (c/fft-batch.c: 10, c/fft-batch-broad.c: 5) */
+    int device;        /* CUDA device ordinal */
+    int arith;         /* FSEA_ARITH_* */
+    int reserved[7];
+} fsea_config;
+
+typedef struct fsea_plan fsea_plan;
+
+/* number of CUDA devices visible (0 when none: nothing else will work) */
+int fsea_device_count(void);
+const char *fsea_strerror(int code);
+/* text of the last CUDA error seen by this thread's calls ("" if none) */
+const char *fsea_last_cuda_error(void);
+
+void fsea_config_default(fsea_config *cfg, int fft_size);
+int fsea_plan_create(const fsea_config *cfg, fsea_plan **plan);
+int fsea_plan_destroy(fsea_plan *plan);
+
+/* bytes of input needed for n_frames, and bytes of output produced */
+size_t fsea_input_bytes(const fsea_plan *plan, long n_frames);
+size_t fsea_output_bytes(const fsea_plan *plan, long n_frames);
+/* frames that fit in `n_samples` complex samples */
+long fsea_frames_in(const fsea_plan *plan, size_t n_samples);
+
+/* Device-resident batch: d_in / d_out are device pointers on plan's device,
+ * d_in 16-byte aligned.  Asynchronous on `stream` (a cudaStream_t, NULL =
+ * default stream).  This is what bench.py's `value` times. */
+int fsea_exec_device(fsea_plan *plan, const void *d_in, void *d_out, long n_frames, void *stream);
+
+/* Host buffers: chunked, double-buffered H2D -> kernel -> D2H through pinned
+ * staging on two streams; returns when h_out is complete.  This is the call
+ * the nrf_fft shim and bench.py's `e2e` use. */
+int fsea_exec_host(fsea_plan *plan, const void *h_in, void *h_out, long n_frames);
+
+/* Number of kernel launches issued by this plan so far (bench gpu_launches). */
+long fsea_plan_launch_count(const fsea_plan *plan);
+/* Name of the kernel variant the plan dispatches to, e.g. "direct<1024:32x32,f32x2>". */
+const char *fsea_plan_kernel_name(const fsea_plan *plan);
+
+/* ---- waterfall history kept on the device ----------
+ * The reference scrolls an N x H float64 image by memcpy on every frame
+ * (src/nrf.c:617) and copies it whole on every read (src/nrf.c:633-635). */
+
+/* Mean of |X| over the first `rows` frames of a PIX/MAG batch -- the
+ * "interesting?" gate of c/fft-batch-broad.c:80-98 -- computed on the device
+ * from raw input.  Writes one double. */
+int fsea_gate_mean_host(fsea_plan *plan, const void *h_in, long rows, double *mean_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FSEA_H */

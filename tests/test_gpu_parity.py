@@ -1,0 +1,239 @@
+"""GPU suite (-m gpu): the CUDA path, called through the C ABI, against the
+oracle on the same inputs.
+
+Tolerances (north star: spectra within 1e-5 relative of a float64 DFT):
+  MAG     max_k |y - y_ref| <= 1e-5 * rms_k(y_ref)            per frame (fp32 kernels)
+  LOGMAG  |dB - dB_ref| <= 2e-3 dB wherever |X_ref| >= 1e-3 * rms (log of a cancelling bin is ill-conditioned)
+  PIX     |pix - pix_ref| <= 1 and fewer than 0.5 % of pixels differ (trunc() of a float)
+  F64     max |y - y_ref| <= 1e-11 * rms
+"""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import orc
+from conftest import BLOCK, synth_s8, synth_u8
+
+pytestmark = pytest.mark.gpu
+
+MAG_TOL = 1e-5
+
+
+def rel_err(got, ref):
+    ref = np.asarray(ref, dtype=np.float64)
+    rms = np.sqrt(np.mean(ref ** 2, axis=-1, keepdims=True))
+    return float(np.max(np.abs(got - ref) / rms))
+
+
+def oracle_rows(data, n, hop, frames, fmt, win, out, scale=10.0, flags=0):
+    per = 2
+    rows = []
+    for f in range(frames):
+        rows.append(orc.engine_frame(data[f * hop * per:], n, fmt, win, out, scale, flags))
+    return np.stack(rows)
+
+
+@pytest.fixture(scope="module")
+def fbg(fb):
+    assert fb.device_count() > 0, "-m gpu tests need a CUDA device (the product has no CPU path)"
+    return fb
+
+
+@pytest.mark.parametrize("arith", [1, 2])
+@pytest.mark.parametrize("n", [128, 1024])
+def test_golden_fixture_frames(fbg, iq, golden, n, arith):
+    """cfg2: every frame of the reference's capture block, nrf_fft semantics."""
+    fb = fbg
+    for name, raw in (("rf433", iq["rf433"]), ("rf200big", iq["rf200big4"][:BLOCK])):
+        frames = BLOCK // (2 * n)
+        plan = fb.Plan(n, in_format=fb.IN_S8, out_mode=fb.OUT_MAG, flags=fb.FLAG_DC_PATCH, arith=arith)
+        got = plan.exec_host(raw, frames)
+        first8 = golden[f"np_mag_{name}_n{n}_first8"]
+        assert rel_err(got[:8], first8) < MAG_TOL
+        sums = golden[f"np_magsum_{name}_n{n}"]
+        np.testing.assert_allclose(got.astype(np.float64).sum(axis=1), sums, rtol=2e-6)
+        ref = oracle_rows(raw, n, n, frames, orc.IN_S8, orc.WIN_NONE, orc.OUT_MAG, flags=orc.FLAG_DC_PATCH)
+        assert rel_err(got, ref) < MAG_TOL
+        # the reference's DC quirk: bin N/2 duplicates bin N/2-1 exactly
+        assert np.array_equal(got[:, n // 2], got[:, n // 2 - 1])
+        # and without the patch the uncentred DC term is there (|X[N/2]| ~ N/2*sqrt(2))
+        plan2 = fb.Plan(n, in_format=fb.IN_S8, out_mode=fb.OUT_MAG, arith=arith)
+        got2 = plan2.exec_host(raw, 1)
+        assert abs(got2[0, n // 2] - float(golden[f"np_dcbin_{name}_n{n}"])) < 1e-4 * n
+
+
+@pytest.mark.parametrize("n", [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192])
+@pytest.mark.parametrize("arith", [1, 2])
+def test_all_sizes_mag(fbg, n, arith):
+    fb = fbg
+    frames = 7                                   # odd: exercises the half-empty frame pair
+    data = synth_u8(n * frames, seed=n)
+    plan = fb.Plan(n, in_format=fb.IN_U8, out_mode=fb.OUT_MAG, flags=fb.FLAG_DC_PATCH, arith=arith)
+    got = plan.exec_host(data, frames)
+    ref = oracle_rows(data, n, n, frames, orc.IN_U8, orc.WIN_NONE, orc.OUT_MAG, flags=orc.FLAG_DC_PATCH)
+    assert rel_err(got, ref) < MAG_TOL, plan.kernel_name
+    plan = fb.Plan(n, in_format=fb.IN_U8, out_mode=fb.OUT_MAG, arith=arith)    # uncentred DC kept
+    got = plan.exec_host(data, frames)
+    ref = oracle_rows(data, n, n, frames, orc.IN_U8, orc.WIN_NONE, orc.OUT_MAG)
+    k = np.arange(n) != n // 2
+    assert rel_err(got[:, k], ref[:, k]) < MAG_TOL
+    np.testing.assert_allclose(got[:, n // 2], ref[:, n // 2], rtol=2e-6)
+
+
+@pytest.mark.parametrize("n,hop", [(256, 128), (1024, 512), (1024, 1000), (8192, 4096), (64, 8)])
+def test_hann_overlap_logmag(fbg, n, hop):
+    """cfg3 shape: Hann window, overlapping frames, log-magnitude."""
+    fb = fbg
+    frames = 9
+    data = synth_u8((frames - 1) * hop + n, seed=hop)
+    plan = fb.Plan(n, hop=hop, in_format=fb.IN_U8, window=fb.WIN_HANN, out_mode=fb.OUT_LOGMAG)
+    got = plan.exec_host(data, frames).astype(np.float64)
+    ref = oracle_rows(data, n, hop, frames, orc.IN_U8, orc.WIN_HANN, orc.OUT_LOGMAG)
+    lin = 10 ** (ref / 20)
+    ok = lin >= 1e-3 * np.sqrt(np.mean(lin ** 2, axis=1, keepdims=True))
+    assert ok.mean() > 0.95
+    assert np.max(np.abs(got - ref)[ok]) < 2e-3
+    plan = fb.Plan(n, hop=hop, in_format=fb.IN_U8, window=fb.WIN_HANN, out_mode=fb.OUT_MAG)
+    got = plan.exec_host(data, frames)
+    ref = oracle_rows(data, n, hop, frames, orc.IN_U8, orc.WIN_HANN, orc.OUT_MAG)
+    assert rel_err(got, ref) < MAG_TOL
+
+
+def test_sweep_pixels_match_reference_tools(fbg, iq, golden):
+    """cfg1 / cfg4 semantics: c/fft-batch.c (S=10, no patch) and c/fft-batch-broad.c (S=5, DC patch)."""
+    fb = fbg
+    raw = iq["rf200big4"]
+    for n, scale, flags, key in ((1024, 10.0, 0, "np_pix_batch_n1024"), (256, 5.0, fb.FLAG_DC_PATCH, "np_pix_broad_n256")):
+        plan = fb.Plan(n, hop=BLOCK // 2, in_format=fb.IN_S8, out_mode=fb.OUT_PIX, pix_scale=scale, flags=flags)
+        got = plan.exec_host(raw, 4)                       # one row per 262144-byte block, as the tools do
+        ref = golden[key]
+        d = np.abs(got.astype(int) - ref.astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 0.005
+        if n == 1024:
+            assert got[0, 512] == 255                      # SURVEY golden: DC pixel saturates without the patch
+        # all frames of block 0 against the oracle
+        frames = BLOCK // (2 * n)
+        plan = fb.Plan(n, in_format=fb.IN_S8, out_mode=fb.OUT_PIX, pix_scale=scale, flags=flags)
+        got = plan.exec_host(raw, frames)
+        ref = oracle_rows(raw, n, n, frames, orc.IN_S8, orc.WIN_NONE, orc.OUT_PIX, scale, flags)
+        d = np.abs(got.astype(int) - ref.astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 0.005
+
+
+def test_gate_mean(fbg, iq, golden):
+    fb = fbg
+    raw = iq["rf200big4"]
+    plan = fb.Plan(256, hop=BLOCK // 2, in_format=fb.IN_S8, out_mode=fb.OUT_MAG)
+    got = plan.gate_mean(raw, 4)
+    rows = np.stack([orc.batch_row(raw[b * BLOCK:], 256, 5.0, True)[1] for b in range(4)])
+    assert abs(got - orc.broad_gate_mean(rows)) < 1e-5 * got
+
+
+@pytest.mark.parametrize("n", [16, 256, 1024, 4096])
+def test_f64_and_f32c_inputs(fbg, n):
+    fb = fbg
+    rng = np.random.default_rng(n)
+    frames = 3
+    x = rng.standard_normal(2 * n * frames) * 0.3 + 0.5          # like the shifter's output (+0.5 offset)
+    plan = fb.Plan(n, in_format=fb.IN_F64C, out_mode=fb.OUT_MAG, flags=fb.FLAG_DC_PATCH)
+    got = plan.exec_host(x, frames)
+    assert got.dtype == np.float64
+    ref = np.stack([orc.nrf_fft_frame_f64(x[2 * n * f:], n) for f in range(frames)])
+    assert rel_err(got, ref) < 1e-11
+    xc = (x - 0.5).astype(np.float32)
+    plan = fb.Plan(n, in_format=fb.IN_F32C, out_mode=fb.OUT_MAG)
+    got = plan.exec_host(xc, frames)
+    ref = oracle_rows(xc, n, n, frames, orc.IN_F32C, orc.WIN_NONE, orc.OUT_MAG)
+    assert rel_err(got, ref) < MAG_TOL
+
+
+def test_edge_cases(fbg):
+    fb = fbg
+    plan = fb.Plan(1024, in_format=fb.IN_U8)
+    assert plan.exec_host(np.zeros(0, np.uint8), 0).shape == (0, 1024)      # empty batch
+    one = plan.exec_host(synth_u8(1024), 1)                                   # single frame (half pair)
+    assert one.shape == (1, 1024) and np.isfinite(one).all()
+    with pytest.raises(ValueError):
+        plan.exec_host(np.zeros(100, np.uint8), 1)                            # ragged: too short
+    # extreme bytes: all 0x00 / 0xFF / 0x80
+    for byte in (0, 255, 128):
+        data = np.full(2048, byte, np.uint8)
+        got = plan.exec_host(data, 1)
+        ref = orc.engine_frame(data, 1024, orc.IN_U8, orc.WIN_NONE, orc.OUT_MAG)
+        np.testing.assert_allclose(got[0], ref, atol=1e-3 * max(1.0, ref.max()) * 1e-2)
+
+
+def test_large_batch_properties(fbg):
+    """BASELINE-size batch through the device-resident call: Parseval per frame,
+    frame independence (a frame's spectrum does not depend on its neighbours /
+    position in the batch), determinism."""
+    import torch
+    fb = fbg
+    n, frames = 1024, 1 << 16
+    g = torch.Generator(device="cuda").manual_seed(1)
+    d_in = torch.randint(0, 256, (frames * n * 2,), dtype=torch.uint8, device="cuda", generator=g)
+    d_out = torch.empty((frames, n), dtype=torch.float32, device="cuda")
+    plan = fb.Plan(n, in_format=fb.IN_U8, out_mode=fb.OUT_MAG)
+    s = torch.cuda.current_stream().cuda_stream
+    plan.exec_device(d_in.data_ptr(), d_out.data_ptr(), frames, s)
+    torch.cuda.synchronize()
+    x = d_in.view(frames, n, 2).to(torch.float64) / 256.0
+    energy_t = (x ** 2).sum(dim=(1, 2)) * n
+    energy_f = (d_out.to(torch.float64) ** 2).sum(dim=1)
+    assert torch.max(torch.abs(energy_f / energy_t - 1)).item() < 1e-5        # Parseval
+    # spot-check frames against the oracle, including the last (odd positions too)
+    h_in = d_in.cpu().numpy()
+    for f in (0, 1, 12345, frames - 2, frames - 1):
+        ref = orc.engine_frame(h_in[f * 2 * n:], n, orc.IN_U8, orc.WIN_NONE, orc.OUT_MAG)
+        k = np.arange(n) != n // 2
+        assert rel_err(d_out[f].cpu().numpy()[k], ref[k]) < MAG_TOL
+    # permuting frames permutes rows (independence) and re-running is bit-identical
+    perm = torch.randperm(frames, device="cuda")
+    d_in2 = d_in.view(frames, -1)[perm].contiguous()
+    d_out2 = torch.empty_like(d_out)
+    plan.exec_device(d_in2.data_ptr(), d_out2.data_ptr(), frames, s)
+    torch.cuda.synchronize()
+    assert torch.equal(d_out2, d_out[perm])
+
+
+def test_nrf_fft_operator_matches_reference(fbg, iq, golden):
+    """The reference's own call sequence (lua/fft.lua:42-50) against the history the
+    compiled reference produced on the same four blocks."""
+    fb = fbg
+    nrf = fb.nrf
+    raw = iq["rf200big4"]
+    for n in (128, 1024):
+        fft = nrf.fft_new(n, 6)
+        for b in range(4):
+            u8 = orc.device_unpack(raw[b * BLOCK:(b + 1) * BLOCK])
+            buf = nrf.nut_buffer_new_u8(131072, 2, u8)
+            nrf.fft_process(fft, buf)
+        out = nrf.fft_get_buffer(fft)
+        assert (out.type, out.length, out.channels) == (2, n * 6, 1)
+        hist = out.numpy().reshape(6, n)
+        ref = golden[f"ref_nrf_fft_hist_n{n}_h6"]
+        assert rel_err(hist[:4], ref[:4]) < MAG_TOL
+        assert not hist[4:].any()
+        nrf.fft_shift(fft, 3.7)
+        shifted = nrf.fft_get_buffer(fft).numpy().reshape(6, n)
+        s = int(round(n / 3.7))
+        assert np.array_equal(shifted[:, : n - s], hist[:, s:]) and not shifted[:, n - s:].any()
+        nrf.fft_free(fft)
+
+
+def test_nrf_fft_f64_chain(fbg, iq, golden):
+    """lua/fft-shifted.lua:52-54: device -> freq shifter -> fft (float64 buffer, oversize)."""
+    fb = fbg
+    nrf = fb.nrf
+    u8 = orc.device_unpack(iq["rf200big4"][:BLOCK])
+    sh = nrf.freq_shifter_new(-10000, 5000000)
+    buf = nrf.nut_buffer_new_u8(131072, 2, u8)
+    nrf.freq_shifter_process(sh, buf)
+    sb = nrf.freq_shifter_get_buffer(sh)
+    fft = nrf.fft_new(1024, 2)
+    nrf.fft_process(fft, sb)                       # 262144 "samples": clamped, not overflowed
+    row = nrf.fft_get_buffer(fft).numpy().reshape(2, 1024)[0]
+    assert rel_err(row, golden["ref_shifted_fft_n1024"]) < 1e-11
+    nrf.fft_free(fft)
+    nrf.freq_shifter_free(sh)
