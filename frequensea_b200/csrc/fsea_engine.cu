@@ -164,6 +164,8 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
     if (cfg->window != FSEA_WIN_NONE && cfg->window != FSEA_WIN_HANN) return FSEA_ERR_INVALID;
     if (cfg->out_mode < FSEA_OUT_MAG || cfg->out_mode > FSEA_OUT_PIX) return FSEA_ERR_INVALID;
     if (cfg->hop < 0) return FSEA_ERR_INVALID;
+    if ((cfg->in_format == FSEA_IN_U8 || cfg->in_format == FSEA_IN_S8) && (cfg->hop % 8) != 0)
+        return FSEA_ERR_INVALID;          /* 8-bit frames are fetched in 16-byte pieces */
     if (fsea_device_count() <= 0) return FSEA_ERR_NO_DEVICE;
     if (cfg->device < 0 || cfg->device >= fsea_device_count()) return FSEA_ERR_INVALID;
     CU(cudaSetDevice(cfg->device));
@@ -276,6 +278,7 @@ static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cu
 
 extern "C" int fsea_exec_device(fsea_plan* p, const void* d_in, void* d_out, long n_frames, void* stream) {
     if (!p || n_frames < 0 || (n_frames > 0 && (!d_in || !d_out))) return FSEA_ERR_INVALID;
+    if (((uintptr_t)d_in & 15) != 0) return FSEA_ERR_INVALID;
     CU(cudaSetDevice(p->cfg.device));
     return launch(p, d_in, d_out, n_frames, (cudaStream_t)stream);
 }

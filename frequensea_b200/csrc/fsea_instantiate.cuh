@@ -15,12 +15,22 @@ struct fsea_cfg {
     static const int G_0 = G_T < G_S ? G_T : G_S;
     static const int G = (SH::T > 32 && G_0 > 15) ? 15 : G_0;                   // named barriers 1..15
     static const size_t SMEM = (size_t)G * XBYTES + (TWS ? TWBYTES : 0);
+    // resident blocks per SM the register allocator must allow: what shared memory
+    // permits, capped so that a thread keeps >= REGCAP registers
+    static const int REGCAP = (sizeof(V) >= 8 ? 168 : 96);
+    static const int THREADS = SH::T * G;
+    static const int B_SMEM = SMEM ? (int)((227 * 1024) / (SMEM + 1024)) : 16;
+    static const int B_REG = 65536 / (THREADS * REGCAP);
+    static const int B_THR = 2048 / THREADS;
+    static const int MINB_0 = B_SMEM < B_REG ? B_SMEM : B_REG;
+    static const int MINB_1 = MINB_0 < B_THR ? MINB_0 : B_THR;
+    static const int MINB = MINB_1 < 1 ? 1 : (MINB_1 > 16 ? 16 : MINB_1);
 };
 
 template <class SH, typename V, int FMT>
 static bool fsea_fill(fsea_kernel_info* o, const char* name) {
     typedef fsea_cfg<SH, V> C;
-    o->fn = (const void*)&fsea_fft_kernel<SH, V, FMT, C::G, C::TWS>;
+    o->fn = (const void*)&fsea_fft_kernel<SH, V, FMT, C::G, C::TWS, C::MINB>;
     o->threads = SH::T * C::G;
     o->groups = C::G;
     o->lanes = fsea_vt<V>::lanes;

@@ -86,6 +86,42 @@ __device__ __forceinline__ float fsea_lane(f2 v, int l) { return l ? v.v.y : v.v
 // argument) or FSEA_IN_F32C.
 template <int FMT, typename V> struct fsea_in;
 
+__device__ __forceinline__ void fsea_prefetch_l2(const void* p) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+// every thread of the group touches its share of the sequence's 128-byte lines
+template <int BYTES, int T>
+__device__ __forceinline__ void fsea_prefetch_seq(const uint8_t* p, int t) {
+    constexpr int LINES = (BYTES + 127) / 128;
+#pragma unroll
+    for (int l = 0; l < (LINES + T - 1) / T; l++) {
+        const int line = t + l * T;
+        if (line < LINES) fsea_prefetch_l2(p + (size_t)line * 128);
+    }
+}
+
+// One frame of 8-bit IQ (2N bytes) -> shared memory with 16-byte loads spread over
+// the group's T threads; the two's-complement flip is applied on the way (4 bytes per LOP3).
+template <int N, int T>
+__device__ __forceinline__ void fsea_stage_seq(const uint8_t* p, unsigned char* sm, int t, uint32_t xm) {
+    constexpr int CHUNKS = (2 * N) / 16;
+    const uint32_t x4 = xm | (xm << 16);
+    uint4 w[(CHUNKS + T - 1) / T];
+#pragma unroll
+    for (int c = 0; c < (CHUNKS + T - 1) / T; c++) {
+        const int q = t + c * T;
+        if (q < CHUNKS) w[c] = __ldg((const uint4*)p + q);
+    }
+#pragma unroll
+    for (int c = 0; c < (CHUNKS + T - 1) / T; c++) {
+        const int q = t + c * T;
+        if (q < CHUNKS) {
+            w[c].x ^= x4; w[c].y ^= x4; w[c].z ^= x4; w[c].w ^= x4;
+            ((uint4*)sm)[q] = w[c];
+        }
+    }
+}
+
 template <int FMT> struct fsea_in<FMT, float> {
     const uint8_t* p;
     uint32_t xm;
@@ -104,6 +140,18 @@ template <int FMT> struct fsea_in<FMT, float> {
             re = __uint_as_float(__byte_perm(w, 0x47000000u, 0x7650)) - 32768.5f;
             im = __uint_as_float(__byte_perm(w, 0x47000000u, 0x7651)) - 32768.5f;
         }
+    }
+    template <int N, int T> __device__ __forceinline__ void prefetch(int t) const {
+        fsea_prefetch_seq<N * (FMT == FSEA_IN_F32C ? 8 : 2), T>(p, t);
+    }
+    // 8-bit only: coalesced 16-byte loads of the whole frame into shared memory
+    template <int N, int T> __device__ __forceinline__ void stage(int t, unsigned char* sm) const {
+        fsea_stage_seq<N, T>(p, sm, t, xm);
+    }
+    template <int N> __device__ __forceinline__ void load_staged(const unsigned char* sm, int e, float& re, float& im) const {
+        const uint32_t w = ((const unsigned short*)sm)[e];
+        re = __uint_as_float(__byte_perm(w, 0x47000000u, 0x7650)) - 32768.5f;
+        im = __uint_as_float(__byte_perm(w, 0x47000000u, 0x7651)) - 32768.5f;
     }
 };
 
@@ -135,6 +183,24 @@ template <int FMT> struct fsea_in<FMT, f2> {
             re = vsub(r, off); im = vsub(i, off);
         }
     }
+    template <int N, int T> __device__ __forceinline__ void prefetch(int t) const {
+        fsea_prefetch_seq<N * (FMT == FSEA_IN_F32C ? 8 : 2), T>(pa, t);
+        fsea_prefetch_seq<N * (FMT == FSEA_IN_F32C ? 8 : 2), T>(pb, t);
+    }
+    template <int N, int T> __device__ __forceinline__ void stage(int t, unsigned char* sm) const {
+        fsea_stage_seq<N, T>(pa, sm, t, xm);
+        fsea_stage_seq<N, T>(pb, sm + 2 * N, t, xm);
+    }
+    template <int N> __device__ __forceinline__ void load_staged(const unsigned char* sm, int e, f2& re, f2& im) const {
+        const uint32_t wa = ((const unsigned short*)sm)[e];
+        const uint32_t wb = ((const unsigned short*)(sm + 2 * N))[e];
+        f2 r = mk2(__uint_as_float(__byte_perm(wa, 0x47000000u, 0x7650)),
+                   __uint_as_float(__byte_perm(wb, 0x47000000u, 0x7650)));
+        f2 i = mk2(__uint_as_float(__byte_perm(wa, 0x47000000u, 0x7651)),
+                   __uint_as_float(__byte_perm(wb, 0x47000000u, 0x7651)));
+        const f2 off = mk2(32768.5f, 32768.5f);
+        re = vsub(r, off); im = vsub(i, off);
+    }
 };
 
 template <> struct fsea_in<FSEA_IN_F64C, double> {
@@ -148,6 +214,11 @@ template <> struct fsea_in<FSEA_IN_F64C, double> {
         double2 v = __ldg(p + e);
         re = v.x; im = v.y;
     }
+    template <int N, int T> __device__ __forceinline__ void prefetch(int t) const {
+        fsea_prefetch_seq<N * 16, T>((const uint8_t*)p, t);
+    }
+    template <int N, int T> __device__ __forceinline__ void stage(int, unsigned char*) const {}
+    template <int N> __device__ __forceinline__ void load_staged(const unsigned char*, int, double&, double&) const {}
 };
 
 // ---- output side: bin k of the unit's sequence(s) ---------------------------
@@ -224,14 +295,14 @@ template <int T> __device__ __forceinline__ void fsea_group_sync(int group) {
 // ---- the kernel -------------------------------------------------------------
 // block = G groups of T threads; grid-stride over units; dynamic smem =
 // G * UNITS * sizeof(unit) [+ twiddle tables when TWS].
-template <class SH, typename V, int FMT, int G, bool TWS>
-__global__ void __launch_bounds__(SH::T* G)
+template <class SH, typename V, int FMT, int G, bool TWS, int MINB>
+__global__ void __launch_bounds__(SH::T* G, MINB)
 fsea_fft_kernel(const fsea_kparams kp) {
     typedef typename fsea_vt<V>::scalar S;
     typedef typename fsea_cplx<V>::t S2;
     constexpr int N = SH::N, R0 = SH::R0, R1 = SH::R1, R2 = SH::R2, P = SH::P, T = SH::T;
     constexpr int L0 = SH::L0, NPASS = SH::NPASS;
-    struct alignas(16) unit_t { V re, im; };
+    struct alignas(2 * sizeof(V)) unit_t { V re, im; };
 
     extern __shared__ __align__(16) unsigned char fsea_smem[];
     unit_t* xbuf_all = reinterpret_cast<unit_t*>(fsea_smem);
@@ -263,30 +334,53 @@ fsea_fft_kernel(const fsea_kparams kp) {
         in.init(kp, unit, live);
         fsea_out<N, V> out;
         out.init(kp, live ? unit : 0, live, out_esz);
+        {   // pull the NEXT unit's raw samples into L2 while this one is transformed
+            const long nxt = unit + (long)gridDim.x * G;
+            if (nxt < n_units) {
+                bool nl;
+                fsea_in<FMT, V> in_next;
+                in_next.init(kp, nxt, nl);
+                in_next.template prefetch<N, T>(t);
+            }
+        }
 
         V re[P], im[P];
 
         // ---------------- pass 0: radix R0, p_prev = 1 ----------------
         {
             constexpr int M = N / R0, B = P / R0;
-            if (kp.window) {
+            constexpr bool CAN_STAGE = (FMT == FSEA_IN_U8) && NPASS > 1 && sizeof(S) == 4;
+            if (CAN_STAGE) {
+                // raw bytes -> the (idle) exchange buffer with a few wide loads, then
+                // strided 16-bit reads from shared memory (coalesced HBM loads)
+                unsigned char* raw = reinterpret_cast<unsigned char*>(xb);
+                in.template stage<N, T>(t, raw);
+                fsea_group_sync<T>(g);
 #pragma unroll
                 for (int b = 0; b < B; b++) {
                     const int i = t + b * T;
 #pragma unroll
-                    for (int j = 0; j < R0; j++) {
-                        in.load(i + j * M, re[b * R0 + j], im[b * R0 + j]);
-                        const S w = (S)__ldg(kp.window + i + j * M);
-                        re[b * R0 + j] = vmuls(re[b * R0 + j], w);
-                        im[b * R0 + j] = vmuls(im[b * R0 + j], w);
-                    }
+                    for (int j = 0; j < R0; j++) in.template load_staged<N>(raw, i + j * M, re[b * R0 + j], im[b * R0 + j]);
                 }
+                fsea_group_sync<T>(g);               // raw region is overwritten by the exchange
             } else {
 #pragma unroll
                 for (int b = 0; b < B; b++) {
                     const int i = t + b * T;
 #pragma unroll
                     for (int j = 0; j < R0; j++) in.load(i + j * M, re[b * R0 + j], im[b * R0 + j]);
+                }
+            }
+            if (kp.window) {
+#pragma unroll
+                for (int b = 0; b < B; b++) {
+                    const int i = t + b * T;
+#pragma unroll
+                    for (int j = 0; j < R0; j++) {
+                        const S w = (S)__ldg(kp.window + i + j * M);
+                        re[b * R0 + j] = vmuls(re[b * R0 + j], w);
+                        im[b * R0 + j] = vmuls(im[b * R0 + j], w);
+                    }
                 }
             }
 #pragma unroll

@@ -62,7 +62,7 @@ enum {
 
 typedef struct {
     int fft_size;      /* N: power of two, 16..65536 */
-    int hop;           /* complex samples between frame starts; 0 = N (no overlap); multiple of 8 */
+    int hop;           /* complex samples between frame starts; 0 = N (no overlap); must be a multiple of 8 for 8-bit input */
     int in_format;     /* FSEA_IN_* */
     int window;        /* FSEA_WIN_* */
     int out_mode;      /* FSEA_OUT_* */
