@@ -3,11 +3,12 @@
 #include "fsea_kernels.cuh"
 #include "fsea_dispatch.h"
 
-template <class SH, typename V>
+template <class SH, typename V, int FMT>
 struct fsea_cfg {
     static const int UNIT_BYTES = 2 * (int)sizeof(V);
     static const int SB = (int)sizeof(typename fsea_vt<V>::scalar);
-    static const int XBYTES = SH::NPASS > 1 ? SH::UNITS * UNIT_BYTES : 0;      // exchange per group
+    static const bool STAGED = SH::NPASS > 1 && SB == 4 && FMT == FSEA_IN_U8;
+    static const int XBYTES = SH::NPASS > 1 ? SH::UNITS * (int)sizeof(V) + (STAGED ? fsea_vt<V>::lanes * 2 * SH::N : 0) : 0;   // exchange plane + raw ring per group
     static const int TWBYTES = (SH::TW1 + SH::TW2) * 2 * SB;
     static const bool TWS = SH::NPASS > 1 && TWBYTES <= 16384;
     static const int G_T = (128 / SH::T) > 1 ? (128 / SH::T) : 1;                // ~128 threads per block
@@ -29,7 +30,7 @@ struct fsea_cfg {
 
 template <class SH, typename V, int FMT>
 static bool fsea_fill(fsea_kernel_info* o, const char* name) {
-    typedef fsea_cfg<SH, V> C;
+    typedef fsea_cfg<SH, V, FMT> C;
     o->fn = (const void*)&fsea_fft_kernel<SH, V, FMT, C::G, C::TWS, C::MINB>;
     o->threads = SH::T * C::G;
     o->groups = C::G;

@@ -100,28 +100,6 @@ __device__ __forceinline__ void fsea_prefetch_seq(const uint8_t* p, int t) {
     }
 }
 
-// One frame of 8-bit IQ (2N bytes) -> shared memory with 16-byte loads spread over
-// the group's T threads; the two's-complement flip is applied on the way (4 bytes per LOP3).
-template <int N, int T>
-__device__ __forceinline__ void fsea_stage_seq(const uint8_t* p, unsigned char* sm, int t, uint32_t xm) {
-    constexpr int CHUNKS = (2 * N) / 16;
-    const uint32_t x4 = xm | (xm << 16);
-    uint4 w[(CHUNKS + T - 1) / T];
-#pragma unroll
-    for (int c = 0; c < (CHUNKS + T - 1) / T; c++) {
-        const int q = t + c * T;
-        if (q < CHUNKS) w[c] = __ldg((const uint4*)p + q);
-    }
-#pragma unroll
-    for (int c = 0; c < (CHUNKS + T - 1) / T; c++) {
-        const int q = t + c * T;
-        if (q < CHUNKS) {
-            w[c].x ^= x4; w[c].y ^= x4; w[c].z ^= x4; w[c].w ^= x4;
-            ((uint4*)sm)[q] = w[c];
-        }
-    }
-}
-
 template <int FMT> struct fsea_in<FMT, float> {
     const uint8_t* p;
     uint32_t xm;
@@ -145,11 +123,9 @@ template <int FMT> struct fsea_in<FMT, float> {
         fsea_prefetch_seq<N * (FMT == FSEA_IN_F32C ? 8 : 2), T>(p, t);
     }
     // 8-bit only: coalesced 16-byte loads of the whole frame into shared memory
-    template <int N, int T> __device__ __forceinline__ void stage(int t, unsigned char* sm) const {
-        fsea_stage_seq<N, T>(p, sm, t, xm);
-    }
+    template <int N, int T> __device__ __forceinline__ void async_stage(int t, unsigned char* sm) const;
     template <int N> __device__ __forceinline__ void load_staged(const unsigned char* sm, int e, float& re, float& im) const {
-        const uint32_t w = ((const unsigned short*)sm)[e];
+        const uint32_t w = (uint32_t)((const unsigned short*)sm)[e] ^ xm;
         re = __uint_as_float(__byte_perm(w, 0x47000000u, 0x7650)) - 32768.5f;
         im = __uint_as_float(__byte_perm(w, 0x47000000u, 0x7651)) - 32768.5f;
     }
@@ -187,13 +163,10 @@ template <int FMT> struct fsea_in<FMT, f2> {
         fsea_prefetch_seq<N * (FMT == FSEA_IN_F32C ? 8 : 2), T>(pa, t);
         fsea_prefetch_seq<N * (FMT == FSEA_IN_F32C ? 8 : 2), T>(pb, t);
     }
-    template <int N, int T> __device__ __forceinline__ void stage(int t, unsigned char* sm) const {
-        fsea_stage_seq<N, T>(pa, sm, t, xm);
-        fsea_stage_seq<N, T>(pb, sm + 2 * N, t, xm);
-    }
+    template <int N, int T> __device__ __forceinline__ void async_stage(int t, unsigned char* sm) const;
     template <int N> __device__ __forceinline__ void load_staged(const unsigned char* sm, int e, f2& re, f2& im) const {
-        const uint32_t wa = ((const unsigned short*)sm)[e];
-        const uint32_t wb = ((const unsigned short*)(sm + 2 * N))[e];
+        const uint32_t wa = (uint32_t)((const unsigned short*)sm)[e] ^ xm;
+        const uint32_t wb = (uint32_t)((const unsigned short*)(sm + 2 * N))[e] ^ xm;
         f2 r = mk2(__uint_as_float(__byte_perm(wa, 0x47000000u, 0x7650)),
                    __uint_as_float(__byte_perm(wb, 0x47000000u, 0x7650)));
         f2 i = mk2(__uint_as_float(__byte_perm(wa, 0x47000000u, 0x7651)),
@@ -217,7 +190,7 @@ template <> struct fsea_in<FSEA_IN_F64C, double> {
     template <int N, int T> __device__ __forceinline__ void prefetch(int t) const {
         fsea_prefetch_seq<N * 16, T>((const uint8_t*)p, t);
     }
-    template <int N, int T> __device__ __forceinline__ void stage(int, unsigned char*) const {}
+    template <int N, int T> __device__ __forceinline__ void async_stage(int, unsigned char*) const {}
     template <int N> __device__ __forceinline__ void load_staged(const unsigned char*, int, double&, double&) const {}
 };
 
@@ -292,9 +265,64 @@ template <int T> __device__ __forceinline__ void fsea_group_sync(int group) {
     }
 }
 
+// ---- asynchronous global -> shared copies (LDGSTS, 16 bytes, L2 only) ----------
+__device__ __forceinline__ void fsea_cp_async16(void* smem_dst, const void* gsrc) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void fsea_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void fsea_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// one frame of 8-bit IQ (2N bytes) -> shared memory, 16-byte pieces spread over the group
+template <int N, int T>
+__device__ __forceinline__ void fsea_async_frame(const uint8_t* p, unsigned char* sm, int t) {
+    constexpr int CHUNKS = (2 * N) / 16;
+#pragma unroll
+    for (int c = 0; c < (CHUNKS + T - 1) / T; c++) {
+        const int q = t + c * T;
+        if (q < CHUNKS) fsea_cp_async16(sm + 16 * q, p + 16 * q);
+    }
+}
+
+template <int FMT> template <int N, int T>
+__device__ __forceinline__ void fsea_in<FMT, float>::async_stage(int t, unsigned char* sm) const {
+    fsea_async_frame<N, T>(p, sm, t);
+}
+template <int FMT> template <int N, int T>
+__device__ __forceinline__ void fsea_in<FMT, f2>::async_stage(int t, unsigned char* sm) const {
+    fsea_async_frame<N, T>(pa, sm, t);
+    fsea_async_frame<N, T>(pb, sm + 2 * N, t);
+}
+
+// ---- dynamic work distribution ------------------------------------------------
+// Units are handed out by a global ticket counter instead of a fixed stride:
+// the SM's warp arbiter is not fair, and with a static split the favoured
+// blocks finish early and leave their SM under-occupied for the rest of the
+// launch (ncu: 9.4 of 12 resident warps on average).  The group leader takes
+// the ticket at the top of an iteration and the group reads it at the bottom,
+// so the atomic's round trip to L2 is hidden behind a whole transform.
+template <int T>
+__device__ __forceinline__ unsigned long long fsea_ticket_share(unsigned long long v, int t, int g,
+                                                                volatile unsigned long long* slot) {
+    if (T <= 32) {
+        return __shfl_sync(0xffffffffu, v, (threadIdx.x & 31) - t);
+    } else {
+        if (t == 0) slot[g] = v;
+        fsea_group_sync<T>(g);
+        v = slot[g];
+        fsea_group_sync<T>(g);
+        return v;
+    }
+}
+
 // ---- the kernel -------------------------------------------------------------
-// block = G groups of T threads; grid-stride over units; dynamic smem =
-// G * UNITS * sizeof(unit) [+ twiddle tables when TWS].
+// block = G groups of T threads, each group transforms one unit at a time,
+// grid-stride over units.  Dynamic shared memory per block:
+//   G x exchange plane   UNITS x sizeof(V)   (re and im cross in two half-exchanges,
+//                                             so STS/LDS move whole V registers: no repacking)
+//   G x raw ring         lanes x 2N bytes    (8-bit formats: the NEXT unit's IQ bytes land
+//                                             here by cp.async while this one is transformed)
+//   twiddle tables       when TWS
 template <class SH, typename V, int FMT, int G, bool TWS, int MINB>
 __global__ void __launch_bounds__(SH::T* G, MINB)
 fsea_fft_kernel(const fsea_kparams kp) {
@@ -302,19 +330,22 @@ fsea_fft_kernel(const fsea_kparams kp) {
     typedef typename fsea_cplx<V>::t S2;
     constexpr int N = SH::N, R0 = SH::R0, R1 = SH::R1, R2 = SH::R2, P = SH::P, T = SH::T;
     constexpr int L0 = SH::L0, NPASS = SH::NPASS;
-    struct alignas(2 * sizeof(V)) unit_t { V re, im; };
+    constexpr int LANES = fsea_vt<V>::lanes;
+    constexpr bool STAGED = (FMT == FSEA_IN_U8) && NPASS > 1 && sizeof(S) == 4;
+    constexpr int XB = NPASS > 1 ? SH::UNITS * (int)sizeof(V) : 0;     // exchange plane bytes per group
+    constexpr int RB = STAGED ? LANES * 2 * N : 0;                      // raw ring bytes per group
 
     extern __shared__ __align__(16) unsigned char fsea_smem[];
-    unit_t* xbuf_all = reinterpret_cast<unit_t*>(fsea_smem);
     const int tid = threadIdx.x;
     const int g = tid / T;
     const int t = tid - g * T;
-    unit_t* xb = xbuf_all + (size_t)g * SH::UNITS;
+    V* xp = reinterpret_cast<V*>(fsea_smem + (size_t)g * XB);
+    unsigned char* raw = fsea_smem + (size_t)G * XB + (size_t)g * RB;
 
     const S2* tw1 = (const S2*)kp.tw1;
     const S2* tw2 = (const S2*)kp.tw2;
     if (TWS && NPASS > 1) {
-        S2* stw = reinterpret_cast<S2*>(xbuf_all + (size_t)G * SH::UNITS);
+        S2* stw = reinterpret_cast<S2*>(fsea_smem + (size_t)G * (XB + RB));
         for (int q = tid; q < SH::TW1 + SH::TW2; q += T * G)
             stw[q] = (q < SH::TW1) ? tw1[q] : tw2[q - SH::TW1];
         __syncthreads();
@@ -325,36 +356,42 @@ fsea_fft_kernel(const fsea_kparams kp) {
     const bool dc_patch = (kp.flags & FSEA_FLAG_DC_PATCH) != 0;
     const int out_mode = kp.out_mode;
     const int out_esz = (out_mode == FSEA_OUT_PIX) ? 1 : (int)sizeof(S);
-    const long n_units = (kp.n_seq + fsea_vt<V>::lanes - 1) / fsea_vt<V>::lanes;
+    const long n_units = (kp.n_seq + LANES - 1) / LANES;
+    unsigned long long* ticket = kp.ticket;                       // [0] next unit, [1] blocks finished
+    __shared__ unsigned long long fsea_slot[G > 0 ? G : 1];
 
-    for (long base = (long)blockIdx.x * G; base < n_units; base += (long)gridDim.x * G) {
-        const long unit = base + g;
-        bool live;
-        fsea_in<FMT, V> in;
-        in.init(kp, unit, live);
+    unsigned long long pend = 0;
+    if (t == 0) pend = atomicAdd(ticket, 1ULL);
+    long cur = (long)fsea_ticket_share<T>(pend, t, g, fsea_slot);
+    if (t == 0) pend = atomicAdd(ticket, 1ULL);
+    long nxt = (long)fsea_ticket_share<T>(pend, t, g, fsea_slot);
+
+    fsea_in<FMT, V> in;
+    bool live;
+    in.init(kp, cur, live);
+    if (STAGED) {                                        // prologue: first unit's bytes
+        in.template async_stage<N, T>(t, raw);
+        fsea_cp_async_commit();
+    }
+
+    // groups that share a warp (T < 32) leave the loop together
+    while (T >= 32 ? (cur < n_units) : (__any_sync(0xffffffffu, cur < n_units) != 0)) {
+        if (t == 0) pend = atomicAdd(ticket, 1ULL);      // the unit after next; read at the bottom
+        const long unit = cur;
         fsea_out<N, V> out;
         out.init(kp, live ? unit : 0, live, out_esz);
-        {   // pull the NEXT unit's raw samples into L2 while this one is transformed
-            const long nxt = unit + (long)gridDim.x * G;
-            if (nxt < n_units) {
-                bool nl;
-                fsea_in<FMT, V> in_next;
-                in_next.init(kp, nxt, nl);
-                in_next.template prefetch<N, T>(t);
-            }
-        }
+        fsea_in<FMT, V> in_next;
+        bool live_next;
+        in_next.init(kp, nxt, live_next);
+        const bool more = live_next;
 
         V re[P], im[P];
 
         // ---------------- pass 0: radix R0, p_prev = 1 ----------------
         {
             constexpr int M = N / R0, B = P / R0;
-            constexpr bool CAN_STAGE = (FMT == FSEA_IN_U8) && NPASS > 1 && sizeof(S) == 4;
-            if (CAN_STAGE) {
-                // raw bytes -> the (idle) exchange buffer with a few wide loads, then
-                // strided 16-bit reads from shared memory (coalesced HBM loads)
-                unsigned char* raw = reinterpret_cast<unsigned char*>(xb);
-                in.template stage<N, T>(t, raw);
+            if (STAGED) {
+                fsea_cp_async_wait_all();
                 fsea_group_sync<T>(g);
 #pragma unroll
                 for (int b = 0; b < B; b++) {
@@ -362,8 +399,13 @@ fsea_fft_kernel(const fsea_kparams kp) {
 #pragma unroll
                     for (int j = 0; j < R0; j++) in.template load_staged<N>(raw, i + j * M, re[b * R0 + j], im[b * R0 + j]);
                 }
-                fsea_group_sync<T>(g);               // raw region is overwritten by the exchange
+                fsea_group_sync<T>(g);                   // ring is free again: fetch the next unit
+                if (more) {
+                    in_next.template async_stage<N, T>(t, raw);
+                    fsea_cp_async_commit();
+                }
             } else {
+                if (more) in_next.template prefetch<N, T>(t);
 #pragma unroll
                 for (int b = 0; b < B; b++) {
                     const int i = t + b * T;
@@ -389,30 +431,43 @@ fsea_fft_kernel(const fsea_kparams kp) {
                 // N = R0, T = 1: bins m
                 if (kp.dc_term) { re[0] = vadd(re[0], vsplat((S)(N / 2), re[0])); im[0] = vadd(im[0], vsplat((S)(N / 2), im[0])); }
                 out.template store_sel<R0, 1>(out_mode, 0, re, im, dc_patch);
-            } else {
-#pragma unroll
-                for (int b = 0; b < B; b++) {
-                    const int i = t + b * T;
-                    unit_t* w = xb + i * (R0 + 1);                 // a' = i (R0 + 1) + m
-#pragma unroll
-                    for (int m = 0; m < R0; m++) { w[m].re = re[b * R0 + m]; w[m].im = im[b * R0 + m]; }
-                }
             }
         }
-        if (NPASS == 1) continue;
-        fsea_group_sync<T>(g);
-
-        // ---------------- pass 1: radix R1, p_prev = R0 ----------------
-        {
+        if (NPASS > 1) {
+            // ---------------- exchange 0 -> 1 and pass 1: radix R1, p_prev = R0 ----------------
+            constexpr int B0 = P / R0;
             constexpr int M = N / R1, B = P / R1;
             constexpr int JSTR = M + (M >> L0);                    // padded stride of j
+            // write a' = i (R0 + 1) + m ; read a' = i + (i >> L0) + j JSTR  (one plane at a time)
+#pragma unroll
+            for (int b = 0; b < B0; b++) {
+                V* w = xp + (t + b * T) * (R0 + 1);
+#pragma unroll
+                for (int m = 0; m < R0; m++) w[m] = re[b * R0 + m];
+            }
+            fsea_group_sync<T>(g);
+#pragma unroll
+            for (int b = 0; b < B; b++) {
+                const int i = t + b * T;
+                const V* r = xp + i + (i >> L0);
+#pragma unroll
+                for (int j = 0; j < R1; j++) re[b * R1 + j] = r[j * JSTR];
+            }
+            fsea_group_sync<T>(g);
+#pragma unroll
+            for (int b = 0; b < B0; b++) {
+                V* w = xp + (t + b * T) * (R0 + 1);
+#pragma unroll
+                for (int m = 0; m < R0; m++) w[m] = im[b * R0 + m];
+            }
+            fsea_group_sync<T>(g);
 #pragma unroll
             for (int b = 0; b < B; b++) {
                 const int i = t + b * T;
                 const int k = i & (R0 - 1);
-                const unit_t* r = xb + i + (i >> L0);
+                const V* r = xp + i + (i >> L0);
 #pragma unroll
-                for (int j = 0; j < R1; j++) { re[b * R1 + j] = r[j * JSTR].re; im[b * R1 + j] = r[j * JSTR].im; }
+                for (int j = 0; j < R1; j++) im[b * R1 + j] = r[j * JSTR];
 #pragma unroll
                 for (int j = 1; j < R1; j++) {
                     const S2 w = tw1[(j - 1) * R0 + k];
@@ -427,31 +482,45 @@ fsea_fft_kernel(const fsea_kparams kp) {
 #pragma unroll
                 for (int b = 0; b < B; b++)
                     out.template store_sel<R1, M>(out_mode, t + b * T, re + b * R1, im + b * R1, dc_patch);
-            } else {
-                fsea_group_sync<T>(g);                             // all pass-1 reads done (WAR)
-#pragma unroll
-                for (int b = 0; b < B; b++) {
-                    const int i = t + b * T;
-                    const int k = i & (R0 - 1), hi = i >> L0;
-                    unit_t* w = xb + hi * (R0 * R1 + R1) + k;      // a' = hi (R0 R1 + R1) + k + m (R0 + 1)
-#pragma unroll
-                    for (int m = 0; m < R1; m++) { w[m * (R0 + 1)].re = re[b * R1 + m]; w[m * (R0 + 1)].im = im[b * R1 + m]; }
-                }
             }
         }
-        if (NPASS == 2) { fsea_group_sync<T>(g); continue; }      // the next unit rewrites the exchange
-        fsea_group_sync<T>(g);
-
-        // ---------------- pass 2: radix R2, p_prev = R0 R1 ----------------
-        {
+        if (NPASS > 2) {
+            // ---------------- exchange 1 -> 2 and pass 2: radix R2, p_prev = R0 R1 ----------------
+            constexpr int B1 = P / R1;
             constexpr int M = N / R2, B = P / R2;
             constexpr int JSTR = M + (M >> L0);
+            // write a' = hi (R0 R1 + R1) + k + m (R0 + 1), i = hi R0 + k ; read a' = i + (i >> L0) + j JSTR
+            fsea_group_sync<T>(g);                                 // all pass-1 reads done (WAR)
+#pragma unroll
+            for (int b = 0; b < B1; b++) {
+                const int i = t + b * T;
+                V* w = xp + (i >> L0) * (R0 * R1 + R1) + (i & (R0 - 1));
+#pragma unroll
+                for (int m = 0; m < R1; m++) w[m * (R0 + 1)] = re[b * R1 + m];
+            }
+            fsea_group_sync<T>(g);
+#pragma unroll
+            for (int b = 0; b < B; b++) {
+                const int i = t + b * T;
+                const V* r = xp + i + (i >> L0);
+#pragma unroll
+                for (int j = 0; j < R2; j++) re[b * R2 + j] = r[j * JSTR];
+            }
+            fsea_group_sync<T>(g);
+#pragma unroll
+            for (int b = 0; b < B1; b++) {
+                const int i = t + b * T;
+                V* w = xp + (i >> L0) * (R0 * R1 + R1) + (i & (R0 - 1));
+#pragma unroll
+                for (int m = 0; m < R1; m++) w[m * (R0 + 1)] = im[b * R1 + m];
+            }
+            fsea_group_sync<T>(g);
 #pragma unroll
             for (int b = 0; b < B; b++) {
                 const int i = t + b * T;                           // k = i
-                const unit_t* r = xb + i + (i >> L0);
+                const V* r = xp + i + (i >> L0);
 #pragma unroll
-                for (int j = 0; j < R2; j++) { re[b * R2 + j] = r[j * JSTR].re; im[b * R2 + j] = r[j * JSTR].im; }
+                for (int j = 0; j < R2; j++) im[b * R2 + j] = r[j * JSTR];
 #pragma unroll
                 for (int j = 1; j < R2; j++) {
                     const S2 w = tw2[(j - 1) * M + i];
@@ -465,6 +534,20 @@ fsea_fft_kernel(const fsea_kparams kp) {
             for (int b = 0; b < B; b++)
                 out.template store_sel<R2, M>(out_mode, t + b * T, re + b * R2, im + b * R2, dc_patch);
         }
-        fsea_group_sync<T>(g);
+        if (NPASS > 1) fsea_group_sync<T>(g);                      // the next unit rewrites the exchange plane
+        in = in_next;
+        live = live_next;
+        cur = nxt;
+        nxt = (long)fsea_ticket_share<T>(pend, t, g, fsea_slot);
+    }
+    // last block out re-arms the counters for the next launch that uses this slot
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(ticket + 1, 1ULL) == (unsigned long long)gridDim.x - 1) {
+            ticket[0] = 0ULL;
+            ticket[1] = 0ULL;
+            __threadfence();
+        }
     }
 }

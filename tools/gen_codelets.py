@@ -75,15 +75,17 @@ class Gen:
     def fnma(self, a, c, b): return self.emit(f"vfnma({a}, {self.lit(c)}, {b})")   # b - a*c
     def fms(self, a, c, b): return self.emit(f"vfms({a}, {self.lit(c)}, {b})")     # a*c - b
 
-    def butterfly(self, E, O, k, L):
-        er, ei = E
+    # ---- one butterfly, split in two phases so that a stage can be emitted
+    # ---- "all first halves, then all second halves" (independent neighbours)
+    def bfly_pre(self, O, k, L):
+        """Phase 1: the twiddled odd input, up to the final scale. Returns a closure state."""
         orr, oi = O
         fr = Fraction(k, L)
         if k == 0:
-            return (self.add(er, orr), self.add(ei, oi)), (self.sub(er, orr), self.sub(ei, oi))
-        if fr == Fraction(1, 4):      # w = -i : w*O = (oi, -or)
-            return (self.add(er, oi), self.sub(ei, orr)), (self.sub(er, oi), self.add(ei, orr))
-        c, s = _cos_sin(fr)           # w = c - i s ; w*O = (c or + s oi, c oi - s or)
+            return ("one", orr, oi, None)
+        if fr == Fraction(1, 4):                  # w = -i : w*O = (oi, -or)
+            return ("mi", orr, oi, None)
+        c, s = _cos_sin(fr)                       # w = c - i s ; w*O = (c or + s oi, c oi - s or)
         if abs(c) >= abs(s) or abs(abs(c) - abs(s)) < Decimal(10) ** (-40):
             t = s / c
             if abs(abs(t) - 1) < Decimal(10) ** (-40):
@@ -92,28 +94,49 @@ class Gen:
                 else:
                     ur, ui = self.sub(orr, oi), self.add(oi, orr)
             else:
-                ur = self.fma(oi, t, orr)        # or + t*oi
-                ui = self.fnma(orr, t, oi)       # oi - t*or
+                ur = self.fma(oi, t, orr)         # or + t*oi
+                ui = self.fnma(orr, t, oi)        # oi - t*or
             m = c
         else:
             t = c / s
-            ur = self.fma(orr, t, oi)            # t*or + oi
-            ui = self.fms(oi, t, orr)            # t*oi - or
+            ur = self.fma(orr, t, oi)             # t*or + oi
+            ui = self.fms(oi, t, orr)             # t*oi - or
             m = s
+        return ("gen", ur, ui, m)
+
+    def bfly_post(self, E, st):
+        er, ei = E
+        kind, ur, ui, m = st
+        if kind == "one":
+            return (self.add(er, ur), self.add(ei, ui)), (self.sub(er, ur), self.sub(ei, ui))
+        if kind == "mi":                          # (ur, ui) = (or, oi); w*O = (oi, -or)
+            return (self.add(er, ui), self.sub(ei, ur)), (self.sub(er, ui), self.add(ei, ur))
         x0 = (self.fma(ur, m, er), self.fma(ui, m, ei))
         x1 = (self.fnma(ur, m, er), self.fnma(ui, m, ei))
         return x0, x1
 
-    def fft(self, xs):
-        L = len(xs)
-        if L == 1:
-            return xs
-        E = self.fft(xs[0::2])
-        O = self.fft(xs[1::2])
-        out = [None] * L
-        for k in range(L // 2):
-            out[k], out[k + L // 2] = self.butterfly(E[k], O[k], k, L)
-        return out
+    def fft(self, xs, chunk=4):
+        """Iterative radix-2 DIT, emitted stage by stage (breadth first): within a
+        stage the butterflies are independent, and they are written out `chunk` at
+        a time -- first every butterfly's twiddle half, then every butterfly's
+        add/sub half -- so that neighbouring instructions never depend on each
+        other (the packed FFMA2 pipe has few warps to hide its latency behind)."""
+        R = len(xs)
+        lg = R.bit_length() - 1
+        v = [xs[int(format(j, f"0{lg}b")[::-1], 2)] if lg else xs[j] for j in range(R)]
+        half = 1
+        while half < R:
+            L = 2 * half
+            pairs = [(base + k, base + k + half, k) for base in range(0, R, L) for k in range(half)]
+            # trivial-twiddle butterflies first, then the twiddled ones, each in chunks
+            pairs.sort(key=lambda p: (0 if (p[2] == 0 or Fraction(p[2], L) == Fraction(1, 4)) else 1))
+            for c0 in range(0, len(pairs), chunk):
+                grp = pairs[c0:c0 + chunk]
+                pre = [self.bfly_pre(v[b], k, L) for (_, b, k) in grp]
+                for (a, b, k), st in zip(grp, pre):
+                    v[a], v[b] = self.bfly_post(v[a], st)
+            half = L
+        return v
 
 
 def codelet(R):
