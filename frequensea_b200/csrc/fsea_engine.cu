@@ -80,8 +80,9 @@ struct fsea_plan {
     fsea_stage stage[NSTAGE];
     long stage_frames = 0;
     double* d_gate = nullptr;
-    unsigned long long* d_tickets = nullptr;   // TICKET_SLOTS x {ticket, done}, zero between launches
+    unsigned* d_tickets = nullptr;             // TICKET_SLOTS x {ticket, done}, zero between launches
     static const int TICKET_SLOTS = 64;
+    void* d_dump = nullptr;
 };
 
 static fsea_get_kernel_fn size_table(int n) {
@@ -152,6 +153,7 @@ extern "C" int fsea_plan_destroy(fsea_plan* p) {
     if (p->d_window) cudaFree(p->d_window);
     if (p->d_gate) cudaFree(p->d_gate);
     if (p->d_tickets) cudaFree(p->d_tickets);
+    if (p->d_dump) cudaFree(p->d_dump);
     delete p;
     return FSEA_OK;
 }
@@ -223,10 +225,11 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
                 rc = cuda_fail(e, "twiddle upload"); break;
             }
         }
-        if ((e = cudaMalloc(&p->d_tickets, sizeof(unsigned long long) * 2 * fsea_plan::TICKET_SLOTS)) != cudaSuccess ||
-            (e = cudaMemset(p->d_tickets, 0, sizeof(unsigned long long) * 2 * fsea_plan::TICKET_SLOTS)) != cudaSuccess) {
+        if ((e = cudaMalloc(&p->d_tickets, sizeof(unsigned) * 2 * fsea_plan::TICKET_SLOTS)) != cudaSuccess ||
+            (e = cudaMemset(p->d_tickets, 0, sizeof(unsigned) * 2 * fsea_plan::TICKET_SLOTS)) != cudaSuccess) {
             rc = cuda_fail(e, "ticket counters"); break;
         }
+        if ((e = cudaMalloc(&p->d_dump, (size_t)n * 8)) != cudaSuccess) { rc = cuda_fail(e, "dump row"); break; }
         if (cfg->window == FSEA_WIN_HANN) {
             std::vector<float> w(n);
             const long double PI2 = 6.283185307179586476925286766559005768L;
@@ -275,6 +278,7 @@ static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cu
     kp.out_mode = p->cfg.out_mode;
     kp.xor_mask = p->cfg.in_format == FSEA_IN_S8 ? 0x8080u : 0u;
     kp.ticket = p->d_tickets + 2 * (p->launches % fsea_plan::TICKET_SLOTS);
+    kp.dump = p->d_dump;
     const long units = (n_frames + p->ki.lanes - 1) / p->ki.lanes;
     long blocks = (units + p->ki.groups - 1) / p->ki.groups;
     if (blocks > p->max_blocks) blocks = p->max_blocks;

@@ -34,6 +34,10 @@
 #include "../../include/fsea.h"
 #include "fsea_kparams.h"
 
+// internal input / output kinds of the four-step (N = N1 x N2) kernels
+enum { FSEA_IN_COLS8 = 16, FSEA_IN_ROWS = 17 };
+enum { FSEA_OK_SPECTRUM = 0, FSEA_OK_SCRATCH = 1, FSEA_OK_STRIDED = 2 };
+
 
 template <int X> struct fsea_log2 { static const int v = 1 + fsea_log2<X / 2>::v; };
 template <> struct fsea_log2<1> { static const int v = 0; };
@@ -107,6 +111,7 @@ template <int FMT> struct fsea_in<FMT, float> {
         long s = unit < kp.n_seq ? unit : kp.n_seq - 1;
         live = unit < kp.n_seq;
         xm = kp.xor_mask;
+        win = kp.window;
         p = (const uint8_t*)kp.in + s * kp.seq_stride * (FMT == FSEA_IN_F32C ? 8 : 2);
     }
     __device__ __forceinline__ void load(int e, float& re, float& im) const {
@@ -119,6 +124,8 @@ template <int FMT> struct fsea_in<FMT, float> {
             im = __uint_as_float(__byte_perm(w, 0x47000000u, 0x7651)) - 32768.5f;
         }
     }
+    const float* win;
+    __device__ __forceinline__ float window(int e) const { return __ldg(win + e); }
     template <int N, int T> __device__ __forceinline__ void prefetch(int t) const {
         fsea_prefetch_seq<N * (FMT == FSEA_IN_F32C ? 8 : 2), T>(p, t);
     }
@@ -140,6 +147,7 @@ template <int FMT> struct fsea_in<FMT, f2> {
         if (s0 >= kp.n_seq) s0 = kp.n_seq - 1;
         if (s1 >= kp.n_seq) s1 = kp.n_seq - 1;
         xm = kp.xor_mask;
+        win = kp.window;
         const long b = (FMT == FSEA_IN_F32C ? 8 : 2);
         pa = (const uint8_t*)kp.in + s0 * kp.seq_stride * b;
         pb = (const uint8_t*)kp.in + s1 * kp.seq_stride * b;
@@ -159,6 +167,8 @@ template <int FMT> struct fsea_in<FMT, f2> {
             re = vsub(r, off); im = vsub(i, off);
         }
     }
+    const float* win;
+    __device__ __forceinline__ f2 window(int e) const { const float w = __ldg(win + e); return mk2(w, w); }
     template <int N, int T> __device__ __forceinline__ void prefetch(int t) const {
         fsea_prefetch_seq<N * (FMT == FSEA_IN_F32C ? 8 : 2), T>(pa, t);
         fsea_prefetch_seq<N * (FMT == FSEA_IN_F32C ? 8 : 2), T>(pb, t);
@@ -181,17 +191,80 @@ template <> struct fsea_in<FSEA_IN_F64C, double> {
     __device__ __forceinline__ void init(const fsea_kparams& kp, long unit, bool& live) {
         long s = unit < kp.n_seq ? unit : kp.n_seq - 1;
         live = unit < kp.n_seq;
+        win = kp.window;
         p = (const double2*)kp.in + s * kp.seq_stride;
     }
     __device__ __forceinline__ void load(int e, double& re, double& im) const {
         double2 v = __ldg(p + e);
         re = v.x; im = v.y;
     }
+    const float* win;
+    __device__ __forceinline__ double window(int e) const { return (double)__ldg(win + e); }
     template <int N, int T> __device__ __forceinline__ void prefetch(int t) const {
         fsea_prefetch_seq<N * 16, T>((const uint8_t*)p, t);
     }
     template <int N, int T> __device__ __forceinline__ void async_stage(int, unsigned char*) const {}
     template <int N> __device__ __forceinline__ void load_staged(const unsigned char*, int, double&, double&) const {}
+};
+
+// ---- four-step loaders (N = N1 x N2, SURVEY 7 "N = 65536") ----------------------
+// Step A transforms the N2 columns of a frame (sequence n1 -> x[N2 n1 + n2]); a unit is a
+// PAIR OF ADJACENT COLUMNS, so one 32-bit load yields both lanes' I/Q bytes.
+template <> struct fsea_in<FSEA_IN_COLS8, f2> {
+    const uint8_t* p;
+    const float* win;
+    uint32_t x4;
+    long cstride;          // bytes between consecutive n1
+    __device__ __forceinline__ void init(const fsea_kparams& kp, long unit, bool& live) {
+        long s0 = 2 * unit;
+        live = s0 < kp.n_seq;
+        if (!live) s0 = kp.n_seq - 2;
+        const long f = s0 / kp.n2, c = s0 - f * kp.n2;
+        x4 = kp.xor_mask | (kp.xor_mask << 16);
+        cstride = 2L * kp.n2;
+        p = (const uint8_t*)kp.in + 2 * (f * kp.seq_stride + c);
+        win = kp.window ? kp.window + c : nullptr;
+    }
+    __device__ __forceinline__ void load(int e, f2& re, f2& im) const {
+        const uint32_t w = __ldg((const uint32_t*)(p + (size_t)e * cstride)) ^ x4;
+        f2 r = mk2(__uint_as_float(__byte_perm(w, 0x47000000u, 0x7650)),
+                   __uint_as_float(__byte_perm(w, 0x47000000u, 0x7652)));
+        f2 i = mk2(__uint_as_float(__byte_perm(w, 0x47000000u, 0x7651)),
+                   __uint_as_float(__byte_perm(w, 0x47000000u, 0x7653)));
+        const f2 off = mk2(32768.5f, 32768.5f);
+        re = vsub(r, off); im = vsub(i, off);
+    }
+    __device__ __forceinline__ f2 window(int e) const {      // w[N2 e + n2], w[N2 e + n2 + 1]
+        const float2 w = __ldg((const float2*)(win + (size_t)e * (cstride >> 1)));
+        return mk2(w.x, w.y);
+    }
+    template <int N, int T> __device__ __forceinline__ void prefetch(int) const {}
+    template <int N, int T> __device__ __forceinline__ void async_stage(int, unsigned char*) const {}
+    template <int N> __device__ __forceinline__ void load_staged(const unsigned char*, int, f2&, f2&) const {}
+};
+
+// Step B transforms the N1 rows of the twiddled intermediate (float2, contiguous); a unit
+// is a PAIR OF ADJACENT ROWS (k1, k1 + 1), whose outputs are adjacent bins.
+template <> struct fsea_in<FSEA_IN_ROWS, f2> {
+    const float2 *pa, *pb;
+    __device__ __forceinline__ void init(const fsea_kparams& kp, long unit, bool& live) {
+        long s0 = 2 * unit;
+        live = s0 < kp.n_seq;
+        if (!live) s0 = kp.n_seq - 2;
+        pa = (const float2*)kp.in + s0 * kp.n2;
+        pb = pa + kp.n2;
+    }
+    __device__ __forceinline__ void load(int e, f2& re, f2& im) const {
+        const float2 a = __ldg(pa + e), b = __ldg(pb + e);
+        re = mk2(a.x, b.x); im = mk2(a.y, b.y);
+    }
+    __device__ __forceinline__ f2 window(int) const { return mk2(1.f, 1.f); }
+    template <int N, int T> __device__ __forceinline__ void prefetch(int t) const {
+        fsea_prefetch_seq<N * 8, T>((const uint8_t*)pa, t);
+        fsea_prefetch_seq<N * 8, T>((const uint8_t*)pb, t);
+    }
+    template <int N, int T> __device__ __forceinline__ void async_stage(int, unsigned char*) const {}
+    template <int N> __device__ __forceinline__ void load_staged(const unsigned char*, int, f2&, f2&) const {}
 };
 
 // ---- output side: bin k of the unit's sequence(s) ---------------------------
@@ -211,11 +284,12 @@ template <int N, typename V> struct fsea_out {
         for (int l = 0; l < LANES; l++) {
             long s = unit * LANES + l;
             live[l] = unit_live && s < kp.n_seq;
-            row[l] = (uint8_t*)kp.out + (size_t)(live[l] ? s : 0) * N * esz;
+            // sequences past the end of the batch (odd tail, idle group) write to a dump row:
+            // the stores themselves stay unconditional
+            row[l] = live[l] ? (uint8_t*)kp.out + (size_t)s * N * esz : (uint8_t*)kp.dump;
         }
     }
     template <int OUT> __device__ __forceinline__ void put(int l, int pos, S pwr) const {
-        if (!live[l]) return;
         if (OUT == FSEA_OUT_MAG) {
             if (sizeof(S) == 8) ((double*)row[l])[pos] = sqrt((double)pwr);
             else ((float*)row[l])[pos] = fsea_sqrt_approx((float)pwr);
@@ -254,7 +328,100 @@ template <int N, typename V> struct fsea_out {
         else if (mode == FSEA_OUT_LOGMAG) store_bfly<FSEA_OUT_LOGMAG, R, M>(i, re, im, dc_patch);
         else store_bfly<FSEA_OUT_PIX, R, M>(i, re, im, dc_patch);
     }
+    // uncentred 8-bit input: the analytic DC term N/2 (1+i) belongs to bin 0 (thread 0, m = 0)
+    __device__ __forceinline__ void dc_adjust(const fsea_kparams& kp, int t, V& re0, V& im0) const {
+        if (kp.dc_term && t == 0) { re0 = vadd(re0, vsplat((S)(N / 2), re0)); im0 = vadd(im0, vsplat((S)(N / 2), im0)); }
+    }
 };
+
+// Four-step, step A: bin k1 of columns (n2, n2+1) times W_N^{n2 k1} -> scratch[f][k1][n2..n2+1]
+template <int N1> struct fsea_out_scratch {
+    float2* base;          // scratch + (f N1 N2 + n2)
+    const float2* tw;      // tw4 + n2
+    long rstride;          // N2
+    bool live;
+    __device__ __forceinline__ void init(const fsea_kparams& kp, long unit, bool unit_live, int) {
+        long s0 = 2 * unit;
+        live = unit_live;
+        if (!live) s0 = kp.n_seq - 2;
+        const long f = s0 / kp.n2, c = s0 - f * kp.n2;
+        rstride = kp.n2;
+        base = (float2*)kp.out + (size_t)f * N1 * kp.n2 + c;
+        tw = (const float2*)kp.tw4 + c;
+    }
+    template <int R, int M>
+    __device__ __forceinline__ void store_sel(int, int i, const f2* re, const f2* im, bool) const {
+        if (!live) return;
+#pragma unroll
+        for (int m = 0; m < R; m++) {
+            const long k1 = i + m * M;
+            const float4 w = __ldg((const float4*)(tw + k1 * rstride));      // (wA.re, wA.im, wB.re, wB.im)
+            const f2 wr = mk2(w.x, w.z), wi = mk2(w.y, w.w);
+            const f2 r = vsub(vmul(re[m], wr), vmul(im[m], wi));
+            const f2 q = vfma2(re[m], wi, vmul(im[m], wr));
+            *(float4*)(base + k1 * rstride) = make_float4(r.v.x, q.v.x, r.v.y, q.v.y);
+        }
+    }
+    __device__ __forceinline__ void dc_adjust(const fsea_kparams&, int, f2&, f2&) const {}
+};
+
+// Four-step, step B: rows (k1, k1+1), FFT bin k2 -> spectrum bin k1 + N1 k2 (two adjacent bins)
+template <int NTOT> struct fsea_out_strided {
+    uint8_t* row;
+    int k1, n1;
+    bool live;
+    float pix_scale;
+    __device__ __forceinline__ void init(const fsea_kparams& kp, long unit, bool unit_live, int esz) {
+        long s0 = 2 * unit;
+        live = unit_live;
+        if (!live) s0 = kp.n_seq - 2;
+        n1 = kp.n1;
+        const long f = s0 / n1;
+        k1 = (int)(s0 - f * n1);
+        pix_scale = kp.pix_scale;
+        row = (uint8_t*)kp.out + (size_t)f * NTOT * esz;
+    }
+    template <int OUT> __device__ __forceinline__ void put1(int pos, float pwr) const {
+        if (OUT == FSEA_OUT_MAG) ((float*)row)[pos] = fsea_sqrt_approx(pwr);
+        else if (OUT == FSEA_OUT_LOGMAG) ((float*)row)[pos] = fsea_db(pwr);
+        else row[pos] = fsea_pix(fsea_db(pwr), pix_scale);
+    }
+    template <int OUT, int R, int M>
+    __device__ __forceinline__ void store_bfly(int i, const f2* re, const f2* im, bool dc_patch) const {
+        if (!live) return;
+#pragma unroll
+        for (int m = 0; m < R; m++) {
+            const int k2 = i + m * M;
+            const int pos = (k1 + n1 * k2 + NTOT / 2) & (NTOT - 1);           // even: k1 and n1 are
+            const f2 pw = vfma2(re[m], re[m], vmul(im[m], im[m]));
+            const bool bin0 = (m == 0) && dc_patch && i == 0 && k1 == 0;      // bin 0: overwritten by its neighbour
+            if (bin0) {
+                put1<OUT>(pos + 1, pw.v.y);
+            } else if (OUT == FSEA_OUT_MAG) {
+                *(float2*)((float*)row + pos) = make_float2(fsea_sqrt_approx(pw.v.x), fsea_sqrt_approx(pw.v.y));
+            } else if (OUT == FSEA_OUT_LOGMAG) {
+                *(float2*)((float*)row + pos) = make_float2(fsea_db(pw.v.x), fsea_db(pw.v.y));
+            } else {
+                *(uchar2*)(row + pos) = make_uchar2(fsea_pix(fsea_db(pw.v.x), pix_scale), fsea_pix(fsea_db(pw.v.y), pix_scale));
+            }
+            // bin N-1 (k1 + 1 == N1 - 1, k2 == N2 - 1) also fills the DC slot (src/nrf.c:621-622)
+            if (m == R - 1 && dc_patch && i == M - 1 && k1 + 2 == n1) put1<OUT>(NTOT / 2, pw.v.y);
+        }
+    }
+    template <int R, int M>
+    __device__ __forceinline__ void store_sel(int mode, int i, const f2* re, const f2* im, bool dc_patch) const {
+        if (mode == FSEA_OUT_MAG) store_bfly<FSEA_OUT_MAG, R, M>(i, re, im, dc_patch);
+        else if (mode == FSEA_OUT_LOGMAG) store_bfly<FSEA_OUT_LOGMAG, R, M>(i, re, im, dc_patch);
+        else store_bfly<FSEA_OUT_PIX, R, M>(i, re, im, dc_patch);
+    }
+    __device__ __forceinline__ void dc_adjust(const fsea_kparams& kp, int t, f2& re0, f2& im0) const {
+        if (kp.dc_term && t == 0 && k1 == 0) { re0.v.x += (float)(NTOT / 2); im0.v.x += (float)(NTOT / 2); }
+    }
+};
+
+template <int OK, int N, int NTOT, typename V> struct fsea_out_sel { typedef fsea_out<N, V> type; };
+template <int N, int NTOT> struct fsea_out_sel<FSEA_OK_SCRATCH, N, NTOT, f2> { typedef fsea_out_scratch<N> type; };
+template <int N, int NTOT> struct fsea_out_sel<FSEA_OK_STRIDED, N, NTOT, f2> { typedef fsea_out_strided<NTOT> type; };
 
 // ---- group barrier ----------------------------------------------------------
 template <int T> __device__ __forceinline__ void fsea_group_sync(int group) {
@@ -302,10 +469,14 @@ __device__ __forceinline__ void fsea_in<FMT, f2>::async_stage(int t, unsigned ch
 // the ticket at the top of an iteration and the group reads it at the bottom,
 // so the atomic's round trip to L2 is hidden behind a whole transform.
 template <int T>
-__device__ __forceinline__ unsigned long long fsea_ticket_share(unsigned long long v, int t, int g,
-                                                                volatile unsigned long long* slot) {
+__device__ __forceinline__ unsigned fsea_ticket_share(unsigned v, int t, int g, volatile unsigned* slot) {
     if (T <= 32) {
-        return __shfl_sync(0xffffffffu, v, (threadIdx.x & 31) - t);
+        // asm volatile + "memory": the broadcast must stay at the bottom of the
+        // iteration (after the stores); the compiler otherwise hoists it next to the atomic
+        unsigned r;
+        const int src = (threadIdx.x & 31) - t;
+        asm volatile("shfl.sync.idx.b32 %0, %1, %2, 0x1f, 0xffffffff;" : "=r"(r) : "r"(v), "r"(src) : "memory");
+        return r;
     } else {
         if (t == 0) slot[g] = v;
         fsea_group_sync<T>(g);
@@ -357,14 +528,18 @@ fsea_fft_kernel(const fsea_kparams kp) {
     const int out_mode = kp.out_mode;
     const int out_esz = (out_mode == FSEA_OUT_PIX) ? 1 : (int)sizeof(S);
     const long n_units = (kp.n_seq + LANES - 1) / LANES;
-    unsigned long long* ticket = kp.ticket;                       // [0] next unit, [1] blocks finished
-    __shared__ unsigned long long fsea_slot[G > 0 ? G : 1];
+    unsigned* ticket = kp.ticket;                                 // [0] next unit, [1] blocks finished
+    __shared__ unsigned fsea_slot[G > 0 ? G : 1];
 
-    unsigned long long pend = 0;
-    if (t == 0) pend = atomicAdd(ticket, 1ULL);
+    unsigned pend = 0;
+    if (t == 0) pend = atomicAdd(ticket, 1u);
     long cur = (long)fsea_ticket_share<T>(pend, t, g, fsea_slot);
-    if (t == 0) pend = atomicAdd(ticket, 1ULL);
+    if (t == 0) pend = atomicAdd(ticket, 1u);
     long nxt = (long)fsea_ticket_share<T>(pend, t, g, fsea_slot);
+    // two tickets are always in flight: the one read at the bottom of an iteration was
+    // requested a whole iteration earlier, wherever the compiler schedules the broadcast
+    unsigned pend_prev = 0;
+    if (t == 0) pend_prev = atomicAdd(ticket, 1u);
 
     fsea_in<FMT, V> in;
     bool live;
@@ -376,7 +551,7 @@ fsea_fft_kernel(const fsea_kparams kp) {
 
     // groups that share a warp (T < 32) leave the loop together
     while (T >= 32 ? (cur < n_units) : (__any_sync(0xffffffffu, cur < n_units) != 0)) {
-        if (t == 0) pend = atomicAdd(ticket, 1ULL);      // the unit after next; read at the bottom
+        if (t == 0) pend = atomicAdd(ticket, 1u);        // the unit after next; read at the bottom
         const long unit = cur;
         fsea_out<N, V> out;
         out.init(kp, live ? unit : 0, live, out_esz);
@@ -538,15 +713,16 @@ fsea_fft_kernel(const fsea_kparams kp) {
         in = in_next;
         live = live_next;
         cur = nxt;
-        nxt = (long)fsea_ticket_share<T>(pend, t, g, fsea_slot);
+        nxt = (long)fsea_ticket_share<T>(pend_prev, t, g, fsea_slot);
+        pend_prev = pend;
     }
     // last block out re-arms the counters for the next launch that uses this slot
     __syncthreads();
     if (tid == 0) {
         __threadfence();
-        if (atomicAdd(ticket + 1, 1ULL) == (unsigned long long)gridDim.x - 1) {
-            ticket[0] = 0ULL;
-            ticket[1] = 0ULL;
+        if (atomicAdd(ticket + 1, 1u) == gridDim.x - 1) {
+            ticket[0] = 0u;
+            ticket[1] = 0u;
             __threadfence();
         }
     }

@@ -15,6 +15,7 @@ struct fsea_kparams {
     int flags;             // FSEA_FLAG_*
     int dc_term;           // 1: add N/2 (1+i) to bin k=0 (uncentred 8-bit input, no patch)
     int out_mode;          // FSEA_OUT_*
-    unsigned long long* ticket;   // 2 counters: work tickets, finished blocks (self re-arming)
+    unsigned* ticket;      // 2 counters: work tickets, finished blocks (self re-arming)
+    void* dump;            // N x 8 bytes: where sequences beyond the batch are written
     uint32_t xor_mask;     // 0x8080 for two's-complement input (FSEA_IN_S8), else 0
 };
