@@ -38,3 +38,11 @@ FSEA_DECL_SIZE(2048)
 FSEA_DECL_SIZE(4096)
 FSEA_DECL_SIZE(8192)
 #undef FSEA_DECL_SIZE
+
+// Four-step plans (N = N1 x N2 >= 16384): step A transforms column pairs into an
+// L2-resident intermediate, step B transforms row pairs into the spectrum.
+struct fsea_kernel_info4 {
+    fsea_kernel_info a, b;
+    int n1, n2;
+};
+bool fsea_get_kernel4(int n, fsea_kernel_info4* out);

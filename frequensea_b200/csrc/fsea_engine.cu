@@ -83,6 +83,15 @@ struct fsea_plan {
     unsigned* d_tickets = nullptr;             // TICKET_SLOTS x {ticket, done}, zero between launches
     static const int TICKET_SLOTS = 64;
     void* d_dump = nullptr;
+    // four-step (N >= 16384): two kernels per chunk of frames, intermediate kept L2-sized
+    bool four = false;
+    fsea_kernel_info4 k4;
+    void *d_tw1b = nullptr, *d_tw2b = nullptr;   // step-B sub-FFT tables (step A uses d_tw1/d_tw2)
+    void* d_tw4 = nullptr;                       // W_N^{n2 k1}, float2 [N1][N2]
+    static const int SCRATCH_SLOTS = 4;           // slot 0: fsea_exec_device, 1..3: host pipeline stages
+    void* d_scratch[SCRATCH_SLOTS] = {nullptr, nullptr, nullptr, nullptr};   // chunk_frames x N float2 each
+    long chunk_frames = 0;
+    int max_blocks_b = 0;
 };
 
 static fsea_get_kernel_fn size_table(int n) {
@@ -154,7 +163,42 @@ extern "C" int fsea_plan_destroy(fsea_plan* p) {
     if (p->d_gate) cudaFree(p->d_gate);
     if (p->d_tickets) cudaFree(p->d_tickets);
     if (p->d_dump) cudaFree(p->d_dump);
+    if (p->d_tw1b) cudaFree(p->d_tw1b);
+    if (p->d_tw2b) cudaFree(p->d_tw2b);
+    if (p->d_tw4) cudaFree(p->d_tw4);
+    for (int q = 0; q < fsea_plan::SCRATCH_SLOTS; q++) if (p->d_scratch[q]) cudaFree(p->d_scratch[q]);
     delete p;
+    return FSEA_OK;
+}
+
+// shared-memory opt-in + resident-block count of one kernel
+static int setup_kernel(const fsea_kernel_info& ki, int device, int* max_blocks) {
+    CU(cudaFuncSetAttribute(ki.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ki.smem));
+    int per_sm = 0, sms = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, ki.fn, ki.threads, ki.smem));
+    CU(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    if (per_sm < 1) per_sm = 1;
+    *max_blocks = per_sm * sms;
+    return FSEA_OK;
+}
+
+// inter-pass twiddle tables of one kernel: evaluated in long double, stored in its precision
+static int upload_twiddles(const fsea_kernel_info& ki, void** d1, void** d2) {
+    if (ki.scalar_bytes == 4) {
+        std::vector<float2> t1, t2;
+        fill_twiddles(t1, t2, ki);
+        CU(cudaMalloc(d1, t1.size() * sizeof(float2)));
+        CU(cudaMalloc(d2, t2.size() * sizeof(float2)));
+        CU(cudaMemcpy(*d1, t1.data(), t1.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(*d2, t2.data(), t2.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    } else {
+        std::vector<double2> t1, t2;
+        fill_twiddles(t1, t2, ki);
+        CU(cudaMalloc(d1, t1.size() * sizeof(double2)));
+        CU(cudaMalloc(d2, t2.size() * sizeof(double2)));
+        CU(cudaMemcpy(*d1, t1.data(), t1.size() * sizeof(double2), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(*d2, t2.data(), t2.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    }
     return FSEA_OK;
 }
 
@@ -164,7 +208,10 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
     const int n = cfg->fft_size;
     if (n < 16 || n > 65536 || (n & (n - 1))) return FSEA_ERR_UNSUPPORTED;
     fsea_get_kernel_fn get = size_table(n);
-    if (!get) return FSEA_ERR_UNSUPPORTED;
+    fsea_kernel_info4 k4;
+    const bool four = !get && fsea_get_kernel4(n, &k4);
+    if (!get && !four) return FSEA_ERR_UNSUPPORTED;
+    if (four && cfg->in_format != FSEA_IN_U8 && cfg->in_format != FSEA_IN_S8) return FSEA_ERR_UNSUPPORTED;
     if (cfg->in_format < FSEA_IN_U8 || cfg->in_format > FSEA_IN_F64C) return FSEA_ERR_INVALID;
     if (cfg->window != FSEA_WIN_NONE && cfg->window != FSEA_WIN_HANN) return FSEA_ERR_INVALID;
     if (cfg->out_mode < FSEA_OUT_MAG || cfg->out_mode > FSEA_OUT_PIX) return FSEA_ERR_INVALID;
@@ -188,41 +235,37 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
         case FSEA_IN_F32C: p->variant = FSEA_VAR_F32C; p->sample_bytes = 8; break;
         default: p->variant = FSEA_VAR_F64; p->sample_bytes = 16; break;
     }
-    if (!get(p->variant, &p->ki)) { delete p; return FSEA_ERR_UNSUPPORTED; }
+    if (four) {
+        p->four = true;
+        p->k4 = k4;
+        p->ki = k4.a;                     // step A doubles as "the" kernel for tables, lanes, names
+        p->variant = FSEA_VAR_F32X2;
+    } else if (!get(p->variant, &p->ki)) { delete p; return FSEA_ERR_UNSUPPORTED; }
     p->out_elem_bytes = (cfg->out_mode == FSEA_OUT_PIX) ? 1 : p->ki.scalar_bytes;
 
     int rc = FSEA_OK;
     do {
         cudaError_t e;
-        if ((e = cudaFuncSetAttribute(p->ki.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ki.smem)) != cudaSuccess) {
-            rc = cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)"); break;
-        }
-        int per_sm = 0, sms = 0;
-        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, p->ki.fn, p->ki.threads, p->ki.smem)) != cudaSuccess) {
-            rc = cuda_fail(e, "cudaOccupancyMaxActiveBlocksPerMultiprocessor"); break;
-        }
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, cfg->device);
-        if (per_sm < 1) per_sm = 1;
-        p->max_blocks = per_sm * sms;
-
-        // twiddle tables, evaluated in long double, stored in the kernel's precision
-        if (p->ki.scalar_bytes == 4) {
-            std::vector<float2> t1, t2;
-            fill_twiddles(t1, t2, p->ki);
-            if ((e = cudaMalloc(&p->d_tw1, t1.size() * sizeof(float2))) != cudaSuccess ||
-                (e = cudaMalloc(&p->d_tw2, t2.size() * sizeof(float2))) != cudaSuccess ||
-                (e = cudaMemcpy(p->d_tw1, t1.data(), t1.size() * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess ||
-                (e = cudaMemcpy(p->d_tw2, t2.data(), t2.size() * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess) {
-                rc = cuda_fail(e, "twiddle upload"); break;
-            }
-        } else {
-            std::vector<double2> t1, t2;
-            fill_twiddles(t1, t2, p->ki);
-            if ((e = cudaMalloc(&p->d_tw1, t1.size() * sizeof(double2))) != cudaSuccess ||
-                (e = cudaMalloc(&p->d_tw2, t2.size() * sizeof(double2))) != cudaSuccess ||
-                (e = cudaMemcpy(p->d_tw1, t1.data(), t1.size() * sizeof(double2), cudaMemcpyHostToDevice)) != cudaSuccess ||
-                (e = cudaMemcpy(p->d_tw2, t2.data(), t2.size() * sizeof(double2), cudaMemcpyHostToDevice)) != cudaSuccess) {
-                rc = cuda_fail(e, "twiddle upload"); break;
+        if ((rc = setup_kernel(p->ki, cfg->device, &p->max_blocks)) != FSEA_OK) break;
+        if ((rc = upload_twiddles(p->ki, &p->d_tw1, &p->d_tw2)) != FSEA_OK) break;
+        if (p->four) {
+            if ((rc = setup_kernel(p->k4.b, cfg->device, &p->max_blocks_b)) != FSEA_OK) break;
+            if ((rc = upload_twiddles(p->k4.b, &p->d_tw1b, &p->d_tw2b)) != FSEA_OK) break;
+            const int n1 = p->k4.n1, n2 = p->k4.n2;
+            std::vector<float2> t4((size_t)n);
+            const long double PI2 = 6.283185307179586476925286766559005768L;
+            for (int k1 = 0; k1 < n1; k1++)
+                for (int c = 0; c < n2; c++) {
+                    const long double a = -PI2 * (long double)((long)k1 * c) / (long double)n;
+                    t4[(size_t)k1 * n2 + c].x = (float)cosl(a);
+                    t4[(size_t)k1 * n2 + c].y = (float)sinl(a);
+                }
+            // the intermediate of one chunk must stay in L2 (126 MB): 32 MiB of float2
+            p->chunk_frames = std::max<long>(1, (32L << 20) / ((long)n * 8));
+            if ((e = cudaMalloc(&p->d_tw4, (size_t)n * sizeof(float2))) != cudaSuccess ||
+                (e = cudaMemcpy(p->d_tw4, t4.data(), (size_t)n * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess ||
+                (e = cudaMalloc(&p->d_scratch[0], (size_t)p->chunk_frames * n * sizeof(float2))) != cudaSuccess) {
+                rc = cuda_fail(e, "four-step tables"); break;
             }
         }
         if ((e = cudaMalloc(&p->d_tickets, sizeof(unsigned) * 2 * fsea_plan::TICKET_SLOTS)) != cudaSuccess ||
@@ -261,7 +304,7 @@ extern "C" long fsea_plan_launch_count(const fsea_plan* p) { return p ? p->launc
 extern "C" const char* fsea_plan_kernel_name(const fsea_plan* p) { return p ? p->ki.name : ""; }
 
 
-static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cudaStream_t stream) {
+static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cudaStream_t stream, int slot = 0) {
     if (n_frames <= 0) return FSEA_OK;
     fsea_kparams kp;
     kp.in = d_in;
@@ -277,8 +320,43 @@ static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cu
     kp.dc_term = (eight_bit && p->cfg.window == FSEA_WIN_NONE && !(p->cfg.flags & FSEA_FLAG_DC_PATCH)) ? 1 : 0;
     kp.out_mode = p->cfg.out_mode;
     kp.xor_mask = p->cfg.in_format == FSEA_IN_S8 ? 0x8080u : 0u;
-    kp.ticket = p->d_tickets + 2 * (p->launches % fsea_plan::TICKET_SLOTS);
     kp.dump = p->d_dump;
+    kp.tw4 = p->d_tw4;
+    kp.n1 = kp.n2 = 0;
+    if (p->four) {
+        // N = N1 x N2: per chunk, step A (column pairs -> twiddled intermediate) then
+        // step B (row pairs -> spectrum); the intermediate never leaves L2
+        const int n = p->cfg.fft_size, n1 = p->k4.n1, n2 = p->k4.n2;
+        if (!p->d_scratch[slot]) CU(cudaMalloc(&p->d_scratch[slot], (size_t)p->chunk_frames * n * sizeof(float2)));
+        void* scratch = p->d_scratch[slot];
+        for (long f0 = 0; f0 < n_frames; f0 += p->chunk_frames) {
+            const long cf = std::min(p->chunk_frames, n_frames - f0);
+            fsea_kparams ka = kp, kb = kp;
+            ka.in = (const uint8_t*)d_in + (size_t)f0 * p->hop * p->sample_bytes;
+            ka.out = scratch;
+            ka.n_seq = cf * n2;
+            ka.n1 = n1; ka.n2 = n2;
+            ka.ticket = p->d_tickets + 2 * (p->launches % fsea_plan::TICKET_SLOTS);
+            long units = ka.n_seq / 2, blocks = std::min<long>((units + p->k4.a.groups - 1) / p->k4.a.groups, p->max_blocks);
+            void* aa[] = {&ka};
+            CU(cudaLaunchKernel(p->k4.a.fn, dim3((unsigned)blocks), dim3((unsigned)p->k4.a.threads), aa, p->k4.a.smem, stream));
+            p->launches++;
+            kb.in = scratch;
+            kb.out = (uint8_t*)d_out + (size_t)f0 * n * p->out_elem_bytes;
+            kb.n_seq = cf * n1;
+            kb.n1 = n1; kb.n2 = n2;
+            kb.tw1 = p->d_tw1b; kb.tw2 = p->d_tw2b;
+            kb.window = nullptr;
+            kb.ticket = p->d_tickets + 2 * (p->launches % fsea_plan::TICKET_SLOTS);
+            units = kb.n_seq / 2;
+            blocks = std::min<long>((units + p->k4.b.groups - 1) / p->k4.b.groups, p->max_blocks_b);
+            void* ab[] = {&kb};
+            CU(cudaLaunchKernel(p->k4.b.fn, dim3((unsigned)blocks), dim3((unsigned)p->k4.b.threads), ab, p->k4.b.smem, stream));
+            p->launches++;
+        }
+        return FSEA_OK;
+    }
+    kp.ticket = p->d_tickets + 2 * (p->launches % fsea_plan::TICKET_SLOTS);
     const long units = (n_frames + p->ki.lanes - 1) / p->ki.lanes;
     long blocks = (units + p->ki.groups - 1) / p->ki.groups;
     if (blocks > p->max_blocks) blocks = p->max_blocks;
@@ -370,7 +448,7 @@ extern "C" int fsea_exec_host(fsea_plan* p, const void* h_in, void* h_out, long 
         uint8_t* dst = (uint8_t*)h_out + (size_t)issued * out_per;
         if (!direct) { memcpy(st.h_in, src, ib); src = (const uint8_t*)st.h_in; dst = (uint8_t*)st.h_out; }
         CU(cudaMemcpyAsync(st.d_in, src, ib, cudaMemcpyHostToDevice, st.stream));
-        if ((rc = launch(p, st.d_in, st.d_out, nf, st.stream)) != FSEA_OK) return rc;
+        if ((rc = launch(p, st.d_in, st.d_out, nf, st.stream, 1 + slot)) != FSEA_OK) return rc;
         CU(cudaMemcpyAsync(dst, st.d_out, (size_t)nf * out_per, cudaMemcpyDeviceToHost, st.stream));
         CU(cudaEventRecord(st.done, st.stream));
         pending[slot] = nf;

@@ -11,14 +11,16 @@ struct fsea_cfg {
     static const int XBYTES = SH::NPASS > 1 ? SH::UNITS * (int)sizeof(V) + (STAGED ? fsea_vt<V>::lanes * 2 * SH::N : 0) : 0;   // exchange plane + raw ring per group
     static const int TWBYTES = (SH::TW1 + SH::TW2) * 2 * SB;
     static const bool TWS = SH::NPASS > 1 && TWBYTES <= 16384;
-    static const int G_T = (128 / SH::T) > 1 ? (128 / SH::T) : 1;                // ~128 threads per block
+    static const bool TILED = (FMT == FSEA_IN_COLS8) || (FMT == FSEA_IN_ROWS);
+    static const int TPB = TILED ? 256 : 128;                                     // target threads per block
+    static const int G_T = (TPB / SH::T) > 1 ? (TPB / SH::T) : 1;
     static const int G_S = XBYTES ? ((96 * 1024) / XBYTES > 1 ? (96 * 1024) / XBYTES : 1) : 1024;
     static const int G_0 = G_T < G_S ? G_T : G_S;
     static const int G = (SH::T > 32 && G_0 > 15) ? 15 : G_0;                   // named barriers 1..15
     static const size_t SMEM = (size_t)G * XBYTES + (TWS ? TWBYTES : 0);
     // resident blocks per SM the register allocator must allow: what shared memory
     // permits, capped so that a thread keeps >= REGCAP registers
-    static const int REGCAP = (sizeof(V) >= 8 ? 168 : 96);
+    static const int REGCAP = (sizeof(V) >= 8 ? (SH::P >= 32 ? 168 : (SH::P >= 16 ? 112 : 80)) : (SH::P >= 32 ? 96 : 64));
     static const int THREADS = SH::T * G;
     static const int B_SMEM = SMEM ? (int)((227 * 1024) / (SMEM + 1024)) : 16;
     static const int B_REG = 65536 / (THREADS * REGCAP);
@@ -28,10 +30,10 @@ struct fsea_cfg {
     static const int MINB = MINB_1 < 1 ? 1 : (MINB_1 > 16 ? 16 : MINB_1);
 };
 
-template <class SH, typename V, int FMT>
+template <class SH, typename V, int FMT, int OK = FSEA_OK_SPECTRUM, int NTOT = SH::N>
 static bool fsea_fill(fsea_kernel_info* o, const char* name) {
     typedef fsea_cfg<SH, V, FMT> C;
-    o->fn = (const void*)&fsea_fft_kernel<SH, V, FMT, C::G, C::TWS, C::MINB>;
+    o->fn = (const void*)&fsea_fft_kernel<SH, V, FMT, OK, NTOT, C::G, C::TWS, C::MINB>;
     o->threads = SH::T * C::G;
     o->groups = C::G;
     o->lanes = fsea_vt<V>::lanes;

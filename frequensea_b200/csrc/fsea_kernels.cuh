@@ -494,7 +494,7 @@ __device__ __forceinline__ unsigned fsea_ticket_share(unsigned v, int t, int g, 
 //   G x raw ring         lanes x 2N bytes    (8-bit formats: the NEXT unit's IQ bytes land
 //                                             here by cp.async while this one is transformed)
 //   twiddle tables       when TWS
-template <class SH, typename V, int FMT, int G, bool TWS, int MINB>
+template <class SH, typename V, int FMT, int OK, int NTOT, int G, bool TWS, int MINB>
 __global__ void __launch_bounds__(SH::T* G, MINB)
 fsea_fft_kernel(const fsea_kparams kp) {
     typedef typename fsea_vt<V>::scalar S;
@@ -503,6 +503,9 @@ fsea_fft_kernel(const fsea_kparams kp) {
     constexpr int L0 = SH::L0, NPASS = SH::NPASS;
     constexpr int LANES = fsea_vt<V>::lanes;
     constexpr bool STAGED = (FMT == FSEA_IN_U8) && NPASS > 1 && sizeof(S) == 4;
+    // four-step kernels hand out TILES of G neighbouring units per block (adjacent columns /
+    // rows -> contiguous bytes across the block); the others hand out single units per group
+    constexpr bool TILED = (FMT == FSEA_IN_COLS8) || (FMT == FSEA_IN_ROWS);
     constexpr int XB = NPASS > 1 ? SH::UNITS * (int)sizeof(V) : 0;     // exchange plane bytes per group
     constexpr int RB = STAGED ? LANES * 2 * N : 0;                      // raw ring bytes per group
 
@@ -530,16 +533,30 @@ fsea_fft_kernel(const fsea_kparams kp) {
     const long n_units = (kp.n_seq + LANES - 1) / LANES;
     unsigned* ticket = kp.ticket;                                 // [0] next unit, [1] blocks finished
     __shared__ unsigned fsea_slot[G > 0 ? G : 1];
+    __shared__ unsigned fsea_tile_slot;
+    const bool leader = TILED ? (tid == 0) : (t == 0);
+
+    auto share = [&](unsigned v) -> long {
+        if (TILED) {                                              // one ticket per block = G units
+            if (tid == 0) fsea_tile_slot = v;
+            __syncthreads();
+            const unsigned tile = fsea_tile_slot;
+            __syncthreads();
+            return (long)tile * G + g;
+        }
+        return (long)fsea_ticket_share<T>(v, t, g, fsea_slot);
+    };
+    const long n_claims = TILED ? (n_units + G - 1) / G * G : n_units;   // tiles run to completion
 
     unsigned pend = 0;
-    if (t == 0) pend = atomicAdd(ticket, 1u);
-    long cur = (long)fsea_ticket_share<T>(pend, t, g, fsea_slot);
-    if (t == 0) pend = atomicAdd(ticket, 1u);
-    long nxt = (long)fsea_ticket_share<T>(pend, t, g, fsea_slot);
+    if (leader) pend = atomicAdd(ticket, 1u);
+    long cur = share(pend);
+    if (leader) pend = atomicAdd(ticket, 1u);
+    long nxt = share(pend);
     // two tickets are always in flight: the one read at the bottom of an iteration was
     // requested a whole iteration earlier, wherever the compiler schedules the broadcast
     unsigned pend_prev = 0;
-    if (t == 0) pend_prev = atomicAdd(ticket, 1u);
+    if (leader) pend_prev = atomicAdd(ticket, 1u);
 
     fsea_in<FMT, V> in;
     bool live;
@@ -550,10 +567,10 @@ fsea_fft_kernel(const fsea_kparams kp) {
     }
 
     // groups that share a warp (T < 32) leave the loop together
-    while (T >= 32 ? (cur < n_units) : (__any_sync(0xffffffffu, cur < n_units) != 0)) {
-        if (t == 0) pend = atomicAdd(ticket, 1u);        // the unit after next; read at the bottom
+    while (TILED ? (cur - g < n_claims) : (T >= 32 ? (cur < n_units) : (__any_sync(0xffffffffu, cur < n_units) != 0))) {
+        if (leader) pend = atomicAdd(ticket, 1u);        // the unit after next; read at the bottom
         const long unit = cur;
-        fsea_out<N, V> out;
+        typename fsea_out_sel<OK, N, NTOT, V>::type out;
         out.init(kp, live ? unit : 0, live, out_esz);
         fsea_in<FMT, V> in_next;
         bool live_next;
@@ -594,9 +611,9 @@ fsea_fft_kernel(const fsea_kparams kp) {
                     const int i = t + b * T;
 #pragma unroll
                     for (int j = 0; j < R0; j++) {
-                        const S w = (S)__ldg(kp.window + i + j * M);
-                        re[b * R0 + j] = vmuls(re[b * R0 + j], w);
-                        im[b * R0 + j] = vmuls(im[b * R0 + j], w);
+                        const V w = in.window(i + j * M);
+                        re[b * R0 + j] = vmul(re[b * R0 + j], w);
+                        im[b * R0 + j] = vmul(im[b * R0 + j], w);
                     }
                 }
             }
@@ -604,7 +621,7 @@ fsea_fft_kernel(const fsea_kparams kp) {
             for (int b = 0; b < B; b++) fsea_dft<R0, V>::run(re + b * R0, im + b * R0);
             if (NPASS == 1) {
                 // N = R0, T = 1: bins m
-                if (kp.dc_term) { re[0] = vadd(re[0], vsplat((S)(N / 2), re[0])); im[0] = vadd(im[0], vsplat((S)(N / 2), im[0])); }
+                out.dc_adjust(kp, 0, re[0], im[0]);
                 out.template store_sel<R0, 1>(out_mode, 0, re, im, dc_patch);
             }
         }
@@ -653,7 +670,7 @@ fsea_fft_kernel(const fsea_kparams kp) {
             for (int b = 0; b < B; b++) fsea_dft<R1, V>::run(re + b * R1, im + b * R1);
             if (NPASS == 2) {
                 // N = R0 R1: i < R0 = M, k = i, bins i + m R0
-                if (kp.dc_term && t == 0) { re[0] = vadd(re[0], vsplat((S)(N / 2), re[0])); im[0] = vadd(im[0], vsplat((S)(N / 2), im[0])); }
+                out.dc_adjust(kp, t, re[0], im[0]);
 #pragma unroll
                 for (int b = 0; b < B; b++)
                     out.template store_sel<R1, M>(out_mode, t + b * T, re + b * R1, im + b * R1, dc_patch);
@@ -704,7 +721,7 @@ fsea_fft_kernel(const fsea_kparams kp) {
             }
 #pragma unroll
             for (int b = 0; b < B; b++) fsea_dft<R2, V>::run(re + b * R2, im + b * R2);
-            if (kp.dc_term && t == 0) { re[0] = vadd(re[0], vsplat((S)(N / 2), re[0])); im[0] = vadd(im[0], vsplat((S)(N / 2), im[0])); }
+            out.dc_adjust(kp, t, re[0], im[0]);
 #pragma unroll
             for (int b = 0; b < B; b++)
                 out.template store_sel<R2, M>(out_mode, t + b * T, re + b * R2, im + b * R2, dc_patch);
@@ -713,7 +730,7 @@ fsea_fft_kernel(const fsea_kparams kp) {
         in = in_next;
         live = live_next;
         cur = nxt;
-        nxt = (long)fsea_ticket_share<T>(pend_prev, t, g, fsea_slot);
+        nxt = share(pend_prev);
         pend_prev = pend;
     }
     // last block out re-arms the counters for the next launch that uses this slot

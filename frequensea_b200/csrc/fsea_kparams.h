@@ -16,6 +16,8 @@ struct fsea_kparams {
     int dc_term;           // 1: add N/2 (1+i) to bin k=0 (uncentred 8-bit input, no patch)
     int out_mode;          // FSEA_OUT_*
     unsigned* ticket;      // 2 counters: work tickets, finished blocks (self re-arming)
+    const void* tw4;       // four-step twiddles W_N^{n2 k1}, float2 [N1][N2]
+    int n1, n2;            // four-step factors (0 otherwise)
     void* dump;            // N x 8 bytes: where sequences beyond the batch are written
     uint32_t xor_mask;     // 0x8080 for two's-complement input (FSEA_IN_S8), else 0
 };

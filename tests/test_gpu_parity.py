@@ -100,6 +100,57 @@ def test_hann_overlap_logmag(fbg, n, hop):
     assert rel_err(got, ref) < MAG_TOL
 
 
+@pytest.mark.parametrize("n", [16384, 32768, 65536])
+def test_four_step_sizes(fbg, n):
+    """cfg4 / cfg5 sizes: N = N1 x N2 through the L2-resident intermediate."""
+    fb = fbg
+    frames = 3
+    data = synth_s8(n * frames, seed=n)
+    plan = fb.Plan(n, in_format=fb.IN_S8, out_mode=fb.OUT_MAG, flags=fb.FLAG_DC_PATCH)
+    got = plan.exec_host(data, frames)
+    ref = oracle_rows(data, n, n, frames, orc.IN_S8, orc.WIN_NONE, orc.OUT_MAG, flags=orc.FLAG_DC_PATCH)
+    assert rel_err(got, ref) < MAG_TOL, plan.kernel_name
+    assert np.array_equal(got[:, n // 2], got[:, n // 2 - 1])
+    # uncentred DC kept (no patch), log-magnitude as cfg5 asks
+    plan = fb.Plan(n, in_format=fb.IN_S8, out_mode=fb.OUT_LOGMAG)
+    got = plan.exec_host(data, frames).astype(np.float64)
+    ref = oracle_rows(data, n, n, frames, orc.IN_S8, orc.WIN_NONE, orc.OUT_LOGMAG)
+    lin = 10 ** (ref / 20)
+    ok = lin >= 1e-3 * np.sqrt(np.mean(lin ** 2, axis=1, keepdims=True))
+    assert np.max(np.abs(got - ref)[ok]) < 2e-3
+    assert abs(got[0, n // 2] - ref[0, n // 2]) < 2e-3          # the analytic DC bin
+    # Hann + 50 % overlap + pixels (sweep product), odd frame count
+    hop = n // 2
+    data = synth_u8((frames - 1) * hop + n, seed=n + 1)
+    plan = fb.Plan(n, hop=hop, in_format=fb.IN_U8, window=fb.WIN_HANN, out_mode=fb.OUT_PIX, pix_scale=5.0, flags=fb.FLAG_DC_PATCH)
+    got = plan.exec_host(data, frames)
+    ref = oracle_rows(data, n, hop, frames, orc.IN_U8, orc.WIN_HANN, orc.OUT_PIX, 5.0, orc.FLAG_DC_PATCH)
+    d = np.abs(got.astype(int) - ref.astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 0.005
+
+
+def test_four_step_many_frames(fbg):
+    """More frames than one L2-sized chunk (chunk = 32 MiB of intermediate = 64 frames at N = 65536)."""
+    import torch
+    fb = fbg
+    n, frames = 65536, 150
+    g = torch.Generator(device="cuda").manual_seed(3)
+    d_in = torch.randint(0, 256, (frames * n * 2,), dtype=torch.uint8, device="cuda", generator=g)
+    d_out = torch.empty((frames, n), dtype=torch.float32, device="cuda")
+    plan = fb.Plan(n, in_format=fb.IN_S8, out_mode=fb.OUT_MAG)
+    plan.exec_device(d_in.data_ptr(), d_out.data_ptr(), frames, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    x = (d_in.view(frames, n, 2).to(torch.int16) ^ 0x80).to(torch.float64) / 256.0
+    energy_t = (x ** 2).sum(dim=(1, 2)) * n
+    energy_f = (d_out.to(torch.float64) ** 2).sum(dim=1)
+    assert torch.max(torch.abs(energy_f / energy_t - 1)).item() < 1e-5          # Parseval
+    h_in = d_in.cpu().numpy()
+    for f in (0, 63, 64, 149):
+        ref = orc.engine_frame(h_in[f * 2 * n:], n, orc.IN_S8, orc.WIN_NONE, orc.OUT_MAG)
+        k = np.arange(n) != n // 2
+        assert rel_err(d_out[f].cpu().numpy()[k], ref[k]) < MAG_TOL
+
+
 def test_sweep_pixels_match_reference_tools(fbg, iq, golden):
     """cfg1 / cfg4 semantics: c/fft-batch.c (S=10, no patch) and c/fft-batch-broad.c (S=5, DC patch)."""
     fb = fbg
