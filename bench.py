@@ -176,8 +176,9 @@ def secondary(args):
     fmt = fb.IN_S8 if w["fmt"] == "s8" else fb.IN_U8
     out_mode = {"mag": fb.OUT_MAG, "logmag": fb.OUT_LOGMAG, "pix": fb.OUT_PIX}[w["out"]]
     flags = fb.FLAG_DC_PATCH if w["patch"] else 0
+    arith = {"auto": fb.ARITH_AUTO, "f32": fb.ARITH_F32, "f32x2": fb.ARITH_F32X2}[args.arith]
     plan = fb.Plan(n, hop=hop, in_format=fmt, window=fb.WIN_HANN if w["window"] else fb.WIN_NONE,
-                   out_mode=out_mode, flags=flags, pix_scale=w.get("scale", 10.0))
+                   out_mode=out_mode, flags=flags, pix_scale=w.get("scale", 10.0), arith=arith)
     dev = torch.device("cuda", 0)
     g = torch.Generator(device=dev).manual_seed(20260925)
     d_in = torch.randint(0, 256, (plan.input_bytes(frames),), dtype=torch.uint8, device=dev, generator=g)

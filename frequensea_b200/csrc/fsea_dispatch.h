@@ -9,7 +9,9 @@ enum {
     FSEA_VAR_F32X2 = 1,  // 8-bit IQ, frame PAIR per group, packed FADD2/FMUL2/FFMA2
     FSEA_VAR_F32C = 2,   // float2 samples, scalar fp32
     FSEA_VAR_F64 = 3,    // double2 samples, fp64
-    FSEA_VAR_COUNT = 4
+    FSEA_VAR_F32_WIN = 4,    // as F32 / F32X2 with the Hann multiply compiled in
+    FSEA_VAR_F32X2_WIN = 5,
+    FSEA_VAR_COUNT = 6
 };
 
 struct fsea_kernel_info {
@@ -45,4 +47,4 @@ struct fsea_kernel_info4 {
     fsea_kernel_info a, b;
     int n1, n2;
 };
-bool fsea_get_kernel4(int n, fsea_kernel_info4* out);
+bool fsea_get_kernel4(int n, bool window, fsea_kernel_info4* out);

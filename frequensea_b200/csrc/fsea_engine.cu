@@ -183,10 +183,11 @@ static int setup_kernel(const fsea_kernel_info& ki, int device, int* max_blocks)
 }
 
 // inter-pass twiddle tables of one kernel: evaluated in long double, stored in its precision
-static int upload_twiddles(const fsea_kernel_info& ki, void** d1, void** d2) {
+static int upload_twiddles(const fsea_kernel_info& ki, void** d1, void** d2, float scale1 = 1.0f) {
     if (ki.scalar_bytes == 4) {
         std::vector<float2> t1, t2;
         fill_twiddles(t1, t2, ki);
+        for (auto& w : t1) { w.x *= scale1; w.y *= scale1; }   // exact: a power of two
         CU(cudaMalloc(d1, t1.size() * sizeof(float2)));
         CU(cudaMalloc(d2, t2.size() * sizeof(float2)));
         CU(cudaMemcpy(*d1, t1.data(), t1.size() * sizeof(float2), cudaMemcpyHostToDevice));
@@ -209,7 +210,7 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
     if (n < 16 || n > 65536 || (n & (n - 1))) return FSEA_ERR_UNSUPPORTED;
     fsea_get_kernel_fn get = size_table(n);
     fsea_kernel_info4 k4;
-    const bool four = !get && fsea_get_kernel4(n, &k4);
+    const bool four = !get && fsea_get_kernel4(n, cfg->window == FSEA_WIN_HANN, &k4);
     if (!get && !four) return FSEA_ERR_UNSUPPORTED;
     if (four && cfg->in_format != FSEA_IN_U8 && cfg->in_format != FSEA_IN_S8) return FSEA_ERR_UNSUPPORTED;
     if (cfg->in_format < FSEA_IN_U8 || cfg->in_format > FSEA_IN_F64C) return FSEA_ERR_INVALID;
@@ -230,6 +231,7 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
         case FSEA_IN_U8:
         case FSEA_IN_S8:
             p->variant = (cfg->arith == FSEA_ARITH_F32) ? FSEA_VAR_F32 : FSEA_VAR_F32X2;
+            if (cfg->window == FSEA_WIN_HANN) p->variant = (p->variant == FSEA_VAR_F32) ? FSEA_VAR_F32_WIN : FSEA_VAR_F32X2_WIN;
             p->sample_bytes = 2;
             break;
         case FSEA_IN_F32C: p->variant = FSEA_VAR_F32C; p->sample_bytes = 8; break;
@@ -247,7 +249,11 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
     do {
         cudaError_t e;
         if ((rc = setup_kernel(p->ki, cfg->device, &p->max_blocks)) != FSEA_OK) break;
-        if ((rc = upload_twiddles(p->ki, &p->d_tw1, &p->d_tw2)) != FSEA_OK) break;
+        // staged 8-bit kernels transform integer-scaled samples (b - 128): the 1/256 of
+        // src/nrf.c:605-606 rides on the pass-1 twiddles
+        const bool staged = !p->four && (p->variant == FSEA_VAR_F32 || p->variant == FSEA_VAR_F32X2 ||
+                                         p->variant == FSEA_VAR_F32_WIN || p->variant == FSEA_VAR_F32X2_WIN) && p->ki.r1 > 1;
+        if ((rc = upload_twiddles(p->ki, &p->d_tw1, &p->d_tw2, staged ? 1.0f / 256.0f : 1.0f)) != FSEA_OK) break;
         if (p->four) {
             if ((rc = setup_kernel(p->k4.b, cfg->device, &p->max_blocks_b)) != FSEA_OK) break;
             if ((rc = upload_twiddles(p->k4.b, &p->d_tw1b, &p->d_tw2b)) != FSEA_OK) break;
@@ -261,7 +267,9 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
                     t4[(size_t)k1 * n2 + c].y = (float)sinl(a);
                 }
             // the intermediate of one chunk must stay in L2 (126 MB): 32 MiB of float2
-            p->chunk_frames = std::max<long>(1, (32L << 20) / ((long)n * 8));
+            long chunk_mb = 32;
+            if (const char* ev = getenv("FSEA_CHUNK_MB")) chunk_mb = std::max(1L, atol(ev));   // experiments
+            p->chunk_frames = std::max<long>(1, (chunk_mb << 20) / ((long)n * 8));
             if ((e = cudaMalloc(&p->d_tw4, (size_t)n * sizeof(float2))) != cudaSuccess ||
                 (e = cudaMemcpy(p->d_tw4, t4.data(), (size_t)n * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess ||
                 (e = cudaMalloc(&p->d_scratch[0], (size_t)p->chunk_frames * n * sizeof(float2))) != cudaSuccess) {

@@ -30,10 +30,10 @@ struct fsea_cfg {
     static const int MINB = MINB_1 < 1 ? 1 : (MINB_1 > 16 ? 16 : MINB_1);
 };
 
-template <class SH, typename V, int FMT, int OK = FSEA_OK_SPECTRUM, int NTOT = SH::N>
+template <class SH, typename V, int FMT, int OK = FSEA_OK_SPECTRUM, int NTOT = SH::N, bool WIN = false>
 static bool fsea_fill(fsea_kernel_info* o, const char* name) {
     typedef fsea_cfg<SH, V, FMT> C;
-    o->fn = (const void*)&fsea_fft_kernel<SH, V, FMT, OK, NTOT, C::G, C::TWS, C::MINB>;
+    o->fn = (const void*)&fsea_fft_kernel<SH, V, FMT, OK, NTOT, C::G, C::TWS, C::MINB, WIN>;
     o->threads = SH::T * C::G;
     o->groups = C::G;
     o->lanes = fsea_vt<V>::lanes;
@@ -55,6 +55,10 @@ static bool fsea_fill(fsea_kernel_info* o, const char* name) {
                 return fsea_fill<SH, float, FSEA_IN_U8>(out, "fft<" FSEA_STR(N) ":" FSEA_STR(R0) "x" FSEA_STR(R1) "x" FSEA_STR(R2) ",f32>");      \
             case FSEA_VAR_F32X2:                                                                         \
                 return fsea_fill<SH, f2, FSEA_IN_U8>(out, "fft<" FSEA_STR(N) ":" FSEA_STR(R0) "x" FSEA_STR(R1) "x" FSEA_STR(R2) ",f32x2>");       \
+            case FSEA_VAR_F32_WIN:                                                                       \
+                return fsea_fill<SH, float, FSEA_IN_U8, FSEA_OK_SPECTRUM, N, true>(out, "fft<" FSEA_STR(N) ":" FSEA_STR(R0) "x" FSEA_STR(R1) "x" FSEA_STR(R2) ",f32,win>");      \
+            case FSEA_VAR_F32X2_WIN:                                                                     \
+                return fsea_fill<SH, f2, FSEA_IN_U8, FSEA_OK_SPECTRUM, N, true>(out, "fft<" FSEA_STR(N) ":" FSEA_STR(R0) "x" FSEA_STR(R1) "x" FSEA_STR(R2) ",f32x2,win>");       \
             case FSEA_VAR_F32C:                                                                          \
                 return fsea_fill<SH, float, FSEA_IN_F32C>(out, "fft<" FSEA_STR(N) ":" FSEA_STR(R0) "x" FSEA_STR(R1) "x" FSEA_STR(R2) ",f32c>");   \
             case FSEA_VAR_F64:                                                                           \

@@ -131,10 +131,18 @@ template <int FMT> struct fsea_in<FMT, float> {
     }
     // 8-bit only: coalesced 16-byte loads of the whole frame into shared memory
     template <int N, int T> __device__ __forceinline__ void async_stage(int t, unsigned char* sm) const;
+    // Staged kernels work on INTEGER-scaled samples (byte in mantissa bits 8..15:
+    // 0x47000000 | b << 8 = 32768 + b); the 1/256 of src/nrf.c:605-606 is folded into the
+    // pass-1 twiddle table.  load_staged: centred value b - 128; load_staged_raw: the magic
+    // float itself (the first butterfly stage of fsea_dft*_raw removes the bias).
     template <int N> __device__ __forceinline__ void load_staged(const unsigned char* sm, int e, float& re, float& im) const {
+        load_staged_raw<N>(sm, e, re, im);
+        re -= 32896.0f; im -= 32896.0f;
+    }
+    template <int N> __device__ __forceinline__ void load_staged_raw(const unsigned char* sm, int e, float& re, float& im) const {
         const uint32_t w = (uint32_t)((const unsigned short*)sm)[e] ^ xm;
-        re = __uint_as_float(__byte_perm(w, 0x47000000u, 0x7650)) - 32768.5f;
-        im = __uint_as_float(__byte_perm(w, 0x47000000u, 0x7651)) - 32768.5f;
+        re = __uint_as_float(__byte_perm(w, 0x47000000u, 0x7504));
+        im = __uint_as_float(__byte_perm(w, 0x47000000u, 0x7514));
     }
 };
 
@@ -175,14 +183,17 @@ template <int FMT> struct fsea_in<FMT, f2> {
     }
     template <int N, int T> __device__ __forceinline__ void async_stage(int t, unsigned char* sm) const;
     template <int N> __device__ __forceinline__ void load_staged(const unsigned char* sm, int e, f2& re, f2& im) const {
+        load_staged_raw<N>(sm, e, re, im);
+        const f2 off = mk2(32896.0f, 32896.0f);
+        re = vsub(re, off); im = vsub(im, off);
+    }
+    template <int N> __device__ __forceinline__ void load_staged_raw(const unsigned char* sm, int e, f2& re, f2& im) const {
         const uint32_t wa = (uint32_t)((const unsigned short*)sm)[e] ^ xm;
         const uint32_t wb = (uint32_t)((const unsigned short*)(sm + 2 * N))[e] ^ xm;
-        f2 r = mk2(__uint_as_float(__byte_perm(wa, 0x47000000u, 0x7650)),
-                   __uint_as_float(__byte_perm(wb, 0x47000000u, 0x7650)));
-        f2 i = mk2(__uint_as_float(__byte_perm(wa, 0x47000000u, 0x7651)),
-                   __uint_as_float(__byte_perm(wb, 0x47000000u, 0x7651)));
-        const f2 off = mk2(32768.5f, 32768.5f);
-        re = vsub(r, off); im = vsub(i, off);
+        re = mk2(__uint_as_float(__byte_perm(wa, 0x47000000u, 0x7504)),
+                 __uint_as_float(__byte_perm(wb, 0x47000000u, 0x7504)));
+        im = mk2(__uint_as_float(__byte_perm(wa, 0x47000000u, 0x7514)),
+                 __uint_as_float(__byte_perm(wb, 0x47000000u, 0x7514)));
     }
 };
 
@@ -205,6 +216,7 @@ template <> struct fsea_in<FSEA_IN_F64C, double> {
     }
     template <int N, int T> __device__ __forceinline__ void async_stage(int, unsigned char*) const {}
     template <int N> __device__ __forceinline__ void load_staged(const unsigned char*, int, double&, double&) const {}
+    template <int N> __device__ __forceinline__ void load_staged_raw(const unsigned char*, int, double&, double&) const {}
 };
 
 // ---- four-step loaders (N = N1 x N2, SURVEY 7 "N = 65536") ----------------------
@@ -241,6 +253,7 @@ template <> struct fsea_in<FSEA_IN_COLS8, f2> {
     template <int N, int T> __device__ __forceinline__ void prefetch(int) const {}
     template <int N, int T> __device__ __forceinline__ void async_stage(int, unsigned char*) const {}
     template <int N> __device__ __forceinline__ void load_staged(const unsigned char*, int, f2&, f2&) const {}
+    template <int N> __device__ __forceinline__ void load_staged_raw(const unsigned char*, int, f2&, f2&) const {}
 };
 
 // Step B transforms the N1 rows of the twiddled intermediate (float2, contiguous); a unit
@@ -265,6 +278,7 @@ template <> struct fsea_in<FSEA_IN_ROWS, f2> {
     }
     template <int N, int T> __device__ __forceinline__ void async_stage(int, unsigned char*) const {}
     template <int N> __device__ __forceinline__ void load_staged(const unsigned char*, int, f2&, f2&) const {}
+    template <int N> __device__ __forceinline__ void load_staged_raw(const unsigned char*, int, f2&, f2&) const {}
 };
 
 // ---- output side: bin k of the unit's sequence(s) ---------------------------
@@ -494,7 +508,7 @@ __device__ __forceinline__ unsigned fsea_ticket_share(unsigned v, int t, int g, 
 //   G x raw ring         lanes x 2N bytes    (8-bit formats: the NEXT unit's IQ bytes land
 //                                             here by cp.async while this one is transformed)
 //   twiddle tables       when TWS
-template <class SH, typename V, int FMT, int OK, int NTOT, int G, bool TWS, int MINB>
+template <class SH, typename V, int FMT, int OK, int NTOT, int G, bool TWS, int MINB, bool WIN>
 __global__ void __launch_bounds__(SH::T* G, MINB)
 fsea_fft_kernel(const fsea_kparams kp) {
     typedef typename fsea_vt<V>::scalar S;
@@ -582,14 +596,25 @@ fsea_fft_kernel(const fsea_kparams kp) {
         // ---------------- pass 0: radix R0, p_prev = 1 ----------------
         {
             constexpr int M = N / R0, B = P / R0;
+            bool raw_stage = false;                      // pass 0 ran on biased magic floats
             if (STAGED) {
                 fsea_cp_async_wait_all();
                 fsea_group_sync<T>(g);
+                raw_stage = !WIN;
+                if (raw_stage) {
 #pragma unroll
-                for (int b = 0; b < B; b++) {
-                    const int i = t + b * T;
+                    for (int b = 0; b < B; b++) {
+                        const int i = t + b * T;
 #pragma unroll
-                    for (int j = 0; j < R0; j++) in.template load_staged<N>(raw, i + j * M, re[b * R0 + j], im[b * R0 + j]);
+                        for (int j = 0; j < R0; j++) in.template load_staged_raw<N>(raw, i + j * M, re[b * R0 + j], im[b * R0 + j]);
+                    }
+                } else {
+#pragma unroll
+                    for (int b = 0; b < B; b++) {
+                        const int i = t + b * T;
+#pragma unroll
+                        for (int j = 0; j < R0; j++) in.template load_staged<N>(raw, i + j * M, re[b * R0 + j], im[b * R0 + j]);
+                    }
                 }
                 fsea_group_sync<T>(g);                   // ring is free again: fetch the next unit
                 if (more) {
@@ -605,7 +630,7 @@ fsea_fft_kernel(const fsea_kparams kp) {
                     for (int j = 0; j < R0; j++) in.load(i + j * M, re[b * R0 + j], im[b * R0 + j]);
                 }
             }
-            if (kp.window) {
+            if (WIN) {
 #pragma unroll
                 for (int b = 0; b < B; b++) {
                     const int i = t + b * T;
@@ -617,8 +642,13 @@ fsea_fft_kernel(const fsea_kparams kp) {
                     }
                 }
             }
+            if (STAGED && R0 >= 8 && raw_stage) {
 #pragma unroll
-            for (int b = 0; b < B; b++) fsea_dft<R0, V>::run(re + b * R0, im + b * R0);
+                for (int b = 0; b < B; b++) fsea_dft_raw<(R0 >= 8 ? R0 : 8), V>::run(re + b * R0, im + b * R0);
+            } else {
+#pragma unroll
+                for (int b = 0; b < B; b++) fsea_dft<R0, V>::run(re + b * R0, im + b * R0);
+            }
             if (NPASS == 1) {
                 // N = R0, T = 1: bins m
                 out.dc_adjust(kp, 0, re[0], im[0]);
@@ -660,6 +690,10 @@ fsea_fft_kernel(const fsea_kparams kp) {
                 const V* r = xp + i + (i >> L0);
 #pragma unroll
                 for (int j = 0; j < R1; j++) im[b * R1 + j] = r[j * JSTR];
+                if (STAGED) {                                      // integer-scaled samples: tw1 carries 1/256,
+                    re[b * R1] = vmuls(re[b * R1], (S)(1.0 / 256.0));   // the untwiddled j = 0 input takes it here
+                    im[b * R1] = vmuls(im[b * R1], (S)(1.0 / 256.0));
+                }
 #pragma unroll
                 for (int j = 1; j < R1; j++) {
                     const S2 w = tw1[(j - 1) * R0 + k];

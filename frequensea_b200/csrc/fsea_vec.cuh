@@ -38,6 +38,7 @@ template <> struct fsea_vt<double> { typedef double scalar; static const int lan
     FSEA_HD T vmuls(T a, T s) { return a * s; }                                   \
     FSEA_HD T vfmas(T a, T s, T b) { return a * s + b; }                          \
     FSEA_HD T vfnmas(T a, T s, T b) { return b - a * s; }                         \
+    FSEA_HD T vaddc(T a, T c) { return a + c; }                                   \
     FSEA_HD T vsplat(T s, T) { return s; }
 FSEA_SCALAR_OPS(float)
 FSEA_SCALAR_OPS(double)
@@ -72,6 +73,7 @@ FSEA_D f2 vfms(f2 a, float c, f2 b) { return mk2(a.v.x * c - b.v.x, a.v.y * c - 
 FSEA_D f2 vfma2(f2 a, f2 c, f2 b) { return mk2(a.v.x * c.v.x + b.v.x, a.v.y * c.v.y + b.v.y); }
 FSEA_D f2 vmuls(f2 a, float s) { return mk2(a.v.x * s, a.v.y * s); }
 #endif
+FSEA_D f2 vaddc(f2 a, float c) { return vadd(a, mk2(c, c)); }
 FSEA_D f2 vfmas(f2 a, float s, f2 b) { return vfma(a, s, b); }
 FSEA_D f2 vfnmas(f2 a, float s, f2 b) { return vfnma(a, s, b); }
 FSEA_D f2 vsplat(float s, f2) { return mk2(s, s); }

@@ -143,6 +143,13 @@ extern "C" void nrf_device_step(nrf_device* device) {
     if (++device->dummy_block_index >= device->dummy_block_length) device->dummy_block_index = 0;
 }
 
+// Extension (not in the reference): publish the current capture block synchronously, so a
+// paused device (nrf_device_set_paused + nrf_device_step, src/nrf.c:341-350) can be replayed
+// block by block without waiting for the 60 Hz producer thread.  Used by tools/fsea-lua --step.
+extern "C" void nrf_device_publish_now(nrf_device* device) {
+    device_ingest_block(device, device->receive_buffer + (size_t)device->dummy_block_index * NRF_BUFFER_SIZE_BYTES);
+}
+
 extern "C" nut_buffer* nrf_device_get_samples_buffer(nrf_device* device) {
     pthread_mutex_lock(&device->data_mutex);
     nut_buffer* snapshot = nut_buffer_new_u8(NRF_SAMPLES_LENGTH, 2, device->samples);

@@ -102,6 +102,8 @@ void nrf_device_set_paused(nrf_device *device, int paused);
 void nrf_device_step(nrf_device *device);
 nut_buffer *nrf_device_get_samples_buffer(nrf_device *device);
 void nrf_device_free(nrf_device *device);
+/* extension: publish the current block now (deterministic replay of a paused device) */
+void nrf_device_publish_now(nrf_device *device);
 
 /* ---- FFT analysis (src/nrf.h:126-142) ----------------------------------- */
 typedef struct {

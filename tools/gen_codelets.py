@@ -115,7 +115,9 @@ class Gen:
         x1 = (self.fnma(ur, m, er), self.fnma(ui, m, ei))
         return x0, x1
 
-    def fft(self, xs, chunk=4):
+    def addc(self, a, c): return self.emit(f"vaddc({a}, {self.lit(c)})")             # a + c
+
+    def fft(self, xs, chunk=4, raw_bias=None):
         """Iterative radix-2 DIT, emitted stage by stage (breadth first): within a
         stage the butterflies are independent, and they are written out `chunk` at
         a time -- first every butterfly's twiddle half, then every butterfly's
@@ -130,6 +132,16 @@ class Gen:
             pairs = [(base + k, base + k + half, k) for base in range(0, R, L) for k in range(half)]
             # trivial-twiddle butterflies first, then the twiddled ones, each in chunks
             pairs.sort(key=lambda p: (0 if (p[2] == 0 or Fraction(p[2], L) == Fraction(1, 4)) else 1))
+            if half == 1 and raw_bias is not None:
+                # inputs are raw "magic" floats f = bias + c: the difference needs no
+                # unpacking at all (the bias cancels), the sum loses 2*bias in one add
+                for (a, b, k) in pairs:
+                    (er, ei), (orr, oi) = v[a], v[b]
+                    x0 = (self.addc(self.add(er, orr), -2 * raw_bias), self.addc(self.add(ei, oi), -2 * raw_bias))
+                    x1 = (self.sub(er, orr), self.sub(ei, oi))
+                    v[a], v[b] = x0, x1
+                half = L
+                continue
             for c0 in range(0, len(pairs), chunk):
                 grp = pairs[c0:c0 + chunk]
                 pre = [self.bfly_pre(v[b], k, L) for (_, b, k) in grp]
@@ -139,14 +151,20 @@ class Gen:
         return v
 
 
-def codelet(R):
+RAW_BIAS = Decimal(32896)      # 0x47000000 | (byte << 8) = 32768 + byte ; centred = f - 32896
+
+
+def codelet(R, raw=False):
     g = Gen()
     xs = [(f"re[{j}]", f"im[{j}]") for j in range(R)]
-    out = g.fft(xs)
+    out = g.fft(xs, raw_bias=RAW_BIAS if raw else None)
     body = "\n".join(g.lines)
     stores = "\n".join(f"    re[{k}] = {o[0]}; im[{k}] = {o[1]};" for k, o in enumerate(out))
-    return (f"// radix-{R}: {g.ops} fused ops ({g.ops / R:.2f} per point)\n"
-            f"template <typename V>\nFSEA_HD void fsea_dft{R}(V* __restrict__ re, V* __restrict__ im) {{\n"
+    name = f"fsea_dft{R}_raw" if raw else f"fsea_dft{R}"
+    note = (" -- inputs are raw magic floats 32768 + byte (8-bit IQ placed in mantissa bits 8..15);\n"
+            "// the byte-unpack subtraction is folded into the first butterfly stage") if raw else ""
+    return (f"// radix-{R}{' raw' if raw else ''}: {g.ops} fused ops ({g.ops / R:.2f} per point){note}\n"
+            f"template <typename V>\nFSEA_HD void {name}(V* __restrict__ re, V* __restrict__ im) {{\n"
             f"    typedef typename fsea_vt<V>::scalar S;\n{body}\n{stores}\n}}\n"), g.ops
 
 
@@ -159,9 +177,15 @@ def main():
     for R in (2, 4, 8, 16, 32):
         src, ops = codelet(R)
         out.append(src)
+    for R in (8, 16, 32):
+        src, ops = codelet(R, raw=True)
+        out.append(src)
     out.append("template <int R, typename V> struct fsea_dft;\n" + "".join(
         f"template <typename V> struct fsea_dft<{R}, V> {{ static FSEA_HD void run(V* re, V* im) {{ fsea_dft{R}<V>(re, im); }} }};\n"
         for R in (1, 2, 4, 8, 16, 32)))
+    out.append("template <int R, typename V> struct fsea_dft_raw;\n" + "".join(
+        f"template <typename V> struct fsea_dft_raw<{R}, V> {{ static FSEA_HD void run(V* re, V* im) {{ fsea_dft{R}_raw<V>(re, im); }} }};\n"
+        for R in (8, 16, 32)))
     sys.stdout.write("\n".join(out))
 
 
