@@ -476,6 +476,15 @@ __device__ __forceinline__ void fsea_in<FMT, f2>::async_stage(int t, unsigned ch
 }
 
 // ---- dynamic work distribution ------------------------------------------------
+// atom.add as opaque PTX: nvcc turns atomicAdd() in a one-lane branch into its
+// warp-aggregated form (elect + atom + SHFL of the result), and that compiler-made SHFL
+// waits for the atomic's round trip right where it is issued.
+__device__ __forceinline__ unsigned fsea_take_ticket(unsigned* counter) {
+    unsigned old;
+    asm volatile("atom.global.inc.u32 %0, [%1], 0xfffffffe;" : "=r"(old) : "l"(counter) : "memory");
+    return old;
+}
+
 // Units are handed out by a global ticket counter instead of a fixed stride:
 // the SM's warp arbiter is not fair, and with a static split the favoured
 // blocks finish early and leave their SM under-occupied for the rest of the
@@ -483,12 +492,15 @@ __device__ __forceinline__ void fsea_in<FMT, f2>::async_stage(int t, unsigned ch
 // the ticket at the top of an iteration and the group reads it at the bottom,
 // so the atomic's round trip to L2 is hidden behind a whole transform.
 template <int T>
-__device__ __forceinline__ unsigned fsea_ticket_share(unsigned v, int t, int g, volatile unsigned* slot) {
+__device__ __forceinline__ unsigned fsea_ticket_share(unsigned v, int t, int g, volatile unsigned* slot, int late = 0) {
     if (T <= 32) {
-        // asm volatile + "memory": the broadcast must stay at the bottom of the
-        // iteration (after the stores); the compiler otherwise hoists it next to the atomic
+        // The broadcast must stay at the bottom of the iteration: hoisted next to the atomic
+        // (which is what the compiler does with it, volatile or not) the warp sits out the
+        // atomic's whole round trip (ncu: 6.7 % of all stall samples on this one SHFL).
+        // `late` is a value computed from the last stored bin that is always 0 but not
+        // provably so; adding it to the source lane pins the shuffle behind the epilogue.
         unsigned r;
-        const int src = (threadIdx.x & 31) - t;
+        const int src = (threadIdx.x & 31) - t + late;
         asm volatile("shfl.sync.idx.b32 %0, %1, %2, 0x1f, 0xffffffff;" : "=r"(r) : "r"(v), "r"(src) : "memory");
         return r;
     } else {
@@ -550,7 +562,7 @@ fsea_fft_kernel(const fsea_kparams kp) {
     __shared__ unsigned fsea_tile_slot;
     const bool leader = TILED ? (tid == 0) : (t == 0);
 
-    auto share = [&](unsigned v) -> long {
+    auto share = [&](unsigned v, int late = 0) -> long {
         if (TILED) {                                              // one ticket per block = G units
             if (tid == 0) fsea_tile_slot = v;
             __syncthreads();
@@ -558,19 +570,19 @@ fsea_fft_kernel(const fsea_kparams kp) {
             __syncthreads();
             return (long)tile * G + g;
         }
-        return (long)fsea_ticket_share<T>(v, t, g, fsea_slot);
+        return (long)fsea_ticket_share<T>(v, t, g, fsea_slot, late);
     };
     const long n_claims = TILED ? (n_units + G - 1) / G * G : n_units;   // tiles run to completion
 
     unsigned pend = 0;
-    if (leader) pend = atomicAdd(ticket, 1u);
+    if (leader) pend = fsea_take_ticket(ticket);
     long cur = share(pend);
-    if (leader) pend = atomicAdd(ticket, 1u);
+    if (leader) pend = fsea_take_ticket(ticket);
     long nxt = share(pend);
     // two tickets are always in flight: the one read at the bottom of an iteration was
     // requested a whole iteration earlier, wherever the compiler schedules the broadcast
     unsigned pend_prev = 0;
-    if (leader) pend_prev = atomicAdd(ticket, 1u);
+    if (leader) pend_prev = fsea_take_ticket(ticket);
 
     fsea_in<FMT, V> in;
     bool live;
@@ -582,7 +594,7 @@ fsea_fft_kernel(const fsea_kparams kp) {
 
     // groups that share a warp (T < 32) leave the loop together
     while (TILED ? (cur - g < n_claims) : (T >= 32 ? (cur < n_units) : (__any_sync(0xffffffffu, cur < n_units) != 0))) {
-        if (leader) pend = atomicAdd(ticket, 1u);        // the unit after next; read at the bottom
+        if (leader) pend = fsea_take_ticket(ticket);      // the unit after next; read at the bottom
         const long unit = cur;
         typename fsea_out_sel<OK, N, NTOT, V>::type out;
         out.init(kp, live ? unit : 0, live, out_esz);
@@ -764,7 +776,9 @@ fsea_fft_kernel(const fsea_kparams kp) {
         in = in_next;
         live = live_next;
         cur = nxt;
-        nxt = share(pend_prev);
+        // (never true: no finite transform produces this NaN payload in its last register)
+        const int late = (__float_as_uint((float)fsea_lane(re[P - 1], 0)) == 0x7fc0deadu) ? 1 : 0;
+        nxt = share(pend_prev, late);
         pend_prev = pend;
     }
     // last block out re-arms the counters for the next launch that uses this slot
