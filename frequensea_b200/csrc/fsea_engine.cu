@@ -232,6 +232,10 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
         case FSEA_IN_S8:
             p->variant = (cfg->arith == FSEA_ARITH_F32) ? FSEA_VAR_F32 : FSEA_VAR_F32X2;
             if (cfg->window == FSEA_WIN_HANN) p->variant = (p->variant == FSEA_VAR_F32) ? FSEA_VAR_F32_WIN : FSEA_VAR_F32X2_WIN;
+            else if (const char* ex = getenv("FSEA_EXP")) {          // kernel-geometry experiments
+                if (!strcmp(ex, "g1")) p->variant = FSEA_VAR_EXP1;
+                if (!strcmp(ex, "g2")) p->variant = FSEA_VAR_EXP2;
+            }
             p->sample_bytes = 2;
             break;
         case FSEA_IN_F32C: p->variant = FSEA_VAR_F32C; p->sample_bytes = 8; break;
@@ -251,9 +255,9 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
         if ((rc = setup_kernel(p->ki, cfg->device, &p->max_blocks)) != FSEA_OK) break;
         // staged 8-bit kernels transform integer-scaled samples (b - 128): the 1/256 of
         // src/nrf.c:605-606 rides on the pass-1 twiddles
-        const bool staged = !p->four && (p->variant == FSEA_VAR_F32 || p->variant == FSEA_VAR_F32X2 ||
+        const bool staged = !p->four && (p->variant == FSEA_VAR_F32 || p->variant == FSEA_VAR_F32X2 || p->variant >= FSEA_VAR_EXP1 ||
                                          p->variant == FSEA_VAR_F32_WIN || p->variant == FSEA_VAR_F32X2_WIN) && p->ki.r1 > 1;
-        if ((rc = upload_twiddles(p->ki, &p->d_tw1, &p->d_tw2, staged ? 1.0f / 256.0f : 1.0f)) != FSEA_OK) break;
+        if (!p->four && (rc = upload_twiddles(p->ki, &p->d_tw1, &p->d_tw2, staged ? 1.0f / 256.0f : 1.0f)) != FSEA_OK) break;
         if (p->four) {
             if ((rc = setup_kernel(p->k4.b, cfg->device, &p->max_blocks_b)) != FSEA_OK) break;
             if ((rc = upload_twiddles(p->k4.b, &p->d_tw1b, &p->d_tw2b)) != FSEA_OK) break;
@@ -263,8 +267,9 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
             for (int k1 = 0; k1 < n1; k1++)
                 for (int c = 0; c < n2; c++) {
                     const long double a = -PI2 * (long double)((long)k1 * c) / (long double)n;
-                    t4[(size_t)k1 * n2 + c].x = (float)cosl(a);
-                    t4[(size_t)k1 * n2 + c].y = (float)sinl(a);
+                    // step A leaves integer-scaled samples: 1/256 (src/nrf.c:605-606) rides here, exactly
+                    t4[(size_t)k1 * n2 + c].x = (float)(cosl(a) / 256.0L);
+                    t4[(size_t)k1 * n2 + c].y = (float)(sinl(a) / 256.0L);
                 }
             // the intermediate of one chunk must stay in L2 (126 MB): 32 MiB of float2
             long chunk_mb = 32;
@@ -345,7 +350,7 @@ static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cu
             ka.n_seq = cf * n2;
             ka.n1 = n1; ka.n2 = n2;
             ka.ticket = p->d_tickets + 2 * (p->launches % fsea_plan::TICKET_SLOTS);
-            long units = ka.n_seq / 2, blocks = std::min<long>((units + p->k4.a.groups - 1) / p->k4.a.groups, p->max_blocks);
+            long units = ka.n_seq / 2, blocks = std::min<long>((units + p->k4.a.threads - 1) / p->k4.a.threads, (long)p->max_blocks * 4);
             void* aa[] = {&ka};
             CU(cudaLaunchKernel(p->k4.a.fn, dim3((unsigned)blocks), dim3((unsigned)p->k4.a.threads), aa, p->k4.a.smem, stream));
             p->launches++;

@@ -3,24 +3,27 @@
 #include "fsea_kernels.cuh"
 #include "fsea_dispatch.h"
 
-template <class SH, typename V, int FMT>
+template <class SH, typename V, int FMT, int GOV = 0, int TWSOV = -1>
 struct fsea_cfg {
     static const int UNIT_BYTES = 2 * (int)sizeof(V);
     static const int SB = (int)sizeof(typename fsea_vt<V>::scalar);
     static const bool STAGED = SH::NPASS > 1 && SB == 4 && FMT == FSEA_IN_U8;
     static const int XBYTES = SH::NPASS > 1 ? SH::UNITS * (int)sizeof(V) + (STAGED ? fsea_vt<V>::lanes * 2 * SH::N : 0) : 0;   // exchange plane + raw ring per group
     static const int TWBYTES = (SH::TW1 + SH::TW2) * 2 * SB;
-    static const bool TWS = SH::NPASS > 1 && TWBYTES <= 16384;
-    static const bool TILED = (FMT == FSEA_IN_COLS8) || (FMT == FSEA_IN_ROWS);
-    static const int TPB = TILED ? 256 : 128;                                     // target threads per block
+    static const bool TWS = TWSOV >= 0 ? (TWSOV != 0) : (SH::NPASS > 1 && TWBYTES <= 16384);
+    static const bool TILED = (FMT == FSEA_IN_ROWS);
+    static const int TPB = 128;                                                   // target threads per block
     static const int G_T = (TPB / SH::T) > 1 ? (TPB / SH::T) : 1;
     static const int G_S = XBYTES ? ((96 * 1024) / XBYTES > 1 ? (96 * 1024) / XBYTES : 1) : 1024;
     static const int G_0 = G_T < G_S ? G_T : G_S;
-    static const int G = (SH::T > 32 && G_0 > 15) ? 15 : G_0;                   // named barriers 1..15
+    static const int G_1 = (SH::T > 32 && G_0 > 15) ? 15 : G_0;                 // named barriers 1..15
+    static const int G_2 = TILED ? (G_1 >= 16 ? 16 : (G_1 >= 8 ? 8 : (G_1 >= 4 ? 4 : (G_1 >= 2 ? 2 : 1)))) : G_1;   // 2G rows divide 32
+    static const int G = GOV > 0 ? GOV : G_2;
     static const size_t SMEM = (size_t)G * XBYTES + (TWS ? TWBYTES : 0);
     // resident blocks per SM the register allocator must allow: what shared memory
     // permits, capped so that a thread keeps >= REGCAP registers
-    static const int REGCAP = (sizeof(V) >= 8 ? (SH::P >= 32 ? 168 : (SH::P >= 16 ? 112 : 80)) : (SH::P >= 32 ? 96 : 64));
+    static const int REGCAP_0 = (sizeof(V) >= 8 ? (SH::P >= 32 ? 168 : (SH::P >= 16 ? 112 : 80)) : (SH::P >= 32 ? 96 : 64));
+    static const int REGCAP = (GOV == 1 || GOV == 2) ? 152 : REGCAP_0;   // 13 warps per SM in the g1 experiment
     static const int THREADS = SH::T * G;
     static const int B_SMEM = SMEM ? (int)((227 * 1024) / (SMEM + 1024)) : 16;
     static const int B_REG = 65536 / (THREADS * REGCAP);
@@ -30,9 +33,9 @@ struct fsea_cfg {
     static const int MINB = MINB_1 < 1 ? 1 : (MINB_1 > 16 ? 16 : MINB_1);
 };
 
-template <class SH, typename V, int FMT, int OK = FSEA_OK_SPECTRUM, int NTOT = SH::N, bool WIN = false>
+template <class SH, typename V, int FMT, int OK = FSEA_OK_SPECTRUM, int NTOT = SH::N, bool WIN = false, int GOV = 0, int TWSOV = -1>
 static bool fsea_fill(fsea_kernel_info* o, const char* name) {
-    typedef fsea_cfg<SH, V, FMT> C;
+    typedef fsea_cfg<SH, V, FMT, GOV, TWSOV> C;
     o->fn = (const void*)&fsea_fft_kernel<SH, V, FMT, OK, NTOT, C::G, C::TWS, C::MINB, WIN>;
     o->threads = SH::T * C::G;
     o->groups = C::G;
@@ -59,6 +62,10 @@ static bool fsea_fill(fsea_kernel_info* o, const char* name) {
                 return fsea_fill<SH, float, FSEA_IN_U8, FSEA_OK_SPECTRUM, N, true>(out, "fft<" FSEA_STR(N) ":" FSEA_STR(R0) "x" FSEA_STR(R1) "x" FSEA_STR(R2) ",f32,win>");      \
             case FSEA_VAR_F32X2_WIN:                                                                     \
                 return fsea_fill<SH, f2, FSEA_IN_U8, FSEA_OK_SPECTRUM, N, true>(out, "fft<" FSEA_STR(N) ":" FSEA_STR(R0) "x" FSEA_STR(R1) "x" FSEA_STR(R2) ",f32x2,win>");       \
+            case FSEA_VAR_EXP1:   /* experiment: one group per block, twiddles through L1 */             \
+                return fsea_fill<SH, f2, FSEA_IN_U8, FSEA_OK_SPECTRUM, N, false, 1, 0>(out, "fft<" FSEA_STR(N) ":" FSEA_STR(R0) "x" FSEA_STR(R1) "x" FSEA_STR(R2) ",f32x2,g1>");   \
+            case FSEA_VAR_EXP2:   /* experiment: two groups per block, twiddles through L1 */            \
+                return fsea_fill<SH, f2, FSEA_IN_U8, FSEA_OK_SPECTRUM, N, false, 2, 0>(out, "fft<" FSEA_STR(N) ":" FSEA_STR(R0) "x" FSEA_STR(R1) "x" FSEA_STR(R2) ",f32x2,g2>");   \
             case FSEA_VAR_F32C:                                                                          \
                 return fsea_fill<SH, float, FSEA_IN_F32C>(out, "fft<" FSEA_STR(N) ":" FSEA_STR(R0) "x" FSEA_STR(R1) "x" FSEA_STR(R2) ",f32c>");   \
             case FSEA_VAR_F64:                                                                           \

@@ -35,8 +35,8 @@
 #include "fsea_kparams.h"
 
 // internal input / output kinds of the four-step (N = N1 x N2) kernels
-enum { FSEA_IN_COLS8 = 16, FSEA_IN_ROWS = 17 };
-enum { FSEA_OK_SPECTRUM = 0, FSEA_OK_SCRATCH = 1, FSEA_OK_STRIDED = 2 };
+enum { FSEA_IN_ROWS = 17 };
+enum { FSEA_OK_SPECTRUM = 0, FSEA_OK_STRIDED = 2 };
 
 
 template <int X> struct fsea_log2 { static const int v = 1 + fsea_log2<X / 2>::v; };
@@ -219,57 +219,32 @@ template <> struct fsea_in<FSEA_IN_F64C, double> {
     template <int N> __device__ __forceinline__ void load_staged_raw(const unsigned char*, int, double&, double&) const {}
 };
 
-// ---- four-step loaders (N = N1 x N2, SURVEY 7 "N = 65536") ----------------------
-// Step A transforms the N2 columns of a frame (sequence n1 -> x[N2 n1 + n2]); a unit is a
-// PAIR OF ADJACENT COLUMNS, so one 32-bit load yields both lanes' I/Q bytes.
-template <> struct fsea_in<FSEA_IN_COLS8, f2> {
-    const uint8_t* p;
-    const float* win;
-    uint32_t x4;
-    long cstride;          // bytes between consecutive n1
-    __device__ __forceinline__ void init(const fsea_kparams& kp, long unit, bool& live) {
-        long s0 = 2 * unit;
-        live = s0 < kp.n_seq;
-        if (!live) s0 = kp.n_seq - 2;
-        const long f = s0 / kp.n2, c = s0 - f * kp.n2;
-        x4 = kp.xor_mask | (kp.xor_mask << 16);
-        cstride = 2L * kp.n2;
-        p = (const uint8_t*)kp.in + 2 * (f * kp.seq_stride + c);
-        win = kp.window ? kp.window + c : nullptr;
-    }
-    __device__ __forceinline__ void load(int e, f2& re, f2& im) const {
-        const uint32_t w = __ldg((const uint32_t*)(p + (size_t)e * cstride)) ^ x4;
-        f2 r = mk2(__uint_as_float(__byte_perm(w, 0x47000000u, 0x7650)),
-                   __uint_as_float(__byte_perm(w, 0x47000000u, 0x7652)));
-        f2 i = mk2(__uint_as_float(__byte_perm(w, 0x47000000u, 0x7651)),
-                   __uint_as_float(__byte_perm(w, 0x47000000u, 0x7653)));
-        const f2 off = mk2(32768.5f, 32768.5f);
-        re = vsub(r, off); im = vsub(i, off);
-    }
-    __device__ __forceinline__ f2 window(int e) const {      // w[N2 e + n2], w[N2 e + n2 + 1]
-        const float2 w = __ldg((const float2*)(win + (size_t)e * (cstride >> 1)));
-        return mk2(w.x, w.y);
-    }
-    template <int N, int T> __device__ __forceinline__ void prefetch(int) const {}
-    template <int N, int T> __device__ __forceinline__ void async_stage(int, unsigned char*) const {}
-    template <int N> __device__ __forceinline__ void load_staged(const unsigned char*, int, f2&, f2&) const {}
-    template <int N> __device__ __forceinline__ void load_staged_raw(const unsigned char*, int, f2&, f2&) const {}
-};
-
-// Step B transforms the N1 rows of the twiddled intermediate (float2, contiguous); a unit
-// is a PAIR OF ADJACENT ROWS (k1, k1 + 1), whose outputs are adjacent bins.
+// ---- four-step (N = 32 x N2, SURVEY 7 "N = 65536") ------------------------------
+// Step A (fsea_cols32_kernel, below) transforms the N2 columns of a frame with one
+// radix-32 register codelet per column pair -- lanes are neighbouring columns, so every
+// load and store is a contiguous 128- or 512-byte row piece and no shared memory is
+// involved -- and leaves Y[k1][n2] (k1 < 32) in an intermediate buffer.
+// Step B is this file's kernel on the rows: a unit is a PAIR OF ADJACENT ROWS (k1, k1+1),
+// the loader applies the four-step twiddle W_N^{n2 k1} on the way in, and the bins
+// k1 + 32 k2 of the block's rows are assembled in shared memory into contiguous pieces.
 template <> struct fsea_in<FSEA_IN_ROWS, f2> {
-    const float2 *pa, *pb;
+    const float2 *pa, *pb, *ta, *tb;
     __device__ __forceinline__ void init(const fsea_kparams& kp, long unit, bool& live) {
         long s0 = 2 * unit;
         live = s0 < kp.n_seq;
         if (!live) s0 = kp.n_seq - 2;
+        const long k1 = s0 % kp.n1;
         pa = (const float2*)kp.in + s0 * kp.n2;
         pb = pa + kp.n2;
+        ta = (const float2*)kp.tw4 + k1 * kp.n2;
+        tb = ta + kp.n2;
     }
     __device__ __forceinline__ void load(int e, f2& re, f2& im) const {
         const float2 a = __ldg(pa + e), b = __ldg(pb + e);
-        re = mk2(a.x, b.x); im = mk2(a.y, b.y);
+        const float2 wa = __ldg(ta + e), wb = __ldg(tb + e);
+        const f2 r = mk2(a.x, b.x), i = mk2(a.y, b.y), wr = mk2(wa.x, wb.x), wi = mk2(wa.y, wb.y);
+        re = vsub(vmul(r, wr), vmul(i, wi));
+        im = vfma2(r, wi, vmul(i, wr));
     }
     __device__ __forceinline__ f2 window(int) const { return mk2(1.f, 1.f); }
     template <int N, int T> __device__ __forceinline__ void prefetch(int t) const {
@@ -348,40 +323,12 @@ template <int N, typename V> struct fsea_out {
     }
 };
 
-// Four-step, step A: bin k1 of columns (n2, n2+1) times W_N^{n2 k1} -> scratch[f][k1][n2..n2+1]
-template <int N1> struct fsea_out_scratch {
-    float2* base;          // scratch + (f N1 N2 + n2)
-    const float2* tw;      // tw4 + n2
-    long rstride;          // N2
-    bool live;
-    __device__ __forceinline__ void init(const fsea_kparams& kp, long unit, bool unit_live, int) {
-        long s0 = 2 * unit;
-        live = unit_live;
-        if (!live) s0 = kp.n_seq - 2;
-        const long f = s0 / kp.n2, c = s0 - f * kp.n2;
-        rstride = kp.n2;
-        base = (float2*)kp.out + (size_t)f * N1 * kp.n2 + c;
-        tw = (const float2*)kp.tw4 + c;
-    }
-    template <int R, int M>
-    __device__ __forceinline__ void store_sel(int, int i, const f2* re, const f2* im, bool) const {
-        if (!live) return;
-#pragma unroll
-        for (int m = 0; m < R; m++) {
-            const long k1 = i + m * M;
-            const float4 w = __ldg((const float4*)(tw + k1 * rstride));      // (wA.re, wA.im, wB.re, wB.im)
-            const f2 wr = mk2(w.x, w.z), wi = mk2(w.y, w.w);
-            const f2 r = vsub(vmul(re[m], wr), vmul(im[m], wi));
-            const f2 q = vfma2(re[m], wi, vmul(im[m], wr));
-            *(float4*)(base + k1 * rstride) = make_float4(r.v.x, q.v.x, r.v.y, q.v.y);
-        }
-    }
-    __device__ __forceinline__ void dc_adjust(const fsea_kparams&, int, f2&, f2&) const {}
-};
-
-// Four-step, step B: rows (k1, k1+1), FFT bin k2 -> spectrum bin k1 + N1 k2 (two adjacent bins)
+// Four-step, step B: rows (k1, k1+1) of a frame; FFT bin k2 of row k1 is spectrum bin
+// k1 + 32 k2.  A block holds G units = 2G neighbouring rows, so for every k2 its 2G bins
+// are contiguous in the spectrum: the values are first written to a shared-memory tile
+// [k2][2G] and then copied out as contiguous pieces (fsea_strided_store, below).
 template <int NTOT> struct fsea_out_strided {
-    uint8_t* row;
+    uint8_t* row;          // spectrum row of the unit's frame
     int k1, n1;
     bool live;
     float pix_scale;
@@ -395,46 +342,78 @@ template <int NTOT> struct fsea_out_strided {
         pix_scale = kp.pix_scale;
         row = (uint8_t*)kp.out + (size_t)f * NTOT * esz;
     }
-    template <int OUT> __device__ __forceinline__ void put1(int pos, float pwr) const {
-        if (OUT == FSEA_OUT_MAG) ((float*)row)[pos] = fsea_sqrt_approx(pwr);
-        else if (OUT == FSEA_OUT_LOGMAG) ((float*)row)[pos] = fsea_db(pwr);
-        else row[pos] = fsea_pix(fsea_db(pwr), pix_scale);
-    }
-    template <int OUT, int R, int M>
-    __device__ __forceinline__ void store_bfly(int i, const f2* re, const f2* im, bool dc_patch) const {
-        if (!live) return;
-#pragma unroll
-        for (int m = 0; m < R; m++) {
-            const int k2 = i + m * M;
-            const int pos = (k1 + n1 * k2 + NTOT / 2) & (NTOT - 1);           // even: k1 and n1 are
-            const f2 pw = vfma2(re[m], re[m], vmul(im[m], im[m]));
-            const bool bin0 = (m == 0) && dc_patch && i == 0 && k1 == 0;      // bin 0: overwritten by its neighbour
-            if (bin0) {
-                put1<OUT>(pos + 1, pw.v.y);
-            } else if (OUT == FSEA_OUT_MAG) {
-                *(float2*)((float*)row + pos) = make_float2(fsea_sqrt_approx(pw.v.x), fsea_sqrt_approx(pw.v.y));
-            } else if (OUT == FSEA_OUT_LOGMAG) {
-                *(float2*)((float*)row + pos) = make_float2(fsea_db(pw.v.x), fsea_db(pw.v.y));
-            } else {
-                *(uchar2*)(row + pos) = make_uchar2(fsea_pix(fsea_db(pw.v.x), pix_scale), fsea_pix(fsea_db(pw.v.y), pix_scale));
-            }
-            // bin N-1 (k1 + 1 == N1 - 1, k2 == N2 - 1) also fills the DC slot (src/nrf.c:621-622)
-            if (m == R - 1 && dc_patch && i == M - 1 && k1 + 2 == n1) put1<OUT>(NTOT / 2, pw.v.y);
-        }
-    }
     template <int R, int M>
-    __device__ __forceinline__ void store_sel(int mode, int i, const f2* re, const f2* im, bool dc_patch) const {
-        if (mode == FSEA_OUT_MAG) store_bfly<FSEA_OUT_MAG, R, M>(i, re, im, dc_patch);
-        else if (mode == FSEA_OUT_LOGMAG) store_bfly<FSEA_OUT_LOGMAG, R, M>(i, re, im, dc_patch);
-        else store_bfly<FSEA_OUT_PIX, R, M>(i, re, im, dc_patch);
-    }
+    __device__ __forceinline__ void store_sel(int, int, const f2*, const f2*, bool) const {}   // unused (staged path)
     __device__ __forceinline__ void dc_adjust(const fsea_kparams& kp, int t, f2& re0, f2& im0) const {
         if (kp.dc_term && t == 0 && k1 == 0) { re0.v.x += (float)(NTOT / 2); im0.v.x += (float)(NTOT / 2); }
     }
 };
 
+// values of one bin pair in the output element type
+template <int OUT> __device__ __forceinline__ void fsea_tile_put(unsigned char* p, f2 pw, float pix_scale) {
+    if (OUT == FSEA_OUT_MAG) *(float2*)p = make_float2(fsea_sqrt_approx(pw.v.x), fsea_sqrt_approx(pw.v.y));
+    else if (OUT == FSEA_OUT_LOGMAG) *(float2*)p = make_float2(fsea_db(pw.v.x), fsea_db(pw.v.y));
+    else *(uchar2*)p = make_uchar2(fsea_pix(fsea_db(pw.v.x), pix_scale), fsea_pix(fsea_db(pw.v.y), pix_scale));
+}
+
+// Last pass of step B: the block's bins -> shared tile -> contiguous global pieces, in
+// ROUNDS rounds of R / ROUNDS values of m (the tile reuses the exchange planes).
+template <int OUT, int NTOT, int G, int T, int R, int M, int B, int REGION>
+__device__ __forceinline__ void fsea_strided_store(const fsea_out_strided<NTOT>& out, int t, int g, int tid,
+                                                   const f2* re, const f2* im, bool dc_patch, unsigned char* tile) {
+    constexpr int ESZ = (OUT == FSEA_OUT_PIX) ? 1 : 4;
+    constexpr int ROWB = 2 * G * ESZ;                     // bytes of one k2 row of the tile
+    constexpr int PITCH = ROWB + 8;
+    constexpr int ROUNDS = (R * M * PITCH <= REGION) ? 1 : ((R * M * PITCH <= 2 * REGION) ? 2 : (R * M * PITCH <= 4 * REGION ? 4 : R));
+    constexpr int MR = R / ROUNDS;
+    static_assert(MR >= 1 && MR * M * PITCH <= REGION, "output tile does not fit the exchange region");
+    constexpr int CB = (ROWB % 8 == 0) ? 8 : 4;           // bytes per copied piece
+    static_assert(ROWB % 4 == 0, "a block must hold at least two units (four rows)");
+    constexpr int CPR = ROWB / CB;                        // pieces per row
+    const int k1_0 = out.k1 - 2 * g;                      // first row of the block's tile (2G-aligned)
+    const int n1 = out.n1;
+#pragma unroll
+    for (int r = 0; r < ROUNDS; r++) {
+        __syncthreads();                                  // planes / previous round's tile are free
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            const int i = t + b * T;
+#pragma unroll
+            for (int mm = 0; mm < MR; mm++) {
+                const int m = r * MR + mm;
+                const f2 pw = vfma2(re[b * R + m], re[b * R + m], vmul(im[b * R + m], im[b * R + m]));
+                fsea_tile_put<OUT>(tile + (size_t)(i + mm * M) * PITCH + 2 * g * ESZ, pw, out.pix_scale);
+                // bin N-1 = row 31, last k2: it also fills the DC slot N/2 (src/nrf.c:621-622)
+                if (dc_patch && out.live && m == R - 1 && i == M - 1 && out.k1 + 2 == n1) {
+                    __align__(8) unsigned char tmp[8];
+                    fsea_tile_put<OUT>(tmp, pw, out.pix_scale);
+                    if (ESZ == 4) ((float*)out.row)[NTOT / 2] = ((float*)tmp)[1];
+                    else out.row[NTOT / 2] = tmp[1];
+                }
+            }
+        }
+        __syncthreads();
+        // contiguous pieces: tile row k2 holds spectrum positions (n1 k2 + k1_0 + N/2) mod N ...
+        for (int q = tid; q < MR * M * CPR; q += T * G) {
+            const int rr = q / CPR, cc = q - rr * CPR;
+            const int k2 = r * MR * M + rr;
+            const int pos = ((n1 * k2 + k1_0 + NTOT / 2) & (NTOT - 1)) + cc * (CB / ESZ);
+            const unsigned char* src = tile + (size_t)rr * PITCH + cc * CB;
+            unsigned char* dst = out.row + (size_t)pos * ESZ;
+            if (dc_patch && k2 == 0 && k1_0 == 0 && cc == 0) {           // bin 0 is overwritten by bin N-1
+                if (ESZ == 4) ((float*)dst)[1] = ((const float*)src)[1];
+                else { for (int z = 1; z < CB; z++) dst[z] = src[z]; }
+            } else if (CB == 8) {
+                *(uint2*)dst = *(const uint2*)src;        // (tiles never straddle frames: 2G divides 32)
+            } else {
+                *(uint32_t*)dst = *(const uint32_t*)src;
+            }
+        }
+    }
+    __syncthreads();
+}
+
 template <int OK, int N, int NTOT, typename V> struct fsea_out_sel { typedef fsea_out<N, V> type; };
-template <int N, int NTOT> struct fsea_out_sel<FSEA_OK_SCRATCH, N, NTOT, f2> { typedef fsea_out_scratch<N> type; };
 template <int N, int NTOT> struct fsea_out_sel<FSEA_OK_STRIDED, N, NTOT, f2> { typedef fsea_out_strided<NTOT> type; };
 
 // ---- group barrier ----------------------------------------------------------
@@ -531,7 +510,7 @@ fsea_fft_kernel(const fsea_kparams kp) {
     constexpr bool STAGED = (FMT == FSEA_IN_U8) && NPASS > 1 && sizeof(S) == 4;
     // four-step kernels hand out TILES of G neighbouring units per block (adjacent columns /
     // rows -> contiguous bytes across the block); the others hand out single units per group
-    constexpr bool TILED = (FMT == FSEA_IN_COLS8) || (FMT == FSEA_IN_ROWS);
+    constexpr bool TILED = (FMT == FSEA_IN_ROWS);
     constexpr int XB = NPASS > 1 ? SH::UNITS * (int)sizeof(V) : 0;     // exchange plane bytes per group
     constexpr int RB = STAGED ? LANES * 2 * N : 0;                      // raw ring bytes per group
 
@@ -667,7 +646,7 @@ fsea_fft_kernel(const fsea_kparams kp) {
                 out.template store_sel<R0, 1>(out_mode, 0, re, im, dc_patch);
             }
         }
-        if (NPASS > 1) {
+        if constexpr (NPASS > 1) {
             // ---------------- exchange 0 -> 1 and pass 1: radix R1, p_prev = R0 ----------------
             constexpr int B0 = P / R0;
             constexpr int M = N / R1, B = P / R1;
@@ -714,15 +693,22 @@ fsea_fft_kernel(const fsea_kparams kp) {
             }
 #pragma unroll
             for (int b = 0; b < B; b++) fsea_dft<R1, V>::run(re + b * R1, im + b * R1);
-            if (NPASS == 2) {
+            if constexpr (NPASS == 2) {
                 // N = R0 R1: i < R0 = M, k = i, bins i + m R0
                 out.dc_adjust(kp, t, re[0], im[0]);
+                if constexpr (OK == FSEA_OK_STRIDED) {
+                    unsigned char* tile = fsea_smem;
+                    if (out_mode == FSEA_OUT_MAG) fsea_strided_store<FSEA_OUT_MAG, NTOT, G, T, R1, M, B, G * XB>(out, t, g, tid, re, im, dc_patch, tile);
+                    else if (out_mode == FSEA_OUT_LOGMAG) fsea_strided_store<FSEA_OUT_LOGMAG, NTOT, G, T, R1, M, B, G * XB>(out, t, g, tid, re, im, dc_patch, tile);
+                    else fsea_strided_store<FSEA_OUT_PIX, NTOT, G, T, R1, M, B, G * XB>(out, t, g, tid, re, im, dc_patch, tile);
+                } else {
 #pragma unroll
-                for (int b = 0; b < B; b++)
-                    out.template store_sel<R1, M>(out_mode, t + b * T, re + b * R1, im + b * R1, dc_patch);
+                    for (int b = 0; b < B; b++)
+                        out.template store_sel<R1, M>(out_mode, t + b * T, re + b * R1, im + b * R1, dc_patch);
+                }
             }
         }
-        if (NPASS > 2) {
+        if constexpr (NPASS > 2) {
             // ---------------- exchange 1 -> 2 and pass 2: radix R2, p_prev = R0 R1 ----------------
             constexpr int B1 = P / R1;
             constexpr int M = N / R2, B = P / R2;
@@ -768,9 +754,16 @@ fsea_fft_kernel(const fsea_kparams kp) {
 #pragma unroll
             for (int b = 0; b < B; b++) fsea_dft<R2, V>::run(re + b * R2, im + b * R2);
             out.dc_adjust(kp, t, re[0], im[0]);
+            if constexpr (OK == FSEA_OK_STRIDED) {
+                unsigned char* tile = fsea_smem;
+                if (out_mode == FSEA_OUT_MAG) fsea_strided_store<FSEA_OUT_MAG, NTOT, G, T, R2, M, B, G * XB>(out, t, g, tid, re, im, dc_patch, tile);
+                else if (out_mode == FSEA_OUT_LOGMAG) fsea_strided_store<FSEA_OUT_LOGMAG, NTOT, G, T, R2, M, B, G * XB>(out, t, g, tid, re, im, dc_patch, tile);
+                else fsea_strided_store<FSEA_OUT_PIX, NTOT, G, T, R2, M, B, G * XB>(out, t, g, tid, re, im, dc_patch, tile);
+            } else {
 #pragma unroll
-            for (int b = 0; b < B; b++)
-                out.template store_sel<R2, M>(out_mode, t + b * T, re + b * R2, im + b * R2, dc_patch);
+                for (int b = 0; b < B; b++)
+                    out.template store_sel<R2, M>(out_mode, t + b * T, re + b * R2, im + b * R2, dc_patch);
+            }
         }
         if (NPASS > 1) fsea_group_sync<T>(g);                      // the next unit rewrites the exchange plane
         in = in_next;
@@ -790,5 +783,46 @@ fsea_fft_kernel(const fsea_kparams kp) {
             ticket[1] = 0u;
             __threadfence();
         }
+    }
+}
+
+// ---- four-step, step A: radix-32 over the columns, all in registers -----------------
+// Thread = one pair of neighbouring columns (n2, n2+1) of one frame: 32 strided 32-bit
+// loads (a warp covers 128 contiguous bytes of every row), one packed radix-32 codelet,
+// 32 float4 stores (a warp covers 512 contiguous bytes of every output row).  Samples stay
+// integer-scaled (b - 128); the 1/256 of src/nrf.c:605-606 rides on the four-step twiddles.
+template <bool WIN>
+__global__ void __launch_bounds__(128, 3)
+fsea_cols32_kernel(const fsea_kparams kp) {
+    const long pairs = kp.n_seq / 2;                       // column pairs in the chunk
+    const long n2 = kp.n2;
+    const uint32_t x4 = kp.xor_mask | (kp.xor_mask << 16);
+    for (long u = (long)blockIdx.x * blockDim.x + threadIdx.x; u < pairs; u += (long)gridDim.x * blockDim.x) {
+        const long s0 = 2 * u;
+        const long f = s0 / n2, c = s0 - f * n2;
+        const uint8_t* p = (const uint8_t*)kp.in + 2 * (f * kp.seq_stride + c);
+        f2 re[32], im[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const uint32_t w = __ldg((const uint32_t*)(p + (size_t)j * 2 * n2)) ^ x4;
+            re[j] = mk2(__uint_as_float(__byte_perm(w, 0x47000000u, 0x7504)), __uint_as_float(__byte_perm(w, 0x47000000u, 0x7524)));
+            im[j] = mk2(__uint_as_float(__byte_perm(w, 0x47000000u, 0x7514)), __uint_as_float(__byte_perm(w, 0x47000000u, 0x7534)));
+        }
+        if (WIN) {
+            const f2 off = mk2(32896.0f, 32896.0f);
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const float2 w = __ldg((const float2*)(kp.window + (size_t)j * n2 + c));
+                re[j] = vmul(vsub(re[j], off), mk2(w.x, w.y));
+                im[j] = vmul(vsub(im[j], off), mk2(w.x, w.y));
+            }
+            fsea_dft32<f2>(re, im);
+        } else {
+            fsea_dft32_raw<f2>(re, im);
+        }
+        float4* o = (float4*)((float2*)kp.out + (size_t)f * 32 * n2 + c);
+#pragma unroll
+        for (int k1 = 0; k1 < 32; k1++)
+            o[(size_t)k1 * (n2 / 2)] = make_float4(re[k1].v.x, im[k1].v.x, re[k1].v.y, im[k1].v.y);
     }
 }
