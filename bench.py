@@ -47,6 +47,12 @@ UNIT = "frames/s"
 # Secondary workloads; the headline line is always cfg2.  Synthetic IQ is
 # drawn on the device (uniform bytes): throughput does not depend on the sample values and
 # the parity gate checks the very frames that are timed.
+def _size_workload(n):
+    frames = max(256, (1 << 28) // n)            # 512 MiB of raw IQ per step
+    return dict(n=n, hop=n, fmt="s8", window=False, out="mag", patch=True, frames=frames,
+                desc=f"size ladder: {n}-pt FFT, int8 IQ -> f32 magnitude + DC patch")
+
+
 WORKLOADS = {
     "cfg2": dict(n=1024, hop=1024, fmt="s8", window=False, out="mag", patch=True, frames=1 << 18,
                  desc="cfg2 nrf_fft path: 1024-pt FFT, all frames of rf-433.000.raw, int8 IQ -> f32 magnitude + DC patch"),
@@ -57,6 +63,8 @@ WORKLOADS = {
     "cfg5": dict(n=65536, hop=65536, fmt="s8", window=False, out="logmag", patch=False, frames=4096,
                  desc="cfg5: 65536-pt FFT, synthetic int8 HackRF IQ -> f32 log-magnitude"),
 }
+for _n in (128, 256, 512, 2048, 4096, 8192, 16384, 32768, 65536):
+    WORKLOADS[f"n{_n}"] = _size_workload(_n)
 
 
 def load_capture():

@@ -11,9 +11,7 @@ enum {
     FSEA_VAR_F64 = 3,    // double2 samples, fp64
     FSEA_VAR_F32_WIN = 4,    // as F32 / F32X2 with the Hann multiply compiled in
     FSEA_VAR_F32X2_WIN = 5,
-    FSEA_VAR_EXP1 = 6,
-    FSEA_VAR_EXP2 = 7,
-    FSEA_VAR_COUNT = 8
+    FSEA_VAR_COUNT = 6
 };
 
 struct fsea_kernel_info {

@@ -232,10 +232,6 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
         case FSEA_IN_S8:
             p->variant = (cfg->arith == FSEA_ARITH_F32) ? FSEA_VAR_F32 : FSEA_VAR_F32X2;
             if (cfg->window == FSEA_WIN_HANN) p->variant = (p->variant == FSEA_VAR_F32) ? FSEA_VAR_F32_WIN : FSEA_VAR_F32X2_WIN;
-            else if (const char* ex = getenv("FSEA_EXP")) {          // kernel-geometry experiments
-                if (!strcmp(ex, "g1")) p->variant = FSEA_VAR_EXP1;
-                if (!strcmp(ex, "g2")) p->variant = FSEA_VAR_EXP2;
-            }
             p->sample_bytes = 2;
             break;
         case FSEA_IN_F32C: p->variant = FSEA_VAR_F32C; p->sample_bytes = 8; break;
@@ -255,11 +251,12 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
         if ((rc = setup_kernel(p->ki, cfg->device, &p->max_blocks)) != FSEA_OK) break;
         // staged 8-bit kernels transform integer-scaled samples (b - 128): the 1/256 of
         // src/nrf.c:605-606 rides on the pass-1 twiddles
-        const bool staged = !p->four && (p->variant == FSEA_VAR_F32 || p->variant == FSEA_VAR_F32X2 || p->variant >= FSEA_VAR_EXP1 ||
+        const bool staged = !p->four && (p->variant == FSEA_VAR_F32 || p->variant == FSEA_VAR_F32X2 ||
                                          p->variant == FSEA_VAR_F32_WIN || p->variant == FSEA_VAR_F32X2_WIN) && p->ki.r1 > 1;
         if (!p->four && (rc = upload_twiddles(p->ki, &p->d_tw1, &p->d_tw2, staged ? 1.0f / 256.0f : 1.0f)) != FSEA_OK) break;
         if (p->four) {
             if ((rc = setup_kernel(p->k4.b, cfg->device, &p->max_blocks_b)) != FSEA_OK) break;
+
             if ((rc = upload_twiddles(p->k4.b, &p->d_tw1b, &p->d_tw2b)) != FSEA_OK) break;
             const int n1 = p->k4.n1, n2 = p->k4.n2;
             std::vector<float2> t4((size_t)n);
@@ -271,8 +268,11 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
                     t4[(size_t)k1 * n2 + c].x = (float)(cosl(a) / 256.0L);
                     t4[(size_t)k1 * n2 + c].y = (float)(sinl(a) / 256.0L);
                 }
-            // the intermediate of one chunk must stay in L2 (126 MB): 32 MiB of float2
-            long chunk_mb = 32;
+            // The intermediate (8 bytes per point) is streamed through HBM in chunks of 256 MiB.
+            // Keeping it L2-resident was tried twice -- 32 MiB chunks (two launches per 64 frames:
+            // launch-bound, 2x slower) and a persistent fused kernel with per-frame dependency
+            // counters (5-10 % slower: the row step is LSU/latency-bound, not DRAM-bound) -- see DESIGN.md.
+            long chunk_mb = 256;
             if (const char* ev = getenv("FSEA_CHUNK_MB")) chunk_mb = std::max(1L, atol(ev));   // experiments
             p->chunk_frames = std::max<long>(1, (chunk_mb << 20) / ((long)n * 8));
             if ((e = cudaMalloc(&p->d_tw4, (size_t)n * sizeof(float2))) != cudaSuccess ||

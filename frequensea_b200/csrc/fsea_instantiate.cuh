@@ -12,7 +12,7 @@ struct fsea_cfg {
     static const int TWBYTES = (SH::TW1 + SH::TW2) * 2 * SB;
     static const bool TWS = TWSOV >= 0 ? (TWSOV != 0) : (SH::NPASS > 1 && TWBYTES <= 16384);
     static const bool TILED = (FMT == FSEA_IN_ROWS);
-    static const int TPB = 128;                                                   // target threads per block
+    static const int TPB = (TILED && SH::P <= 16) ? 256 : 128;                    // target threads per block
     static const int G_T = (TPB / SH::T) > 1 ? (TPB / SH::T) : 1;
     static const int G_S = XBYTES ? ((96 * 1024) / XBYTES > 1 ? (96 * 1024) / XBYTES : 1) : 1024;
     static const int G_0 = G_T < G_S ? G_T : G_S;
@@ -23,7 +23,7 @@ struct fsea_cfg {
     // resident blocks per SM the register allocator must allow: what shared memory
     // permits, capped so that a thread keeps >= REGCAP registers
     static const int REGCAP_0 = (sizeof(V) >= 8 ? (SH::P >= 32 ? 168 : (SH::P >= 16 ? 112 : 80)) : (SH::P >= 32 ? 96 : 64));
-    static const int REGCAP = (GOV == 1 || GOV == 2) ? 152 : REGCAP_0;   // 13 warps per SM in the g1 experiment
+    static const int REGCAP = REGCAP_0;
     static const int THREADS = SH::T * G;
     static const int B_SMEM = SMEM ? (int)((227 * 1024) / (SMEM + 1024)) : 16;
     static const int B_REG = 65536 / (THREADS * REGCAP);
@@ -62,10 +62,6 @@ static bool fsea_fill(fsea_kernel_info* o, const char* name) {
                 return fsea_fill<SH, float, FSEA_IN_U8, FSEA_OK_SPECTRUM, N, true>(out, "fft<" FSEA_STR(N) ":" FSEA_STR(R0) "x" FSEA_STR(R1) "x" FSEA_STR(R2) ",f32,win>");      \
             case FSEA_VAR_F32X2_WIN:                                                                     \
                 return fsea_fill<SH, f2, FSEA_IN_U8, FSEA_OK_SPECTRUM, N, true>(out, "fft<" FSEA_STR(N) ":" FSEA_STR(R0) "x" FSEA_STR(R1) "x" FSEA_STR(R2) ",f32x2,win>");       \
-            case FSEA_VAR_EXP1:   /* experiment: one group per block, twiddles through L1 */             \
-                return fsea_fill<SH, f2, FSEA_IN_U8, FSEA_OK_SPECTRUM, N, false, 1, 0>(out, "fft<" FSEA_STR(N) ":" FSEA_STR(R0) "x" FSEA_STR(R1) "x" FSEA_STR(R2) ",f32x2,g1>");   \
-            case FSEA_VAR_EXP2:   /* experiment: two groups per block, twiddles through L1 */            \
-                return fsea_fill<SH, f2, FSEA_IN_U8, FSEA_OK_SPECTRUM, N, false, 2, 0>(out, "fft<" FSEA_STR(N) ":" FSEA_STR(R0) "x" FSEA_STR(R1) "x" FSEA_STR(R2) ",f32x2,g2>");   \
             case FSEA_VAR_F32C:                                                                          \
                 return fsea_fill<SH, float, FSEA_IN_F32C>(out, "fft<" FSEA_STR(N) ":" FSEA_STR(R0) "x" FSEA_STR(R1) "x" FSEA_STR(R2) ",f32c>");   \
             case FSEA_VAR_F64:                                                                           \

@@ -225,26 +225,20 @@ template <> struct fsea_in<FSEA_IN_F64C, double> {
 // load and store is a contiguous 128- or 512-byte row piece and no shared memory is
 // involved -- and leaves Y[k1][n2] (k1 < 32) in an intermediate buffer.
 // Step B is this file's kernel on the rows: a unit is a PAIR OF ADJACENT ROWS (k1, k1+1),
-// the loader applies the four-step twiddle W_N^{n2 k1} on the way in, and the bins
+// (step A already applied the four-step twiddle W_N^{n2 k1}), and the bins
 // k1 + 32 k2 of the block's rows are assembled in shared memory into contiguous pieces.
 template <> struct fsea_in<FSEA_IN_ROWS, f2> {
-    const float2 *pa, *pb, *ta, *tb;
+    const float2 *pa, *pb;
     __device__ __forceinline__ void init(const fsea_kparams& kp, long unit, bool& live) {
         long s0 = 2 * unit;
         live = s0 < kp.n_seq;
         if (!live) s0 = kp.n_seq - 2;
-        const long k1 = s0 % kp.n1;
         pa = (const float2*)kp.in + s0 * kp.n2;
         pb = pa + kp.n2;
-        ta = (const float2*)kp.tw4 + k1 * kp.n2;
-        tb = ta + kp.n2;
     }
     __device__ __forceinline__ void load(int e, f2& re, f2& im) const {
-        const float2 a = __ldg(pa + e), b = __ldg(pb + e);
-        const float2 wa = __ldg(ta + e), wb = __ldg(tb + e);
-        const f2 r = mk2(a.x, b.x), i = mk2(a.y, b.y), wr = mk2(wa.x, wb.x), wi = mk2(wa.y, wb.y);
-        re = vsub(vmul(r, wr), vmul(i, wi));
-        im = vfma2(r, wi, vmul(i, wr));
+        const float2 a = __ldcg(pa + e), b = __ldcg(pb + e);       // L2 only: written by step A
+        re = mk2(a.x, b.x); im = mk2(a.y, b.y);
     }
     __device__ __forceinline__ f2 window(int) const { return mk2(1.f, 1.f); }
     template <int N, int T> __device__ __forceinline__ void prefetch(int t) const {
@@ -491,6 +485,210 @@ __device__ __forceinline__ unsigned fsea_ticket_share(unsigned v, int t, int g, 
     }
 }
 
+// ---- one unit through all passes ---------------------------------------------------
+// Shared by the batched kernel (fsea_fft_kernel) and the fused four-step kernel.  Returns
+// a float of the last butterfly register (the ticket broadcast is pinned behind it).
+template <class SH, typename V, int FMT, int OK, int NTOT, int G, bool WIN, class OUTP>
+__device__ __forceinline__ float fsea_transform(const fsea_kparams& kp, const fsea_in<FMT, V>& in,
+                                                const fsea_in<FMT, V>& in_next, bool more, const OUTP& out,
+                                                V* xp, unsigned char* raw,
+                                                const typename fsea_cplx<V>::t* tw1, const typename fsea_cplx<V>::t* tw2,
+                                                int t, int g, int tid, bool dc_patch, int out_mode,
+                                                unsigned char* smem_base,
+                                                const typename fsea_vt<V>::scalar* wreg = nullptr) {
+    typedef typename fsea_vt<V>::scalar S;
+    typedef typename fsea_cplx<V>::t S2;
+    constexpr int N = SH::N, R0 = SH::R0, R1 = SH::R1, R2 = SH::R2, P = SH::P, T = SH::T;
+    constexpr int L0 = SH::L0, NPASS = SH::NPASS;
+    constexpr bool STAGED = (FMT == FSEA_IN_U8) && NPASS > 1 && sizeof(S) == 4;
+    constexpr int XB = NPASS > 1 ? SH::UNITS * (int)sizeof(V) : 0;
+    (void)tw1; (void)tw2; (void)xp; (void)raw; (void)smem_base; (void)tid; (void)more;
+    V re[P], im[P];
+
+    // ---------------- pass 0: radix R0, p_prev = 1 ----------------
+    {
+        constexpr int M = N / R0, B = P / R0;
+        bool raw_stage = false;                      // pass 0 ran on biased magic floats
+        if (STAGED) {
+            fsea_cp_async_wait_all();
+            fsea_group_sync<T>(g);
+            raw_stage = !WIN;
+            if (raw_stage) {
+#pragma unroll
+                for (int b = 0; b < B; b++) {
+                    const int i = t + b * T;
+#pragma unroll
+                    for (int j = 0; j < R0; j++) in.template load_staged_raw<N>(raw, i + j * M, re[b * R0 + j], im[b * R0 + j]);
+                }
+            } else {
+#pragma unroll
+                for (int b = 0; b < B; b++) {
+                    const int i = t + b * T;
+#pragma unroll
+                    for (int j = 0; j < R0; j++) in.template load_staged<N>(raw, i + j * M, re[b * R0 + j], im[b * R0 + j]);
+                }
+            }
+            fsea_group_sync<T>(g);                   // ring is free again: fetch the next unit
+            if (more) {
+                in_next.template async_stage<N, T>(t, raw);
+                fsea_cp_async_commit();
+            }
+        } else {
+            if (more) in_next.template prefetch<N, T>(t);
+#pragma unroll
+            for (int b = 0; b < B; b++) {
+                const int i = t + b * T;
+#pragma unroll
+                for (int j = 0; j < R0; j++) in.load(i + j * M, re[b * R0 + j], im[b * R0 + j]);
+            }
+        }
+        if (WIN) {
+#pragma unroll
+            for (int b = 0; b < B; b++) {
+                const int i = t + b * T;
+#pragma unroll
+                for (int j = 0; j < R0; j++) {
+                    const V w = in.window(i + j * M);
+                    re[b * R0 + j] = vmul(re[b * R0 + j], w);
+                    im[b * R0 + j] = vmul(im[b * R0 + j], w);
+                }
+            }
+        }
+        if (STAGED && R0 >= 8 && raw_stage) {
+#pragma unroll
+            for (int b = 0; b < B; b++) fsea_dft_raw<(R0 >= 8 ? R0 : 8), V>::run(re + b * R0, im + b * R0);
+        } else {
+#pragma unroll
+            for (int b = 0; b < B; b++) fsea_dft<R0, V>::run(re + b * R0, im + b * R0);
+        }
+        if (NPASS == 1) {
+            // N = R0, T = 1: bins m
+            out.dc_adjust(kp, 0, re[0], im[0]);
+            out.template store_sel<R0, 1>(out_mode, 0, re, im, dc_patch);
+        }
+    }
+    if constexpr (NPASS > 1) {
+        // ---------------- exchange 0 -> 1 and pass 1: radix R1, p_prev = R0 ----------------
+        constexpr int B0 = P / R0;
+        constexpr int M = N / R1, B = P / R1;
+        constexpr int JSTR = M + (M >> L0);                    // padded stride of j
+        // write a' = i (R0 + 1) + m ; read a' = i + (i >> L0) + j JSTR  (one plane at a time)
+#pragma unroll
+        for (int b = 0; b < B0; b++) {
+            V* w = xp + (t + b * T) * (R0 + 1);
+#pragma unroll
+            for (int m = 0; m < R0; m++) w[m] = re[b * R0 + m];
+        }
+        fsea_group_sync<T>(g);
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            const int i = t + b * T;
+            const V* r = xp + i + (i >> L0);
+#pragma unroll
+            for (int j = 0; j < R1; j++) re[b * R1 + j] = r[j * JSTR];
+        }
+        fsea_group_sync<T>(g);
+#pragma unroll
+        for (int b = 0; b < B0; b++) {
+            V* w = xp + (t + b * T) * (R0 + 1);
+#pragma unroll
+            for (int m = 0; m < R0; m++) w[m] = im[b * R0 + m];
+        }
+        fsea_group_sync<T>(g);
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            const int i = t + b * T;
+            const int k = i & (R0 - 1);
+            const V* r = xp + i + (i >> L0);
+#pragma unroll
+            for (int j = 0; j < R1; j++) im[b * R1 + j] = r[j * JSTR];
+            if (STAGED) {                                      // integer-scaled samples: tw1 carries 1/256,
+                re[b * R1] = vmuls(re[b * R1], (S)(1.0 / 256.0));   // the untwiddled j = 0 input takes it here
+                im[b * R1] = vmuls(im[b * R1], (S)(1.0 / 256.0));
+            }
+#pragma unroll
+            for (int j = 1; j < R1; j++) {
+                const S2 w = tw1[(j - 1) * R0 + k];
+                vcmul(re[b * R1 + j], im[b * R1 + j], w.x, w.y);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < B; b++) fsea_dft<R1, V>::run(re + b * R1, im + b * R1);
+        if constexpr (NPASS == 2) {
+            // N = R0 R1: i < R0 = M, k = i, bins i + m R0
+            out.dc_adjust(kp, t, re[0], im[0]);
+            if constexpr (OK == FSEA_OK_STRIDED) {
+                unsigned char* tile = smem_base;
+                if (out_mode == FSEA_OUT_MAG) fsea_strided_store<FSEA_OUT_MAG, NTOT, G, T, R1, M, B, G * XB>(out, t, g, tid, re, im, dc_patch, tile);
+                else if (out_mode == FSEA_OUT_LOGMAG) fsea_strided_store<FSEA_OUT_LOGMAG, NTOT, G, T, R1, M, B, G * XB>(out, t, g, tid, re, im, dc_patch, tile);
+                else fsea_strided_store<FSEA_OUT_PIX, NTOT, G, T, R1, M, B, G * XB>(out, t, g, tid, re, im, dc_patch, tile);
+            } else {
+#pragma unroll
+                for (int b = 0; b < B; b++)
+                    out.template store_sel<R1, M>(out_mode, t + b * T, re + b * R1, im + b * R1, dc_patch);
+            }
+        }
+    }
+    if constexpr (NPASS > 2) {
+        // ---------------- exchange 1 -> 2 and pass 2: radix R2, p_prev = R0 R1 ----------------
+        constexpr int B1 = P / R1;
+        constexpr int M = N / R2, B = P / R2;
+        constexpr int JSTR = M + (M >> L0);
+        // write a' = hi (R0 R1 + R1) + k + m (R0 + 1), i = hi R0 + k ; read a' = i + (i >> L0) + j JSTR
+        fsea_group_sync<T>(g);                                 // all pass-1 reads done (WAR)
+#pragma unroll
+        for (int b = 0; b < B1; b++) {
+            const int i = t + b * T;
+            V* w = xp + (i >> L0) * (R0 * R1 + R1) + (i & (R0 - 1));
+#pragma unroll
+            for (int m = 0; m < R1; m++) w[m * (R0 + 1)] = re[b * R1 + m];
+        }
+        fsea_group_sync<T>(g);
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            const int i = t + b * T;
+            const V* r = xp + i + (i >> L0);
+#pragma unroll
+            for (int j = 0; j < R2; j++) re[b * R2 + j] = r[j * JSTR];
+        }
+        fsea_group_sync<T>(g);
+#pragma unroll
+        for (int b = 0; b < B1; b++) {
+            const int i = t + b * T;
+            V* w = xp + (i >> L0) * (R0 * R1 + R1) + (i & (R0 - 1));
+#pragma unroll
+            for (int m = 0; m < R1; m++) w[m * (R0 + 1)] = im[b * R1 + m];
+        }
+        fsea_group_sync<T>(g);
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            const int i = t + b * T;                           // k = i
+            const V* r = xp + i + (i >> L0);
+#pragma unroll
+            for (int j = 0; j < R2; j++) im[b * R2 + j] = r[j * JSTR];
+#pragma unroll
+            for (int j = 1; j < R2; j++) {
+                const S2 w = tw2[(j - 1) * M + i];
+                vcmul(re[b * R2 + j], im[b * R2 + j], w.x, w.y);
+            }
+        }
+#pragma unroll
+        for (int b = 0; b < B; b++) fsea_dft<R2, V>::run(re + b * R2, im + b * R2);
+        out.dc_adjust(kp, t, re[0], im[0]);
+        if constexpr (OK == FSEA_OK_STRIDED) {
+            unsigned char* tile = smem_base;
+            if (out_mode == FSEA_OUT_MAG) fsea_strided_store<FSEA_OUT_MAG, NTOT, G, T, R2, M, B, G * XB>(out, t, g, tid, re, im, dc_patch, tile);
+            else if (out_mode == FSEA_OUT_LOGMAG) fsea_strided_store<FSEA_OUT_LOGMAG, NTOT, G, T, R2, M, B, G * XB>(out, t, g, tid, re, im, dc_patch, tile);
+            else fsea_strided_store<FSEA_OUT_PIX, NTOT, G, T, R2, M, B, G * XB>(out, t, g, tid, re, im, dc_patch, tile);
+        } else {
+#pragma unroll
+            for (int b = 0; b < B; b++)
+                out.template store_sel<R2, M>(out_mode, t + b * T, re + b * R2, im + b * R2, dc_patch);
+        }
+    }
+    return (float)fsea_lane(re[P - 1], 0);
+}
+
 // ---- the kernel -------------------------------------------------------------
 // block = G groups of T threads, each group transforms one unit at a time,
 // grid-stride over units.  Dynamic shared memory per block:
@@ -539,15 +737,27 @@ fsea_fft_kernel(const fsea_kparams kp) {
     unsigned* ticket = kp.ticket;                                 // [0] next unit, [1] blocks finished
     __shared__ unsigned fsea_slot[G > 0 ? G : 1];
     __shared__ unsigned fsea_tile_slot;
-    const bool leader = TILED ? (tid == 0) : (t == 0);
+    // Scheduling entity and ticket size: a block (TILED: one tile of G units), a group
+    // (T >= 32: one unit), or -- for small transforms, where one atomic per unit would make
+    // the ticket counter itself the bottleneck (N = 128: 0.9 G units/s) -- a WARP, which takes
+    // KB units for each of its GW = 32/T groups per ticket.
+    constexpr int GW = (!TILED && T < 32) ? 32 / T : 1;
+    constexpr int KB = (!TILED && T < 32) ? 8 : 1;
+    const int gw = (GW > 1) ? ((tid & 31) / T) : 0;               // group within its warp
+    const bool leader = TILED ? (tid == 0) : (GW > 1 ? ((tid & 31) == 0) : (t == 0));
 
-    auto share = [&](unsigned v, int late = 0) -> long {
+    auto share = [&](unsigned v, int late = 0) -> long {           // -> base unit of the ticket
         if (TILED) {                                              // one ticket per block = G units
             if (tid == 0) fsea_tile_slot = v;
             __syncthreads();
             const unsigned tile = fsea_tile_slot;
             __syncthreads();
             return (long)tile * G + g;
+        }
+        if (GW > 1) {
+            unsigned r;
+            asm volatile("shfl.sync.idx.b32 %0, %1, %2, 0x1f, 0xffffffff;" : "=r"(r) : "r"(v), "r"(late) : "memory");
+            return (long)r * (GW * KB) + gw;
         }
         return (long)fsea_ticket_share<T>(v, t, g, fsea_slot, late);
     };
@@ -557,11 +767,25 @@ fsea_fft_kernel(const fsea_kparams kp) {
     if (leader) pend = fsea_take_ticket(ticket);
     long cur = share(pend);
     if (leader) pend = fsea_take_ticket(ticket);
-    long nxt = share(pend);
+    long nxt_base = share(pend);
     // two tickets are always in flight: the one read at the bottom of an iteration was
     // requested a whole iteration earlier, wherever the compiler schedules the broadcast
     unsigned pend_prev = 0;
     if (leader) pend_prev = fsea_take_ticket(ticket);
+    int kb = 0;                                                   // position inside the current ticket
+
+    // A thread multiplies the same P window values into every unit; where one block per SM is
+    // all that fits anyway (MINB == 1) they live in registers instead of being re-read
+    // (ncu, N = 8192 Hann: the window loads were the top long-scoreboard stall).
+    constexpr bool WREG = WIN && MINB == 1 && FMT == FSEA_IN_U8;
+    S wreg[WREG ? P : 1];
+    if (WREG) {
+        constexpr int M0 = N / R0, B0 = P / R0;
+#pragma unroll
+        for (int b = 0; b < B0; b++)
+#pragma unroll
+            for (int j = 0; j < R0; j++) wreg[b * R0 + j] = (S)__ldg(kp.window + (t + b * T) + j * M0);
+    }
 
     fsea_in<FMT, V> in;
     bool live;
@@ -571,10 +795,12 @@ fsea_fft_kernel(const fsea_kparams kp) {
         fsea_cp_async_commit();
     }
 
-    // groups that share a warp (T < 32) leave the loop together
-    while (TILED ? (cur - g < n_claims) : (T >= 32 ? (cur < n_units) : (__any_sync(0xffffffffu, cur < n_units) != 0))) {
-        if (leader) pend = fsea_take_ticket(ticket);      // the unit after next; read at the bottom
+    // (cur - gw is the same for all groups of a warp: they leave the loop together)
+    while (TILED ? (cur - g < n_claims) : (cur - gw < n_units)) {
+        const bool last_of_ticket = (kb == KB - 1);
+        if (leader && kb == 0) pend = fsea_take_ticket(ticket);   // the ticket after next; read at the bottom
         const long unit = cur;
+        const long nxt = last_of_ticket ? nxt_base : cur + GW;
         typename fsea_out_sel<OK, N, NTOT, V>::type out;
         out.init(kp, live ? unit : 0, live, out_esz);
         fsea_in<FMT, V> in_next;
@@ -582,197 +808,22 @@ fsea_fft_kernel(const fsea_kparams kp) {
         in_next.init(kp, nxt, live_next);
         const bool more = live_next;
 
-        V re[P], im[P];
-
-        // ---------------- pass 0: radix R0, p_prev = 1 ----------------
-        {
-            constexpr int M = N / R0, B = P / R0;
-            bool raw_stage = false;                      // pass 0 ran on biased magic floats
-            if (STAGED) {
-                fsea_cp_async_wait_all();
-                fsea_group_sync<T>(g);
-                raw_stage = !WIN;
-                if (raw_stage) {
-#pragma unroll
-                    for (int b = 0; b < B; b++) {
-                        const int i = t + b * T;
-#pragma unroll
-                        for (int j = 0; j < R0; j++) in.template load_staged_raw<N>(raw, i + j * M, re[b * R0 + j], im[b * R0 + j]);
-                    }
-                } else {
-#pragma unroll
-                    for (int b = 0; b < B; b++) {
-                        const int i = t + b * T;
-#pragma unroll
-                        for (int j = 0; j < R0; j++) in.template load_staged<N>(raw, i + j * M, re[b * R0 + j], im[b * R0 + j]);
-                    }
-                }
-                fsea_group_sync<T>(g);                   // ring is free again: fetch the next unit
-                if (more) {
-                    in_next.template async_stage<N, T>(t, raw);
-                    fsea_cp_async_commit();
-                }
-            } else {
-                if (more) in_next.template prefetch<N, T>(t);
-#pragma unroll
-                for (int b = 0; b < B; b++) {
-                    const int i = t + b * T;
-#pragma unroll
-                    for (int j = 0; j < R0; j++) in.load(i + j * M, re[b * R0 + j], im[b * R0 + j]);
-                }
-            }
-            if (WIN) {
-#pragma unroll
-                for (int b = 0; b < B; b++) {
-                    const int i = t + b * T;
-#pragma unroll
-                    for (int j = 0; j < R0; j++) {
-                        const V w = in.window(i + j * M);
-                        re[b * R0 + j] = vmul(re[b * R0 + j], w);
-                        im[b * R0 + j] = vmul(im[b * R0 + j], w);
-                    }
-                }
-            }
-            if (STAGED && R0 >= 8 && raw_stage) {
-#pragma unroll
-                for (int b = 0; b < B; b++) fsea_dft_raw<(R0 >= 8 ? R0 : 8), V>::run(re + b * R0, im + b * R0);
-            } else {
-#pragma unroll
-                for (int b = 0; b < B; b++) fsea_dft<R0, V>::run(re + b * R0, im + b * R0);
-            }
-            if (NPASS == 1) {
-                // N = R0, T = 1: bins m
-                out.dc_adjust(kp, 0, re[0], im[0]);
-                out.template store_sel<R0, 1>(out_mode, 0, re, im, dc_patch);
-            }
-        }
-        if constexpr (NPASS > 1) {
-            // ---------------- exchange 0 -> 1 and pass 1: radix R1, p_prev = R0 ----------------
-            constexpr int B0 = P / R0;
-            constexpr int M = N / R1, B = P / R1;
-            constexpr int JSTR = M + (M >> L0);                    // padded stride of j
-            // write a' = i (R0 + 1) + m ; read a' = i + (i >> L0) + j JSTR  (one plane at a time)
-#pragma unroll
-            for (int b = 0; b < B0; b++) {
-                V* w = xp + (t + b * T) * (R0 + 1);
-#pragma unroll
-                for (int m = 0; m < R0; m++) w[m] = re[b * R0 + m];
-            }
-            fsea_group_sync<T>(g);
-#pragma unroll
-            for (int b = 0; b < B; b++) {
-                const int i = t + b * T;
-                const V* r = xp + i + (i >> L0);
-#pragma unroll
-                for (int j = 0; j < R1; j++) re[b * R1 + j] = r[j * JSTR];
-            }
-            fsea_group_sync<T>(g);
-#pragma unroll
-            for (int b = 0; b < B0; b++) {
-                V* w = xp + (t + b * T) * (R0 + 1);
-#pragma unroll
-                for (int m = 0; m < R0; m++) w[m] = im[b * R0 + m];
-            }
-            fsea_group_sync<T>(g);
-#pragma unroll
-            for (int b = 0; b < B; b++) {
-                const int i = t + b * T;
-                const int k = i & (R0 - 1);
-                const V* r = xp + i + (i >> L0);
-#pragma unroll
-                for (int j = 0; j < R1; j++) im[b * R1 + j] = r[j * JSTR];
-                if (STAGED) {                                      // integer-scaled samples: tw1 carries 1/256,
-                    re[b * R1] = vmuls(re[b * R1], (S)(1.0 / 256.0));   // the untwiddled j = 0 input takes it here
-                    im[b * R1] = vmuls(im[b * R1], (S)(1.0 / 256.0));
-                }
-#pragma unroll
-                for (int j = 1; j < R1; j++) {
-                    const S2 w = tw1[(j - 1) * R0 + k];
-                    vcmul(re[b * R1 + j], im[b * R1 + j], w.x, w.y);
-                }
-            }
-#pragma unroll
-            for (int b = 0; b < B; b++) fsea_dft<R1, V>::run(re + b * R1, im + b * R1);
-            if constexpr (NPASS == 2) {
-                // N = R0 R1: i < R0 = M, k = i, bins i + m R0
-                out.dc_adjust(kp, t, re[0], im[0]);
-                if constexpr (OK == FSEA_OK_STRIDED) {
-                    unsigned char* tile = fsea_smem;
-                    if (out_mode == FSEA_OUT_MAG) fsea_strided_store<FSEA_OUT_MAG, NTOT, G, T, R1, M, B, G * XB>(out, t, g, tid, re, im, dc_patch, tile);
-                    else if (out_mode == FSEA_OUT_LOGMAG) fsea_strided_store<FSEA_OUT_LOGMAG, NTOT, G, T, R1, M, B, G * XB>(out, t, g, tid, re, im, dc_patch, tile);
-                    else fsea_strided_store<FSEA_OUT_PIX, NTOT, G, T, R1, M, B, G * XB>(out, t, g, tid, re, im, dc_patch, tile);
-                } else {
-#pragma unroll
-                    for (int b = 0; b < B; b++)
-                        out.template store_sel<R1, M>(out_mode, t + b * T, re + b * R1, im + b * R1, dc_patch);
-                }
-            }
-        }
-        if constexpr (NPASS > 2) {
-            // ---------------- exchange 1 -> 2 and pass 2: radix R2, p_prev = R0 R1 ----------------
-            constexpr int B1 = P / R1;
-            constexpr int M = N / R2, B = P / R2;
-            constexpr int JSTR = M + (M >> L0);
-            // write a' = hi (R0 R1 + R1) + k + m (R0 + 1), i = hi R0 + k ; read a' = i + (i >> L0) + j JSTR
-            fsea_group_sync<T>(g);                                 // all pass-1 reads done (WAR)
-#pragma unroll
-            for (int b = 0; b < B1; b++) {
-                const int i = t + b * T;
-                V* w = xp + (i >> L0) * (R0 * R1 + R1) + (i & (R0 - 1));
-#pragma unroll
-                for (int m = 0; m < R1; m++) w[m * (R0 + 1)] = re[b * R1 + m];
-            }
-            fsea_group_sync<T>(g);
-#pragma unroll
-            for (int b = 0; b < B; b++) {
-                const int i = t + b * T;
-                const V* r = xp + i + (i >> L0);
-#pragma unroll
-                for (int j = 0; j < R2; j++) re[b * R2 + j] = r[j * JSTR];
-            }
-            fsea_group_sync<T>(g);
-#pragma unroll
-            for (int b = 0; b < B1; b++) {
-                const int i = t + b * T;
-                V* w = xp + (i >> L0) * (R0 * R1 + R1) + (i & (R0 - 1));
-#pragma unroll
-                for (int m = 0; m < R1; m++) w[m * (R0 + 1)] = im[b * R1 + m];
-            }
-            fsea_group_sync<T>(g);
-#pragma unroll
-            for (int b = 0; b < B; b++) {
-                const int i = t + b * T;                           // k = i
-                const V* r = xp + i + (i >> L0);
-#pragma unroll
-                for (int j = 0; j < R2; j++) im[b * R2 + j] = r[j * JSTR];
-#pragma unroll
-                for (int j = 1; j < R2; j++) {
-                    const S2 w = tw2[(j - 1) * M + i];
-                    vcmul(re[b * R2 + j], im[b * R2 + j], w.x, w.y);
-                }
-            }
-#pragma unroll
-            for (int b = 0; b < B; b++) fsea_dft<R2, V>::run(re + b * R2, im + b * R2);
-            out.dc_adjust(kp, t, re[0], im[0]);
-            if constexpr (OK == FSEA_OK_STRIDED) {
-                unsigned char* tile = fsea_smem;
-                if (out_mode == FSEA_OUT_MAG) fsea_strided_store<FSEA_OUT_MAG, NTOT, G, T, R2, M, B, G * XB>(out, t, g, tid, re, im, dc_patch, tile);
-                else if (out_mode == FSEA_OUT_LOGMAG) fsea_strided_store<FSEA_OUT_LOGMAG, NTOT, G, T, R2, M, B, G * XB>(out, t, g, tid, re, im, dc_patch, tile);
-                else fsea_strided_store<FSEA_OUT_PIX, NTOT, G, T, R2, M, B, G * XB>(out, t, g, tid, re, im, dc_patch, tile);
-            } else {
-#pragma unroll
-                for (int b = 0; b < B; b++)
-                    out.template store_sel<R2, M>(out_mode, t + b * T, re + b * R2, im + b * R2, dc_patch);
-            }
-        }
+        const float probe = fsea_transform<SH, V, FMT, OK, NTOT, G, WIN>(kp, in, in_next, more, out, xp, raw, tw1, tw2,
+                                                                         t, g, tid, dc_patch, out_mode, fsea_smem,
+                                                                         WREG ? wreg : nullptr);
         if (NPASS > 1) fsea_group_sync<T>(g);                      // the next unit rewrites the exchange plane
         in = in_next;
         live = live_next;
         cur = nxt;
-        // (never true: no finite transform produces this NaN payload in its last register)
-        const int late = (__float_as_uint((float)fsea_lane(re[P - 1], 0)) == 0x7fc0deadu) ? 1 : 0;
-        nxt = share(pend_prev, late);
-        pend_prev = pend;
+        if (last_of_ticket) {
+            // (never true: no finite transform produces this NaN payload in its last register)
+            const int late = (__float_as_uint(probe) == 0x7fc0deadu) ? 1 : 0;
+            nxt_base = share(pend_prev, late);
+            pend_prev = pend;
+            kb = 0;
+        } else {
+            kb++;
+        }
     }
     // last block out re-arms the counters for the next launch that uses this slot
     __syncthreads();
@@ -791,6 +842,41 @@ fsea_fft_kernel(const fsea_kparams kp) {
 // loads (a warp covers 128 contiguous bytes of every row), one packed radix-32 codelet,
 // 32 float4 stores (a warp covers 512 contiguous bytes of every output row).  Samples stay
 // integer-scaled (b - 128); the 1/256 of src/nrf.c:605-606 rides on the four-step twiddles.
+// one column pair: frame base `p` (already offset to the pair's first column), output `o`
+template <bool WIN>
+__device__ __forceinline__ void fsea_cols32_pair(const uint8_t* p, const float* win, const float4* tw, float4* o,
+                                                 long n2, uint32_t x4) {
+    f2 re[32], im[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        const uint32_t w = __ldg((const uint32_t*)(p + (size_t)j * 2 * n2)) ^ x4;
+        re[j] = mk2(__uint_as_float(__byte_perm(w, 0x47000000u, 0x7504)), __uint_as_float(__byte_perm(w, 0x47000000u, 0x7524)));
+        im[j] = mk2(__uint_as_float(__byte_perm(w, 0x47000000u, 0x7514)), __uint_as_float(__byte_perm(w, 0x47000000u, 0x7534)));
+    }
+    if (WIN) {
+        const f2 off = mk2(32896.0f, 32896.0f);
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const float2 w = __ldg((const float2*)(win + (size_t)j * n2));
+            re[j] = vmul(vsub(re[j], off), mk2(w.x, w.y));
+            im[j] = vmul(vsub(im[j], off), mk2(w.x, w.y));
+        }
+        fsea_dft32<f2>(re, im);
+    } else {
+        fsea_dft32_raw<f2>(re, im);
+    }
+    // four-step twiddle W_N^{n2 k1} (x 1/256): the column step is DRAM-bound with the LSU at
+    // 17 %, so the table (L2-resident, 8 N bytes) is read here rather than in the row step
+#pragma unroll
+    for (int k1 = 0; k1 < 32; k1++) {
+        const float4 w = __ldg(tw + (size_t)k1 * (n2 / 2));              // (wA.re, wA.im, wB.re, wB.im)
+        const f2 wr = mk2(w.x, w.z), wi = mk2(w.y, w.w);
+        const f2 r = vsub(vmul(re[k1], wr), vmul(im[k1], wi));
+        const f2 q = vfma2(re[k1], wi, vmul(im[k1], wr));
+        o[(size_t)k1 * (n2 / 2)] = make_float4(r.v.x, q.v.x, r.v.y, q.v.y);
+    }
+}
+
 template <bool WIN>
 __global__ void __launch_bounds__(128, 3)
 fsea_cols32_kernel(const fsea_kparams kp) {
@@ -800,29 +886,8 @@ fsea_cols32_kernel(const fsea_kparams kp) {
     for (long u = (long)blockIdx.x * blockDim.x + threadIdx.x; u < pairs; u += (long)gridDim.x * blockDim.x) {
         const long s0 = 2 * u;
         const long f = s0 / n2, c = s0 - f * n2;
-        const uint8_t* p = (const uint8_t*)kp.in + 2 * (f * kp.seq_stride + c);
-        f2 re[32], im[32];
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-            const uint32_t w = __ldg((const uint32_t*)(p + (size_t)j * 2 * n2)) ^ x4;
-            re[j] = mk2(__uint_as_float(__byte_perm(w, 0x47000000u, 0x7504)), __uint_as_float(__byte_perm(w, 0x47000000u, 0x7524)));
-            im[j] = mk2(__uint_as_float(__byte_perm(w, 0x47000000u, 0x7514)), __uint_as_float(__byte_perm(w, 0x47000000u, 0x7534)));
-        }
-        if (WIN) {
-            const f2 off = mk2(32896.0f, 32896.0f);
-#pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const float2 w = __ldg((const float2*)(kp.window + (size_t)j * n2 + c));
-                re[j] = vmul(vsub(re[j], off), mk2(w.x, w.y));
-                im[j] = vmul(vsub(im[j], off), mk2(w.x, w.y));
-            }
-            fsea_dft32<f2>(re, im);
-        } else {
-            fsea_dft32_raw<f2>(re, im);
-        }
-        float4* o = (float4*)((float2*)kp.out + (size_t)f * 32 * n2 + c);
-#pragma unroll
-        for (int k1 = 0; k1 < 32; k1++)
-            o[(size_t)k1 * (n2 / 2)] = make_float4(re[k1].v.x, im[k1].v.x, re[k1].v.y, im[k1].v.y);
+        fsea_cols32_pair<WIN>((const uint8_t*)kp.in + 2 * (f * kp.seq_stride + c), WIN ? kp.window + c : nullptr,
+                              (const float4*)((const float2*)kp.tw4 + c),
+                              (float4*)((float2*)kp.out + (size_t)f * 32 * n2 + c), n2, x4);
     }
 }

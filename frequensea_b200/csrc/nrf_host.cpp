@@ -172,6 +172,11 @@ extern "C" void nrf_device_free(nrf_device* device) {
 // size/2 entries); buffers longer than the reference's 131072-sample fft_in
 // (lua/fft-shifted.lua produces one) are clamped instead of overflowing.
 struct nrf_fft_engine {
+    // The history image is a RING of rows in fft->buffer: `head` is the row that holds the
+    // newest spectrum.  The reference scrolls the whole N x H image by one row on every frame
+    // (an 8 MiB memmove at 1024 x 1024, src/nrf.c:617); here a frame costs one row write, and
+    // nrf_fft_get_buffer() unrolls the ring into the reference's layout (row 0 newest).
+    int head = 0;
     fsea_plan* plan_u8 = nullptr;
     fsea_plan* plan_f64 = nullptr;
     uint8_t* stage_u8 = nullptr;     // 2N bytes
@@ -212,15 +217,15 @@ extern "C" void nrf_fft_process(nrf_fft* fft, nut_buffer* buffer) {
     const int n = fft->fft_size;
     const size_t have = (size_t)buffer->length * (size_t)buffer->channels / 2;   // complex samples offered
     const size_t take = have < (size_t)n ? have : (size_t)n;                      // only the first N matter
-    double* row0 = fft->buffer;
-    const size_t hist = (size_t)n * (size_t)(fft->fft_history_size - 1);
+    const int rows = fft->fft_history_size > 0 ? fft->fft_history_size : 1;
+    eng->head = (eng->head + rows - 1) % rows;                   // newest row moves "up" by one
+    double* row0 = fft->buffer + (size_t)eng->head * n;
     int rc;
     if (buffer->type == NUT_BUFFER_U8) {
         memcpy(eng->stage_u8, buffer->data.u8, 2 * take);
         rc = fsea_exec_host(eng->plan_u8, eng->stage_u8, eng->row_f32, 1);
         if (rc != FSEA_OK) nrf_die("nrf_fft_process", rc);
-        if (fft->fft_history_size > 1) memmove(row0 + n, row0, hist * sizeof(double));   // src/nrf.c:617
-        for (int i = 0; i < n; i++) row0[i] = (double)eng->row_f32[i];
+        for (int i = 0; i < n; i++) row0[i] = (double)eng->row_f32[i];       // D2H moved this one row only
     } else {
         if (!eng->plan_f64) {
             eng->plan_f64 = make_plan(n, FSEA_IN_F64C);
@@ -230,7 +235,6 @@ extern "C" void nrf_fft_process(nrf_fft* fft, nut_buffer* buffer) {
         memcpy(eng->stage_f64, buffer->data.f64, 2 * take * sizeof(double));
         rc = fsea_exec_host(eng->plan_f64, eng->stage_f64, eng->row_f64, 1);
         if (rc != FSEA_OK) nrf_die("nrf_fft_process", rc);
-        if (fft->fft_history_size > 1) memmove(row0 + n, row0, hist * sizeof(double));
         memcpy(row0, eng->row_f64, (size_t)n * sizeof(double));
     }
 }
@@ -257,7 +261,13 @@ extern "C" void nrf_fft_shift(nrf_fft* fft, double d) {
 }
 
 extern "C" nut_buffer* nrf_fft_get_buffer(nrf_fft* fft) {
-    return nut_buffer_new_f64(fft->fft_size * fft->fft_history_size, 1, fft->buffer);
+    nrf_fft_engine* eng = (nrf_fft_engine*)fft->engine;
+    const size_t n = (size_t)fft->fft_size, rows = (size_t)fft->fft_history_size;
+    nut_buffer* out = nut_buffer_new_f64((int)(n * rows), 1, NULL);
+    const size_t head = (size_t)eng->head;
+    memcpy(out->data.f64, fft->buffer + head * n, (rows - head) * n * sizeof(double));          // rows head .. H-1
+    if (head) memcpy(out->data.f64 + (rows - head) * n, fft->buffer, head * n * sizeof(double)); // rows 0 .. head-1
+    return out;
 }
 
 extern "C" void nrf_fft_free(nrf_fft* fft) {
