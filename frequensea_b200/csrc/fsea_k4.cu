@@ -16,9 +16,9 @@ static bool fill4(fsea_kernel_info4* o, const char* na, const char* nb, bool win
 
 bool fsea_get_kernel4(int n, bool window, fsea_kernel_info4* out) {
     switch (n) {
-        case 16384: return fill4<16384, fsea_shape<512, 16, 16, 2>>(out, "fft4<16384=32x512: cols32 + rows 16x16x2,f32x2>", "fft4B<16384: rows 512=16x16x2,f32x2>", window);
-        case 32768: return fill4<32768, fsea_shape<1024, 16, 16, 4>>(out, "fft4<32768=32x1024: cols32 + rows 16x16x4,f32x2>", "fft4B<32768: rows 1024=16x16x4,f32x2>", window);
-        case 65536: return fill4<65536, fsea_shape<2048, 16, 16, 8>>(out, "fft4<65536=32x2048: cols32 + rows 16x16x8,f32x2>", "fft4B<65536: rows 2048=16x16x8,f32x2>", window);
+        case 16384: return fill4<16384, fsea_shape<512, 32, 16, 1>>(out, "fft4<16384=32x512: cols32 + rows 32x16,f32x2>", "fft4B<16384: rows 512=32x16,f32x2>", window);
+        case 32768: return fill4<32768, fsea_shape<1024, 32, 32, 1>>(out, "fft4<32768=32x1024: cols32 + rows 32x32,f32x2>", "fft4B<32768: rows 1024=32x32,f32x2>", window);
+        case 65536: return fill4<65536, fsea_shape<2048, 32, 8, 8>>(out, "fft4<65536=32x2048: cols32 + rows 32x8x8,f32x2>", "fft4B<65536: rows 2048=32x8x8,f32x2>", window);
     }
     return false;
 }
