@@ -77,6 +77,8 @@ def lib() -> C.CDLL:
     L.fsea_plan_launch_count.argtypes = [vp]; L.fsea_plan_launch_count.restype = l
     L.fsea_plan_kernel_name.argtypes = [vp]; L.fsea_plan_kernel_name.restype = C.c_char_p
     L.fsea_gate_mean_host.argtypes = [vp, vp, l, C.POINTER(C.c_double)]; L.fsea_gate_mean_host.restype = i
+    L.fsea_stitch_host.argtypes = [i, vp, i, i, i, i, vp]; L.fsea_stitch_host.restype = i
+    L.fsea_stitch_device.argtypes = [vp, i, i, i, i, vp, vp]; L.fsea_stitch_device.restype = i
     _lib = L
     return L
 
@@ -92,6 +94,16 @@ def _check(rc: int, what: str) -> None:
         if rc == ERR_CUDA:
             detail += ": " + L.fsea_last_cuda_error().decode()
         raise FseaError(rc, what, detail)
+
+
+def stitch(images: np.ndarray, width_step: int, device: int = 0) -> np.ndarray:
+    """Max-blend sweep images (n_images, rows, width) side by side (c/fft-stitch-broad.c)."""
+    images = np.ascontiguousarray(images, dtype=np.uint8)
+    n_images, rows, width = images.shape
+    out = np.empty((rows, width + (n_images - 1) * width_step), dtype=np.uint8)
+    _check(lib().fsea_stitch_host(device, images.ctypes.data_as(C.c_void_p), n_images, rows, width, width_step,
+                                  out.ctypes.data_as(C.c_void_p)), "fsea_stitch_host")
+    return out
 
 
 _IN_NP = {IN_U8: np.uint8, IN_S8: np.uint8, IN_F32C: np.float32, IN_F64C: np.float64}

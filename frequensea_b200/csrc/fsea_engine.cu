@@ -511,3 +511,67 @@ extern "C" int fsea_gate_mean_host(fsea_plan* p, const void* h_in, long rows, do
     cudaFree(d_out);
     return rc;
 }
+
+// ------------------------------------------------------------------ sweep stitch
+// c/fft-stitch-broad.c:28-36,66-88 (and c/fft-stitch.c:46-54,167-189): the per-frequency
+// pixel images of a sweep are max-blended side by side, image i at column i * width_step,
+// into one picture of width  width + (n_images - 1) * width_step  (zero where nothing lands).
+// One thread per 4 output pixels; every source pixel is read once per output it covers.
+__global__ void fsea_stitch_kernel(const uint8_t* __restrict__ img, int n_images, int rows, int width, int step,
+                                   int out_width, uint8_t* __restrict__ out) {
+    const long quads_per_row = (out_width + 3) / 4;
+    const long total = (long)rows * quads_per_row;
+    for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long)gridDim.x * blockDim.x) {
+        const long y = q / quads_per_row;
+        const int x0 = (int)(q - y * quads_per_row) * 4;
+        uint8_t v[4] = {0, 0, 0, 0};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int x = x0 + k;
+            if (x >= out_width) break;
+            // images i with 0 <= x - i*step < width
+            int hi = x / step;
+            if (hi > n_images - 1) hi = n_images - 1;
+            int lo = (x - width + step) / step;          // ceil((x - width + 1) / step)
+            if (x - width + 1 <= 0) lo = 0;
+            uint8_t m = 0;
+            for (int i = lo; i <= hi; i++) {
+                const uint8_t s = img[((size_t)i * rows + y) * width + (x - i * step)];
+                m = s > m ? s : m;
+            }
+            v[k] = m;
+        }
+        uint8_t* o = out + (size_t)y * out_width + x0;
+        for (int k = 0; k < 4 && x0 + k < out_width; k++) o[k] = v[k];
+    }
+}
+
+extern "C" int fsea_stitch_device(const uint8_t* d_images, int n_images, int rows, int width, int width_step,
+                                  uint8_t* d_out, void* stream) {
+    if (!d_images || !d_out || n_images <= 0 || rows <= 0 || width <= 0 || width_step <= 0) return FSEA_ERR_INVALID;
+    const int out_width = width + (n_images - 1) * width_step;
+    const long quads = (long)rows * ((out_width + 3) / 4);
+    const int blocks = (int)std::min<long>((quads + 255) / 256, 148 * 16);
+    fsea_stitch_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_images, n_images, rows, width, width_step, out_width, d_out);
+    CU(cudaGetLastError());
+    return FSEA_OK;
+}
+
+extern "C" int fsea_stitch_host(int device, const uint8_t* h_images, int n_images, int rows, int width, int width_step,
+                                uint8_t* h_out) {
+    if (!h_images || !h_out || n_images <= 0 || rows <= 0 || width <= 0 || width_step <= 0) return FSEA_ERR_INVALID;
+    if (fsea_device_count() <= 0) return FSEA_ERR_NO_DEVICE;
+    CU(cudaSetDevice(device));
+    const size_t ib = (size_t)n_images * rows * width, ob = (size_t)rows * (width + (size_t)(n_images - 1) * width_step);
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    CU(cudaMalloc(&d_in, ib));
+    cudaError_t e = cudaMalloc(&d_out, ob);
+    if (e != cudaSuccess) { cudaFree(d_in); return cuda_fail(e, "cudaMalloc"); }
+    int rc = FSEA_OK;
+    if ((e = cudaMemcpy(d_in, h_images, ib, cudaMemcpyHostToDevice)) != cudaSuccess) rc = cuda_fail(e, "H2D");
+    if (rc == FSEA_OK) rc = fsea_stitch_device(d_in, n_images, rows, width, width_step, d_out, nullptr);
+    if (rc == FSEA_OK && (e = cudaMemcpy(h_out, d_out, ob, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "D2H");
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return rc;
+}

@@ -1,3 +1,3 @@
-// fsea_k_4096.cu -- 4096-point instantiations (N = 16 x 16 x 16)
+// fsea_k_4096.cu -- 4096-point instantiations (N = 32 x 32 x 4)
 #include "fsea_instantiate.cuh"
-FSEA_DEFINE_SIZE(4096, 16, 16, 16)
+FSEA_DEFINE_SIZE(4096, 32, 32, 4)

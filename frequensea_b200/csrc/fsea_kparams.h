@@ -11,7 +11,7 @@ struct fsea_kparams {
     const void* tw1;       // pass-1 twiddles [j-1][k], k < R0            (S2 = float2/double2)
     const void* tw2;       // pass-2 twiddles [j-1][k], k < R0*R1
     const float* window;   // N floats or nullptr
-    float pix_scale;       // S * 10/log2(10) folded on the host? no: plain S
+    float pix_scale;       // S of FSEA_OUT_PIX (c/fft-batch.c: 10, c/fft-batch-broad.c: 5)
     int flags;             // FSEA_FLAG_*
     int dc_term;           // 1: add N/2 (1+i) to bin k=0 (uncentred 8-bit input, no patch)
     int out_mode;          // FSEA_OUT_*

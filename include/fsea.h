@@ -97,23 +97,31 @@ long fsea_frames_in(const fsea_plan *plan, size_t n_samples);
 int fsea_exec_device(fsea_plan *plan, const void *d_in, void *d_out, long n_frames, void *stream);
 
 /* Host buffers: chunked, double-buffered H2D -> kernel -> D2H through pinned
- * staging on two streams; returns when h_out is complete.  This is the call
+ * staging on three streams (page-locked caller memory is used directly); returns when h_out is complete.  This is the call
  * the nrf_fft shim and bench.py's `e2e` use. */
 int fsea_exec_host(fsea_plan *plan, const void *h_in, void *h_out, long n_frames);
 
 /* Number of kernel launches issued by this plan so far (bench gpu_launches). */
 long fsea_plan_launch_count(const fsea_plan *plan);
-/* Name of the kernel variant the plan dispatches to, e.g. "direct<1024:32x32,f32x2>". */
+/* Name of the kernel variant the plan dispatches to, e.g. "fft<1024:32x32x1,f32x2>". */
 const char *fsea_plan_kernel_name(const fsea_plan *plan);
 
-/* ---- waterfall history kept on the device ----------
- * The reference scrolls an N x H float64 image by memcpy on every frame
- * (src/nrf.c:617) and copies it whole on every read (src/nrf.c:633-635). */
+/* ---- sweep post-processing -------------------------- */
 
 /* Mean of |X| over the first `rows` frames of a PIX/MAG batch -- the
  * "interesting?" gate of c/fft-batch-broad.c:80-98 -- computed on the device
  * from raw input.  Writes one double. */
 int fsea_gate_mean_host(fsea_plan *plan, const void *h_in, long rows, double *mean_out);
+
+/* Max-blend the per-frequency pixel images of a sweep side by side
+ * (c/fft-stitch-broad.c:28-36,66-88; c/fft-stitch.c:46-54,167-189): image i
+ * (rows x width, uint8, row-major, images contiguous) lands at column
+ * i * width_step of an output of width  width + (n_images-1) * width_step,
+ * out = max(out, image), zero where no image lands. */
+int fsea_stitch_device(const uint8_t *d_images, int n_images, int rows, int width, int width_step,
+                       uint8_t *d_out, void *stream);
+int fsea_stitch_host(int device, const uint8_t *h_images, int n_images, int rows, int width, int width_step,
+                     uint8_t *h_out);
 
 #ifdef __cplusplus
 }

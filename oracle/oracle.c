@@ -201,6 +201,23 @@ double orc_broad_gate_mean(const double *cplx_rows, int n, int rows) {
     return total / (double)size;
 }
 
+/* c/fft-stitch-broad.c:28-36 (img_gray_copy) and :66-88 (placement loop) */
+void orc_stitch(const uint8_t *images, int n_images, int rows, int width, int width_step, uint8_t *out) {
+    int out_width = width + (n_images - 1) * width_step;
+    memset(out, 0, (size_t)rows * out_width);                 /* calloc, :63 */
+    int x = 0;
+    for (int i = 0; i < n_images; i++) {
+        const uint8_t *src = images + (size_t)i * rows * width;
+        for (int y = 0; y < rows; y++)
+            for (int j = 0; j < width; j++) {
+                uint8_t *d = out + (size_t)y * out_width + x + j;
+                uint8_t s = src[(size_t)y * width + j];
+                *d = *d > s ? *d : s;                          /* max_u8, :22-24 */
+            }
+        x += width_step;
+    }
+}
+
 /* c/fft.c:45-56,181-197 (as intended, see oracle.h) */
 void orc_scope_row(int n, const uint8_t *raw, double intensity, double *out) {
     double *x = (double *)malloc(sizeof(double) * 4 * (size_t)n), *X = x + 2 * n;

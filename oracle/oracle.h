@@ -72,6 +72,10 @@ void orc_batch_row(int n, const uint8_t *raw, double scale, int dc_patch,
 /* c/fft-batch-broad.c:80-98 -- mean |X| over `rows` complex rows of width n. */
 double orc_broad_gate_mean(const double *cplx_rows, int n, int rows);
 
+/* c/fft-stitch-broad.c:28-36,66-88 -- max-blend n_images gray images (rows x width) side by
+ * side at column offsets i*width_step; out is rows x (width + (n_images-1)*width_step). */
+void orc_stitch(const uint8_t *images, int n_images, int rows, int width, int width_step, uint8_t *out);
+
 /* c/fft.c:45-56,181-197 -- 512-pt scope: bytes/255.0 (no offset conversion),
  * half-swap fftshift; "as intended" variant (1/N on re and im, power from the
  * same bin); the upstream precedence bug (*pt[1] == pt[1][0]) is described in

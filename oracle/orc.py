@@ -56,6 +56,8 @@ def lib() -> C.CDLL:
         L.orc_broad_gate_mean.argtypes = [vp, i, i]
         L.orc_broad_gate_mean.restype = d
         L.orc_scope_row.argtypes = [i, vp, d, vp]
+        L.orc_stitch.argtypes = [vp, i, i, i, i, vp]
+        L.orc_stitch.restype = None
         L.orc_engine_frame.argtypes = [i, i, i, i, d, i, vp, vp]
         L.orc_engine_batch.argtypes = [i, i, i, i, i, d, i, vp, l, vp, i]
         for f in ("orc_device_unpack", "orc_dft_forward", "orc_dft_naive", "orc_nrf_fft_frame_u8",
@@ -123,6 +125,14 @@ def broad_gate_mean(cplx_rows: np.ndarray) -> float:
     cplx_rows = np.ascontiguousarray(cplx_rows, dtype=np.complex128)
     rows, n = cplx_rows.shape
     return float(lib().orc_broad_gate_mean(_p(cplx_rows), n, rows))
+
+
+def stitch(images: np.ndarray, width_step: int) -> np.ndarray:
+    images = np.ascontiguousarray(images, dtype=np.uint8)
+    n_images, rows, width = images.shape
+    out = np.empty((rows, width + (n_images - 1) * width_step), dtype=np.uint8)
+    lib().orc_stitch(_p(images), n_images, rows, width, width_step, _p(out))
+    return out
 
 
 def scope_row(raw: np.ndarray, n: int, intensity: float) -> np.ndarray:

@@ -172,6 +172,24 @@ def test_sweep_pixels_match_reference_tools(fbg, iq, golden):
         assert d.max() <= 1 and (d > 0).mean() < 0.005
 
 
+def test_sweep_stitch(fbg, iq):
+    """Sweep product: per-frequency pixel images (c/fft-batch-broad.c rows) max-blended side by side
+    (c/fft-stitch-broad.c), against the oracle.  Four 'frequencies' = the four capture blocks."""
+    fb = fbg
+    rng = np.random.default_rng(4)
+    imgs = rng.integers(0, 256, (7, 33, 256), dtype=np.uint8)
+    for step in (256, 102, 40, 300):                        # WIDTH_STEP = N / (fs / step)
+        assert np.array_equal(fb.stitch(imgs, step), orc.stitch(imgs, step))
+    raw = iq["rf200big4"]
+    n, rows = 256, 64
+    plan = fb.Plan(n, in_format=fb.IN_S8, out_mode=fb.OUT_PIX, pix_scale=5.0, flags=fb.FLAG_DC_PATCH)
+    images = np.stack([plan.exec_host(raw[b * BLOCK:], rows) for b in range(4)])
+    ref_images = np.stack([oracle_rows(raw[b * BLOCK:], n, n, rows, orc.IN_S8, orc.WIN_NONE, orc.OUT_PIX, 5.0, orc.FLAG_DC_PATCH)
+                           for b in range(4)])
+    d = np.abs(fb.stitch(images, 102).astype(int) - orc.stitch(ref_images, 102).astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 0.005
+
+
 def test_gate_mean(fbg, iq, golden):
     fb = fbg
     raw = iq["rf200big4"]

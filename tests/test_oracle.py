@@ -118,6 +118,17 @@ def test_history_and_shift_against_reference_semantics(golden):
             assert np.array_equal(img, golden[f"ref_shift_d{d}"])
 
 
+def test_stitch_definition():
+    """c/fft-stitch-broad.c:28-36,66-88: max-blend at i * WIDTH_STEP."""
+    rng = np.random.default_rng(2)
+    imgs = rng.integers(0, 256, (6, 9, 32), dtype=np.uint8)
+    for step in (32, 12, 5, 50):
+        ref = np.zeros((9, 32 + 5 * step), np.uint8)
+        for i in range(6):
+            ref[:, i * step:i * step + 32] = np.maximum(ref[:, i * step:i * step + 32], imgs[i])
+        assert np.array_equal(orc.stitch(imgs, step), ref)
+
+
 def test_scope_row_definition(iq):
     raw = iq["rf433"]
     n = 512
