@@ -173,10 +173,14 @@ def cpu_reference_rate(raw, threads, target_s=12.0, impl_only=False):
 
 
 def secondary(args):
-    """Device-resident throughput + roofline of a secondary workload (one GPU)."""
+    """Device-resident throughput + roofline of a secondary workload; under torchrun every
+    rank runs the same per-GPU batch on its own device (independent frames / sweep
+    frequencies: no collective, weak scaling), time = max over ranks."""
     import torch
     import frequensea_b200 as fb
     from oracle import orc
+    rank, world, local = dist_setup(args.gpus)
+    torch.cuda.set_device(local)
     w = WORKLOADS[args.workload]
     n, hop, frames = w["n"], w["hop"], w["frames"]
     if args.frames != DEFAULT_FRAMES:
@@ -186,9 +190,9 @@ def secondary(args):
     flags = fb.FLAG_DC_PATCH if w["patch"] else 0
     arith = {"auto": fb.ARITH_AUTO, "f32": fb.ARITH_F32, "f32x2": fb.ARITH_F32X2}[args.arith]
     plan = fb.Plan(n, hop=hop, in_format=fmt, window=fb.WIN_HANN if w["window"] else fb.WIN_NONE,
-                   out_mode=out_mode, flags=flags, pix_scale=w.get("scale", 10.0), arith=arith)
-    dev = torch.device("cuda", 0)
-    g = torch.Generator(device=dev).manual_seed(20260925)
+                   out_mode=out_mode, flags=flags, pix_scale=w.get("scale", 10.0), arith=arith, device=local)
+    dev = torch.device("cuda", local)
+    g = torch.Generator(device=dev).manual_seed(20260925 + rank)
     d_in = torch.randint(0, 256, (plan.input_bytes(frames),), dtype=torch.uint8, device=dev, generator=g)
     d_out = torch.empty((frames, n), dtype=torch.uint8 if out_mode == fb.OUT_PIX else torch.float32, device=dev)
     stream = torch.cuda.current_stream()
@@ -219,33 +223,55 @@ def secondary(args):
             raise SystemExit(f"bench.py: parity gate failed on {args.workload} ({worst})")
     for _ in range(args.warmup):
         plan.exec_device(d_in.data_ptr(), d_out.data_ptr(), frames, stream.cuda_stream)
-    torch.cuda.synchronize()
-    sampler = ClockSampler(0)
-    sampler.start()
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     l0 = plan.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
     e0.record(stream)
     for _ in range(args.steps):
         plan.exec_device(d_in.data_ptr(), d_out.data_ptr(), frames, stream.cuda_stream)
     e1.record(stream)
-    torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
-    clocks = sampler.stop()
+    barrier()
+    tms = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms[0])
+    clocks = sampler.stop() if rank == 0 else None
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+            dist.destroy_process_group()
+        return 0
     peak, peak_src = peak_hbm()
     out_b = 1 if w["out"] == "pix" else 4
     alg = frames * (2 * hop + out_b * n)
     achieved = alg / (ms * 1e-3) / 1e9
     print(json.dumps({
-        "metric": METRIC, "value": frames / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC, "value": world * frames / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic uniform 8-bit IQ drawn on the device",
-        "config": {"workload": w["desc"], "fft_size": n, "hop": hop, "frames_per_step": frames, "kernel": plan.kernel_name,
+        "config": {"workload": w["desc"], "fft_size": n, "hop": hop, "frames_per_gpu_per_step": frames, "kernel": plan.kernel_name,
+                   "parallelism": f"frames / sweep frequencies sharded over {world} GPU(s), no collective",
                    "l2": f"inputs larger than L2: {plan.input_bytes(frames) >> 20} MiB in + {plan.output_bytes(frames) >> 20} MiB out per step"},
-        "iq_gsps": frames * hop / (ms * 1e-3) / 1e9, "parity_gate": worst, "gpu_launches": plan.launches - l0, "clocks": clocks,
+        "iq_gsps": world * frames * hop / (ms * 1e-3) / 1e9, "parity_gate": worst, "gpu_launches": plan.launches - l0, "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": plan.kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_step": alg, "peak_source": peak_src,
-                     "note": "per step (all launches of the step)"},
+                     "note": "per GPU, per step (all launches of the step)"},
     }))
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
     return 0
 
 

@@ -8,7 +8,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libfsea.so")
+_LIB_PATH = os.environ.get("FSEA_LIB") or os.path.join(_HERE, "libfsea.so")   # FSEA_LIB: A/B builds
 
 IN_U8, IN_S8, IN_F32C, IN_F64C = 0, 1, 2, 3
 WIN_NONE, WIN_HANN = 0, 1

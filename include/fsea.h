@@ -11,6 +11,9 @@
  * a whole batch of frames in hand-written sm_100a kernels.  include/nrf.h
  * (the reference's own operator names) is a one-frame client of this API.
  *
+ * Threading: a plan is a single-threaded object (one host thread at a time; its
+ * launches may go to any streams); different plans are independent.
+ *
  * Plain C: pointers and sizes only.  Every function returns FSEA_OK (0) or a
  * negative FSEA_ERR_* code; fsea_strerror() names it.  There is NO CPU
  * fallback: without a CUDA device every compute entry point fails with

@@ -117,7 +117,9 @@ class Gen:
 
     def addc(self, a, c): return self.emit(f"vaddc({a}, {self.lit(c)})")             # a + c
 
-    def fft(self, xs, chunk=4, raw_bias=None):
+    def fft(self, xs, chunk=None, raw_bias=None):
+        import os
+        chunk = chunk or int(os.environ.get("FSEA_CODELET_CHUNK", "4"))
         """Iterative radix-2 DIT, emitted stage by stage (breadth first): within a
         stage the butterflies are independent, and they are written out `chunk` at
         a time -- first every butterfly's twiddle half, then every butterfly's
