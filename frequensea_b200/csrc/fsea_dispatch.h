@@ -47,4 +47,5 @@ struct fsea_kernel_info4 {
     fsea_kernel_info a, b;
     int n1, n2;
 };
-bool fsea_get_kernel4(int n, bool window, fsea_kernel_info4* out);
+bool fsea_get_kernel4(int n, bool window, int out_mode, fsea_kernel_info4* out);
+bool fsea_get_kernel4_old(int n, bool window, fsea_kernel_info4* out);

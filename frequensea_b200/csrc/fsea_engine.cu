@@ -85,12 +85,14 @@ struct fsea_plan {
     void* d_dump = nullptr;
     // four-step (N >= 16384): two kernels per chunk of frames, intermediate kept L2-sized
     bool four = false;
+    bool four_old = false;
     fsea_kernel_info4 k4;
     void *d_tw1b = nullptr, *d_tw2b = nullptr;   // step-B sub-FFT tables (step A uses d_tw1/d_tw2)
     void* d_tw4 = nullptr;                       // W_N^{n2 k1}, float2 [N1][N2]
     static const int SCRATCH_SLOTS = 4;           // slot 0: fsea_exec_device, 1..3: host pipeline stages
     void* d_scratch[SCRATCH_SLOTS] = {nullptr, nullptr, nullptr, nullptr};   // chunk_frames x N float2 each
     long chunk_frames = 0;
+    long scratch_frames[SCRATCH_SLOTS] = {0, 0, 0, 0};
     int max_blocks_b = 0;
 };
 
@@ -210,7 +212,9 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
     if (n < 16 || n > 65536 || (n & (n - 1))) return FSEA_ERR_UNSUPPORTED;
     fsea_get_kernel_fn get = size_table(n);
     fsea_kernel_info4 k4;
-    const bool four = !get && fsea_get_kernel4(n, cfg->window == FSEA_WIN_HANN, &k4);
+    const bool four_old = getenv("FSEA_FOUR_OLD") != nullptr;          // A/B against the previous organisation
+    const bool four = !get && (four_old ? fsea_get_kernel4_old(n, cfg->window == FSEA_WIN_HANN, &k4)
+                                        : fsea_get_kernel4(n, cfg->window == FSEA_WIN_HANN, cfg->out_mode, &k4));
     if (!get && !four) return FSEA_ERR_UNSUPPORTED;
     if (four && cfg->in_format != FSEA_IN_U8 && cfg->in_format != FSEA_IN_S8) return FSEA_ERR_UNSUPPORTED;
     if (cfg->in_format < FSEA_IN_U8 || cfg->in_format > FSEA_IN_F64C) return FSEA_ERR_INVALID;
@@ -239,6 +243,7 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
     }
     if (four) {
         p->four = true;
+        p->four_old = four_old;
         p->k4 = k4;
         p->ki = k4.a;                     // step A doubles as "the" kernel for tables, lanes, names
         p->variant = FSEA_VAR_F32X2;
@@ -256,28 +261,39 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
         if (!p->four && (rc = upload_twiddles(p->ki, &p->d_tw1, &p->d_tw2, staged ? 1.0f / 256.0f : 1.0f)) != FSEA_OK) break;
         if (p->four) {
             if ((rc = setup_kernel(p->k4.b, cfg->device, &p->max_blocks_b)) != FSEA_OK) break;
-
-            if ((rc = upload_twiddles(p->k4.b, &p->d_tw1b, &p->d_tw2b)) != FSEA_OK) break;
             const int n1 = p->k4.n1, n2 = p->k4.n2;
             std::vector<float2> t4((size_t)n);
             const long double PI2 = 6.283185307179586476925286766559005768L;
-            for (int k1 = 0; k1 < n1; k1++)
-                for (int c = 0; c < n2; c++) {
-                    const long double a = -PI2 * (long double)((long)k1 * c) / (long double)n;
-                    // step A leaves integer-scaled samples: 1/256 (src/nrf.c:605-606) rides here, exactly
-                    t4[(size_t)k1 * n2 + c].x = (float)(cosl(a) / 256.0L);
-                    t4[(size_t)k1 * n2 + c].y = (float)(sinl(a) / 256.0L);
-                }
-            // The intermediate (8 bytes per point) is streamed through HBM in chunks of 256 MiB.
+            if (p->four_old) {
+                if ((rc = upload_twiddles(p->k4.b, &p->d_tw1b, &p->d_tw2b)) != FSEA_OK) break;
+                for (int k1 = 0; k1 < n1; k1++)
+                    for (int c = 0; c < n2; c++) {
+                        const long double a = -PI2 * (long double)((long)k1 * c) / (long double)n;
+                        // step A leaves integer-scaled samples: 1/256 (src/nrf.c:605-606) rides here, exactly
+                        t4[(size_t)k1 * n2 + c].x = (float)(cosl(a) / 256.0L);
+                        t4[(size_t)k1 * n2 + c].y = (float)(sinl(a) / 256.0L);
+                    }
+            } else {
+                // step A is a staged kernel: 1/256 rides on its pass-1 twiddles.  Step B builds
+                // W_N^{n2 k} from the rows n2 = 1, 2, 4, 8, 16 of this table.
+                if ((rc = upload_twiddles(p->k4.a, &p->d_tw1, &p->d_tw2, 1.0f / 256.0f)) != FSEA_OK) break;
+                for (int r = 0; r < 5; r++)
+                    for (int k = 0; k < n1; k++) {
+                        const long double a = -PI2 * (long double)(((long)k) << r) / (long double)n;
+                        t4[(size_t)r * n1 + k].x = (float)cosl(a);
+                        t4[(size_t)r * n1 + k].y = (float)sinl(a);
+                    }
+            }
+            // The intermediate (8 bytes per point) is streamed through HBM in chunks of at most
+            // 2 GiB, allocated on first use at the size the call needs (grow-only).
             // Keeping it L2-resident was tried twice -- 32 MiB chunks (two launches per 64 frames:
             // launch-bound, 2x slower) and a persistent fused kernel with per-frame dependency
             // counters (5-10 % slower: the row step is LSU/latency-bound, not DRAM-bound) -- see DESIGN.md.
-            long chunk_mb = 256;
+            long chunk_mb = 2048;
             if (const char* ev = getenv("FSEA_CHUNK_MB")) chunk_mb = std::max(1L, atol(ev));   // experiments
             p->chunk_frames = std::max<long>(1, (chunk_mb << 20) / ((long)n * 8));
             if ((e = cudaMalloc(&p->d_tw4, (size_t)n * sizeof(float2))) != cudaSuccess ||
-                (e = cudaMemcpy(p->d_tw4, t4.data(), (size_t)n * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess ||
-                (e = cudaMalloc(&p->d_scratch[0], (size_t)p->chunk_frames * n * sizeof(float2))) != cudaSuccess) {
+                (e = cudaMemcpy(p->d_tw4, t4.data(), (size_t)n * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess) {
                 rc = cuda_fail(e, "four-step tables"); break;
             }
         }
@@ -338,10 +354,40 @@ static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cu
     kp.n1 = kp.n2 = 0;
     if (p->four) {
         // N = N1 x N2: per chunk, step A (column pairs -> twiddled intermediate) then
-        // step B (row pairs -> spectrum); the intermediate never leaves L2
+        // step B (row pairs -> spectrum)
         const int n = p->cfg.fft_size, n1 = p->k4.n1, n2 = p->k4.n2;
-        if (!p->d_scratch[slot]) CU(cudaMalloc(&p->d_scratch[slot], (size_t)p->chunk_frames * n * sizeof(float2)));
+        const long want = std::min(p->chunk_frames, n_frames);
+        if (p->scratch_frames[slot] < want) {            // grow-only; cudaFree waits for work still using the old one
+            if (p->d_scratch[slot]) CU(cudaFree(p->d_scratch[slot]));
+            p->d_scratch[slot] = nullptr; p->scratch_frames[slot] = 0;
+            CU(cudaMalloc(&p->d_scratch[slot], (size_t)want * n * sizeof(float2)));
+            p->scratch_frames[slot] = want;
+        }
         void* scratch = p->d_scratch[slot];
+        if (!p->four_old) {
+            // decimation in time: A = sub-spectra of the 32 interleaved sub-sequences, B = comb
+            for (long f0 = 0; f0 < n_frames; f0 += p->chunk_frames) {
+                const long cf = std::min(p->chunk_frames, n_frames - f0);
+                fsea_kparams ka = kp, kb = kp;
+                ka.in = (const uint8_t*)d_in + (size_t)f0 * p->hop * p->sample_bytes;
+                ka.out = scratch;
+                ka.n_seq = cf * 32;
+                ka.ticket = p->d_tickets + 2 * (p->launches % fsea_plan::TICKET_SLOTS);
+                long blocks = std::min<long>(cf * 16 / p->k4.a.groups, (long)p->max_blocks);   // (>= tiles)
+                void* aa[] = {&ka};
+                CU(cudaLaunchKernel(p->k4.a.fn, dim3((unsigned)blocks), dim3((unsigned)p->k4.a.threads), aa, p->k4.a.smem, stream));
+                p->launches++;
+                kb.in = scratch;
+                kb.out = (uint8_t*)d_out + (size_t)f0 * n * p->out_elem_bytes;
+                kb.n_seq = cf * (n1 / 2);
+                kb.n1 = n1; kb.n2 = n2;
+                blocks = std::min<long>((kb.n_seq + 127) / 128, (long)p->max_blocks_b * 8);
+                void* ab[] = {&kb};
+                CU(cudaLaunchKernel(p->k4.b.fn, dim3((unsigned)blocks), dim3((unsigned)p->k4.b.threads), ab, p->k4.b.smem, stream));
+                p->launches++;
+            }
+            return FSEA_OK;
+        }
         for (long f0 = 0; f0 < n_frames; f0 += p->chunk_frames) {
             const long cf = std::min(p->chunk_frames, n_frames - f0);
             fsea_kparams ka = kp, kb = kp;

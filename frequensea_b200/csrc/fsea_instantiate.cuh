@@ -7,11 +7,13 @@ template <class SH, typename V, int FMT, int GOV = 0, int TWSOV = -1>
 struct fsea_cfg {
     static const int UNIT_BYTES = 2 * (int)sizeof(V);
     static const int SB = (int)sizeof(typename fsea_vt<V>::scalar);
-    static const bool STAGED = SH::NPASS > 1 && SB == 4 && FMT == FSEA_IN_U8;
-    static const int XBYTES = SH::NPASS > 1 ? SH::UNITS * (int)sizeof(V) + (STAGED ? fsea_vt<V>::lanes * 2 * SH::N : 0) : 0;   // exchange plane + raw ring per group
+    static const bool COLS = (FMT == FSEA_IN_COLS);
+    static const bool STAGED = SH::NPASS > 1 && SB == 4 && (FMT == FSEA_IN_U8 || COLS);
+    static const int RINGB = COLS ? 4 * fsea_cols_rounds<SH::N>::v * SH::N : fsea_vt<V>::lanes * 2 * SH::N;     // (COLS: per group, of the block's tile ring)
+    static const int XBYTES = SH::NPASS > 1 ? SH::UNITS * (int)sizeof(V) + (STAGED ? RINGB : 0) : 0;   // exchange plane + raw ring per group
     static const int TWBYTES = (SH::TW1 + SH::TW2) * 2 * SB;
     static const bool TWS = TWSOV >= 0 ? (TWSOV != 0) : (SH::NPASS > 1 && TWBYTES <= 16384);
-    static const bool TILED = (FMT == FSEA_IN_ROWS);
+    static const bool TILED = (FMT == FSEA_IN_ROWS) || COLS;
     static const int TPB = (TILED && SH::P <= 16) ? 256 : 128;                    // target threads per block
     static const int G_T = (TPB / SH::T) > 1 ? (TPB / SH::T) : 1;
     static const int G_S = XBYTES ? ((96 * 1024) / XBYTES > 1 ? (96 * 1024) / XBYTES : 1) : 1024;
@@ -19,7 +21,7 @@ struct fsea_cfg {
     static const int G_1 = (SH::T > 32 && G_0 > 15) ? 15 : G_0;                 // named barriers 1..15
     static const int G_2 = TILED ? (G_1 >= 16 ? 16 : (G_1 >= 8 ? 8 : (G_1 >= 4 ? 4 : (G_1 >= 2 ? 2 : 1)))) : G_1;   // 2G rows divide 32
     static const int G = GOV > 0 ? GOV : G_2;
-    static const size_t SMEM = (size_t)G * XBYTES + (TWS ? TWBYTES : 0);
+    static const size_t SMEM = (size_t)G * XBYTES + (COLS ? 128 : 0) + (TWS ? TWBYTES : 0);
     // resident blocks per SM the register allocator must allow: what shared memory
     // permits, capped so that a thread keeps >= REGCAP registers
     static const int REGCAP_0 = (sizeof(V) >= 8 ? (SH::P >= 32 ? 168 : (SH::P >= 16 ? 112 : 80)) : (SH::P >= 32 ? 96 : 64));

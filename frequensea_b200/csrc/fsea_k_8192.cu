@@ -1,3 +1,9 @@
-// fsea_k_8192.cu -- 8192-point instantiations (N = 32 x 16 x 16)
+// fsea_k_8192.cu -- 8192-point instantiations (N = 32 x 16 x 16; -DFSEA_S8192_R0=.. _R1 _R2 for A/B builds)
 #include "fsea_instantiate.cuh"
-FSEA_DEFINE_SIZE(8192, 32, 16, 16)
+#ifndef FSEA_S8192_R0
+#define FSEA_S8192_R0 32
+#define FSEA_S8192_R1 16
+#define FSEA_S8192_R2 16
+#endif
+#define FSEA_DEF(...) FSEA_DEFINE_SIZE(__VA_ARGS__)
+FSEA_DEF(8192, FSEA_S8192_R0, FSEA_S8192_R1, FSEA_S8192_R2)

@@ -35,8 +35,8 @@
 #include "fsea_kparams.h"
 
 // internal input / output kinds of the four-step (N = N1 x N2) kernels
-enum { FSEA_IN_ROWS = 17 };
-enum { FSEA_OK_SPECTRUM = 0, FSEA_OK_STRIDED = 2 };
+enum { FSEA_IN_ROWS = 17, FSEA_IN_COLS = 18 };
+enum { FSEA_OK_SPECTRUM = 0, FSEA_OK_STRIDED = 2, FSEA_OK_CPLX = 3 };
 
 
 template <int X> struct fsea_log2 { static const int v = 1 + fsea_log2<X / 2>::v; };
@@ -250,6 +250,77 @@ template <> struct fsea_in<FSEA_IN_ROWS, f2> {
     template <int N> __device__ __forceinline__ void load_staged_raw(const unsigned char*, int, f2&, f2&) const {}
 };
 
+// ---- four-step, decimation in time (N = N1 x 32, n = 32 n1 + n2) ------------------
+// Step A is this file's kernel on the 32 interleaved sub-sequences x[32 n1 + n2] of a frame:
+// a unit is the PAIR of neighbouring sub-sequences (n2, n2+1) -- four adjacent bytes per n1,
+// the two packed lanes.  A block takes a TILE of G x ROUNDS units of one frame and transforms
+// them in ROUNDS rounds of G; the tile's bytes (16 or 32 per n1) reach shared memory as
+// 8-byte pieces laid out ring[h][n1]
+// (h = unit pair), so a group reads its samples with one LDS.32 per point.  (Narrower
+// tiles cost LSU time out of proportion: an LDGSTS is replayed once per 128-byte line it
+// gathers from -- ncu, 8 bytes per row: 16 wavefronts per instruction instead of 2.)
+// The sub-spectra go to the intermediate as complex rows Y[n2][k1]; step B
+// (fsea_comb32_kernel, below) twiddles them and does the radix-32 across n2 in registers.
+template <int N> struct fsea_cols_rounds { static const int v = (N >= 2048) ? 2 : 1; };   // measured: see DESIGN.md
+template <> struct fsea_in<FSEA_IN_COLS, f2> {
+    const uint8_t* p;      // the unit's first byte in its frame
+    const float* win;
+    uint32_t x4;
+    __device__ __forceinline__ void init(const fsea_kparams& kp, long unit, bool& live) {
+        long s0 = 2 * unit;                                    // sub-sequence index in the batch
+        live = s0 < kp.n_seq;
+        if (!live) s0 = kp.n_seq - 2;
+        const long f = s0 >> 5;
+        const int c = (int)(s0 & 31);
+        p = (const uint8_t*)kp.in + 2 * (f * kp.seq_stride + c);
+        win = kp.window + c;
+        x4 = kp.xor_mask | (kp.xor_mask << 16);
+    }
+    __device__ __forceinline__ void load(int, f2&, f2&) const {}
+    __device__ __forceinline__ f2 window(int e) const {
+        const float2 w = __ldg((const float2*)(win + 32 * e));
+        return mk2(w.x, w.y);
+    }
+    template <int N, int T> __device__ __forceinline__ void prefetch(int) const {}
+    template <int N, int T> __device__ __forceinline__ void async_stage(int, unsigned char*) const {}
+    // ring geometry: H pieces of 8 bytes per n1; row h of the ring is N + 16/H pieces long
+    // (the pad keeps the LDGSTS writes of a half-warp on distinct banks)
+    template <int N, int G> struct ring {
+        static const int H = G * fsea_cols_rounds<N>::v / 2;
+        static const int ROW = N + 16 / H;                     // pieces per ring row
+        static const int BYTES = H * ROW * 8;
+    };
+    // all TPB threads of the block fetch the tile whose first unit is this (round-0) unit of group g
+    template <int N, int TPB, int G>
+    __device__ __forceinline__ void async_tile(int tid, int g, unsigned char* rg) const {
+        typedef ring<N, G> R;
+        static_assert((N * R::H) % TPB == 0, "tile pieces must divide over the block");
+        const uint8_t* pt = p - 4 * g;
+#pragma unroll
+        for (int c = 0; c < (N * R::H) / TPB; c++) {
+            const int q = tid + c * TPB;
+            const int n1 = q / R::H, h = q - n1 * R::H;
+            const uint32_t d = (uint32_t)__cvta_generic_to_shared(rg + ((size_t)h * R::ROW + n1) * 8);
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(pt + 64 * (size_t)n1 + 8 * h) : "memory");
+        }
+    }
+    // where unit `slot` (0 .. G ROUNDS - 1) of the tile finds its words in the ring
+    template <int N, int G>
+    static __device__ __forceinline__ const unsigned char* ring_of(const unsigned char* rg, int slot) {
+        return rg + (size_t)(slot >> 1) * ring<N, G>::ROW * 8 + (slot & 1) * 4;
+    }
+    template <int N> __device__ __forceinline__ void load_staged_raw(const unsigned char* sm, int e, f2& re, f2& im) const {
+        const uint32_t w = ((const uint32_t*)sm)[2 * e] ^ x4;
+        re = mk2(__uint_as_float(__byte_perm(w, 0x47000000u, 0x7504)), __uint_as_float(__byte_perm(w, 0x47000000u, 0x7524)));
+        im = mk2(__uint_as_float(__byte_perm(w, 0x47000000u, 0x7514)), __uint_as_float(__byte_perm(w, 0x47000000u, 0x7534)));
+    }
+    template <int N> __device__ __forceinline__ void load_staged(const unsigned char* sm, int e, f2& re, f2& im) const {
+        load_staged_raw<N>(sm, e, re, im);
+        const f2 off = mk2(32896.0f, 32896.0f);
+        re = vsub(re, off); im = vsub(im, off);
+    }
+};
+
 // ---- output side: bin k of the unit's sequence(s) ---------------------------
 // The reference's (-1)^n input modulation (src/nrf.c:611-612) is the output
 // rotation by N/2: FFT bin k is stored at position (k + N/2) mod N.  In the
@@ -407,7 +478,26 @@ __device__ __forceinline__ void fsea_strided_store(const fsea_out_strided<NTOT>&
     __syncthreads();
 }
 
+// Four-step step A: the two sub-spectra of a unit as complex rows of the intermediate.
+template <int N> struct fsea_out_cplx {
+    float2 *ra, *rb;
+    __device__ __forceinline__ void init(const fsea_kparams& kp, long unit, bool unit_live, int) {
+        ra = unit_live ? (float2*)kp.out + (size_t)(2 * unit) * N : (float2*)kp.dump;
+        rb = ra + N;
+    }
+    template <int R, int M>
+    __device__ __forceinline__ void store_sel(int, int i, const f2* re, const f2* im, bool) const {
+#pragma unroll
+        for (int m = 0; m < R; m++) {
+            ra[i + m * M] = make_float2(re[m].v.x, im[m].v.x);
+            rb[i + m * M] = make_float2(re[m].v.y, im[m].v.y);
+        }
+    }
+    __device__ __forceinline__ void dc_adjust(const fsea_kparams&, int, f2&, f2&) const {}
+};
+
 template <int OK, int N, int NTOT, typename V> struct fsea_out_sel { typedef fsea_out<N, V> type; };
+template <int N, int NTOT> struct fsea_out_sel<FSEA_OK_CPLX, N, NTOT, f2> { typedef fsea_out_cplx<N> type; };
 template <int N, int NTOT> struct fsea_out_sel<FSEA_OK_STRIDED, N, NTOT, f2> { typedef fsea_out_strided<NTOT> type; };
 
 // ---- group barrier ----------------------------------------------------------
@@ -495,14 +585,16 @@ __device__ __forceinline__ float fsea_transform(const fsea_kparams& kp, const fs
                                                 const typename fsea_cplx<V>::t* tw1, const typename fsea_cplx<V>::t* tw2,
                                                 int t, int g, int tid, bool dc_patch, int out_mode,
                                                 unsigned char* smem_base,
-                                                const typename fsea_vt<V>::scalar* wreg = nullptr) {
+                                                const typename fsea_vt<V>::scalar* wreg = nullptr,
+                                                int slot = 0, bool ring_first = true, bool ring_last = true) {
     typedef typename fsea_vt<V>::scalar S;
     typedef typename fsea_cplx<V>::t S2;
     constexpr int N = SH::N, R0 = SH::R0, R1 = SH::R1, R2 = SH::R2, P = SH::P, T = SH::T;
     constexpr int L0 = SH::L0, NPASS = SH::NPASS;
-    constexpr bool STAGED = (FMT == FSEA_IN_U8) && NPASS > 1 && sizeof(S) == 4;
+    constexpr bool COLS = (FMT == FSEA_IN_COLS);
+    constexpr bool STAGED = (FMT == FSEA_IN_U8 || COLS) && NPASS > 1 && sizeof(S) == 4;
     constexpr int XB = NPASS > 1 ? SH::UNITS * (int)sizeof(V) : 0;
-    (void)tw1; (void)tw2; (void)xp; (void)raw; (void)smem_base; (void)tid; (void)more;
+    (void)tw1; (void)tw2; (void)xp; (void)raw; (void)smem_base; (void)tid; (void)more; (void)slot; (void)ring_first; (void)ring_last;
     V re[P], im[P];
 
     // ---------------- pass 0: radix R0, p_prev = 1 ----------------
@@ -510,28 +602,40 @@ __device__ __forceinline__ float fsea_transform(const fsea_kparams& kp, const fs
         constexpr int M = N / R0, B = P / R0;
         bool raw_stage = false;                      // pass 0 ran on biased magic floats
         if (STAGED) {
-            fsea_cp_async_wait_all();
-            fsea_group_sync<T>(g);
+            // (COLS: the ring holds a tile of the BLOCK, filled once for both rounds)
+            if constexpr (COLS) { if (ring_first) { fsea_cp_async_wait_all(); __syncthreads(); } }
+            else { fsea_cp_async_wait_all(); fsea_group_sync<T>(g); }
+            const unsigned char* rg = raw;
+            if constexpr (COLS) rg = fsea_in<FSEA_IN_COLS, f2>::template ring_of<N, G>(raw, slot);
             raw_stage = !WIN;
             if (raw_stage) {
 #pragma unroll
                 for (int b = 0; b < B; b++) {
                     const int i = t + b * T;
 #pragma unroll
-                    for (int j = 0; j < R0; j++) in.template load_staged_raw<N>(raw, i + j * M, re[b * R0 + j], im[b * R0 + j]);
+                    for (int j = 0; j < R0; j++) in.template load_staged_raw<N>(rg, i + j * M, re[b * R0 + j], im[b * R0 + j]);
                 }
             } else {
 #pragma unroll
                 for (int b = 0; b < B; b++) {
                     const int i = t + b * T;
 #pragma unroll
-                    for (int j = 0; j < R0; j++) in.template load_staged<N>(raw, i + j * M, re[b * R0 + j], im[b * R0 + j]);
+                    for (int j = 0; j < R0; j++) in.template load_staged<N>(rg, i + j * M, re[b * R0 + j], im[b * R0 + j]);
                 }
             }
-            fsea_group_sync<T>(g);                   // ring is free again: fetch the next unit
-            if (more) {
-                in_next.template async_stage<N, T>(t, raw);
-                fsea_cp_async_commit();
+            // ring is free again: fetch the next unit / tile
+            if constexpr (COLS) {
+                if (ring_last) {
+                    __syncthreads();
+                    if (more) in_next.template async_tile<N, T * G, G>(tid, g, raw);
+                    fsea_cp_async_commit();
+                }
+            } else {
+                fsea_group_sync<T>(g);
+                if (more) {
+                    in_next.template async_stage<N, T>(t, raw);
+                    fsea_cp_async_commit();
+                }
             }
         } else {
             if (more) in_next.template prefetch<N, T>(t);
@@ -705,24 +809,25 @@ fsea_fft_kernel(const fsea_kparams kp) {
     constexpr int N = SH::N, R0 = SH::R0, R1 = SH::R1, R2 = SH::R2, P = SH::P, T = SH::T;
     constexpr int L0 = SH::L0, NPASS = SH::NPASS;
     constexpr int LANES = fsea_vt<V>::lanes;
-    constexpr bool STAGED = (FMT == FSEA_IN_U8) && NPASS > 1 && sizeof(S) == 4;
+    constexpr bool COLS = (FMT == FSEA_IN_COLS);
+    constexpr bool STAGED = (FMT == FSEA_IN_U8 || COLS) && NPASS > 1 && sizeof(S) == 4;
     // four-step kernels hand out TILES of G neighbouring units per block (adjacent columns /
     // rows -> contiguous bytes across the block); the others hand out single units per group
-    constexpr bool TILED = (FMT == FSEA_IN_ROWS);
+    constexpr bool TILED = (FMT == FSEA_IN_ROWS) || COLS;
     constexpr int XB = NPASS > 1 ? SH::UNITS * (int)sizeof(V) : 0;     // exchange plane bytes per group
-    constexpr int RB = STAGED ? LANES * 2 * N : 0;                      // raw ring bytes per group
+    constexpr int RB = STAGED ? (COLS ? 0 : LANES * 2 * N) : 0;        // raw ring bytes per group (COLS: one per block)
 
     extern __shared__ __align__(16) unsigned char fsea_smem[];
     const int tid = threadIdx.x;
     const int g = tid / T;
     const int t = tid - g * T;
     V* xp = reinterpret_cast<V*>(fsea_smem + (size_t)g * XB);
-    unsigned char* raw = fsea_smem + (size_t)G * XB + (size_t)g * RB;
+    unsigned char* raw = fsea_smem + (size_t)G * XB + (COLS ? 0 : (size_t)g * RB);   // COLS: one ring per block
 
     const S2* tw1 = (const S2*)kp.tw1;
     const S2* tw2 = (const S2*)kp.tw2;
     if (TWS && NPASS > 1) {
-        S2* stw = reinterpret_cast<S2*>(fsea_smem + (size_t)G * (XB + RB));
+        S2* stw = reinterpret_cast<S2*>(fsea_smem + (size_t)G * (XB + RB) + (COLS ? fsea_in<FSEA_IN_COLS, f2>::template ring<N, G>::BYTES : 0));
         for (int q = tid; q < SH::TW1 + SH::TW2; q += T * G)
             stw[q] = (q < SH::TW1) ? tw1[q] : tw2[q - SH::TW1];
         __syncthreads();
@@ -742,7 +847,8 @@ fsea_fft_kernel(const fsea_kparams kp) {
     // the ticket counter itself the bottleneck (N = 128: 0.9 G units/s) -- a WARP, which takes
     // KB units for each of its GW = 32/T groups per ticket.
     constexpr int GW = (!TILED && T < 32) ? 32 / T : 1;
-    constexpr int KB = (!TILED && T < 32) ? 8 : 1;
+    constexpr int KB = COLS ? fsea_cols_rounds<N>::v : ((!TILED && T < 32) ? 8 : 1);   // units per group and ticket
+    constexpr int STEP = TILED ? G : GW;                                        // ... and how far apart they are
     const int gw = (GW > 1) ? ((tid & 31) / T) : 0;               // group within its warp
     const bool leader = TILED ? (tid == 0) : (GW > 1 ? ((tid & 31) == 0) : (t == 0));
 
@@ -752,7 +858,7 @@ fsea_fft_kernel(const fsea_kparams kp) {
             __syncthreads();
             const unsigned tile = fsea_tile_slot;
             __syncthreads();
-            return (long)tile * G + g;
+            return (long)tile * (G * KB) + g;
         }
         if (GW > 1) {
             unsigned r;
@@ -761,7 +867,7 @@ fsea_fft_kernel(const fsea_kparams kp) {
         }
         return (long)fsea_ticket_share<T>(v, t, g, fsea_slot, late);
     };
-    const long n_claims = TILED ? (n_units + G - 1) / G * G : n_units;   // tiles run to completion
+    const long n_claims = TILED ? (n_units + G * KB - 1) / (G * KB) * (G * KB) : n_units;   // tiles run to completion
 
     unsigned pend = 0;
     if (leader) pend = fsea_take_ticket(ticket);
@@ -791,7 +897,8 @@ fsea_fft_kernel(const fsea_kparams kp) {
     bool live;
     in.init(kp, cur, live);
     if (STAGED) {                                        // prologue: first unit's bytes
-        in.template async_stage<N, T>(t, raw);
+        if constexpr (COLS) { if (live) in.template async_tile<N, T * G, G>(tid, g, raw); }
+        else in.template async_stage<N, T>(t, raw);
         fsea_cp_async_commit();
     }
 
@@ -800,7 +907,7 @@ fsea_fft_kernel(const fsea_kparams kp) {
         const bool last_of_ticket = (kb == KB - 1);
         if (leader && kb == 0) pend = fsea_take_ticket(ticket);   // the ticket after next; read at the bottom
         const long unit = cur;
-        const long nxt = last_of_ticket ? nxt_base : cur + GW;
+        const long nxt = last_of_ticket ? nxt_base : cur + STEP;
         typename fsea_out_sel<OK, N, NTOT, V>::type out;
         out.init(kp, live ? unit : 0, live, out_esz);
         fsea_in<FMT, V> in_next;
@@ -810,7 +917,8 @@ fsea_fft_kernel(const fsea_kparams kp) {
 
         const float probe = fsea_transform<SH, V, FMT, OK, NTOT, G, WIN>(kp, in, in_next, more, out, xp, raw, tw1, tw2,
                                                                          t, g, tid, dc_patch, out_mode, fsea_smem,
-                                                                         WREG ? wreg : nullptr);
+                                                                         WREG ? wreg : nullptr,
+                                                                         kb * G + g, kb == 0, last_of_ticket);
         if (NPASS > 1) fsea_group_sync<T>(g);                      // the next unit rewrites the exchange plane
         in = in_next;
         live = live_next;
@@ -889,5 +997,75 @@ fsea_cols32_kernel(const fsea_kparams kp) {
         fsea_cols32_pair<WIN>((const uint8_t*)kp.in + 2 * (f * kp.seq_stride + c), WIN ? kp.window + c : nullptr,
                               (const float4*)((const float2*)kp.tw4 + c),
                               (float4*)((float2*)kp.out + (size_t)f * 32 * n2 + c), n2, x4);
+    }
+}
+
+// ---- four-step, step B: twiddle + radix-32 across the 32 sub-spectra, all in registers ----
+// Thread = one pair of neighbouring bins (k, k+1), k < N1, of one frame: 32 float4 loads of
+// Y[n2][k..k+1] (a warp covers 512 contiguous bytes of every row), the four-step twiddles
+// W_N^{n2 k} built from the five table rows n2 = 1, 2, 4, 8, 16 (at most four complex
+// products deep), one packed radix-32 codelet, and 32 stores of spectrum positions
+// k + N1 (m ^ 16) (a warp covers 256 contiguous bytes each; the xor is the reference's
+// (-1)^n, src/nrf.c:611-612).
+template <int OUT>
+__global__ void __launch_bounds__(128, 3)
+fsea_comb32_kernel(const fsea_kparams kp) {
+    const int n1 = kp.n1;                                  // sub-spectrum length N1 = N / 32
+    const int hp = n1 >> 1;                                // bin pairs per frame
+    const long pairs = kp.n_seq;
+    const bool dc_patch = (kp.flags & FSEA_FLAG_DC_PATCH) != 0;
+    constexpr int ESZ = (OUT == FSEA_OUT_PIX) ? 1 : 4;
+    for (long u = (long)blockIdx.x * blockDim.x + threadIdx.x; u < pairs; u += (long)gridDim.x * blockDim.x) {
+        const long f = u / hp;
+        const int k = 2 * (int)(u - f * hp);
+        const float4* y = (const float4*)((const float2*)kp.in + (size_t)f * 32 * n1 + k);
+        f2 re[32], im[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const float4 v = __ldcg(y + (size_t)j * hp);                   // L2 only: written by step A
+            re[j] = mk2(v.x, v.z); im[j] = mk2(v.y, v.w);
+        }
+        f2 br[5], bi[5];                                                     // W^(2^r k), r = 0..4
+#pragma unroll
+        for (int r = 0; r < 5; r++) {
+            const float4 w = __ldg((const float4*)((const float2*)kp.tw4 + (size_t)r * n1 + k));
+            br[r] = mk2(w.x, w.z); bi[r] = mk2(w.y, w.w);
+        }
+        f2 wr[32], wi[32];                                                   // (only a chain of <= 5 is live at a time)
+#pragma unroll
+        for (int j = 1; j < 32; j++) {
+            const int low = j & -j;
+            const int r = (low == 1) ? 0 : (low == 2) ? 1 : (low == 4) ? 2 : (low == 8) ? 3 : 4;
+            if (j == low) { wr[j] = br[r]; wi[j] = bi[r]; }
+            else {
+                const int q = j - low;
+                wr[j] = vsub(vmul(wr[q], br[r]), vmul(wi[q], bi[r]));
+                wi[j] = vfma2(wr[q], bi[r], vmul(wi[q], br[r]));
+            }
+            const f2 a = vsub(vmul(re[j], wr[j]), vmul(im[j], wi[j]));
+            im[j] = vfma2(re[j], wi[j], vmul(im[j], wr[j]));
+            re[j] = a;
+        }
+        fsea_dft32<f2>(re, im);
+        if (kp.dc_term && k == 0) { re[0].v.x += 16.0f * (float)n1; im[0].v.x += 16.0f * (float)n1; }   // N/2 (1+i)
+        uint8_t* row = (uint8_t*)kp.out + (size_t)f * 32 * n1 * ESZ;
+#pragma unroll
+        for (int m = 0; m < 32; m++) {
+            const f2 pw = vfma2(re[m], re[m], vmul(im[m], im[m]));
+            uint8_t* dst = row + ((size_t)k + (size_t)n1 * (m ^ 16)) * ESZ;
+            __align__(8) unsigned char tmp[8];
+            fsea_tile_put<OUT>(tmp, pw, kp.pix_scale);
+            if (m == 0 && dc_patch && k == 0) {                              // bin 0 is not stored (src/nrf.c:621-622)
+                if (ESZ == 4) ((float*)dst)[1] = ((const float*)tmp)[1]; else dst[1] = tmp[1];
+            } else if (ESZ == 4) {
+                *(float2*)dst = *(const float2*)tmp;
+            } else {
+                *(uchar2*)dst = *(const uchar2*)tmp;
+            }
+            if (m == 31 && dc_patch && k == n1 - 2) {                        // bin N-1 also fills the DC slot N/2
+                uint8_t* dc = row + (size_t)16 * n1 * ESZ;
+                if (ESZ == 4) ((float*)dc)[0] = ((const float*)tmp)[1]; else dc[0] = tmp[1];
+            }
+        }
     }
 }
