@@ -41,11 +41,13 @@ FSEA_DECL_SIZE(4096)
 FSEA_DECL_SIZE(8192)
 #undef FSEA_DECL_SIZE
 
-// Four-step plans (N = N1 x N2 >= 16384): step A transforms column pairs into an
-// L2-resident intermediate, step B transforms row pairs into the spectrum.
+// Four-step plans (N = N1 x 32 >= 16384): step A (`a`) transforms the 32 interleaved
+// sub-sequences of every frame into an intermediate, step B (`b`) combs them into the spectrum.
 struct fsea_kernel_info4 {
     fsea_kernel_info a, b;
     int n1, n2;
+    const void* fused;       // both steps in one kernel (geometry of `a`, clusters of `cs` blocks), or nullptr
+    int cs;
+    const char* fused_name;
 };
 bool fsea_get_kernel4(int n, bool window, int out_mode, fsea_kernel_info4* out);
-bool fsea_get_kernel4_old(int n, bool window, fsea_kernel_info4* out);

@@ -83,16 +83,17 @@ struct fsea_plan {
     unsigned* d_tickets = nullptr;             // TICKET_SLOTS x {ticket, done}, zero between launches
     static const int TICKET_SLOTS = 64;
     void* d_dump = nullptr;
-    // four-step (N >= 16384): two kernels per chunk of frames, intermediate kept L2-sized
+    // four-step (N >= 16384)
     bool four = false;
-    bool four_old = false;
+    bool fused = false;                          // both steps in one cluster kernel (intermediate stays in L2)
+    int max_clusters = 0;
     fsea_kernel_info4 k4;
-    void *d_tw1b = nullptr, *d_tw2b = nullptr;   // step-B sub-FFT tables (step A uses d_tw1/d_tw2)
-    void* d_tw4 = nullptr;                       // W_N^{n2 k1}, float2 [N1][N2]
+    void* d_tw4 = nullptr;                       // comb twiddles: W_N^{2^r k}, r < 5, as cos / sin planes
     static const int SCRATCH_SLOTS = 4;           // slot 0: fsea_exec_device, 1..3: host pipeline stages
     void* d_scratch[SCRATCH_SLOTS] = {nullptr, nullptr, nullptr, nullptr};   // chunk_frames x N float2 each
     long chunk_frames = 0;
     long scratch_frames[SCRATCH_SLOTS] = {0, 0, 0, 0};
+    void* d_cscratch[SCRATCH_SLOTS] = {nullptr, nullptr, nullptr, nullptr};   // fused: max_clusters x N float2 each
     int max_blocks_b = 0;
 };
 
@@ -165,10 +166,9 @@ extern "C" int fsea_plan_destroy(fsea_plan* p) {
     if (p->d_gate) cudaFree(p->d_gate);
     if (p->d_tickets) cudaFree(p->d_tickets);
     if (p->d_dump) cudaFree(p->d_dump);
-    if (p->d_tw1b) cudaFree(p->d_tw1b);
-    if (p->d_tw2b) cudaFree(p->d_tw2b);
     if (p->d_tw4) cudaFree(p->d_tw4);
     for (int q = 0; q < fsea_plan::SCRATCH_SLOTS; q++) if (p->d_scratch[q]) cudaFree(p->d_scratch[q]);
+    for (int q = 0; q < fsea_plan::SCRATCH_SLOTS; q++) if (p->d_cscratch[q]) cudaFree(p->d_cscratch[q]);
     delete p;
     return FSEA_OK;
 }
@@ -212,9 +212,7 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
     if (n < 16 || n > 65536 || (n & (n - 1))) return FSEA_ERR_UNSUPPORTED;
     fsea_get_kernel_fn get = size_table(n);
     fsea_kernel_info4 k4;
-    const bool four_old = getenv("FSEA_FOUR_OLD") != nullptr;          // A/B against the previous organisation
-    const bool four = !get && (four_old ? fsea_get_kernel4_old(n, cfg->window == FSEA_WIN_HANN, &k4)
-                                        : fsea_get_kernel4(n, cfg->window == FSEA_WIN_HANN, cfg->out_mode, &k4));
+    const bool four = !get && fsea_get_kernel4(n, cfg->window == FSEA_WIN_HANN, cfg->out_mode, &k4);
     if (!get && !four) return FSEA_ERR_UNSUPPORTED;
     if (four && cfg->in_format != FSEA_IN_U8 && cfg->in_format != FSEA_IN_S8) return FSEA_ERR_UNSUPPORTED;
     if (cfg->in_format < FSEA_IN_U8 || cfg->in_format > FSEA_IN_F64C) return FSEA_ERR_INVALID;
@@ -243,7 +241,6 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
     }
     if (four) {
         p->four = true;
-        p->four_old = four_old;
         p->k4 = k4;
         p->ki = k4.a;                     // step A doubles as "the" kernel for tables, lanes, names
         p->variant = FSEA_VAR_F32X2;
@@ -261,40 +258,50 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
         if (!p->four && (rc = upload_twiddles(p->ki, &p->d_tw1, &p->d_tw2, staged ? 1.0f / 256.0f : 1.0f)) != FSEA_OK) break;
         if (p->four) {
             if ((rc = setup_kernel(p->k4.b, cfg->device, &p->max_blocks_b)) != FSEA_OK) break;
-            const int n1 = p->k4.n1, n2 = p->k4.n2;
+            const int n1 = p->k4.n1;
             std::vector<float2> t4((size_t)n);
             const long double PI2 = 6.283185307179586476925286766559005768L;
-            if (p->four_old) {
-                if ((rc = upload_twiddles(p->k4.b, &p->d_tw1b, &p->d_tw2b)) != FSEA_OK) break;
-                for (int k1 = 0; k1 < n1; k1++)
-                    for (int c = 0; c < n2; c++) {
-                        const long double a = -PI2 * (long double)((long)k1 * c) / (long double)n;
-                        // step A leaves integer-scaled samples: 1/256 (src/nrf.c:605-606) rides here, exactly
-                        t4[(size_t)k1 * n2 + c].x = (float)(cosl(a) / 256.0L);
-                        t4[(size_t)k1 * n2 + c].y = (float)(sinl(a) / 256.0L);
-                    }
-            } else {
+            {
                 // step A is a staged kernel: 1/256 rides on its pass-1 twiddles.  Step B builds
                 // W_N^{n2 k} from the rows n2 = 1, 2, 4, 8, 16 of this table.
                 if ((rc = upload_twiddles(p->k4.a, &p->d_tw1, &p->d_tw2, 1.0f / 256.0f)) != FSEA_OK) break;
+                float* t4f = (float*)t4.data();                 // planes: row 2r = cos, row 2r+1 = sin
                 for (int r = 0; r < 5; r++)
                     for (int k = 0; k < n1; k++) {
                         const long double a = -PI2 * (long double)(((long)k) << r) / (long double)n;
-                        t4[(size_t)r * n1 + k].x = (float)cosl(a);
-                        t4[(size_t)r * n1 + k].y = (float)sinl(a);
+                        t4f[(size_t)(2 * r) * n1 + k] = (float)cosl(a);
+                        t4f[(size_t)(2 * r + 1) * n1 + k] = (float)sinl(a);
                     }
             }
-            // The intermediate (8 bytes per point) is streamed through HBM in chunks of at most
-            // 2 GiB, allocated on first use at the size the call needs (grow-only).
-            // Keeping it L2-resident was tried twice -- 32 MiB chunks (two launches per 64 frames:
-            // launch-bound, 2x slower) and a persistent fused kernel with per-frame dependency
-            // counters (5-10 % slower: the row step is LSU/latency-bound, not DRAM-bound) -- see DESIGN.md.
+            // Two-launch form: the intermediate (8 bytes per point) is streamed through HBM in
+            // chunks of at most 2 GiB, allocated on first use at the size the call needs
+            // (grow-only; L2-sized chunks are launch-bound: 8.7 vs 15 M frames/s at N = 16384).
             long chunk_mb = 2048;
             if (const char* ev = getenv("FSEA_CHUNK_MB")) chunk_mb = std::max(1L, atol(ev));   // experiments
             p->chunk_frames = std::max<long>(1, (chunk_mb << 20) / ((long)n * 8));
             if ((e = cudaMalloc(&p->d_tw4, (size_t)n * sizeof(float2))) != cudaSuccess ||
                 (e = cudaMemcpy(p->d_tw4, t4.data(), (size_t)n * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess) {
                 rc = cuda_fail(e, "four-step tables"); break;
+            }
+        }
+        if (p->four && p->k4.fused && !getenv("FSEA_FOUR_SPLIT")) {       // (FSEA_FOUR_SPLIT: A/B against the two-launch form)
+            // cluster launch geometry: how many clusters of `cs` blocks are resident at once
+            cudaLaunchConfig_t lc;
+            memset(&lc, 0, sizeof(lc));
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = p->k4.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            lc.gridDim = dim3((unsigned)(p->k4.cs * 64)); lc.blockDim = dim3((unsigned)p->k4.a.threads);
+            lc.dynamicSmemBytes = p->k4.a.smem; lc.attrs = at; lc.numAttrs = 1;
+            int nc = 0;
+            if ((e = cudaFuncSetAttribute(p->k4.fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->k4.a.smem)) != cudaSuccess ||
+                (e = cudaOccupancyMaxActiveClusters(&nc, p->k4.fused, &lc)) != cudaSuccess) {
+                rc = cuda_fail(e, "cluster kernel setup"); break;
+            }
+            if (nc > 0) {
+                p->fused = true;
+                p->max_clusters = nc;
+                p->ki.name = p->k4.fused_name;
             }
         }
         if ((e = cudaMalloc(&p->d_tickets, sizeof(unsigned) * 2 * fsea_plan::TICKET_SLOTS)) != cudaSuccess ||
@@ -352,10 +359,27 @@ static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cu
     kp.dump = p->d_dump;
     kp.tw4 = p->d_tw4;
     kp.n1 = kp.n2 = 0;
+    kp.scratch = nullptr;
     if (p->four) {
-        // N = N1 x N2: per chunk, step A (column pairs -> twiddled intermediate) then
-        // step B (row pairs -> spectrum)
-        const int n = p->cfg.fft_size, n1 = p->k4.n1, n2 = p->k4.n2;
+        // N = N1 x 32 (decimation in time)
+        const int n = p->cfg.fft_size, n1 = p->k4.n1;
+        if (p->fused) {
+            // one launch: a cluster per frame, the intermediate lives in the clusters' L2-resident slots
+            if (!p->d_cscratch[slot]) CU(cudaMalloc(&p->d_cscratch[slot], (size_t)p->max_clusters * n * sizeof(float2)));
+            kp.scratch = p->d_cscratch[slot];
+            const long nc = std::min<long>(n_frames, p->max_clusters);
+            cudaLaunchConfig_t lc;
+            memset(&lc, 0, sizeof(lc));
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = p->k4.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            lc.gridDim = dim3((unsigned)(nc * p->k4.cs)); lc.blockDim = dim3((unsigned)p->k4.a.threads);
+            lc.dynamicSmemBytes = p->k4.a.smem; lc.stream = stream; lc.attrs = at; lc.numAttrs = 1;
+            void* af[] = {&kp};
+            CU(cudaLaunchKernelExC(&lc, p->k4.fused, af));
+            p->launches++;
+            return FSEA_OK;
+        }
         const long want = std::min(p->chunk_frames, n_frames);
         if (p->scratch_frames[slot] < want) {            // grow-only; cudaFree waits for work still using the old one
             if (p->d_scratch[slot]) CU(cudaFree(p->d_scratch[slot]));
@@ -364,8 +388,8 @@ static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cu
             p->scratch_frames[slot] = want;
         }
         void* scratch = p->d_scratch[slot];
-        if (!p->four_old) {
-            // decimation in time: A = sub-spectra of the 32 interleaved sub-sequences, B = comb
+        {
+            // two launches per chunk: A = sub-spectra of the 32 interleaved sub-sequences, B = comb
             for (long f0 = 0; f0 < n_frames; f0 += p->chunk_frames) {
                 const long cf = std::min(p->chunk_frames, n_frames - f0);
                 fsea_kparams ka = kp, kb = kp;
@@ -380,7 +404,6 @@ static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cu
                 kb.in = scratch;
                 kb.out = (uint8_t*)d_out + (size_t)f0 * n * p->out_elem_bytes;
                 kb.n_seq = cf * (n1 / 2);
-                kb.n1 = n1; kb.n2 = n2;
                 blocks = std::min<long>((kb.n_seq + 127) / 128, (long)p->max_blocks_b * 8);
                 void* ab[] = {&kb};
                 CU(cudaLaunchKernel(p->k4.b.fn, dim3((unsigned)blocks), dim3((unsigned)p->k4.b.threads), ab, p->k4.b.smem, stream));
@@ -388,32 +411,6 @@ static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cu
             }
             return FSEA_OK;
         }
-        for (long f0 = 0; f0 < n_frames; f0 += p->chunk_frames) {
-            const long cf = std::min(p->chunk_frames, n_frames - f0);
-            fsea_kparams ka = kp, kb = kp;
-            ka.in = (const uint8_t*)d_in + (size_t)f0 * p->hop * p->sample_bytes;
-            ka.out = scratch;
-            ka.n_seq = cf * n2;
-            ka.n1 = n1; ka.n2 = n2;
-            ka.ticket = p->d_tickets + 2 * (p->launches % fsea_plan::TICKET_SLOTS);
-            long units = ka.n_seq / 2, blocks = std::min<long>((units + p->k4.a.threads - 1) / p->k4.a.threads, (long)p->max_blocks * 4);
-            void* aa[] = {&ka};
-            CU(cudaLaunchKernel(p->k4.a.fn, dim3((unsigned)blocks), dim3((unsigned)p->k4.a.threads), aa, p->k4.a.smem, stream));
-            p->launches++;
-            kb.in = scratch;
-            kb.out = (uint8_t*)d_out + (size_t)f0 * n * p->out_elem_bytes;
-            kb.n_seq = cf * n1;
-            kb.n1 = n1; kb.n2 = n2;
-            kb.tw1 = p->d_tw1b; kb.tw2 = p->d_tw2b;
-            kb.window = nullptr;
-            kb.ticket = p->d_tickets + 2 * (p->launches % fsea_plan::TICKET_SLOTS);
-            units = kb.n_seq / 2;
-            blocks = std::min<long>((units + p->k4.b.groups - 1) / p->k4.b.groups, p->max_blocks_b);
-            void* ab[] = {&kb};
-            CU(cudaLaunchKernel(p->k4.b.fn, dim3((unsigned)blocks), dim3((unsigned)p->k4.b.threads), ab, p->k4.b.smem, stream));
-            p->launches++;
-        }
-        return FSEA_OK;
     }
     kp.ticket = p->d_tickets + 2 * (p->launches % fsea_plan::TICKET_SLOTS);
     const long units = (n_frames + p->ki.lanes - 1) / p->ki.lanes;

@@ -13,7 +13,7 @@ struct fsea_cfg {
     static const int XBYTES = SH::NPASS > 1 ? SH::UNITS * (int)sizeof(V) + (STAGED ? RINGB : 0) : 0;   // exchange plane + raw ring per group
     static const int TWBYTES = (SH::TW1 + SH::TW2) * 2 * SB;
     static const bool TWS = TWSOV >= 0 ? (TWSOV != 0) : (SH::NPASS > 1 && TWBYTES <= 16384);
-    static const bool TILED = (FMT == FSEA_IN_ROWS) || COLS;
+    static const bool TILED = COLS;
     static const int TPB = (TILED && SH::P <= 16) ? 256 : 128;                    // target threads per block
     static const int G_T = (TPB / SH::T) > 1 ? (TPB / SH::T) : 1;
     static const int G_S = XBYTES ? ((96 * 1024) / XBYTES > 1 ? (96 * 1024) / XBYTES : 1) : 1024;

@@ -1,27 +1,5 @@
-// fsea_k4.cu -- four-step instantiations for N = 16384, 32768, 65536 (N = 32 x N2).
+// fsea_k4.cu -- four-step instantiations for N = 16384, 32768, 65536 (N = N1 x 32).
 #include "fsea_instantiate.cuh"
-
-template <int NTOT, class SHB>
-static bool fill4(fsea_kernel_info4* o, const char* na, const char* nb, bool window) {
-    // step A: the in-register column kernel (its own launch geometry)
-    o->a.fn = window ? (const void*)&fsea_cols32_kernel<true> : (const void*)&fsea_cols32_kernel<false>;
-    o->a.threads = 128; o->a.groups = 128; o->a.lanes = 2; o->a.smem = 0;
-    o->a.n = 32; o->a.r0 = 32; o->a.r1 = 1; o->a.r2 = 1; o->a.tw1 = 0; o->a.tw2 = 0; o->a.scalar_bytes = 4;
-    o->a.name = na;
-    fsea_fill<SHB, f2, FSEA_IN_ROWS, FSEA_OK_STRIDED, NTOT>(&o->b, nb);
-    o->n1 = 32;
-    o->n2 = SHB::N;
-    return true;
-}
-
-bool fsea_get_kernel4_old(int n, bool window, fsea_kernel_info4* out) {
-    switch (n) {
-        case 16384: return fill4<16384, fsea_shape<512, 32, 16, 1>>(out, "fft4<16384=32x512: cols32 + rows 32x16,f32x2>", "fft4B<16384: rows 512=32x16,f32x2>", window);
-        case 32768: return fill4<32768, fsea_shape<1024, 32, 32, 1>>(out, "fft4<32768=32x1024: cols32 + rows 32x32,f32x2>", "fft4B<32768: rows 1024=32x32,f32x2>", window);
-        case 65536: return fill4<65536, fsea_shape<2048, 32, 8, 8>>(out, "fft4<65536=32x2048: cols32 + rows 32x8x8,f32x2>", "fft4B<65536: rows 2048=32x8x8,f32x2>", window);
-    }
-    return false;
-}
 
 // ---- decimation in time: step A = N1-point transforms of the 32 interleaved sub-sequences
 // (fsea_fft_kernel, COLS loader, complex rows out), step B = fsea_comb32_kernel ----
@@ -34,9 +12,9 @@ template <class SHA, int TWS = -1>
 static bool fill4dit(fsea_kernel_info4* o, const char* na, const char* nb, bool window, int out_mode) {
     if (window) fsea_fill<SHA, f2, FSEA_IN_COLS, FSEA_OK_CPLX, SHA::N, true, 0, TWS>(&o->a, na);
     else fsea_fill<SHA, f2, FSEA_IN_COLS, FSEA_OK_CPLX, SHA::N, false, 0, TWS>(&o->a, na);
-    o->b.fn = out_mode == FSEA_OUT_MAG ? (const void*)&fsea_comb32_kernel<FSEA_OUT_MAG>
-            : out_mode == FSEA_OUT_LOGMAG ? (const void*)&fsea_comb32_kernel<FSEA_OUT_LOGMAG>
-                                          : (const void*)&fsea_comb32_kernel<FSEA_OUT_PIX>;
+    o->b.fn = out_mode == FSEA_OUT_MAG ? (const void*)&fsea_comb32_kernel<FSEA_OUT_MAG, SHA::N>
+            : out_mode == FSEA_OUT_LOGMAG ? (const void*)&fsea_comb32_kernel<FSEA_OUT_LOGMAG, SHA::N>
+                                          : (const void*)&fsea_comb32_kernel<FSEA_OUT_PIX, SHA::N>;
     o->b.threads = 128; o->b.groups = 128; o->b.lanes = 2; o->b.smem = 0;
     o->b.n = 32; o->b.r0 = 32; o->b.r1 = 1; o->b.r2 = 1; o->b.tw1 = 0; o->b.tw2 = 0; o->b.scalar_bytes = 4;
     o->b.name = nb;
@@ -45,11 +23,31 @@ static bool fill4dit(fsea_kernel_info4* o, const char* na, const char* nb, bool 
     return true;
 }
 
+// both steps in one kernel, a cluster of CS blocks per frame (fsea_fused4_kernel)
+template <class SHA, int CS>
+static void fill_fused(fsea_kernel_info4* o, bool window, int out_mode, const char* name) {
+    typedef fsea_cfg<SHA, f2, FSEA_IN_COLS> C;
+#define FSEA_FUSED(W, O) (const void*)&fsea_fused4_kernel<SHA, C::G, C::TWS, C::MINB, W, O, CS>
+    o->fused = window ? (out_mode == FSEA_OUT_MAG ? FSEA_FUSED(true, FSEA_OUT_MAG) : out_mode == FSEA_OUT_LOGMAG ? FSEA_FUSED(true, FSEA_OUT_LOGMAG) : FSEA_FUSED(true, FSEA_OUT_PIX))
+                      : (out_mode == FSEA_OUT_MAG ? FSEA_FUSED(false, FSEA_OUT_MAG) : out_mode == FSEA_OUT_LOGMAG ? FSEA_FUSED(false, FSEA_OUT_LOGMAG) : FSEA_FUSED(false, FSEA_OUT_PIX));
+#undef FSEA_FUSED
+    o->cs = CS;
+    o->fused_name = name;
+}
+
 bool fsea_get_kernel4(int n, bool window, int out_mode, fsea_kernel_info4* out) {
     switch (n) {
-        case 16384: return fill4dit<fsea_shape<512, 32, 16, 1>>(out, "fft4<16384=512x32: sub 32x16 + comb32,f32x2>", "fft4B<16384: comb32>", window, out_mode);
-        case 32768: return fill4dit<fsea_shape<1024, 32, 32, 1>>(out, "fft4<32768=1024x32: sub 32x32 + comb32,f32x2>", "fft4B<32768: comb32>", window, out_mode);
-        case 65536: return fill4dit<fsea_shape<2048, 32, 8, 8>, FSEA_COLS2048_TWS>(out, "fft4<65536=2048x32: sub 32x8x8 + comb32,f32x2>", "fft4B<65536: comb32>", window, out_mode);
+        case 16384:
+            fill_fused<fsea_shape<512, 32, 16, 1>, 2>(out, window, out_mode, "fft4<16384=512x32: sub 32x16 + comb32, cluster 2, f32x2>");
+            return fill4dit<fsea_shape<512, 32, 16, 1>>(out, "fft4<16384=512x32: sub 32x16 + comb32,f32x2>", "fft4B<16384: comb32>", window, out_mode);
+        case 32768:
+            fill_fused<fsea_shape<1024, 32, 32, 1>, 4>(out, window, out_mode, "fft4<32768=1024x32: sub 32x32 + comb32, cluster 4, f32x2>");
+            return fill4dit<fsea_shape<1024, 32, 32, 1>>(out, "fft4<32768=1024x32: sub 32x32 + comb32,f32x2>", "fft4B<32768: comb32>", window, out_mode);
+        case 65536:
+            // (a cluster-of-4 fused kernel was measured at 3.38 vs 3.46 M frames/s for the two launches:
+            //  2 resident blocks per SM leave the barrier phases exposed)
+            out->fused = nullptr; out->cs = 0; out->fused_name = "";
+            return fill4dit<fsea_shape<2048, 32, 8, 8>, FSEA_COLS2048_TWS>(out, "fft4<65536=2048x32: sub 32x8x8 + comb32,f32x2>", "fft4B<65536: comb32>", window, out_mode);
     }
     return false;
 }

@@ -35,8 +35,8 @@
 #include "fsea_kparams.h"
 
 // internal input / output kinds of the four-step (N = N1 x N2) kernels
-enum { FSEA_IN_ROWS = 17, FSEA_IN_COLS = 18 };
-enum { FSEA_OK_SPECTRUM = 0, FSEA_OK_STRIDED = 2, FSEA_OK_CPLX = 3 };
+enum { FSEA_IN_COLS = 18 };
+enum { FSEA_OK_SPECTRUM = 0, FSEA_OK_CPLX = 3 };
 
 
 template <int X> struct fsea_log2 { static const int v = 1 + fsea_log2<X / 2>::v; };
@@ -219,37 +219,6 @@ template <> struct fsea_in<FSEA_IN_F64C, double> {
     template <int N> __device__ __forceinline__ void load_staged_raw(const unsigned char*, int, double&, double&) const {}
 };
 
-// ---- four-step (N = 32 x N2, SURVEY 7 "N = 65536") ------------------------------
-// Step A (fsea_cols32_kernel, below) transforms the N2 columns of a frame with one
-// radix-32 register codelet per column pair -- lanes are neighbouring columns, so every
-// load and store is a contiguous 128- or 512-byte row piece and no shared memory is
-// involved -- and leaves Y[k1][n2] (k1 < 32) in an intermediate buffer.
-// Step B is this file's kernel on the rows: a unit is a PAIR OF ADJACENT ROWS (k1, k1+1),
-// (step A already applied the four-step twiddle W_N^{n2 k1}), and the bins
-// k1 + 32 k2 of the block's rows are assembled in shared memory into contiguous pieces.
-template <> struct fsea_in<FSEA_IN_ROWS, f2> {
-    const float2 *pa, *pb;
-    __device__ __forceinline__ void init(const fsea_kparams& kp, long unit, bool& live) {
-        long s0 = 2 * unit;
-        live = s0 < kp.n_seq;
-        if (!live) s0 = kp.n_seq - 2;
-        pa = (const float2*)kp.in + s0 * kp.n2;
-        pb = pa + kp.n2;
-    }
-    __device__ __forceinline__ void load(int e, f2& re, f2& im) const {
-        const float2 a = __ldcg(pa + e), b = __ldcg(pb + e);       // L2 only: written by step A
-        re = mk2(a.x, b.x); im = mk2(a.y, b.y);
-    }
-    __device__ __forceinline__ f2 window(int) const { return mk2(1.f, 1.f); }
-    template <int N, int T> __device__ __forceinline__ void prefetch(int t) const {
-        fsea_prefetch_seq<N * 8, T>((const uint8_t*)pa, t);
-        fsea_prefetch_seq<N * 8, T>((const uint8_t*)pb, t);
-    }
-    template <int N, int T> __device__ __forceinline__ void async_stage(int, unsigned char*) const {}
-    template <int N> __device__ __forceinline__ void load_staged(const unsigned char*, int, f2&, f2&) const {}
-    template <int N> __device__ __forceinline__ void load_staged_raw(const unsigned char*, int, f2&, f2&) const {}
-};
-
 // ---- four-step, decimation in time (N = N1 x 32, n = 32 n1 + n2) ------------------
 // Step A is this file's kernel on the 32 interleaved sub-sequences x[32 n1 + n2] of a frame:
 // a unit is the PAIR of neighbouring sub-sequences (n2, n2+1) -- four adjacent bytes per n1,
@@ -388,32 +357,6 @@ template <int N, typename V> struct fsea_out {
     }
 };
 
-// Four-step, step B: rows (k1, k1+1) of a frame; FFT bin k2 of row k1 is spectrum bin
-// k1 + 32 k2.  A block holds G units = 2G neighbouring rows, so for every k2 its 2G bins
-// are contiguous in the spectrum: the values are first written to a shared-memory tile
-// [k2][2G] and then copied out as contiguous pieces (fsea_strided_store, below).
-template <int NTOT> struct fsea_out_strided {
-    uint8_t* row;          // spectrum row of the unit's frame
-    int k1, n1;
-    bool live;
-    float pix_scale;
-    __device__ __forceinline__ void init(const fsea_kparams& kp, long unit, bool unit_live, int esz) {
-        long s0 = 2 * unit;
-        live = unit_live;
-        if (!live) s0 = kp.n_seq - 2;
-        n1 = kp.n1;
-        const long f = s0 / n1;
-        k1 = (int)(s0 - f * n1);
-        pix_scale = kp.pix_scale;
-        row = (uint8_t*)kp.out + (size_t)f * NTOT * esz;
-    }
-    template <int R, int M>
-    __device__ __forceinline__ void store_sel(int, int, const f2*, const f2*, bool) const {}   // unused (staged path)
-    __device__ __forceinline__ void dc_adjust(const fsea_kparams& kp, int t, f2& re0, f2& im0) const {
-        if (kp.dc_term && t == 0 && k1 == 0) { re0.v.x += (float)(NTOT / 2); im0.v.x += (float)(NTOT / 2); }
-    }
-};
-
 // values of one bin pair in the output element type
 template <int OUT> __device__ __forceinline__ void fsea_tile_put(unsigned char* p, f2 pw, float pix_scale) {
     if (OUT == FSEA_OUT_MAG) *(float2*)p = make_float2(fsea_sqrt_approx(pw.v.x), fsea_sqrt_approx(pw.v.y));
@@ -421,76 +364,30 @@ template <int OUT> __device__ __forceinline__ void fsea_tile_put(unsigned char* 
     else *(uchar2*)p = make_uchar2(fsea_pix(fsea_db(pw.v.x), pix_scale), fsea_pix(fsea_db(pw.v.y), pix_scale));
 }
 
-// Last pass of step B: the block's bins -> shared tile -> contiguous global pieces, in
-// ROUNDS rounds of R / ROUNDS values of m (the tile reuses the exchange planes).
-template <int OUT, int NTOT, int G, int T, int R, int M, int B, int REGION>
-__device__ __forceinline__ void fsea_strided_store(const fsea_out_strided<NTOT>& out, int t, int g, int tid,
-                                                   const f2* re, const f2* im, bool dc_patch, unsigned char* tile) {
-    constexpr int ESZ = (OUT == FSEA_OUT_PIX) ? 1 : 4;
-    constexpr int ROWB = 2 * G * ESZ;                     // bytes of one k2 row of the tile
-    constexpr int PITCH = ROWB + 8;
-    constexpr int ROUNDS = (R * M * PITCH <= REGION) ? 1 : ((R * M * PITCH <= 2 * REGION) ? 2 : (R * M * PITCH <= 4 * REGION ? 4 : R));
-    constexpr int MR = R / ROUNDS;
-    static_assert(MR >= 1 && MR * M * PITCH <= REGION, "output tile does not fit the exchange region");
-    constexpr int CB = (ROWB % 8 == 0) ? 8 : 4;           // bytes per copied piece
-    static_assert(ROWB % 4 == 0, "a block must hold at least two units (four rows)");
-    constexpr int CPR = ROWB / CB;                        // pieces per row
-    const int k1_0 = out.k1 - 2 * g;                      // first row of the block's tile (2G-aligned)
-    const int n1 = out.n1;
-#pragma unroll
-    for (int r = 0; r < ROUNDS; r++) {
-        __syncthreads();                                  // planes / previous round's tile are free
-#pragma unroll
-        for (int b = 0; b < B; b++) {
-            const int i = t + b * T;
-#pragma unroll
-            for (int mm = 0; mm < MR; mm++) {
-                const int m = r * MR + mm;
-                const f2 pw = vfma2(re[b * R + m], re[b * R + m], vmul(im[b * R + m], im[b * R + m]));
-                fsea_tile_put<OUT>(tile + (size_t)(i + mm * M) * PITCH + 2 * g * ESZ, pw, out.pix_scale);
-                // bin N-1 = row 31, last k2: it also fills the DC slot N/2 (src/nrf.c:621-622)
-                if (dc_patch && out.live && m == R - 1 && i == M - 1 && out.k1 + 2 == n1) {
-                    __align__(8) unsigned char tmp[8];
-                    fsea_tile_put<OUT>(tmp, pw, out.pix_scale);
-                    if (ESZ == 4) ((float*)out.row)[NTOT / 2] = ((float*)tmp)[1];
-                    else out.row[NTOT / 2] = tmp[1];
-                }
-            }
-        }
-        __syncthreads();
-        // contiguous pieces: tile row k2 holds spectrum positions (n1 k2 + k1_0 + N/2) mod N ...
-        for (int q = tid; q < MR * M * CPR; q += T * G) {
-            const int rr = q / CPR, cc = q - rr * CPR;
-            const int k2 = r * MR * M + rr;
-            const int pos = ((n1 * k2 + k1_0 + NTOT / 2) & (NTOT - 1)) + cc * (CB / ESZ);
-            const unsigned char* src = tile + (size_t)rr * PITCH + cc * CB;
-            unsigned char* dst = out.row + (size_t)pos * ESZ;
-            if (dc_patch && k2 == 0 && k1_0 == 0 && cc == 0) {           // bin 0 is overwritten by bin N-1
-                if (ESZ == 4) ((float*)dst)[1] = ((const float*)src)[1];
-                else { for (int z = 1; z < CB; z++) dst[z] = src[z]; }
-            } else if (CB == 8) {
-                *(uint2*)dst = *(const uint2*)src;        // (tiles never straddle frames: 2G divides 32)
-            } else {
-                *(uint32_t*)dst = *(const uint32_t*)src;
-            }
-        }
-    }
-    __syncthreads();
-}
-
-// Four-step step A: the two sub-spectra of a unit as complex rows of the intermediate.
+// Four-step step A: the two sub-spectra of a unit as rows of the intermediate, which is kept as
+// two float planes per frame, Yre[32][N1] then Yim[32][N1]: step A stores lanes of its packed
+// registers as they are and step B loads bin PAIRS (k, k+1) of a plane straight into packed
+// registers (an interleaved re/im layout cost ~450 MOVs per thread of repacking in step B).
 template <int N> struct fsea_out_cplx {
-    float2 *ra, *rb;
+    float *ra, *rb;                                       // re rows of the unit's two sub-sequences; im at + 32 N
     __device__ __forceinline__ void init(const fsea_kparams& kp, long unit, bool unit_live, int) {
-        ra = unit_live ? (float2*)kp.out + (size_t)(2 * unit) * N : (float2*)kp.dump;
+        const long f = unit >> 4;
+        const int u16 = (int)(unit & 15);
+        ra = unit_live ? (float*)kp.out + (size_t)f * 64 * N + (size_t)(2 * u16) * N : (float*)kp.dump;
+        rb = ra + N;
+    }
+    __device__ __forceinline__ void set(float* frame_base, int u16) {
+        ra = frame_base + (size_t)(2 * u16) * N;
         rb = ra + N;
     }
     template <int R, int M>
     __device__ __forceinline__ void store_sel(int, int i, const f2* re, const f2* im, bool) const {
 #pragma unroll
         for (int m = 0; m < R; m++) {
-            ra[i + m * M] = make_float2(re[m].v.x, im[m].v.x);
-            rb[i + m * M] = make_float2(re[m].v.y, im[m].v.y);
+            ra[i + m * M] = re[m].v.x;
+            rb[i + m * M] = re[m].v.y;
+            ra[32 * N + i + m * M] = im[m].v.x;
+            rb[32 * N + i + m * M] = im[m].v.y;
         }
     }
     __device__ __forceinline__ void dc_adjust(const fsea_kparams&, int, f2&, f2&) const {}
@@ -498,7 +395,6 @@ template <int N> struct fsea_out_cplx {
 
 template <int OK, int N, int NTOT, typename V> struct fsea_out_sel { typedef fsea_out<N, V> type; };
 template <int N, int NTOT> struct fsea_out_sel<FSEA_OK_CPLX, N, NTOT, f2> { typedef fsea_out_cplx<N> type; };
-template <int N, int NTOT> struct fsea_out_sel<FSEA_OK_STRIDED, N, NTOT, f2> { typedef fsea_out_strided<NTOT> type; };
 
 // ---- group barrier ----------------------------------------------------------
 template <int T> __device__ __forceinline__ void fsea_group_sync(int group) {
@@ -721,16 +617,9 @@ __device__ __forceinline__ float fsea_transform(const fsea_kparams& kp, const fs
         if constexpr (NPASS == 2) {
             // N = R0 R1: i < R0 = M, k = i, bins i + m R0
             out.dc_adjust(kp, t, re[0], im[0]);
-            if constexpr (OK == FSEA_OK_STRIDED) {
-                unsigned char* tile = smem_base;
-                if (out_mode == FSEA_OUT_MAG) fsea_strided_store<FSEA_OUT_MAG, NTOT, G, T, R1, M, B, G * XB>(out, t, g, tid, re, im, dc_patch, tile);
-                else if (out_mode == FSEA_OUT_LOGMAG) fsea_strided_store<FSEA_OUT_LOGMAG, NTOT, G, T, R1, M, B, G * XB>(out, t, g, tid, re, im, dc_patch, tile);
-                else fsea_strided_store<FSEA_OUT_PIX, NTOT, G, T, R1, M, B, G * XB>(out, t, g, tid, re, im, dc_patch, tile);
-            } else {
 #pragma unroll
-                for (int b = 0; b < B; b++)
-                    out.template store_sel<R1, M>(out_mode, t + b * T, re + b * R1, im + b * R1, dc_patch);
-            }
+            for (int b = 0; b < B; b++)
+                out.template store_sel<R1, M>(out_mode, t + b * T, re + b * R1, im + b * R1, dc_patch);
         }
     }
     if constexpr (NPASS > 2) {
@@ -779,16 +668,9 @@ __device__ __forceinline__ float fsea_transform(const fsea_kparams& kp, const fs
 #pragma unroll
         for (int b = 0; b < B; b++) fsea_dft<R2, V>::run(re + b * R2, im + b * R2);
         out.dc_adjust(kp, t, re[0], im[0]);
-        if constexpr (OK == FSEA_OK_STRIDED) {
-            unsigned char* tile = smem_base;
-            if (out_mode == FSEA_OUT_MAG) fsea_strided_store<FSEA_OUT_MAG, NTOT, G, T, R2, M, B, G * XB>(out, t, g, tid, re, im, dc_patch, tile);
-            else if (out_mode == FSEA_OUT_LOGMAG) fsea_strided_store<FSEA_OUT_LOGMAG, NTOT, G, T, R2, M, B, G * XB>(out, t, g, tid, re, im, dc_patch, tile);
-            else fsea_strided_store<FSEA_OUT_PIX, NTOT, G, T, R2, M, B, G * XB>(out, t, g, tid, re, im, dc_patch, tile);
-        } else {
 #pragma unroll
-            for (int b = 0; b < B; b++)
-                out.template store_sel<R2, M>(out_mode, t + b * T, re + b * R2, im + b * R2, dc_patch);
-        }
+        for (int b = 0; b < B; b++)
+            out.template store_sel<R2, M>(out_mode, t + b * T, re + b * R2, im + b * R2, dc_patch);
     }
     return (float)fsea_lane(re[P - 1], 0);
 }
@@ -813,7 +695,7 @@ fsea_fft_kernel(const fsea_kparams kp) {
     constexpr bool STAGED = (FMT == FSEA_IN_U8 || COLS) && NPASS > 1 && sizeof(S) == 4;
     // four-step kernels hand out TILES of G neighbouring units per block (adjacent columns /
     // rows -> contiguous bytes across the block); the others hand out single units per group
-    constexpr bool TILED = (FMT == FSEA_IN_ROWS) || COLS;
+    constexpr bool TILED = COLS;
     constexpr int XB = NPASS > 1 ? SH::UNITS * (int)sizeof(V) : 0;     // exchange plane bytes per group
     constexpr int RB = STAGED ? (COLS ? 0 : LANES * 2 * N) : 0;        // raw ring bytes per group (COLS: one per block)
 
@@ -945,61 +827,6 @@ fsea_fft_kernel(const fsea_kparams kp) {
     }
 }
 
-// ---- four-step, step A: radix-32 over the columns, all in registers -----------------
-// Thread = one pair of neighbouring columns (n2, n2+1) of one frame: 32 strided 32-bit
-// loads (a warp covers 128 contiguous bytes of every row), one packed radix-32 codelet,
-// 32 float4 stores (a warp covers 512 contiguous bytes of every output row).  Samples stay
-// integer-scaled (b - 128); the 1/256 of src/nrf.c:605-606 rides on the four-step twiddles.
-// one column pair: frame base `p` (already offset to the pair's first column), output `o`
-template <bool WIN>
-__device__ __forceinline__ void fsea_cols32_pair(const uint8_t* p, const float* win, const float4* tw, float4* o,
-                                                 long n2, uint32_t x4) {
-    f2 re[32], im[32];
-#pragma unroll
-    for (int j = 0; j < 32; j++) {
-        const uint32_t w = __ldg((const uint32_t*)(p + (size_t)j * 2 * n2)) ^ x4;
-        re[j] = mk2(__uint_as_float(__byte_perm(w, 0x47000000u, 0x7504)), __uint_as_float(__byte_perm(w, 0x47000000u, 0x7524)));
-        im[j] = mk2(__uint_as_float(__byte_perm(w, 0x47000000u, 0x7514)), __uint_as_float(__byte_perm(w, 0x47000000u, 0x7534)));
-    }
-    if (WIN) {
-        const f2 off = mk2(32896.0f, 32896.0f);
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-            const float2 w = __ldg((const float2*)(win + (size_t)j * n2));
-            re[j] = vmul(vsub(re[j], off), mk2(w.x, w.y));
-            im[j] = vmul(vsub(im[j], off), mk2(w.x, w.y));
-        }
-        fsea_dft32<f2>(re, im);
-    } else {
-        fsea_dft32_raw<f2>(re, im);
-    }
-    // four-step twiddle W_N^{n2 k1} (x 1/256): the column step is DRAM-bound with the LSU at
-    // 17 %, so the table (L2-resident, 8 N bytes) is read here rather than in the row step
-#pragma unroll
-    for (int k1 = 0; k1 < 32; k1++) {
-        const float4 w = __ldg(tw + (size_t)k1 * (n2 / 2));              // (wA.re, wA.im, wB.re, wB.im)
-        const f2 wr = mk2(w.x, w.z), wi = mk2(w.y, w.w);
-        const f2 r = vsub(vmul(re[k1], wr), vmul(im[k1], wi));
-        const f2 q = vfma2(re[k1], wi, vmul(im[k1], wr));
-        o[(size_t)k1 * (n2 / 2)] = make_float4(r.v.x, q.v.x, r.v.y, q.v.y);
-    }
-}
-
-template <bool WIN>
-__global__ void __launch_bounds__(128, 3)
-fsea_cols32_kernel(const fsea_kparams kp) {
-    const long pairs = kp.n_seq / 2;                       // column pairs in the chunk
-    const long n2 = kp.n2;
-    const uint32_t x4 = kp.xor_mask | (kp.xor_mask << 16);
-    for (long u = (long)blockIdx.x * blockDim.x + threadIdx.x; u < pairs; u += (long)gridDim.x * blockDim.x) {
-        const long s0 = 2 * u;
-        const long f = s0 / n2, c = s0 - f * n2;
-        fsea_cols32_pair<WIN>((const uint8_t*)kp.in + 2 * (f * kp.seq_stride + c), WIN ? kp.window + c : nullptr,
-                              (const float4*)((const float2*)kp.tw4 + c),
-                              (float4*)((float2*)kp.out + (size_t)f * 32 * n2 + c), n2, x4);
-    }
-}
-
 // ---- four-step, step B: twiddle + radix-32 across the 32 sub-spectra, all in registers ----
 // Thread = one pair of neighbouring bins (k, k+1), k < N1, of one frame: 32 float4 loads of
 // Y[n2][k..k+1] (a warp covers 512 contiguous bytes of every row), the four-step twiddles
@@ -1007,65 +834,176 @@ fsea_cols32_kernel(const fsea_kparams kp) {
 // products deep), one packed radix-32 codelet, and 32 stores of spectrum positions
 // k + N1 (m ^ 16) (a warp covers 256 contiguous bytes each; the xor is the reference's
 // (-1)^n, src/nrf.c:611-612).
-template <int OUT>
+// one bin pair (k, k+1) of one frame: y = &Yre[0][k] of the frame, row = its spectrum row
+// ARRIVE: the fused kernel's "intermediate consumed" signal (see fsea_fused4_kernel)
+template <int OUT, int ARRIVE, int N1>
+__device__ __forceinline__ void fsea_comb32_pair(const fsea_kparams& kp, const float2* y, int k, uint8_t* row, bool dc_patch) {
+    constexpr int ESZ = (OUT == FSEA_OUT_PIX) ? 1 : 4;
+    constexpr int n1 = N1;
+    constexpr int hp = N1 >> 1;
+    f2 re[32], im[32];
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        const float2 a = __ldcg(y + (size_t)j * hp);                    // L2 only: written by step A
+        const float2 b = __ldcg(y + (size_t)(32 + j) * hp);
+        re[j] = mk2(a.x, a.y); im[j] = mk2(b.x, b.y);
+    }
+    f2 br[5], bi[5];                                                     // W^(2^r k), r = 0..4
+#pragma unroll
+    for (int r = 0; r < 5; r++) {
+        const float2 wa = __ldg((const float2*)((const float*)kp.tw4 + (size_t)(2 * r) * n1 + k));       // re plane
+        const float2 wb = __ldg((const float2*)((const float*)kp.tw4 + (size_t)(2 * r + 1) * n1 + k));   // im plane
+        br[r] = mk2(wa.x, wa.y); bi[r] = mk2(wb.x, wb.y);
+    }
+    f2 wr[32], wi[32];                                                   // (only a chain of <= 5 is live at a time)
+#pragma unroll
+    for (int j = 1; j < 32; j++) {
+        const int low = j & -j;
+        const int r = (low == 1) ? 0 : (low == 2) ? 1 : (low == 4) ? 2 : (low == 8) ? 3 : 4;
+        if (j == low) { wr[j] = br[r]; wi[j] = bi[r]; }
+        else {
+            const int q = j - low;
+            wr[j] = vsub(vmul(wr[q], br[r]), vmul(wi[q], bi[r]));
+            wi[j] = vfma2(wr[q], bi[r], vmul(wi[q], br[r]));
+        }
+        const f2 a = vsub(vmul(re[j], wr[j]), vmul(im[j], wi[j]));
+        im[j] = vfma2(re[j], wi[j], vmul(im[j], wr[j]));
+        re[j] = a;
+    }
+    // fused kernel: the intermediate has been consumed -- the cluster may overwrite it
+    // (relaxed when nothing is published here: the loads above have delivered their values)
+    if (ARRIVE == 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    fsea_dft32<f2>(re, im);
+    if (kp.dc_term && k == 0) { re[0].v.x += 16.0f * (float)n1; im[0].v.x += 16.0f * (float)n1; }   // N/2 (1+i)
+#pragma unroll
+    for (int m = 0; m < 32; m++) {
+        const f2 pw = vfma2(re[m], re[m], vmul(im[m], im[m]));
+        uint8_t* dst = row + ((size_t)k + (size_t)n1 * (m ^ 16)) * ESZ;
+        __align__(8) unsigned char tmp[8];
+        fsea_tile_put<OUT>(tmp, pw, kp.pix_scale);
+        if (m == 0 && dc_patch && k == 0) {                              // bin 0 is not stored (src/nrf.c:621-622)
+            if (ESZ == 4) ((float*)dst)[1] = ((const float*)tmp)[1]; else dst[1] = tmp[1];
+        } else if (ESZ == 4) {
+            *(float2*)dst = *(const float2*)tmp;
+        } else {
+            *(uchar2*)dst = *(const uchar2*)tmp;
+        }
+        if (m == 31 && dc_patch && k == n1 - 2) {                        // bin N-1 also fills the DC slot N/2
+            uint8_t* dc = row + (size_t)16 * n1 * ESZ;
+            if (ESZ == 4) ((float*)dc)[0] = ((const float*)tmp)[1]; else dc[0] = tmp[1];
+        }
+    }
+}
+
+template <int OUT, int N1>
 __global__ void __launch_bounds__(128, 3)
 fsea_comb32_kernel(const fsea_kparams kp) {
-    const int n1 = kp.n1;                                  // sub-spectrum length N1 = N / 32
-    const int hp = n1 >> 1;                                // bin pairs per frame
+    constexpr int n1 = N1;                                 // sub-spectrum length N1 = N / 32
+    constexpr int hp = n1 >> 1;                            // bin pairs per frame
     const long pairs = kp.n_seq;
     const bool dc_patch = (kp.flags & FSEA_FLAG_DC_PATCH) != 0;
     constexpr int ESZ = (OUT == FSEA_OUT_PIX) ? 1 : 4;
     for (long u = (long)blockIdx.x * blockDim.x + threadIdx.x; u < pairs; u += (long)gridDim.x * blockDim.x) {
         const long f = u / hp;
         const int k = 2 * (int)(u - f * hp);
-        const float4* y = (const float4*)((const float2*)kp.in + (size_t)f * 32 * n1 + k);
-        f2 re[32], im[32];
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-            const float4 v = __ldcg(y + (size_t)j * hp);                   // L2 only: written by step A
-            re[j] = mk2(v.x, v.z); im[j] = mk2(v.y, v.w);
-        }
-        f2 br[5], bi[5];                                                     // W^(2^r k), r = 0..4
-#pragma unroll
-        for (int r = 0; r < 5; r++) {
-            const float4 w = __ldg((const float4*)((const float2*)kp.tw4 + (size_t)r * n1 + k));
-            br[r] = mk2(w.x, w.z); bi[r] = mk2(w.y, w.w);
-        }
-        f2 wr[32], wi[32];                                                   // (only a chain of <= 5 is live at a time)
-#pragma unroll
-        for (int j = 1; j < 32; j++) {
-            const int low = j & -j;
-            const int r = (low == 1) ? 0 : (low == 2) ? 1 : (low == 4) ? 2 : (low == 8) ? 3 : 4;
-            if (j == low) { wr[j] = br[r]; wi[j] = bi[r]; }
-            else {
-                const int q = j - low;
-                wr[j] = vsub(vmul(wr[q], br[r]), vmul(wi[q], bi[r]));
-                wi[j] = vfma2(wr[q], bi[r], vmul(wi[q], br[r]));
-            }
-            const f2 a = vsub(vmul(re[j], wr[j]), vmul(im[j], wi[j]));
-            im[j] = vfma2(re[j], wi[j], vmul(im[j], wr[j]));
-            re[j] = a;
-        }
-        fsea_dft32<f2>(re, im);
-        if (kp.dc_term && k == 0) { re[0].v.x += 16.0f * (float)n1; im[0].v.x += 16.0f * (float)n1; }   // N/2 (1+i)
-        uint8_t* row = (uint8_t*)kp.out + (size_t)f * 32 * n1 * ESZ;
-#pragma unroll
-        for (int m = 0; m < 32; m++) {
-            const f2 pw = vfma2(re[m], re[m], vmul(im[m], im[m]));
-            uint8_t* dst = row + ((size_t)k + (size_t)n1 * (m ^ 16)) * ESZ;
-            __align__(8) unsigned char tmp[8];
-            fsea_tile_put<OUT>(tmp, pw, kp.pix_scale);
-            if (m == 0 && dc_patch && k == 0) {                              // bin 0 is not stored (src/nrf.c:621-622)
-                if (ESZ == 4) ((float*)dst)[1] = ((const float*)tmp)[1]; else dst[1] = tmp[1];
-            } else if (ESZ == 4) {
-                *(float2*)dst = *(const float2*)tmp;
-            } else {
-                *(uchar2*)dst = *(const uchar2*)tmp;
-            }
-            if (m == 31 && dc_patch && k == n1 - 2) {                        // bin N-1 also fills the DC slot N/2
-                uint8_t* dc = row + (size_t)16 * n1 * ESZ;
-                if (ESZ == 4) ((float*)dc)[0] = ((const float*)tmp)[1]; else dc[0] = tmp[1];
-            }
-        }
+        fsea_comb32_pair<OUT, 0, N1>(kp, (const float2*)((const float*)kp.in + (size_t)f * 64 * n1 + k), k,
+                                         (uint8_t*)kp.out + (size_t)f * 32 * n1 * ESZ, dc_patch);
     }
 }
+
+// ---- four-step, both steps in one kernel: a thread-block CLUSTER per frame -------------------
+// The CS blocks of a cluster transform the sub-sequences of one frame (one tile each, step A),
+// meet at the cluster barrier, and each combs its share of the frame's bins (step B).  The
+// intermediate of a frame (8 N bytes) is written and read back within microseconds by blocks
+// of the same GPC: it lives in L2 (resident clusters x 8 N bytes = 28..57 MB) and never
+// reaches HBM, which leaves the algorithmic 2 + 4 bytes per point as the only DRAM traffic.
+// Frames are dealt to clusters round-robin.  Two barrier phases per frame: "sub-spectra
+// published" (release/acquire, exposed) and "intermediate consumed" (relaxed arrive as soon as
+// step B's loads have landed, waited for at the top of the next frame: hidden).  A two-slot
+// variant that runs step A of frame i ahead of step B of frame i-1 was measured equal
+// (19.6 M frames/s at N = 16384) at twice the L2 footprint, so it is not kept.
+__device__ __forceinline__ unsigned fsea_cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned fsea_cluster_id() { unsigned r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned fsea_cluster_count() { unsigned r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+
+template <class SH, int G, bool TWS, int MINB, bool WIN, int OUT, int CS>
+__global__ void __launch_bounds__(SH::T* G, MINB)
+fsea_fused4_kernel(const fsea_kparams kp) {
+    typedef float2 S2;
+    typedef fsea_in<FSEA_IN_COLS, f2> IN;
+    constexpr int N = SH::N, T = SH::T, NPASS = SH::NPASS;
+    constexpr int RND = fsea_cols_rounds<N>::v;
+    constexpr int UPT = G * RND;                                    // units per tile = per block and frame
+    static_assert(UPT * CS == 16, "the cluster's tiles must cover the 16 unit pairs of a frame");
+    constexpr int XB = SH::UNITS * (int)sizeof(f2);
+    constexpr int ESZ = (OUT == FSEA_OUT_PIX) ? 1 : 4;
+    constexpr int PPB = (N / 2) / CS;                               // bin pairs per block and frame
+    constexpr int BIT = PPB / (T * G);                              // step-B passes of the block per frame
+    static_assert(PPB % (T * G) == 0, "bin pairs must divide over the block");
+
+    extern __shared__ __align__(16) unsigned char fsea_smem[];
+    const int tid = threadIdx.x;
+    const int g = tid / T;
+    const int t = tid - g * T;
+    f2* xp = reinterpret_cast<f2*>(fsea_smem + (size_t)g * XB);
+    unsigned char* ring = fsea_smem + (size_t)G * XB;
+    const S2* tw1 = (const S2*)kp.tw1;
+    const S2* tw2 = (const S2*)kp.tw2;
+    if (TWS) {
+        S2* stw = reinterpret_cast<S2*>(fsea_smem + (size_t)G * XB + IN::template ring<N, G>::BYTES);
+        for (int q = tid; q < SH::TW1 + SH::TW2; q += T * G) stw[q] = (q < SH::TW1) ? tw1[q] : tw2[q - SH::TW1];
+        __syncthreads();
+        tw1 = stw;
+        tw2 = stw + SH::TW1;
+    }
+    const bool dc_patch = (kp.flags & FSEA_FLAG_DC_PATCH) != 0;
+    const unsigned crank = fsea_cluster_ctarank();
+    const long frames = kp.n_seq;
+    const long step = fsea_cluster_count();
+    float* scr = (float*)kp.scratch + (size_t)fsea_cluster_id() * 64 * N;   // the cluster's slot: Yre[32][N], Yim[32][N]
+    fsea_kparams kc = kp;                                            // the loader counts sub-sequences
+    kc.n_seq = frames * 32;
+
+    long f = fsea_cluster_id();
+    {
+        IN in;
+        bool live;
+        in.init(kc, f * 16 + crank * UPT + g, live);
+        if (f < frames) in.template async_tile<N, T * G, G>(tid, g, ring);
+        fsea_cp_async_commit();
+    }
+    // step A of frame f: this block's tile -> the sub-spectra rows of slot `dst`
+    auto step_a = [&](long fa, float* dst) {
+        const bool more = fa + step < frames;
+#pragma unroll 1
+        for (int r = 0; r < RND; r++) {
+            const int u16 = crank * UPT + r * G + g;                 // unit pair of the frame
+            IN in_r, in_next;
+            bool lv;
+            in_r.init(kc, fa * 16 + u16, lv);
+            in_next.init(kc, (fa + step) * 16 + crank * UPT + g, lv);
+            fsea_out_cplx<N> out;
+            out.set(dst, u16);
+            fsea_transform<SH, f2, FSEA_IN_COLS, FSEA_OK_CPLX, N, G, WIN>(kc, in_r, in_next, more, out, xp, ring, tw1, tw2, t, g, tid,
+                                                                          false, 0, fsea_smem, nullptr, r * G + g, r == 0, r == RND - 1);
+            if (NPASS > 1) fsea_group_sync<T>(g);
+        }
+    };
+    bool pending = false;                                        // an arrive of the "intermediate consumed" phase
+    for (; f < frames; f += step) {
+        if (pending) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        step_a(f, scr);
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        uint8_t* row = (uint8_t*)kp.out + (size_t)f * 32 * N * ESZ;
+#pragma unroll 1
+        for (int it = 0; it < BIT; it++) {
+            const int k = 2 * ((int)crank * PPB + it * (T * G) + tid);
+            if (it == BIT - 1) fsea_comb32_pair<OUT, 1, N>(kp, (const float2*)(scr + k), k, row, dc_patch);
+            else fsea_comb32_pair<OUT, 0, N>(kp, (const float2*)(scr + k), k, row, dc_patch);
+        }
+        pending = true;
+    }
+    if (pending) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
