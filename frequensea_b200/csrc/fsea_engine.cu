@@ -18,6 +18,13 @@
 #include "fsea_dispatch.h"
 #include "fsea_kparams.h"
 
+// plain (non-table) kernel launches; -DFSEA_EMU (tests/emu/, test infrastructure) runs them on the CPU fiber machine
+#if defined(FSEA_EMU)
+#define FSEA_LAUNCH(kernel, grid, block, stream, ...) fsea_emu::launch(dim3(grid), dim3(block), 0, 1, [=] { kernel(__VA_ARGS__); })
+#else
+#define FSEA_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#endif
+
 // ------------------------------------------------------------------ errors
 static thread_local char g_cuda_err[256] = "";
 
@@ -544,7 +551,7 @@ extern "C" int fsea_gate_mean_host(fsea_plan* p, const void* h_in, long rows, do
         if ((e = cudaMemset(p->d_gate, 0, sizeof(double))) != cudaSuccess) { rc = cuda_fail(e, "memset"); break; }
         if ((rc = launch(p, d_in, d_out, rows, 0)) != FSEA_OK) break;
         const long n = rows * p->cfg.fft_size;
-        fsea_sum_kernel<<<256, 256>>>((const float*)d_out, n, p->d_gate);
+        FSEA_LAUNCH(fsea_sum_kernel, 256, 256, (cudaStream_t)0, (const float*)d_out, n, p->d_gate);
         p->launches++;
         double total = 0;
         if ((e = cudaMemcpy(&total, p->d_gate, sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess) { rc = cuda_fail(e, "D2H"); break; }
@@ -595,7 +602,7 @@ extern "C" int fsea_stitch_device(const uint8_t* d_images, int n_images, int row
     const int out_width = width + (n_images - 1) * width_step;
     const long quads = (long)rows * ((out_width + 3) / 4);
     const int blocks = (int)std::min<long>((quads + 255) / 256, 148 * 16);
-    fsea_stitch_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(d_images, n_images, rows, width, width_step, out_width, d_out);
+    FSEA_LAUNCH(fsea_stitch_kernel, blocks, 256, (cudaStream_t)stream, d_images, n_images, rows, width, width_step, out_width, d_out);
     CU(cudaGetLastError());
     return FSEA_OK;
 }

@@ -30,6 +30,7 @@
 // N/2 (1+i) in bin N/2 (exact by linearity, keeps fp32 error at 1e-7).
 #pragma once
 #include <stdint.h>
+#include "fsea_ptx.cuh"
 #include "fsea_codelets.cuh"
 #include "../../include/fsea.h"
 #include "fsea_kparams.h"
@@ -57,11 +58,6 @@ struct fsea_shape {
 };
 
 // ---- scalar helpers ---------------------------------------------------------
-__device__ __forceinline__ float fsea_sqrt_approx(float x) {
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
 __device__ __forceinline__ float fsea_db(float pwr) {          // 10 log10(pwr + 1e-20)
     return 3.010299956639812f * __log2f(pwr + 1.0e-20f);
 }
@@ -90,9 +86,6 @@ __device__ __forceinline__ float fsea_lane(f2 v, int l) { return l ? v.v.y : v.v
 // argument) or FSEA_IN_F32C.
 template <int FMT, typename V> struct fsea_in;
 
-__device__ __forceinline__ void fsea_prefetch_l2(const void* p) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-}
 // every thread of the group touches its share of the sequence's 128-byte lines
 template <int BYTES, int T>
 __device__ __forceinline__ void fsea_prefetch_seq(const uint8_t* p, int t) {
@@ -269,8 +262,7 @@ template <> struct fsea_in<FSEA_IN_COLS, f2> {
         for (int c = 0; c < (N * R::H) / TPB; c++) {
             const int q = tid + c * TPB;
             const int n1 = q / R::H, h = q - n1 * R::H;
-            const uint32_t d = (uint32_t)__cvta_generic_to_shared(rg + ((size_t)h * R::ROW + n1) * 8);
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(pt + 64 * (size_t)n1 + 8 * h) : "memory");
+            fsea_cp_async8(rg + ((size_t)h * R::ROW + n1) * 8, pt + 64 * (size_t)n1 + 8 * h);
         }
     }
     // where unit `slot` (0 .. G ROUNDS - 1) of the tile finds its words in the ring
@@ -401,17 +393,9 @@ template <int T> __device__ __forceinline__ void fsea_group_sync(int group) {
     if (T <= 32) {
         __syncwarp();
     } else {
-        asm volatile("bar.sync %0, %1;" ::"r"(group + 1), "n"(T) : "memory");
+        fsea_bar_sync<T>(group + 1);
     }
 }
-
-// ---- asynchronous global -> shared copies (LDGSTS, 16 bytes, L2 only) ----------
-__device__ __forceinline__ void fsea_cp_async16(void* smem_dst, const void* gsrc) {
-    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void fsea_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void fsea_cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // one frame of 8-bit IQ (2N bytes) -> shared memory, 16-byte pieces spread over the group
 template <int N, int T>
@@ -435,14 +419,7 @@ __device__ __forceinline__ void fsea_in<FMT, f2>::async_stage(int t, unsigned ch
 }
 
 // ---- dynamic work distribution ------------------------------------------------
-// atom.add as opaque PTX: nvcc turns atomicAdd() in a one-lane branch into its
-// warp-aggregated form (elect + atom + SHFL of the result), and that compiler-made SHFL
-// waits for the atomic's round trip right where it is issued.
-__device__ __forceinline__ unsigned fsea_take_ticket(unsigned* counter) {
-    unsigned old;
-    asm volatile("atom.global.inc.u32 %0, [%1], 0xfffffffe;" : "=r"(old) : "l"(counter) : "memory");
-    return old;
-}
+__device__ __forceinline__ unsigned fsea_take_ticket(unsigned* counter) { return fsea_atom_inc(counter); }
 
 // Units are handed out by a global ticket counter instead of a fixed stride:
 // the SM's warp arbiter is not fair, and with a static split the favoured
@@ -458,10 +435,7 @@ __device__ __forceinline__ unsigned fsea_ticket_share(unsigned v, int t, int g, 
         // atomic's whole round trip (ncu: 6.7 % of all stall samples on this one SHFL).
         // `late` is a value computed from the last stored bin that is always 0 but not
         // provably so; adding it to the source lane pins the shuffle behind the epilogue.
-        unsigned r;
-        const int src = (threadIdx.x & 31) - t + late;
-        asm volatile("shfl.sync.idx.b32 %0, %1, %2, 0x1f, 0xffffffff;" : "=r"(r) : "r"(v), "r"(src) : "memory");
-        return r;
+        return fsea_shfl_idx(v, (int)(threadIdx.x & 31) - t + late);
     } else {
         if (t == 0) slot[g] = v;
         fsea_group_sync<T>(g);
@@ -699,7 +673,7 @@ fsea_fft_kernel(const fsea_kparams kp) {
     constexpr int XB = NPASS > 1 ? SH::UNITS * (int)sizeof(V) : 0;     // exchange plane bytes per group
     constexpr int RB = STAGED ? (COLS ? 0 : LANES * 2 * N) : 0;        // raw ring bytes per group (COLS: one per block)
 
-    extern __shared__ __align__(16) unsigned char fsea_smem[];
+    FSEA_DYN_SMEM(fsea_smem);
     const int tid = threadIdx.x;
     const int g = tid / T;
     const int t = tid - g * T;
@@ -722,8 +696,9 @@ fsea_fft_kernel(const fsea_kparams kp) {
     const int out_esz = (out_mode == FSEA_OUT_PIX) ? 1 : (int)sizeof(S);
     const long n_units = (kp.n_seq + LANES - 1) / LANES;
     unsigned* ticket = kp.ticket;                                 // [0] next unit, [1] blocks finished
-    __shared__ unsigned fsea_slot[G > 0 ? G : 1];
-    __shared__ unsigned fsea_tile_slot;
+    FSEA_STATIC_SMEM(unsigned, fsea_slot, G > 0 ? G : 1);
+    FSEA_STATIC_SMEM(unsigned, fsea_tile_slot_, 1);
+    unsigned& fsea_tile_slot = fsea_tile_slot_[0];
     // Scheduling entity and ticket size: a block (TILED: one tile of G units), a group
     // (T >= 32: one unit), or -- for small transforms, where one atomic per unit would make
     // the ticket counter itself the bottleneck (N = 128: 0.9 G units/s) -- a WARP, which takes
@@ -743,8 +718,7 @@ fsea_fft_kernel(const fsea_kparams kp) {
             return (long)tile * (G * KB) + g;
         }
         if (GW > 1) {
-            unsigned r;
-            asm volatile("shfl.sync.idx.b32 %0, %1, %2, 0x1f, 0xffffffff;" : "=r"(r) : "r"(v), "r"(late) : "memory");
+            const unsigned r = fsea_shfl_idx(v, late);
             return (long)r * (GW * KB) + gw;
         }
         return (long)fsea_ticket_share<T>(v, t, g, fsea_slot, late);
@@ -872,7 +846,7 @@ __device__ __forceinline__ void fsea_comb32_pair(const fsea_kparams& kp, const f
     }
     // fused kernel: the intermediate has been consumed -- the cluster may overwrite it
     // (relaxed when nothing is published here: the loads above have delivered their values)
-    if (ARRIVE == 1) asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    if (ARRIVE == 1) fsea_cluster_arrive_relaxed();
     fsea_dft32<f2>(re, im);
     if (kp.dc_term && k == 0) { re[0].v.x += 16.0f * (float)n1; im[0].v.x += 16.0f * (float)n1; }   // N/2 (1+i)
 #pragma unroll
@@ -922,9 +896,6 @@ fsea_comb32_kernel(const fsea_kparams kp) {
 // step B's loads have landed, waited for at the top of the next frame: hidden).  A two-slot
 // variant that runs step A of frame i ahead of step B of frame i-1 was measured equal
 // (19.6 M frames/s at N = 16384) at twice the L2 footprint, so it is not kept.
-__device__ __forceinline__ unsigned fsea_cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
-__device__ __forceinline__ unsigned fsea_cluster_id() { unsigned r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
-__device__ __forceinline__ unsigned fsea_cluster_count() { unsigned r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
 
 template <class SH, int G, bool TWS, int MINB, bool WIN, int OUT, int CS>
 __global__ void __launch_bounds__(SH::T* G, MINB)
@@ -941,7 +912,7 @@ fsea_fused4_kernel(const fsea_kparams kp) {
     constexpr int BIT = PPB / (T * G);                              // step-B passes of the block per frame
     static_assert(PPB % (T * G) == 0, "bin pairs must divide over the block");
 
-    extern __shared__ __align__(16) unsigned char fsea_smem[];
+    FSEA_DYN_SMEM(fsea_smem);
     const int tid = threadIdx.x;
     const int g = tid / T;
     const int t = tid - g * T;
@@ -991,10 +962,10 @@ fsea_fused4_kernel(const fsea_kparams kp) {
     };
     bool pending = false;                                        // an arrive of the "intermediate consumed" phase
     for (; f < frames; f += step) {
-        if (pending) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        if (pending) fsea_cluster_wait_acquire();
         step_a(f, scr);
-        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+        fsea_cluster_arrive_release();
+        fsea_cluster_wait_acquire();
         uint8_t* row = (uint8_t*)kp.out + (size_t)f * 32 * N * ESZ;
 #pragma unroll 1
         for (int it = 0; it < BIT; it++) {
@@ -1004,6 +975,6 @@ fsea_fused4_kernel(const fsea_kparams kp) {
         }
         pending = true;
     }
-    if (pending) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (pending) fsea_cluster_wait_acquire();
 }
 

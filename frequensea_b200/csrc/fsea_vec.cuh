@@ -13,7 +13,7 @@
 // both halves (SASS operand form  R.F32).
 #pragma once
 
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) || defined(FSEA_EMU)      // (FSEA_EMU: tests/emu/, the kernel source on a CPU fiber machine)
 #include <cuda_runtime.h>
 #define FSEA_HD __host__ __device__ __forceinline__
 #define FSEA_D __device__ __forceinline__
@@ -45,7 +45,7 @@ FSEA_SCALAR_OPS(double)
 #undef FSEA_SCALAR_OPS
 
 // ---- packed pair of fp32 ---------------------------------------------------
-#if defined(__CUDACC__)
+#if defined(__CUDACC__) || defined(FSEA_EMU)
 struct f2 {
     float2 v;
 };
@@ -79,7 +79,7 @@ FSEA_D f2 vfnmas(f2 a, float s, f2 b) { return vfnma(a, s, b); }
 FSEA_D f2 vsplat(float s, f2) { return mk2(s, s); }
 FSEA_D float vfma2(float a, float c, float b) { return a * c + b; }
 FSEA_D double vfma2(double a, double c, double b) { return a * c + b; }
-#endif  // __CUDACC__
+#endif  // __CUDACC__ || FSEA_EMU
 
 // complex multiply of the value (re, im) by the run-time scalar twiddle (wr + i wi)
 template <typename V, typename S>
