@@ -41,13 +41,18 @@ FSEA_DECL_SIZE(4096)
 FSEA_DECL_SIZE(8192)
 #undef FSEA_DECL_SIZE
 
-// Four-step plans (N = N1 x 32 >= 16384): step A (`a`) transforms the 32 interleaved
-// sub-sequences of every frame into an intermediate, step B (`b`) combs them into the spectrum.
+// Four-step plans (N = N1 x N2, N >= 8192, 8-bit input): one cluster kernel per frame batch
+// (fsea_fused4_kernel) -- step A transforms the N2 interleaved sub-sequences of a frame, step B
+// combs the sub-spectra; the intermediate stays in L2.
 struct fsea_kernel_info4 {
-    fsea_kernel_info a, b;
-    int n1, n2;
-    const void* fused;       // both steps in one kernel (geometry of `a`, clusters of `cs` blocks), or nullptr
-    int cs;
-    const char* fused_name;
+    const void* fn;          // __global__ entry
+    int cs;                  // blocks per cluster (1: plain launch, one block per frame)
+    int threads;             // block size
+    size_t smem;             // dynamic shared memory per block
+    int n1, n2;              // sub-spectrum length, sub-sequences
+    int r0, r1, r2;          // shape of the N1-point transform (twiddle tables)
+    int tw1, tw2;
+    const char* name;
 };
-bool fsea_get_kernel4(int n, bool window, int out_mode, fsea_kernel_info4* out);
+// alt: 0 = the shipped configuration of this length, 1.. = alternatives kept for A/B runs (FSEA_FOUR_ALT)
+bool fsea_get_kernel4(int n, bool window, int out_mode, int alt, fsea_kernel_info4* out);

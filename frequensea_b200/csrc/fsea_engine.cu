@@ -90,18 +90,13 @@ struct fsea_plan {
     unsigned* d_tickets = nullptr;             // TICKET_SLOTS x {ticket, done}, zero between launches
     static const int TICKET_SLOTS = 64;
     void* d_dump = nullptr;
-    // four-step (N >= 16384)
+    // four-step (N = N1 x N2 >= 8192, 8-bit input): both steps in one cluster kernel
     bool four = false;
-    bool fused = false;                          // both steps in one cluster kernel (intermediate stays in L2)
-    int max_clusters = 0;
+    int max_clusters = 0;                        // clusters (frames in flight) resident at once
     fsea_kernel_info4 k4;
-    void* d_tw4 = nullptr;                       // comb twiddles: W_N^{2^r k}, r < 5, as cos / sin planes
+    void* d_tw4 = nullptr;                       // comb twiddles: W_N^{2^r k}, r < log2 N2, as cos / sin planes
     static const int SCRATCH_SLOTS = 4;           // slot 0: fsea_exec_device, 1..3: host pipeline stages
-    void* d_scratch[SCRATCH_SLOTS] = {nullptr, nullptr, nullptr, nullptr};   // chunk_frames x N float2 each
-    long chunk_frames = 0;
-    long scratch_frames[SCRATCH_SLOTS] = {0, 0, 0, 0};
-    void* d_cscratch[SCRATCH_SLOTS] = {nullptr, nullptr, nullptr, nullptr};   // fused: max_clusters x N float2 each
-    int max_blocks_b = 0;
+    void* d_cscratch[SCRATCH_SLOTS] = {nullptr, nullptr, nullptr, nullptr};   // max_clusters x N float2 each (L2-resident)
 };
 
 static fsea_get_kernel_fn size_table(int n) {
@@ -174,7 +169,6 @@ extern "C" int fsea_plan_destroy(fsea_plan* p) {
     if (p->d_tickets) cudaFree(p->d_tickets);
     if (p->d_dump) cudaFree(p->d_dump);
     if (p->d_tw4) cudaFree(p->d_tw4);
-    for (int q = 0; q < fsea_plan::SCRATCH_SLOTS; q++) if (p->d_scratch[q]) cudaFree(p->d_scratch[q]);
     for (int q = 0; q < fsea_plan::SCRATCH_SLOTS; q++) if (p->d_cscratch[q]) cudaFree(p->d_cscratch[q]);
     delete p;
     return FSEA_OK;
@@ -219,9 +213,14 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
     if (n < 16 || n > 65536 || (n & (n - 1))) return FSEA_ERR_UNSUPPORTED;
     fsea_get_kernel_fn get = size_table(n);
     fsea_kernel_info4 k4;
-    const bool four = !get && fsea_get_kernel4(n, cfg->window == FSEA_WIN_HANN, cfg->out_mode, &k4);
+    const bool eight = cfg->in_format == FSEA_IN_U8 || cfg->in_format == FSEA_IN_S8;
+    int alt = 0;
+    if (const char* ev = getenv("FSEA_FOUR_ALT")) alt = atoi(ev);                 // A/B runs
+    // N >= 16384 always runs four-step; N = 8192 does for 8-bit input in the default arithmetic
+    // (FSEA_ARITH_F32 / _F32X2 ask for the single-kernel transform explicitly)
+    bool want4 = !get || (n == 8192 && eight && cfg->arith == FSEA_ARITH_AUTO && !getenv("FSEA_8192_DIRECT"));
+    const bool four = want4 && eight && fsea_get_kernel4(n, cfg->window == FSEA_WIN_HANN, cfg->out_mode, alt, &k4);
     if (!get && !four) return FSEA_ERR_UNSUPPORTED;
-    if (four && cfg->in_format != FSEA_IN_U8 && cfg->in_format != FSEA_IN_S8) return FSEA_ERR_UNSUPPORTED;
     if (cfg->in_format < FSEA_IN_U8 || cfg->in_format > FSEA_IN_F64C) return FSEA_ERR_INVALID;
     if (cfg->window != FSEA_WIN_NONE && cfg->window != FSEA_WIN_HANN) return FSEA_ERR_INVALID;
     if (cfg->out_mode < FSEA_OUT_MAG || cfg->out_mode > FSEA_OUT_PIX) return FSEA_ERR_INVALID;
@@ -249,7 +248,10 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
     if (four) {
         p->four = true;
         p->k4 = k4;
-        p->ki = k4.a;                     // step A doubles as "the" kernel for tables, lanes, names
+        memset(&p->ki, 0, sizeof(p->ki));   // the step-A transform's shape: tables, lanes, names
+        p->ki.fn = k4.fn; p->ki.threads = k4.threads; p->ki.groups = 1; p->ki.lanes = 2; p->ki.smem = k4.smem;
+        p->ki.n = k4.n1; p->ki.r0 = k4.r0; p->ki.r1 = k4.r1; p->ki.r2 = k4.r2;
+        p->ki.tw1 = k4.tw1; p->ki.tw2 = k4.tw2; p->ki.scalar_bytes = 4; p->ki.name = k4.name;
         p->variant = FSEA_VAR_F32X2;
     } else if (!get(p->variant, &p->ki)) { delete p; return FSEA_ERR_UNSUPPORTED; }
     p->out_elem_bytes = (cfg->out_mode == FSEA_OUT_PIX) ? 1 : p->ki.scalar_bytes;
@@ -260,55 +262,41 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
         if ((rc = setup_kernel(p->ki, cfg->device, &p->max_blocks)) != FSEA_OK) break;
         // staged 8-bit kernels transform integer-scaled samples (b - 128): the 1/256 of
         // src/nrf.c:605-606 rides on the pass-1 twiddles
-        const bool staged = !p->four && (p->variant == FSEA_VAR_F32 || p->variant == FSEA_VAR_F32X2 ||
-                                         p->variant == FSEA_VAR_F32_WIN || p->variant == FSEA_VAR_F32X2_WIN) && p->ki.r1 > 1;
-        if (!p->four && (rc = upload_twiddles(p->ki, &p->d_tw1, &p->d_tw2, staged ? 1.0f / 256.0f : 1.0f)) != FSEA_OK) break;
+        const bool staged = p->four || ((p->variant == FSEA_VAR_F32 || p->variant == FSEA_VAR_F32X2 ||
+                                         p->variant == FSEA_VAR_F32_WIN || p->variant == FSEA_VAR_F32X2_WIN) && p->ki.r1 > 1);
+        if ((rc = upload_twiddles(p->ki, &p->d_tw1, &p->d_tw2, staged ? 1.0f / 256.0f : 1.0f)) != FSEA_OK) break;
         if (p->four) {
-            if ((rc = setup_kernel(p->k4.b, cfg->device, &p->max_blocks_b)) != FSEA_OK) break;
+            // step B builds W_N^{n2 k} from the rows n2 = 1, 2, 4, .. of this table
             const int n1 = p->k4.n1;
-            std::vector<float2> t4((size_t)n);
+            int lg = 0;
+            while ((1 << lg) < p->k4.n2) lg++;
+            std::vector<float> t4((size_t)2 * lg * n1);                    // planes: row 2r = cos, row 2r+1 = sin
             const long double PI2 = 6.283185307179586476925286766559005768L;
-            {
-                // step A is a staged kernel: 1/256 rides on its pass-1 twiddles.  Step B builds
-                // W_N^{n2 k} from the rows n2 = 1, 2, 4, 8, 16 of this table.
-                if ((rc = upload_twiddles(p->k4.a, &p->d_tw1, &p->d_tw2, 1.0f / 256.0f)) != FSEA_OK) break;
-                float* t4f = (float*)t4.data();                 // planes: row 2r = cos, row 2r+1 = sin
-                for (int r = 0; r < 5; r++)
-                    for (int k = 0; k < n1; k++) {
-                        const long double a = -PI2 * (long double)(((long)k) << r) / (long double)n;
-                        t4f[(size_t)(2 * r) * n1 + k] = (float)cosl(a);
-                        t4f[(size_t)(2 * r + 1) * n1 + k] = (float)sinl(a);
-                    }
-            }
-            // Two-launch form: the intermediate (8 bytes per point) is streamed through HBM in
-            // chunks of at most 2 GiB, allocated on first use at the size the call needs
-            // (grow-only; L2-sized chunks are launch-bound: 8.7 vs 15 M frames/s at N = 16384).
-            long chunk_mb = 2048;
-            if (const char* ev = getenv("FSEA_CHUNK_MB")) chunk_mb = std::max(1L, atol(ev));   // experiments
-            p->chunk_frames = std::max<long>(1, (chunk_mb << 20) / ((long)n * 8));
-            if ((e = cudaMalloc(&p->d_tw4, (size_t)n * sizeof(float2))) != cudaSuccess ||
-                (e = cudaMemcpy(p->d_tw4, t4.data(), (size_t)n * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess) {
+            for (int r = 0; r < lg; r++)
+                for (int k = 0; k < n1; k++) {
+                    const long double a = -PI2 * (long double)(((long)k) << r) / (long double)n;
+                    t4[(size_t)(2 * r) * n1 + k] = (float)cosl(a);
+                    t4[(size_t)(2 * r + 1) * n1 + k] = (float)sinl(a);
+                }
+            if ((e = cudaMalloc(&p->d_tw4, t4.size() * sizeof(float))) != cudaSuccess ||
+                (e = cudaMemcpy(p->d_tw4, t4.data(), t4.size() * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) {
                 rc = cuda_fail(e, "four-step tables"); break;
             }
-        }
-        if (p->four && p->k4.fused && !getenv("FSEA_FOUR_SPLIT")) {       // (FSEA_FOUR_SPLIT: A/B against the two-launch form)
-            // cluster launch geometry: how many clusters of `cs` blocks are resident at once
-            cudaLaunchConfig_t lc;
-            memset(&lc, 0, sizeof(lc));
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = p->k4.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            lc.gridDim = dim3((unsigned)(p->k4.cs * 64)); lc.blockDim = dim3((unsigned)p->k4.a.threads);
-            lc.dynamicSmemBytes = p->k4.a.smem; lc.attrs = at; lc.numAttrs = 1;
-            int nc = 0;
-            if ((e = cudaFuncSetAttribute(p->k4.fused, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->k4.a.smem)) != cudaSuccess ||
-                (e = cudaOccupancyMaxActiveClusters(&nc, p->k4.fused, &lc)) != cudaSuccess) {
-                rc = cuda_fail(e, "cluster kernel setup"); break;
-            }
-            if (nc > 0) {
-                p->fused = true;
+            // launch geometry: how many clusters of `cs` blocks (= frames in flight) are resident at once
+            if (p->k4.cs > 1) {
+                cudaLaunchConfig_t lc;
+                memset(&lc, 0, sizeof(lc));
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = p->k4.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                lc.gridDim = dim3((unsigned)(p->k4.cs * 64)); lc.blockDim = dim3((unsigned)p->k4.threads);
+                lc.dynamicSmemBytes = p->k4.smem; lc.attrs = at; lc.numAttrs = 1;
+                int nc = 0;
+                if ((e = cudaOccupancyMaxActiveClusters(&nc, p->k4.fn, &lc)) != cudaSuccess) { rc = cuda_fail(e, "cluster kernel setup"); break; }
+                if (nc < 1) { rc = FSEA_ERR_UNSUPPORTED; break; }
                 p->max_clusters = nc;
-                p->ki.name = p->k4.fused_name;
+            } else {
+                p->max_clusters = p->max_blocks;
             }
         }
         if ((e = cudaMalloc(&p->d_tickets, sizeof(unsigned) * 2 * fsea_plan::TICKET_SLOTS)) != cudaSuccess ||
@@ -368,56 +356,28 @@ static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cu
     kp.n1 = kp.n2 = 0;
     kp.scratch = nullptr;
     if (p->four) {
-        // N = N1 x 32 (decimation in time)
-        const int n = p->cfg.fft_size, n1 = p->k4.n1;
-        if (p->fused) {
-            // one launch: a cluster per frame, the intermediate lives in the clusters' L2-resident slots
-            if (!p->d_cscratch[slot]) CU(cudaMalloc(&p->d_cscratch[slot], (size_t)p->max_clusters * n * sizeof(float2)));
-            kp.scratch = p->d_cscratch[slot];
-            const long nc = std::min<long>(n_frames, p->max_clusters);
+        // one launch: a cluster per frame, the intermediate lives in the clusters' L2-resident slots
+        const int n = p->cfg.fft_size;
+        kp.n1 = p->k4.n1; kp.n2 = p->k4.n2;
+        if (!p->d_cscratch[slot]) CU(cudaMalloc(&p->d_cscratch[slot], (size_t)p->max_clusters * n * sizeof(float2)));
+        kp.scratch = p->d_cscratch[slot];
+        kp.ticket = nullptr;
+        const long nc = std::min<long>(n_frames, p->max_clusters);
+        void* af[] = {&kp};
+        if (p->k4.cs > 1) {
             cudaLaunchConfig_t lc;
             memset(&lc, 0, sizeof(lc));
             cudaLaunchAttribute at[1];
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = p->k4.cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            lc.gridDim = dim3((unsigned)(nc * p->k4.cs)); lc.blockDim = dim3((unsigned)p->k4.a.threads);
-            lc.dynamicSmemBytes = p->k4.a.smem; lc.stream = stream; lc.attrs = at; lc.numAttrs = 1;
-            void* af[] = {&kp};
-            CU(cudaLaunchKernelExC(&lc, p->k4.fused, af));
-            p->launches++;
-            return FSEA_OK;
+            lc.gridDim = dim3((unsigned)(nc * p->k4.cs)); lc.blockDim = dim3((unsigned)p->k4.threads);
+            lc.dynamicSmemBytes = p->k4.smem; lc.stream = stream; lc.attrs = at; lc.numAttrs = 1;
+            CU(cudaLaunchKernelExC(&lc, p->k4.fn, af));
+        } else {
+            CU(cudaLaunchKernel(p->k4.fn, dim3((unsigned)nc), dim3((unsigned)p->k4.threads), af, p->k4.smem, stream));
         }
-        const long want = std::min(p->chunk_frames, n_frames);
-        if (p->scratch_frames[slot] < want) {            // grow-only; cudaFree waits for work still using the old one
-            if (p->d_scratch[slot]) CU(cudaFree(p->d_scratch[slot]));
-            p->d_scratch[slot] = nullptr; p->scratch_frames[slot] = 0;
-            CU(cudaMalloc(&p->d_scratch[slot], (size_t)want * n * sizeof(float2)));
-            p->scratch_frames[slot] = want;
-        }
-        void* scratch = p->d_scratch[slot];
-        {
-            // two launches per chunk: A = sub-spectra of the 32 interleaved sub-sequences, B = comb
-            for (long f0 = 0; f0 < n_frames; f0 += p->chunk_frames) {
-                const long cf = std::min(p->chunk_frames, n_frames - f0);
-                fsea_kparams ka = kp, kb = kp;
-                ka.in = (const uint8_t*)d_in + (size_t)f0 * p->hop * p->sample_bytes;
-                ka.out = scratch;
-                ka.n_seq = cf * 32;
-                ka.ticket = p->d_tickets + 2 * (p->launches % fsea_plan::TICKET_SLOTS);
-                long blocks = std::min<long>(cf * 16 / p->k4.a.groups, (long)p->max_blocks);   // (>= tiles)
-                void* aa[] = {&ka};
-                CU(cudaLaunchKernel(p->k4.a.fn, dim3((unsigned)blocks), dim3((unsigned)p->k4.a.threads), aa, p->k4.a.smem, stream));
-                p->launches++;
-                kb.in = scratch;
-                kb.out = (uint8_t*)d_out + (size_t)f0 * n * p->out_elem_bytes;
-                kb.n_seq = cf * (n1 / 2);
-                blocks = std::min<long>((kb.n_seq + 127) / 128, (long)p->max_blocks_b * 8);
-                void* ab[] = {&kb};
-                CU(cudaLaunchKernel(p->k4.b.fn, dim3((unsigned)blocks), dim3((unsigned)p->k4.b.threads), ab, p->k4.b.smem, stream));
-                p->launches++;
-            }
-            return FSEA_OK;
-        }
+        p->launches++;
+        return FSEA_OK;
     }
     kp.ticket = p->d_tickets + 2 * (p->launches % fsea_plan::TICKET_SLOTS);
     const long units = (n_frames + p->ki.lanes - 1) / p->ki.lanes;

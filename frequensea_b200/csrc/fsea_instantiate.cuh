@@ -7,9 +7,9 @@ template <class SH, typename V, int FMT, int GOV = 0, int TWSOV = -1>
 struct fsea_cfg {
     static const int UNIT_BYTES = 2 * (int)sizeof(V);
     static const int SB = (int)sizeof(typename fsea_vt<V>::scalar);
-    static const bool COLS = (FMT == FSEA_IN_COLS);
+    static const bool COLS = fsea_cols_geom<FMT>::COLS;
     static const bool STAGED = SH::NPASS > 1 && SB == 4 && (FMT == FSEA_IN_U8 || COLS);
-    static const int RINGB = COLS ? 4 * fsea_cols_rounds<SH::N>::v * SH::N : fsea_vt<V>::lanes * 2 * SH::N;     // (COLS: per group, of the block's tile ring)
+    static const int RINGB = COLS ? 4 * fsea_cols_geom<FMT>::RND * SH::N : fsea_vt<V>::lanes * 2 * SH::N;     // (COLS: per group, of the block's tile ring)
     static const int XBYTES = SH::NPASS > 1 ? SH::UNITS * (int)sizeof(V) + (STAGED ? RINGB : 0) : 0;   // exchange plane + raw ring per group
     static const int TWBYTES = (SH::TW1 + SH::TW2) * 2 * SB;
     static const bool TWS = TWSOV >= 0 ? (TWSOV != 0) : (SH::NPASS > 1 && TWBYTES <= 16384);
@@ -24,7 +24,7 @@ struct fsea_cfg {
     static const size_t SMEM = (size_t)G * XBYTES + (COLS ? 128 : 0) + (TWS ? TWBYTES : 0);
     // resident blocks per SM the register allocator must allow: what shared memory
     // permits, capped so that a thread keeps >= REGCAP registers
-    static const int REGCAP_0 = (sizeof(V) >= 8 ? (SH::P >= 32 ? 168 : (SH::P >= 16 ? 112 : 80)) : (SH::P >= 32 ? 96 : 64));
+    static const int REGCAP_0 = (sizeof(V) >= 8 ? (SH::P >= 32 ? 168 : (SH::P >= 16 ? 112 : 80)) : (SH::P >= 64 ? 168 : (SH::P >= 32 ? 96 : 64)));
     static const int REGCAP = REGCAP_0;
     static const int THREADS = SH::T * G;
     static const int B_SMEM = SMEM ? (int)((227 * 1024) / (SMEM + 1024)) : 16;
@@ -52,22 +52,27 @@ static bool fsea_fill(fsea_kernel_info* o, const char* name) {
 
 #define FSEA_STR2(x) #x
 #define FSEA_STR(x) FSEA_STR2(x)
-#define FSEA_DEFINE_SIZE(N, R0, R1, R2)                                                                  \
+// SH: shape of the packed (f32x2), float2-sample and fp64 variants; SHS: shape of the scalar fp32
+// variants (a thread may hold 64 points there: 2048 = 64 x 32 and 4096 = 64 x 64 need ONE exchange)
+#define FSEA_SHAPE_NAME(N, R0, R1, R2) FSEA_STR(N) ":" FSEA_STR(R0) "x" FSEA_STR(R1) "x" FSEA_STR(R2)
+#define FSEA_DEFINE_SIZE2(N, R0, R1, R2, S0, S1, S2)                                                     \
     bool fsea_get_kernel_##N(int variant, fsea_kernel_info* out) {                                       \
         typedef fsea_shape<N, R0, R1, R2> SH;                                                            \
+        typedef fsea_shape<N, S0, S1, S2> SHS;                                                           \
         switch (variant) {                                                                               \
             case FSEA_VAR_F32:                                                                           \
-                return fsea_fill<SH, float, FSEA_IN_U8>(out, "fft<" FSEA_STR(N) ":" FSEA_STR(R0) "x" FSEA_STR(R1) "x" FSEA_STR(R2) ",f32>");      \
+                return fsea_fill<SHS, float, FSEA_IN_U8>(out, "fft<" FSEA_SHAPE_NAME(N, S0, S1, S2) ",f32>");      \
             case FSEA_VAR_F32X2:                                                                         \
-                return fsea_fill<SH, f2, FSEA_IN_U8>(out, "fft<" FSEA_STR(N) ":" FSEA_STR(R0) "x" FSEA_STR(R1) "x" FSEA_STR(R2) ",f32x2>");       \
+                return fsea_fill<SH, f2, FSEA_IN_U8>(out, "fft<" FSEA_SHAPE_NAME(N, R0, R1, R2) ",f32x2>");       \
             case FSEA_VAR_F32_WIN:                                                                       \
-                return fsea_fill<SH, float, FSEA_IN_U8, FSEA_OK_SPECTRUM, N, true>(out, "fft<" FSEA_STR(N) ":" FSEA_STR(R0) "x" FSEA_STR(R1) "x" FSEA_STR(R2) ",f32,win>");      \
+                return fsea_fill<SHS, float, FSEA_IN_U8, FSEA_OK_SPECTRUM, N, true>(out, "fft<" FSEA_SHAPE_NAME(N, S0, S1, S2) ",f32,win>");      \
             case FSEA_VAR_F32X2_WIN:                                                                     \
-                return fsea_fill<SH, f2, FSEA_IN_U8, FSEA_OK_SPECTRUM, N, true>(out, "fft<" FSEA_STR(N) ":" FSEA_STR(R0) "x" FSEA_STR(R1) "x" FSEA_STR(R2) ",f32x2,win>");       \
+                return fsea_fill<SH, f2, FSEA_IN_U8, FSEA_OK_SPECTRUM, N, true>(out, "fft<" FSEA_SHAPE_NAME(N, R0, R1, R2) ",f32x2,win>");       \
             case FSEA_VAR_F32C:                                                                          \
-                return fsea_fill<SH, float, FSEA_IN_F32C>(out, "fft<" FSEA_STR(N) ":" FSEA_STR(R0) "x" FSEA_STR(R1) "x" FSEA_STR(R2) ",f32c>");   \
+                return fsea_fill<SH, float, FSEA_IN_F32C>(out, "fft<" FSEA_SHAPE_NAME(N, R0, R1, R2) ",f32c>");   \
             case FSEA_VAR_F64:                                                                           \
-                return fsea_fill<SH, double, FSEA_IN_F64C>(out, "fft<" FSEA_STR(N) ":" FSEA_STR(R0) "x" FSEA_STR(R1) "x" FSEA_STR(R2) ",f64>");   \
+                return fsea_fill<SH, double, FSEA_IN_F64C>(out, "fft<" FSEA_SHAPE_NAME(N, R0, R1, R2) ",f64>");   \
         }                                                                                                \
         return false;                                                                                    \
     }
+#define FSEA_DEFINE_SIZE(N, R0, R1, R2) FSEA_DEFINE_SIZE2(N, R0, R1, R2, R0, R1, R2)

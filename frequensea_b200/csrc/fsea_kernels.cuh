@@ -35,8 +35,14 @@
 #include "../../include/fsea.h"
 #include "fsea_kparams.h"
 
-// internal input / output kinds of the four-step (N = N1 x N2) kernels
-enum { FSEA_IN_COLS = 18 };
+// internal input / output kinds of the four-step (N = N1 x N2) kernels.  The loader format
+// carries its geometry: N2 interleaved sub-sequences, tiles transformed in RND rounds.
+#define FSEA_IN_COLS_FMT(N2, RND) (100 + (N2) + 1000 * (RND))
+template <int FMT> struct fsea_cols_geom {
+    static const bool COLS = FMT >= 100;
+    static const int N2 = COLS ? (FMT % 1000) - 100 : 32;
+    static const int RND = COLS ? FMT / 1000 : 1;
+};
 enum { FSEA_OK_SPECTRUM = 0, FSEA_OK_CPLX = 3 };
 
 
@@ -212,19 +218,18 @@ template <> struct fsea_in<FSEA_IN_F64C, double> {
     template <int N> __device__ __forceinline__ void load_staged_raw(const unsigned char*, int, double&, double&) const {}
 };
 
-// ---- four-step, decimation in time (N = N1 x 32, n = 32 n1 + n2) ------------------
-// Step A is this file's kernel on the 32 interleaved sub-sequences x[32 n1 + n2] of a frame:
+// ---- four-step, decimation in time (N = N1 x N2, n = N2 n1 + n2) ------------------
+// Step A is this file's transform on the N2 interleaved sub-sequences x[N2 n1 + n2] of a frame:
 // a unit is the PAIR of neighbouring sub-sequences (n2, n2+1) -- four adjacent bytes per n1,
-// the two packed lanes.  A block takes a TILE of G x ROUNDS units of one frame and transforms
-// them in ROUNDS rounds of G; the tile's bytes (16 or 32 per n1) reach shared memory as
-// 8-byte pieces laid out ring[h][n1]
-// (h = unit pair), so a group reads its samples with one LDS.32 per point.  (Narrower
-// tiles cost LSU time out of proportion: an LDGSTS is replayed once per 128-byte line it
-// gathers from -- ncu, 8 bytes per row: 16 wavefronts per instruction instead of 2.)
-// The sub-spectra go to the intermediate as complex rows Y[n2][k1]; step B
-// (fsea_comb32_kernel, below) twiddles them and does the radix-32 across n2 in registers.
-template <int N> struct fsea_cols_rounds { static const int v = (N >= 2048) ? 2 : 1; };   // measured: see DESIGN.md
-template <> struct fsea_in<FSEA_IN_COLS, f2> {
+// the two packed lanes.  A block takes a TILE of G x RND units of one frame and transforms
+// them in RND rounds of G; the tile's bytes (8 G RND / 2 per n1) reach shared memory as
+// 8-byte pieces laid out ring[h][n1] (h = unit pair), so a group reads its samples with one
+// LDS.32 per point.  (Narrower tiles cost LSU time out of proportion: an LDGSTS is replayed
+// once per 128-byte line it gathers from.)  The sub-spectra go to the intermediate as planes
+// Yre[n2][k1], Yim[n2][k1]; step B (fsea_comb*, below) twiddles them and does the radix-N2
+// across n2 in registers.
+template <int N2_, int RND_> struct fsea_in_cols {
+    static const int N2 = N2_, RND = RND_;
     const uint8_t* p;      // the unit's first byte in its frame
     const float* win;
     uint32_t x4;
@@ -232,15 +237,15 @@ template <> struct fsea_in<FSEA_IN_COLS, f2> {
         long s0 = 2 * unit;                                    // sub-sequence index in the batch
         live = s0 < kp.n_seq;
         if (!live) s0 = kp.n_seq - 2;
-        const long f = s0 >> 5;
-        const int c = (int)(s0 & 31);
+        const long f = s0 / N2;
+        const int c = (int)(s0 - f * N2);
         p = (const uint8_t*)kp.in + 2 * (f * kp.seq_stride + c);
         win = kp.window + c;
         x4 = kp.xor_mask | (kp.xor_mask << 16);
     }
     __device__ __forceinline__ void load(int, f2&, f2&) const {}
     __device__ __forceinline__ f2 window(int e) const {
-        const float2 w = __ldg((const float2*)(win + 32 * e));
+        const float2 w = __ldg((const float2*)(win + N2 * e));
         return mk2(w.x, w.y);
     }
     template <int N, int T> __device__ __forceinline__ void prefetch(int) const {}
@@ -248,8 +253,8 @@ template <> struct fsea_in<FSEA_IN_COLS, f2> {
     // ring geometry: H pieces of 8 bytes per n1; row h of the ring is N + 16/H pieces long
     // (the pad keeps the LDGSTS writes of a half-warp on distinct banks)
     template <int N, int G> struct ring {
-        static const int H = G * fsea_cols_rounds<N>::v / 2;
-        static const int ROW = N + 16 / H;                     // pieces per ring row
+        static const int H = (G * RND / 2) > 0 ? (G * RND / 2) : 1;
+        static const int ROW = N + (16 / H > 0 ? 16 / H : 1);  // pieces per ring row
         static const int BYTES = H * ROW * 8;
     };
     // all TPB threads of the block fetch the tile whose first unit is this (round-0) unit of group g
@@ -262,10 +267,10 @@ template <> struct fsea_in<FSEA_IN_COLS, f2> {
         for (int c = 0; c < (N * R::H) / TPB; c++) {
             const int q = tid + c * TPB;
             const int n1 = q / R::H, h = q - n1 * R::H;
-            fsea_cp_async8(rg + ((size_t)h * R::ROW + n1) * 8, pt + 64 * (size_t)n1 + 8 * h);
+            fsea_cp_async8(rg + ((size_t)h * R::ROW + n1) * 8, pt + (2 * N2) * (size_t)n1 + 8 * h);
         }
     }
-    // where unit `slot` (0 .. G ROUNDS - 1) of the tile finds its words in the ring
+    // where unit `slot` (0 .. G RND - 1) of the tile finds its words in the ring
     template <int N, int G>
     static __device__ __forceinline__ const unsigned char* ring_of(const unsigned char* rg, int slot) {
         return rg + (size_t)(slot >> 1) * ring<N, G>::ROW * 8 + (slot & 1) * 4;
@@ -281,6 +286,14 @@ template <> struct fsea_in<FSEA_IN_COLS, f2> {
         re = vsub(re, off); im = vsub(im, off);
     }
 };
+#define FSEA_COLS_SPEC(N2, RND) template <> struct fsea_in<FSEA_IN_COLS_FMT(N2, RND), f2> : fsea_in_cols<N2, RND> {};
+FSEA_COLS_SPEC(8, 1)
+FSEA_COLS_SPEC(16, 1)
+FSEA_COLS_SPEC(32, 1)
+FSEA_COLS_SPEC(32, 2)
+FSEA_COLS_SPEC(64, 1)
+FSEA_COLS_SPEC(64, 2)
+#undef FSEA_COLS_SPEC
 
 // ---- output side: bin k of the unit's sequence(s) ---------------------------
 // The reference's (-1)^n input modulation (src/nrf.c:611-612) is the output
@@ -357,19 +370,19 @@ template <int OUT> __device__ __forceinline__ void fsea_tile_put(unsigned char* 
 }
 
 // Four-step step A: the two sub-spectra of a unit as rows of the intermediate, which is kept as
-// two float planes per frame, Yre[32][N1] then Yim[32][N1]: step A stores lanes of its packed
-// registers as they are and step B loads bin PAIRS (k, k+1) of a plane straight into packed
-// registers (an interleaved re/im layout cost ~450 MOVs per thread of repacking in step B).
-template <int N> struct fsea_out_cplx {
-    float *ra, *rb;                                       // re rows of the unit's two sub-sequences; im at + 32 N
+// two float planes per frame, Yre[N2][N1] then Yim[N2][N1]: step A stores lanes of its packed
+// registers as they are and step B loads them straight into packed registers (an interleaved
+// re/im layout cost ~450 MOVs per thread of repacking in step B).
+template <int N, int N2> struct fsea_out_cplx {
+    float *ra, *rb;                                       // re rows of the unit's two sub-sequences; im at + N2 N
     __device__ __forceinline__ void init(const fsea_kparams& kp, long unit, bool unit_live, int) {
-        const long f = unit >> 4;
-        const int u16 = (int)(unit & 15);
-        ra = unit_live ? (float*)kp.out + (size_t)f * 64 * N + (size_t)(2 * u16) * N : (float*)kp.dump;
+        const long f = unit / (N2 / 2);
+        const int u = (int)(unit - f * (N2 / 2));
+        ra = unit_live ? (float*)kp.out + (size_t)f * 2 * N2 * N + (size_t)(2 * u) * N : (float*)kp.dump;
         rb = ra + N;
     }
-    __device__ __forceinline__ void set(float* frame_base, int u16) {
-        ra = frame_base + (size_t)(2 * u16) * N;
+    __device__ __forceinline__ void set(float* frame_base, int u) {
+        ra = frame_base + (size_t)(2 * u) * N;
         rb = ra + N;
     }
     template <int R, int M>
@@ -378,15 +391,16 @@ template <int N> struct fsea_out_cplx {
         for (int m = 0; m < R; m++) {
             ra[i + m * M] = re[m].v.x;
             rb[i + m * M] = re[m].v.y;
-            ra[32 * N + i + m * M] = im[m].v.x;
-            rb[32 * N + i + m * M] = im[m].v.y;
+            ra[N2 * N + i + m * M] = im[m].v.x;
+            rb[N2 * N + i + m * M] = im[m].v.y;
         }
     }
     __device__ __forceinline__ void dc_adjust(const fsea_kparams&, int, f2&, f2&) const {}
 };
 
+// (NTOT: the four-step factor N2 for complex rows, unused for spectra)
 template <int OK, int N, int NTOT, typename V> struct fsea_out_sel { typedef fsea_out<N, V> type; };
-template <int N, int NTOT> struct fsea_out_sel<FSEA_OK_CPLX, N, NTOT, f2> { typedef fsea_out_cplx<N> type; };
+template <int N, int NTOT> struct fsea_out_sel<FSEA_OK_CPLX, N, NTOT, f2> { typedef fsea_out_cplx<N, NTOT> type; };
 
 // ---- group barrier ----------------------------------------------------------
 template <int T> __device__ __forceinline__ void fsea_group_sync(int group) {
@@ -461,7 +475,7 @@ __device__ __forceinline__ float fsea_transform(const fsea_kparams& kp, const fs
     typedef typename fsea_cplx<V>::t S2;
     constexpr int N = SH::N, R0 = SH::R0, R1 = SH::R1, R2 = SH::R2, P = SH::P, T = SH::T;
     constexpr int L0 = SH::L0, NPASS = SH::NPASS;
-    constexpr bool COLS = (FMT == FSEA_IN_COLS);
+    constexpr bool COLS = fsea_cols_geom<FMT>::COLS;
     constexpr bool STAGED = (FMT == FSEA_IN_U8 || COLS) && NPASS > 1 && sizeof(S) == 4;
     constexpr int XB = NPASS > 1 ? SH::UNITS * (int)sizeof(V) : 0;
     (void)tw1; (void)tw2; (void)xp; (void)raw; (void)smem_base; (void)tid; (void)more; (void)slot; (void)ring_first; (void)ring_last;
@@ -476,7 +490,7 @@ __device__ __forceinline__ float fsea_transform(const fsea_kparams& kp, const fs
             if constexpr (COLS) { if (ring_first) { fsea_cp_async_wait_all(); __syncthreads(); } }
             else { fsea_cp_async_wait_all(); fsea_group_sync<T>(g); }
             const unsigned char* rg = raw;
-            if constexpr (COLS) rg = fsea_in<FSEA_IN_COLS, f2>::template ring_of<N, G>(raw, slot);
+            if constexpr (COLS) rg = fsea_in<FMT, V>::template ring_of<N, G>(raw, slot);
             raw_stage = !WIN;
             if (raw_stage) {
 #pragma unroll
@@ -665,7 +679,7 @@ fsea_fft_kernel(const fsea_kparams kp) {
     constexpr int N = SH::N, R0 = SH::R0, R1 = SH::R1, R2 = SH::R2, P = SH::P, T = SH::T;
     constexpr int L0 = SH::L0, NPASS = SH::NPASS;
     constexpr int LANES = fsea_vt<V>::lanes;
-    constexpr bool COLS = (FMT == FSEA_IN_COLS);
+    constexpr bool COLS = fsea_cols_geom<FMT>::COLS;
     constexpr bool STAGED = (FMT == FSEA_IN_U8 || COLS) && NPASS > 1 && sizeof(S) == 4;
     // four-step kernels hand out TILES of G neighbouring units per block (adjacent columns /
     // rows -> contiguous bytes across the block); the others hand out single units per group
@@ -683,7 +697,7 @@ fsea_fft_kernel(const fsea_kparams kp) {
     const S2* tw1 = (const S2*)kp.tw1;
     const S2* tw2 = (const S2*)kp.tw2;
     if (TWS && NPASS > 1) {
-        S2* stw = reinterpret_cast<S2*>(fsea_smem + (size_t)G * (XB + RB) + (COLS ? fsea_in<FSEA_IN_COLS, f2>::template ring<N, G>::BYTES : 0));
+        S2* stw = reinterpret_cast<S2*>(fsea_smem + (size_t)G * (XB + RB) + (COLS ? fsea_in<COLS ? FMT : FSEA_IN_COLS_FMT(32, 1), f2>::template ring<N, G>::BYTES : 0));
         for (int q = tid; q < SH::TW1 + SH::TW2; q += T * G)
             stw[q] = (q < SH::TW1) ? tw1[q] : tw2[q - SH::TW1];
         __syncthreads();
@@ -704,7 +718,7 @@ fsea_fft_kernel(const fsea_kparams kp) {
     // the ticket counter itself the bottleneck (N = 128: 0.9 G units/s) -- a WARP, which takes
     // KB units for each of its GW = 32/T groups per ticket.
     constexpr int GW = (!TILED && T < 32) ? 32 / T : 1;
-    constexpr int KB = COLS ? fsea_cols_rounds<N>::v : ((!TILED && T < 32) ? 8 : 1);   // units per group and ticket
+    constexpr int KB = COLS ? fsea_cols_geom<FMT>::RND : ((!TILED && T < 32) ? 8 : 1);   // units per group and ticket
     constexpr int STEP = TILED ? G : GW;                                        // ... and how far apart they are
     const int gw = (GW > 1) ? ((tid & 31) / T) : 0;               // group within its warp
     const bool leader = TILED ? (tid == 0) : (GW > 1 ? ((tid & 31) == 0) : (t == 0));
@@ -801,87 +815,168 @@ fsea_fft_kernel(const fsea_kparams kp) {
     }
 }
 
-// ---- four-step, step B: twiddle + radix-32 across the 32 sub-spectra, all in registers ----
-// Thread = one pair of neighbouring bins (k, k+1), k < N1, of one frame: 32 float4 loads of
-// Y[n2][k..k+1] (a warp covers 512 contiguous bytes of every row), the four-step twiddles
-// W_N^{n2 k} built from the five table rows n2 = 1, 2, 4, 8, 16 (at most four complex
-// products deep), one packed radix-32 codelet, and 32 stores of spectrum positions
-// k + N1 (m ^ 16) (a warp covers 256 contiguous bytes each; the xor is the reference's
-// (-1)^n, src/nrf.c:611-612).
-// one bin pair (k, k+1) of one frame: y = &Yre[0][k] of the frame, row = its spectrum row
-// ARRIVE: the fused kernel's "intermediate consumed" signal (see fsea_fused4_kernel)
-template <int OUT, int ARRIVE, int N1>
-__device__ __forceinline__ void fsea_comb32_pair(const fsea_kparams& kp, const float2* y, int k, uint8_t* row, bool dc_patch) {
-    constexpr int ESZ = (OUT == FSEA_OUT_PIX) ? 1 : 4;
-    constexpr int n1 = N1;
-    constexpr int hp = N1 >> 1;
-    f2 re[32], im[32];
-#pragma unroll
-    for (int j = 0; j < 32; j++) {
-        const float2 a = __ldcg(y + (size_t)j * hp);                    // L2 only: written by step A
-        const float2 b = __ldcg(y + (size_t)(32 + j) * hp);
-        re[j] = mk2(a.x, a.y); im[j] = mk2(b.x, b.y);
-    }
-    f2 br[5], bi[5];                                                     // W^(2^r k), r = 0..4
-#pragma unroll
-    for (int r = 0; r < 5; r++) {
-        const float2 wa = __ldg((const float2*)((const float*)kp.tw4 + (size_t)(2 * r) * n1 + k));       // re plane
-        const float2 wb = __ldg((const float2*)((const float*)kp.tw4 + (size_t)(2 * r + 1) * n1 + k));   // im plane
-        br[r] = mk2(wa.x, wa.y); bi[r] = mk2(wb.x, wb.y);
-    }
-    f2 wr[32], wi[32];                                                   // (only a chain of <= 5 is live at a time)
-#pragma unroll
-    for (int j = 1; j < 32; j++) {
-        const int low = j & -j;
-        const int r = (low == 1) ? 0 : (low == 2) ? 1 : (low == 4) ? 2 : (low == 8) ? 3 : 4;
-        if (j == low) { wr[j] = br[r]; wi[j] = bi[r]; }
-        else {
-            const int q = j - low;
-            wr[j] = vsub(vmul(wr[q], br[r]), vmul(wi[q], bi[r]));
-            wi[j] = vfma2(wr[q], bi[r], vmul(wi[q], br[r]));
-        }
-        const f2 a = vsub(vmul(re[j], wr[j]), vmul(im[j], wi[j]));
-        im[j] = vfma2(re[j], wi[j], vmul(im[j], wr[j]));
-        re[j] = a;
-    }
-    // fused kernel: the intermediate has been consumed -- the cluster may overwrite it
-    // (relaxed when nothing is published here: the loads above have delivered their values)
-    if (ARRIVE == 1) fsea_cluster_arrive_relaxed();
-    fsea_dft32<f2>(re, im);
-    if (kp.dc_term && k == 0) { re[0].v.x += 16.0f * (float)n1; im[0].v.x += 16.0f * (float)n1; }   // N/2 (1+i)
-#pragma unroll
-    for (int m = 0; m < 32; m++) {
-        const f2 pw = vfma2(re[m], re[m], vmul(im[m], im[m]));
-        uint8_t* dst = row + ((size_t)k + (size_t)n1 * (m ^ 16)) * ESZ;
-        __align__(8) unsigned char tmp[8];
-        fsea_tile_put<OUT>(tmp, pw, kp.pix_scale);
-        if (m == 0 && dc_patch && k == 0) {                              // bin 0 is not stored (src/nrf.c:621-622)
-            if (ESZ == 4) ((float*)dst)[1] = ((const float*)tmp)[1]; else dst[1] = tmp[1];
-        } else if (ESZ == 4) {
-            *(float2*)dst = *(const float2*)tmp;
-        } else {
-            *(uchar2*)dst = *(const uchar2*)tmp;
-        }
-        if (m == 31 && dc_patch && k == n1 - 2) {                        // bin N-1 also fills the DC slot N/2
-            uint8_t* dc = row + (size_t)16 * n1 * ESZ;
-            if (ESZ == 4) ((float*)dc)[0] = ((const float*)tmp)[1]; else dc[0] = tmp[1];
-        }
-    }
-}
+// ---- four-step, step B: twiddle + radix-N2 across the N2 sub-spectra, all in registers ----
+// N2 <= 32: a "pair" is two neighbouring bins (k, k+1), k < N1, of one frame -- the two packed
+// lanes.  2 N2 float2 loads of Y[n2][k..k+1] (a warp covers 256 contiguous bytes of every
+// row), the four-step twiddles W_N^{n2 k} built from the log2 N2 table rows n2 = 1, 2, 4, ..
+// (at most log2 N2 - 1 complex products deep), one packed radix-N2 codelet, and N2 stores of
+// spectrum positions k + N1 (m ^ N2/2) (a warp covers 256 contiguous bytes each; the xor is the
+// reference's (-1)^n, src/nrf.c:611-612).  A thread works on U = 32 / N2 pairs at a time
+// (pair index stride = `pstride`, so that every load and store instruction stays coalesced).
+// tw4: planes [2r][k] = cos, [2r+1][k] = sin of W_N^{2^r k}, r < log2 N2, k < N1.
+template <int OUT, int N1, int N2> struct fsea_comb {
+    static const int ESZ = (OUT == FSEA_OUT_PIX) ? 1 : 4;
+    static const int LG = fsea_log2<N2>::v;
+    static const int U = 32 / N2;
+    static const int PTS = 64;                                        // points per thread and call
 
+    // y = frame's Yre[0][0]; k even
+    static __device__ __forceinline__ void load(const float* yf, int k, f2* re, f2* im) {
+        const float2* y = (const float2*)(yf + k);
+#pragma unroll
+        for (int j = 0; j < N2; j++) {
+            const float2 a = __ldcg(y + (size_t)j * (N1 / 2));                    // L2 only: written by step A
+            const float2 b = __ldcg(y + (size_t)(N2 + j) * (N1 / 2));
+            re[j] = mk2(a.x, a.y); im[j] = mk2(b.x, b.y);
+        }
+    }
+    static __device__ __forceinline__ void twiddle(const fsea_kparams& kp, int k, f2* re, f2* im) {
+        f2 br[LG], bi[LG];                                                       // W^(2^r k), r < LG
+#pragma unroll
+        for (int r = 0; r < LG; r++) {
+            const float2 wa = __ldg((const float2*)((const float*)kp.tw4 + (size_t)(2 * r) * N1 + k));       // re plane
+            const float2 wb = __ldg((const float2*)((const float*)kp.tw4 + (size_t)(2 * r + 1) * N1 + k));   // im plane
+            br[r] = mk2(wa.x, wa.y); bi[r] = mk2(wb.x, wb.y);
+        }
+        f2 wr[N2], wi[N2];                                                       // (only a chain of <= LG is live at a time)
+#pragma unroll
+        for (int j = 1; j < N2; j++) {
+            const int low = j & -j;
+            const int r = (low == 1) ? 0 : (low == 2) ? 1 : (low == 4) ? 2 : (low == 8) ? 3 : 4;
+            if (j == low) { wr[j] = br[r]; wi[j] = bi[r]; }
+            else {
+                const int q = j - low;
+                wr[j] = vsub(vmul(wr[q], br[r]), vmul(wi[q], bi[r]));
+                wi[j] = vfma2(wr[q], bi[r], vmul(wi[q], br[r]));
+            }
+            const f2 a = vsub(vmul(re[j], wr[j]), vmul(im[j], wi[j]));
+            im[j] = vfma2(re[j], wi[j], vmul(im[j], wr[j]));
+            re[j] = a;
+        }
+    }
+    static __device__ __forceinline__ void finish(const fsea_kparams& kp, int k, uint8_t* row, bool dc_patch, f2* re, f2* im) {
+        fsea_dft<N2, f2>::run(re, im);
+        if (kp.dc_term && k == 0) { re[0].v.x += (float)(N2 / 2) * (float)N1; im[0].v.x += (float)(N2 / 2) * (float)N1; }   // N/2 (1+i)
+#pragma unroll
+        for (int m = 0; m < N2; m++) {
+            const f2 pw = vfma2(re[m], re[m], vmul(im[m], im[m]));
+            uint8_t* dst = row + ((size_t)k + (size_t)N1 * (m ^ (N2 / 2))) * ESZ;
+            __align__(8) unsigned char tmp[8];
+            fsea_tile_put<OUT>(tmp, pw, kp.pix_scale);
+            if (m == 0 && dc_patch && k == 0) {                              // bin 0 is not stored (src/nrf.c:621-622)
+                if (ESZ == 4) ((float*)dst)[1] = ((const float*)tmp)[1]; else dst[1] = tmp[1];
+            } else if (ESZ == 4) {
+                *(float2*)dst = *(const float2*)tmp;
+            } else {
+                *(uchar2*)dst = *(const uchar2*)tmp;
+            }
+            if (m == N2 - 1 && dc_patch && k == N1 - 2) {                    // bin N-1 also fills the DC slot N/2
+                uint8_t* dc = row + (size_t)(N2 / 2) * N1 * ESZ;
+                if (ESZ == 4) ((float*)dc)[0] = ((const float*)tmp)[1]; else dc[0] = tmp[1];
+            }
+        }
+    }
+    // the U pairs p0 + u pstride, u < U, of one frame; ARRIVE: the fused kernel's "intermediate
+    // consumed" signal, given as soon as the loads have delivered their values
+    template <int ARRIVE>
+    static __device__ __forceinline__ void run(const fsea_kparams& kp, const float* yf, int p0, int pstride, uint8_t* row, bool dc_patch) {
+        f2 re[U][N2], im[U][N2];
+#pragma unroll
+        for (int u = 0; u < U; u++) load(yf, 2 * (p0 + u * pstride), re[u], im[u]);
+#pragma unroll
+        for (int u = 0; u < U; u++) twiddle(kp, 2 * (p0 + u * pstride), re[u], im[u]);
+        if (ARRIVE == 1) fsea_cluster_arrive_relaxed();
+#pragma unroll
+        for (int u = 0; u < U; u++) finish(kp, 2 * (p0 + u * pstride), row, dc_patch, re[u], im[u]);
+    }
+};
+
+// N2 = 64: a thread combs ONE bin k of one frame; the packed lanes are the even and the odd
+// sub-spectra (n2 = 2j, 2j+1 -- the two lanes step A produced together).  Decimation in time
+// once more: A = DFT32 over the even, B = DFT32 over the odd ones (one packed codelet), then
+// X[m] = A_m + W64^m B_m, X[m+32] = A_m - W64^m B_m across the lanes (fsea_cross64, scalar).
+// Twiddle pairs w[j] = (W^{2j k}, W^{(2j+1) k}) = w[j - low] * W^{2 low k}: the chain runs on
+// packed registers with a broadcast scalar factor.
+template <int OUT, int N1> struct fsea_comb<OUT, N1, 64> {
+    static const int ESZ = (OUT == FSEA_OUT_PIX) ? 1 : 4;
+    static const int U = 1;
+    static const int PTS = 64;
+    template <int ARRIVE>
+    static __device__ __forceinline__ void run(const fsea_kparams& kp, const float* yf, int k, int, uint8_t* row, bool dc_patch) {
+        f2 re[32], im[32];
+        const float* y = yf + k;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            re[j] = mk2(__ldcg(y + (size_t)(2 * j) * N1), __ldcg(y + (size_t)(2 * j + 1) * N1));
+            im[j] = mk2(__ldcg(y + (size_t)(64 + 2 * j) * N1), __ldcg(y + (size_t)(64 + 2 * j + 1) * N1));
+        }
+        float bc[6], bs[6];                                                      // W^(2^r k), r < 6
+#pragma unroll
+        for (int r = 0; r < 6; r++) {
+            bc[r] = __ldg((const float*)kp.tw4 + (size_t)(2 * r) * N1 + k);
+            bs[r] = __ldg((const float*)kp.tw4 + (size_t)(2 * r + 1) * N1 + k);
+        }
+        f2 wr[32], wi[32];
+        wr[0] = mk2(1.0f, bc[0]); wi[0] = mk2(0.0f, bs[0]);
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            if (j > 0) {
+                const int low = j & -j;
+                const int r = (low == 1) ? 1 : (low == 2) ? 2 : (low == 4) ? 3 : (low == 8) ? 4 : 5;   // W^{2 low k}
+                const int q = j - low;
+                wr[j] = vfnmas(wi[q], bs[r], vmuls(wr[q], bc[r]));               // wr c - wi s
+                wi[j] = vfmas(wr[q], bs[r], vmuls(wi[q], bc[r]));                // wr s + wi c
+            }
+            const f2 a = vsub(vmul(re[j], wr[j]), vmul(im[j], wi[j]));
+            im[j] = vfma2(re[j], wi[j], vmul(im[j], wr[j]));
+            re[j] = a;
+        }
+        if (ARRIVE == 1) fsea_cluster_arrive_relaxed();
+        fsea_dft32<f2>(re, im);
+        fsea_cross64(re, im);                                                     // lanes: (X[m], X[m+32])
+        if (kp.dc_term && k == 0) { re[0].v.x += 32.0f * (float)N1; im[0].v.x += 32.0f * (float)N1; }     // N/2 (1+i)
+#pragma unroll
+        for (int m = 0; m < 32; m++) {
+            const f2 pw = vfma2(re[m], re[m], vmul(im[m], im[m]));
+            __align__(8) unsigned char tmp[8];
+            fsea_tile_put<OUT>(tmp, pw, kp.pix_scale);
+            uint8_t* d0 = row + ((size_t)k + (size_t)N1 * (m + 32)) * ESZ;       // bin k + N1 m        (lane x)
+            uint8_t* d1 = row + ((size_t)k + (size_t)N1 * m) * ESZ;              // bin k + N1 (m + 32) (lane y)
+            if (!(m == 0 && dc_patch && k == 0)) {                               // bin 0 is not stored (src/nrf.c:621-622)
+                if (ESZ == 4) *(float*)d0 = ((const float*)tmp)[0]; else d0[0] = tmp[0];
+            }
+            if (ESZ == 4) *(float*)d1 = ((const float*)tmp)[1]; else d1[0] = tmp[1];
+            if (m == 31 && dc_patch && k == N1 - 1) {                            // bin N-1 also fills the DC slot N/2
+                uint8_t* dc = row + (size_t)32 * N1 * ESZ;
+                if (ESZ == 4) *(float*)dc = ((const float*)tmp)[1]; else dc[0] = tmp[1];
+            }
+        }
+    }
+};
+
+// two-launch form of step B (N2 = 32)
 template <int OUT, int N1>
 __global__ void __launch_bounds__(128, 3)
 fsea_comb32_kernel(const fsea_kparams kp) {
-    constexpr int n1 = N1;                                 // sub-spectrum length N1 = N / 32
-    constexpr int hp = n1 >> 1;                            // bin pairs per frame
+    constexpr int hp = N1 >> 1;                            // bin pairs per frame
     const long pairs = kp.n_seq;
     const bool dc_patch = (kp.flags & FSEA_FLAG_DC_PATCH) != 0;
     constexpr int ESZ = (OUT == FSEA_OUT_PIX) ? 1 : 4;
     for (long u = (long)blockIdx.x * blockDim.x + threadIdx.x; u < pairs; u += (long)gridDim.x * blockDim.x) {
         const long f = u / hp;
-        const int k = 2 * (int)(u - f * hp);
-        fsea_comb32_pair<OUT, 0, N1>(kp, (const float2*)((const float*)kp.in + (size_t)f * 64 * n1 + k), k,
-                                         (uint8_t*)kp.out + (size_t)f * 32 * n1 * ESZ, dc_patch);
+        const int p = (int)(u - f * hp);
+        fsea_comb<OUT, N1, 32>::template run<0>(kp, (const float*)kp.in + (size_t)f * 64 * N1, p, 0,
+                                                (uint8_t*)kp.out + (size_t)f * 32 * N1 * ESZ, dc_patch);
     }
 }
 
@@ -889,28 +984,29 @@ fsea_comb32_kernel(const fsea_kparams kp) {
 // The CS blocks of a cluster transform the sub-sequences of one frame (one tile each, step A),
 // meet at the cluster barrier, and each combs its share of the frame's bins (step B).  The
 // intermediate of a frame (8 N bytes) is written and read back within microseconds by blocks
-// of the same GPC: it lives in L2 (resident clusters x 8 N bytes = 28..57 MB) and never
-// reaches HBM, which leaves the algorithmic 2 + 4 bytes per point as the only DRAM traffic.
+// of the same GPC: it lives in L2 (resident clusters x 8 N bytes) and never reaches HBM, which
+// leaves the algorithmic 2 + 4 bytes per point as the only DRAM traffic.
 // Frames are dealt to clusters round-robin.  Two barrier phases per frame: "sub-spectra
 // published" (release/acquire, exposed) and "intermediate consumed" (relaxed arrive as soon as
-// step B's loads have landed, waited for at the top of the next frame: hidden).  A two-slot
-// variant that runs step A of frame i ahead of step B of frame i-1 was measured equal
-// (19.6 M frames/s at N = 16384) at twice the L2 footprint, so it is not kept.
-
-template <class SH, int G, bool TWS, int MINB, bool WIN, int OUT, int CS>
+// step B's loads have landed, waited for at the top of the next frame: hidden).  CS = 1 (one
+// block per frame, N = 8192): the block barrier plays both roles.
+template <class SH, int N2, int G, bool TWS, int MINB, bool WIN, int OUT, int CS>
 __global__ void __launch_bounds__(SH::T* G, MINB)
 fsea_fused4_kernel(const fsea_kparams kp) {
     typedef float2 S2;
-    typedef fsea_in<FSEA_IN_COLS, f2> IN;
-    constexpr int N = SH::N, T = SH::T, NPASS = SH::NPASS;
-    constexpr int RND = fsea_cols_rounds<N>::v;
-    constexpr int UPT = G * RND;                                    // units per tile = per block and frame
-    static_assert(UPT * CS == 16, "the cluster's tiles must cover the 16 unit pairs of a frame");
+    constexpr int N = SH::N, T = SH::T, NPASS = SH::NPASS;            // N: sub-spectrum length N1
+    constexpr int UPT = (N2 / 2) / CS;                                // units per tile = per block and frame
+    constexpr int RND = UPT / G;
+    static_assert(UPT * CS == N2 / 2 && RND * G == UPT, "the cluster's tiles must cover the N2/2 unit pairs of a frame");
+    constexpr int FMT = FSEA_IN_COLS_FMT(N2, RND);
+    typedef fsea_in<FMT, f2> IN;
+    typedef fsea_comb<OUT, N, N2> COMB;
     constexpr int XB = SH::UNITS * (int)sizeof(f2);
     constexpr int ESZ = (OUT == FSEA_OUT_PIX) ? 1 : 4;
-    constexpr int PPB = (N / 2) / CS;                               // bin pairs per block and frame
-    constexpr int BIT = PPB / (T * G);                              // step-B passes of the block per frame
-    static_assert(PPB % (T * G) == 0, "bin pairs must divide over the block");
+    constexpr int TPB = T * G;
+    constexpr int IPB = (N * N2 / COMB::PTS) / CS;                    // step-B thread-calls per block and frame
+    constexpr int BIT = IPB / TPB;                                    // step-B passes of the block per frame
+    static_assert(IPB % TPB == 0 && BIT >= 1, "step B must divide over the block");
 
     FSEA_DYN_SMEM(fsea_smem);
     const int tid = threadIdx.x;
@@ -922,25 +1018,26 @@ fsea_fused4_kernel(const fsea_kparams kp) {
     const S2* tw2 = (const S2*)kp.tw2;
     if (TWS) {
         S2* stw = reinterpret_cast<S2*>(fsea_smem + (size_t)G * XB + IN::template ring<N, G>::BYTES);
-        for (int q = tid; q < SH::TW1 + SH::TW2; q += T * G) stw[q] = (q < SH::TW1) ? tw1[q] : tw2[q - SH::TW1];
+        for (int q = tid; q < SH::TW1 + SH::TW2; q += TPB) stw[q] = (q < SH::TW1) ? tw1[q] : tw2[q - SH::TW1];
         __syncthreads();
         tw1 = stw;
         tw2 = stw + SH::TW1;
     }
     const bool dc_patch = (kp.flags & FSEA_FLAG_DC_PATCH) != 0;
-    const unsigned crank = fsea_cluster_ctarank();
+    const unsigned crank = CS > 1 ? fsea_cluster_ctarank() : 0u;
+    const long cid = CS > 1 ? (long)fsea_cluster_id() : (long)blockIdx.x;
+    const long step = CS > 1 ? (long)fsea_cluster_count() : (long)gridDim.x;
     const long frames = kp.n_seq;
-    const long step = fsea_cluster_count();
-    float* scr = (float*)kp.scratch + (size_t)fsea_cluster_id() * 64 * N;   // the cluster's slot: Yre[32][N], Yim[32][N]
+    float* scr = (float*)kp.scratch + (size_t)cid * 2 * N2 * N;        // the cluster's slot: Yre[N2][N], Yim[N2][N]
     fsea_kparams kc = kp;                                            // the loader counts sub-sequences
-    kc.n_seq = frames * 32;
+    kc.n_seq = frames * N2;
 
-    long f = fsea_cluster_id();
+    long f = cid;
     {
         IN in;
         bool live;
-        in.init(kc, f * 16 + crank * UPT + g, live);
-        if (f < frames) in.template async_tile<N, T * G, G>(tid, g, ring);
+        in.init(kc, f * (N2 / 2) + crank * UPT + g, live);
+        if (f < frames) in.template async_tile<N, TPB, G>(tid, g, ring);
         fsea_cp_async_commit();
     }
     // step A of frame f: this block's tile -> the sub-spectra rows of slot `dst`
@@ -948,33 +1045,38 @@ fsea_fused4_kernel(const fsea_kparams kp) {
         const bool more = fa + step < frames;
 #pragma unroll 1
         for (int r = 0; r < RND; r++) {
-            const int u16 = crank * UPT + r * G + g;                 // unit pair of the frame
+            const int u = crank * UPT + r * G + g;                   // unit pair of the frame
             IN in_r, in_next;
             bool lv;
-            in_r.init(kc, fa * 16 + u16, lv);
-            in_next.init(kc, (fa + step) * 16 + crank * UPT + g, lv);
-            fsea_out_cplx<N> out;
-            out.set(dst, u16);
-            fsea_transform<SH, f2, FSEA_IN_COLS, FSEA_OK_CPLX, N, G, WIN>(kc, in_r, in_next, more, out, xp, ring, tw1, tw2, t, g, tid,
-                                                                          false, 0, fsea_smem, nullptr, r * G + g, r == 0, r == RND - 1);
+            in_r.init(kc, fa * (N2 / 2) + u, lv);
+            in_next.init(kc, (fa + step) * (N2 / 2) + crank * UPT + g, lv);
+            fsea_out_cplx<N, N2> out;
+            out.set(dst, u);
+            fsea_transform<SH, f2, FMT, FSEA_OK_CPLX, N2, G, WIN>(kc, in_r, in_next, more, out, xp, ring, tw1, tw2, t, g, tid,
+                                                                 false, 0, fsea_smem, nullptr, r * G + g, r == 0, r == RND - 1);
             if (NPASS > 1) fsea_group_sync<T>(g);
         }
     };
     bool pending = false;                                        // an arrive of the "intermediate consumed" phase
     for (; f < frames; f += step) {
-        if (pending) fsea_cluster_wait_acquire();
+        if (CS > 1) { if (pending) fsea_cluster_wait_acquire(); }
+        else if (pending) __syncthreads();
         step_a(f, scr);
-        fsea_cluster_arrive_release();
-        fsea_cluster_wait_acquire();
-        uint8_t* row = (uint8_t*)kp.out + (size_t)f * 32 * N * ESZ;
+        if (CS > 1) {
+            fsea_cluster_arrive_release();
+            fsea_cluster_wait_acquire();
+        } else {
+            __syncthreads();
+        }
+        uint8_t* row = (uint8_t*)kp.out + (size_t)f * N2 * N * ESZ;
 #pragma unroll 1
         for (int it = 0; it < BIT; it++) {
-            const int k = 2 * ((int)crank * PPB + it * (T * G) + tid);
-            if (it == BIT - 1) fsea_comb32_pair<OUT, 1, N>(kp, (const float2*)(scr + k), k, row, dc_patch);
-            else fsea_comb32_pair<OUT, 0, N>(kp, (const float2*)(scr + k), k, row, dc_patch);
+            // the block's thread-calls of this pass: first index and stride between a thread's U items
+            const int first = (int)crank * (IPB * COMB::U) + it * TPB + tid;
+            if (CS > 1 && it == BIT - 1) COMB::template run<1>(kp, scr, first, BIT * TPB, row, dc_patch);
+            else COMB::template run<0>(kp, scr, first, BIT * TPB, row, dc_patch);
         }
         pending = true;
     }
-    if (pending) fsea_cluster_wait_acquire();
+    if (CS > 1 && pending) fsea_cluster_wait_acquire();
 }
-

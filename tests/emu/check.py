@@ -1,0 +1,71 @@
+"""TEST INFRASTRUCTURE: parity of the kernel SOURCE, executed on the CPU fiber machine
+(tests/emu/libfsea_emu.so), against the oracle.  Run as a subprocess by
+tests/test_emu_kernels.py with FSEA_LIB pointing at the emulated library.
+
+    FSEA_LIB=tests/emu/libfsea_emu.so python tests/emu/check.py <n> [<n> ...]
+"""
+import json
+import os
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np  # noqa: E402
+
+import frequensea_b200 as fb  # noqa: E402
+from conftest import synth_s8, synth_u8  # noqa: E402
+from oracle import orc  # noqa: E402
+
+
+def rel_err(got, ref):
+    ref = np.asarray(ref, dtype=np.float64)
+    rms = np.sqrt(np.mean(ref ** 2, axis=-1, keepdims=True))
+    return float(np.max(np.abs(got - ref) / rms))
+
+
+def rows(data, n, hop, frames, fmt, win, out, scale=10.0, flags=0):
+    return np.stack([orc.engine_frame(data[f * hop * 2:], n, fmt, win, out, scale, flags) for f in range(frames)])
+
+
+def check(n, frames):
+    res = {"n": n}
+    # (1) two's-complement input, magnitude, DC patch (nrf_fft semantics); more frames than clusters in flight
+    data = synth_s8(n * frames, seed=n)
+    plan = fb.Plan(n, in_format=fb.IN_S8, out_mode=fb.OUT_MAG, flags=fb.FLAG_DC_PATCH)
+    res["kernel"] = plan.kernel_name
+    got = plan.exec_host(data, frames)
+    ref = rows(data, n, n, frames, orc.IN_S8, orc.WIN_NONE, orc.OUT_MAG, flags=orc.FLAG_DC_PATCH)
+    res["mag_patch"] = rel_err(got, ref)
+    res["patch_dup"] = bool(np.array_equal(got[:, n // 2], got[:, n // 2 - 1]))
+    # (2) offset-binary input, uncentred DC kept, log-magnitude
+    data = synth_u8(n * 3, seed=n + 1)
+    plan = fb.Plan(n, in_format=fb.IN_U8, out_mode=fb.OUT_LOGMAG)
+    got = plan.exec_host(data, 3).astype(np.float64)
+    ref = rows(data, n, n, 3, orc.IN_U8, orc.WIN_NONE, orc.OUT_LOGMAG)
+    lin = 10 ** (ref / 20)
+    ok = lin >= 1e-3 * np.sqrt(np.mean(lin ** 2, axis=1, keepdims=True))
+    res["logmag_db"] = float(np.max(np.abs(got - ref)[ok]))
+    res["dc_bin_db"] = float(abs(got[0, n // 2] - ref[0, n // 2]))
+    # (3) Hann + 50 % overlap + pixels (the sweep product)
+    hop = n // 2
+    data = synth_u8(2 * hop + n, seed=n + 2)
+    plan = fb.Plan(n, hop=hop, in_format=fb.IN_U8, window=fb.WIN_HANN, out_mode=fb.OUT_PIX, pix_scale=5.0,
+                   flags=fb.FLAG_DC_PATCH)
+    got = plan.exec_host(data, 3)
+    ref = rows(data, n, hop, 3, orc.IN_U8, orc.WIN_HANN, orc.OUT_PIX, 5.0, orc.FLAG_DC_PATCH)
+    d = np.abs(got.astype(int) - ref.astype(int))
+    res["pix_max"] = int(d.max())
+    res["pix_frac"] = float((d > 0).mean())
+    return res
+
+
+if __name__ == "__main__":
+    assert "emu" in fb.lib_path(), "this script checks the EMULATED library only"
+    out = []
+    for a in sys.argv[1:]:
+        n = int(a)
+        out.append(check(n, 9 if n >= 8192 else 7))
+    print(json.dumps(out))

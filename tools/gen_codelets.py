@@ -1,6 +1,6 @@
 #!/usr/bin/env python3
 """Generate frequensea_b200/csrc/fsea_codelets.cuh: straight-line forward-DFT
-register codelets of size R in {2,4,8,16,32}, type-generic over the vector
+register codelets of size R in {2,4,8,16,32,64}, type-generic over the vector
 type V (float, double, or the packed 2 x fp32 pair f2 -> FADD2/FMUL2/FFMA2).
 
 Structure: recursive radix-2 decimation in time.  Every butterfly
@@ -170,24 +170,55 @@ def codelet(R, raw=False):
             f"    typedef typename fsea_vt<V>::scalar S;\n{body}\n{stores}\n}}\n"), g.ops
 
 
+def cross64():
+    """X[m] = A_m + W64^m B_m, X[m+32] = A_m - W64^m B_m on the two lanes of packed registers
+    (A in .x, B in .y -> X[m] in .x, X[m+32] in .y): the last radix-2 stage of a 64-point
+    decimation in time whose halves were transformed by one packed radix-32 codelet."""
+    L = ["// cross-lane radix-2 stage of a 64-point DIT: in (A_m, B_m), out (X[m], X[m+32]); scalar fp32",
+         "#if defined(__CUDACC__) || defined(FSEA_EMU)",
+         "FSEA_D void fsea_cross64(f2* __restrict__ re, f2* __restrict__ im) {"]
+    for m in range(32):
+        L.append(f"    {{ const float ar = re[{m}].v.x, br = re[{m}].v.y, ai = im[{m}].v.x, bi = im[{m}].v.y;")
+        fr = Fraction(m, 64)
+        if m == 0:
+            L.append("      re[0].v.x = ar + br; re[0].v.y = ar - br; im[0].v.x = ai + bi; im[0].v.y = ai - bi; }")
+            continue
+        if m == 16:                                   # W = -i : W*B = (bi, -br)
+            L.append(f"      re[{m}].v.x = ar + bi; re[{m}].v.y = ar - bi; im[{m}].v.x = ai - br; im[{m}].v.y = ai + br; }}")
+            continue
+        c, s_ = _cos_sin(fr)                          # W = c - i s ; W*B = (c br + s bi, c bi - s br)
+        if abs(c) >= abs(s_):
+            t, mm = s_ / c, c
+            L.append(f"      const float ur = fmaf({float(t)!r}f, bi, br), ui = fmaf({float(-t)!r}f, br, bi);")
+        else:
+            t, mm = c / s_, s_
+            L.append(f"      const float ur = fmaf({float(t)!r}f, br, bi), ui = fmaf({float(t)!r}f, bi, -br);")
+        L.append(f"      re[{m}].v.x = fmaf({float(mm)!r}f, ur, ar); re[{m}].v.y = fmaf({float(-mm)!r}f, ur, ar);"
+                 f" im[{m}].v.x = fmaf({float(mm)!r}f, ui, ai); im[{m}].v.y = fmaf({float(-mm)!r}f, ui, ai); }}")
+    L.append("}")
+    L.append("#endif")
+    return "\n".join(L) + "\n"
+
+
 def main():
     out = ["// GENERATED by tools/gen_codelets.py -- do not edit.\n"
            "// Forward DFT register codelets, X[k] = sum_j x[j] exp(-2 pi i j k / R),\n"
            "// natural order in, natural order out, in place on re[]/im[].\n"
            "#pragma once\n#include \"fsea_vec.cuh\"\n"]
     out.append("template <typename V>\nFSEA_HD void fsea_dft1(V*, V*) {}\n")
-    for R in (2, 4, 8, 16, 32):
+    for R in (2, 4, 8, 16, 32, 64):
         src, ops = codelet(R)
         out.append(src)
-    for R in (8, 16, 32):
+    for R in (8, 16, 32, 64):
         src, ops = codelet(R, raw=True)
         out.append(src)
+    out.append(cross64())
     out.append("template <int R, typename V> struct fsea_dft;\n" + "".join(
         f"template <typename V> struct fsea_dft<{R}, V> {{ static FSEA_HD void run(V* re, V* im) {{ fsea_dft{R}<V>(re, im); }} }};\n"
-        for R in (1, 2, 4, 8, 16, 32)))
+        for R in (1, 2, 4, 8, 16, 32, 64)))
     out.append("template <int R, typename V> struct fsea_dft_raw;\n" + "".join(
         f"template <typename V> struct fsea_dft_raw<{R}, V> {{ static FSEA_HD void run(V* re, V* im) {{ fsea_dft{R}_raw<V>(re, im); }} }};\n"
-        for R in (8, 16, 32)))
+        for R in (8, 16, 32, 64)))
     sys.stdout.write("\n".join(out))
 
 

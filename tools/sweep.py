@@ -42,7 +42,7 @@ def load(path):
     return _libs[path]
 
 
-def run(item, steps=5, warmup=3):
+def run(item, steps=int(os.environ.get("SWEEP_STEPS", "5")), warmup=int(os.environ.get("SWEEP_WARMUP", "3"))):
     parts = (item.split(":") + ["", "", ""])[:4]
     wl, arith, libp = parts[0], parts[1] or "auto", parts[2] or B.lib_path()
     envs = [kv.split("=") for kv in parts[3].split(",") if kv]          # ENV=VAL[,ENV=VAL] for this item only
