@@ -11,7 +11,9 @@ enum {
     FSEA_VAR_F64 = 3,    // double2 samples, fp64
     FSEA_VAR_F32_WIN = 4,    // as F32 / F32X2 with the Hann multiply compiled in
     FSEA_VAR_F32X2_WIN = 5,
-    FSEA_VAR_COUNT = 6
+    FSEA_VAR_F32X2H = 6,     // 8-bit IQ, ONE frame per group: lanes = even / odd samples, radix-2 across the lanes at the end
+    FSEA_VAR_F32X2H_WIN = 7,
+    FSEA_VAR_COUNT = 8
 };
 
 struct fsea_kernel_info {
@@ -23,6 +25,7 @@ struct fsea_kernel_info {
     int n, r0, r1, r2;   // shape
     int tw1, tw2;        // twiddle table entries
     int scalar_bytes;    // 4 or 8
+    int half;            // 1: n, r0.. describe the (N/2)-point transform of a "half" kernel
     const char* name;
 };
 

@@ -79,6 +79,7 @@ struct fsea_plan {
     int out_elem_bytes;
     void* d_tw1 = nullptr;
     void* d_tw2 = nullptr;
+    void* d_twh = nullptr;                       // "half" kernels: W_N^i of the output stage
     float* d_window = nullptr;
     int max_blocks = 0;             // resident blocks on the device
     long launches = 0;
@@ -164,6 +165,7 @@ extern "C" int fsea_plan_destroy(fsea_plan* p) {
     }
     if (p->d_tw1) cudaFree(p->d_tw1);
     if (p->d_tw2) cudaFree(p->d_tw2);
+    if (p->d_twh) cudaFree(p->d_twh);
     if (p->d_window) cudaFree(p->d_window);
     if (p->d_gate) cudaFree(p->d_gate);
     if (p->d_tickets) cudaFree(p->d_tickets);
@@ -216,9 +218,9 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
     const bool eight = cfg->in_format == FSEA_IN_U8 || cfg->in_format == FSEA_IN_S8;
     int alt = 0;
     if (const char* ev = getenv("FSEA_FOUR_ALT")) alt = atoi(ev);                 // A/B runs
-    // N >= 16384 always runs four-step; N = 8192 does for 8-bit input in the default arithmetic
-    // (FSEA_ARITH_F32 / _F32X2 ask for the single-kernel transform explicitly)
-    bool want4 = !get || (n == 8192 && eight && cfg->arith == FSEA_ARITH_AUTO && !getenv("FSEA_8192_DIRECT"));
+    // N >= 16384 always runs four-step; N = 8192 can (FSEA_8192_FOUR, A/B runs: measured slower
+    // than the single-kernel transform)
+    bool want4 = !get || (n == 8192 && eight && cfg->arith == FSEA_ARITH_AUTO && getenv("FSEA_8192_FOUR"));
     const bool four = want4 && eight && fsea_get_kernel4(n, cfg->window == FSEA_WIN_HANN, cfg->out_mode, alt, &k4);
     if (!get && !four) return FSEA_ERR_UNSUPPORTED;
     if (cfg->in_format < FSEA_IN_U8 || cfg->in_format > FSEA_IN_F64C) return FSEA_ERR_INVALID;
@@ -239,7 +241,11 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
         case FSEA_IN_U8:
         case FSEA_IN_S8:
             p->variant = (cfg->arith == FSEA_ARITH_F32) ? FSEA_VAR_F32 : FSEA_VAR_F32X2;
-            if (cfg->window == FSEA_WIN_HANN) p->variant = (p->variant == FSEA_VAR_F32) ? FSEA_VAR_F32_WIN : FSEA_VAR_F32X2_WIN;
+            // one frame per unit where that is the faster arrangement (measured)
+            if (cfg->arith == FSEA_ARITH_F32X2_FRAME || (cfg->arith == FSEA_ARITH_AUTO && (n == 2048 || n == 8192)))
+                p->variant = FSEA_VAR_F32X2H;
+            if (cfg->window == FSEA_WIN_HANN)
+                p->variant = (p->variant == FSEA_VAR_F32) ? FSEA_VAR_F32_WIN : (p->variant == FSEA_VAR_F32X2H ? FSEA_VAR_F32X2H_WIN : FSEA_VAR_F32X2_WIN);
             p->sample_bytes = 2;
             break;
         case FSEA_IN_F32C: p->variant = FSEA_VAR_F32C; p->sample_bytes = 8; break;
@@ -253,7 +259,10 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
         p->ki.n = k4.n1; p->ki.r0 = k4.r0; p->ki.r1 = k4.r1; p->ki.r2 = k4.r2;
         p->ki.tw1 = k4.tw1; p->ki.tw2 = k4.tw2; p->ki.scalar_bytes = 4; p->ki.name = k4.name;
         p->variant = FSEA_VAR_F32X2;
-    } else if (!get(p->variant, &p->ki)) { delete p; return FSEA_ERR_UNSUPPORTED; }
+    } else {
+        memset(&p->ki, 0, sizeof(p->ki));
+        if (!get(p->variant, &p->ki)) { delete p; return FSEA_ERR_UNSUPPORTED; }
+    }
     p->out_elem_bytes = (cfg->out_mode == FSEA_OUT_PIX) ? 1 : p->ki.scalar_bytes;
 
     int rc = FSEA_OK;
@@ -263,8 +272,24 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
         // staged 8-bit kernels transform integer-scaled samples (b - 128): the 1/256 of
         // src/nrf.c:605-606 rides on the pass-1 twiddles
         const bool staged = p->four || ((p->variant == FSEA_VAR_F32 || p->variant == FSEA_VAR_F32X2 ||
-                                         p->variant == FSEA_VAR_F32_WIN || p->variant == FSEA_VAR_F32X2_WIN) && p->ki.r1 > 1);
+                                         p->variant == FSEA_VAR_F32_WIN || p->variant == FSEA_VAR_F32X2_WIN ||
+                                         p->variant == FSEA_VAR_F32X2H || p->variant == FSEA_VAR_F32X2H_WIN) && p->ki.r1 > 1);
         if ((rc = upload_twiddles(p->ki, &p->d_tw1, &p->d_tw2, staged ? 1.0f / 256.0f : 1.0f)) != FSEA_OK) break;
+        if (p->ki.half) {
+            // output stage of the "half" kernels: W_N^i for the butterflies i < M of the last pass
+            const int rl = p->ki.r2 > 1 ? p->ki.r2 : (p->ki.r1 > 1 ? p->ki.r1 : p->ki.r0);
+            const int m = p->ki.n / rl;
+            std::vector<float2> th((size_t)m);
+            const long double PI2 = 6.283185307179586476925286766559005768L;
+            for (int i = 0; i < m; i++) {
+                const long double a = -PI2 * (long double)i / (long double)n;
+                th[i].x = (float)cosl(a); th[i].y = (float)sinl(a);
+            }
+            if ((e = cudaMalloc(&p->d_twh, th.size() * sizeof(float2))) != cudaSuccess ||
+                (e = cudaMemcpy(p->d_twh, th.data(), th.size() * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess) {
+                rc = cuda_fail(e, "half-kernel table"); break;
+            }
+        }
         if (p->four) {
             // step B builds W_N^{n2 k} from the rows n2 = 1, 2, 4, .. of this table
             const int n1 = p->k4.n1;
@@ -353,6 +378,7 @@ static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cu
     kp.xor_mask = p->cfg.in_format == FSEA_IN_S8 ? 0x8080u : 0u;
     kp.dump = p->d_dump;
     kp.tw4 = p->d_tw4;
+    kp.twh = p->d_twh;
     kp.n1 = kp.n2 = 0;
     kp.scratch = nullptr;
     if (p->four) {

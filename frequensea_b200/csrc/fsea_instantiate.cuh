@@ -8,7 +8,7 @@ struct fsea_cfg {
     static const int UNIT_BYTES = 2 * (int)sizeof(V);
     static const int SB = (int)sizeof(typename fsea_vt<V>::scalar);
     static const bool COLS = fsea_cols_geom<FMT>::COLS;
-    static const bool STAGED = SH::NPASS > 1 && SB == 4 && (FMT == FSEA_IN_U8 || COLS);
+    static const bool STAGED = SH::NPASS > 1 && SB == 4 && (FMT == FSEA_IN_U8 || FMT == FSEA_IN_U8H || COLS);
     static const int RINGB = COLS ? 4 * fsea_cols_geom<FMT>::RND * SH::N : fsea_vt<V>::lanes * 2 * SH::N;     // (COLS: per group, of the block's tile ring)
     static const int XBYTES = SH::NPASS > 1 ? SH::UNITS * (int)sizeof(V) + (STAGED ? RINGB : 0) : 0;   // exchange plane + raw ring per group
     static const int TWBYTES = (SH::TW1 + SH::TW2) * 2 * SB;
@@ -41,7 +41,8 @@ static bool fsea_fill(fsea_kernel_info* o, const char* name) {
     o->fn = (const void*)&fsea_fft_kernel<SH, V, FMT, OK, NTOT, C::G, C::TWS, C::MINB, WIN>;
     o->threads = SH::T * C::G;
     o->groups = C::G;
-    o->lanes = fsea_vt<V>::lanes;
+    o->lanes = (FMT == FSEA_IN_U8H) ? 1 : fsea_vt<V>::lanes;     // frames per unit
+    o->half = (FMT == FSEA_IN_U8H) ? 1 : 0;                       // SH is the shape of the half-length transform
     o->smem = C::SMEM;
     o->n = SH::N; o->r0 = SH::R0; o->r1 = SH::R1; o->r2 = SH::R2;
     o->tw1 = SH::TW1; o->tw2 = SH::TW2;
@@ -55,11 +56,19 @@ static bool fsea_fill(fsea_kernel_info* o, const char* name) {
 // SH: shape of the packed (f32x2), float2-sample and fp64 variants; SHS: shape of the scalar fp32
 // variants (a thread may hold 64 points there: 2048 = 64 x 32 and 4096 = 64 x 64 need ONE exchange)
 #define FSEA_SHAPE_NAME(N, R0, R1, R2) FSEA_STR(N) ":" FSEA_STR(R0) "x" FSEA_STR(R1) "x" FSEA_STR(R2)
-#define FSEA_DEFINE_SIZE2(N, R0, R1, R2, S0, S1, S2)                                                     \
+// SHH: shape of the (N/2)-point transform of the "half" variants (one frame per unit, H0 = 0: none)
+#define FSEA_DEFINE_SIZE3(N, R0, R1, R2, S0, S1, S2, H0, H1, H2)                                         \
     bool fsea_get_kernel_##N(int variant, fsea_kernel_info* out) {                                       \
         typedef fsea_shape<N, R0, R1, R2> SH;                                                            \
         typedef fsea_shape<N, S0, S1, S2> SHS;                                                           \
+        typedef fsea_shape<(H0 ? N / 2 : 64), (H0 ? H0 : 8), (H0 ? H1 : 8), (H0 ? H2 : 1)> SHH;          \
         switch (variant) {                                                                               \
+            case FSEA_VAR_F32X2H:                                                                        \
+                if constexpr (H0 == 0) return false; else                                               \
+                return fsea_fill<SHH, f2, FSEA_IN_U8H, FSEA_OK_HALF>(out, "fft<" FSEA_STR(N) "=2x(" FSEA_STR(H0) "x" FSEA_STR(H1) "x" FSEA_STR(H2) "),f32x2 frame/unit>");      \
+            case FSEA_VAR_F32X2H_WIN:                                                                    \
+                if constexpr (H0 == 0) return false; else                                               \
+                return fsea_fill<SHH, f2, FSEA_IN_U8H, FSEA_OK_HALF, N / 2, true>(out, "fft<" FSEA_STR(N) "=2x(" FSEA_STR(H0) "x" FSEA_STR(H1) "x" FSEA_STR(H2) "),f32x2 frame/unit,win>");      \
             case FSEA_VAR_F32:                                                                           \
                 return fsea_fill<SHS, float, FSEA_IN_U8>(out, "fft<" FSEA_SHAPE_NAME(N, S0, S1, S2) ",f32>");      \
             case FSEA_VAR_F32X2:                                                                         \
@@ -75,4 +84,5 @@ static bool fsea_fill(fsea_kernel_info* o, const char* name) {
         }                                                                                                \
         return false;                                                                                    \
     }
+#define FSEA_DEFINE_SIZE2(N, R0, R1, R2, S0, S1, S2) FSEA_DEFINE_SIZE3(N, R0, R1, R2, S0, S1, S2, 0, 0, 0)
 #define FSEA_DEFINE_SIZE(N, R0, R1, R2) FSEA_DEFINE_SIZE2(N, R0, R1, R2, R0, R1, R2)

@@ -1,10 +1,10 @@
-// fsea_k_4096.cu -- 4096-point instantiations: packed N = 32 x 32 x 4, scalar N = 64 x 64
-// (-DFSEA_S4096_R0=.. _R1 _R2 for A/B builds of the packed shape)
+// fsea_k_4096.cu -- 4096-point instantiations: packed pairs N = 32 x 32 x 4, scalar N = 64 x 64,
+// frame per unit 2 x (32 x 8 x 8)   (-DFSEA_S4096_R0=.. _R1 _R2 for A/B builds of the packed shape)
 #include "fsea_instantiate.cuh"
 #ifndef FSEA_S4096_R0
 #define FSEA_S4096_R0 32
 #define FSEA_S4096_R1 32
 #define FSEA_S4096_R2 4
 #endif
-#define FSEA_DEF(...) FSEA_DEFINE_SIZE2(__VA_ARGS__)
-FSEA_DEF(4096, FSEA_S4096_R0, FSEA_S4096_R1, FSEA_S4096_R2, 64, 64, 1)
+#define FSEA_DEF(...) FSEA_DEFINE_SIZE3(__VA_ARGS__)
+FSEA_DEF(4096, FSEA_S4096_R0, FSEA_S4096_R1, FSEA_S4096_R2, 64, 64, 1, 32, 8, 8)

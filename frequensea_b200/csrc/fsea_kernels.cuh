@@ -43,7 +43,12 @@ template <int FMT> struct fsea_cols_geom {
     static const int N2 = COLS ? (FMT % 1000) - 100 : 32;
     static const int RND = COLS ? FMT / 1000 : 1;
 };
-enum { FSEA_OK_SPECTRUM = 0, FSEA_OK_CPLX = 3 };
+enum { FSEA_OK_SPECTRUM = 0, FSEA_OK_CPLX = 3, FSEA_OK_HALF = 4 };
+// "half" kernels: ONE frame of 2 N samples per unit, the packed lanes being its even and odd
+// samples -- the N-point transform runs on both at once and the output stage finishes the
+// radix-2 decimation in time across the lanes (fsea_out_half).  Halves the threads and the
+// shared memory a frame needs: 2048 = 2 x 1024 stays inside one warp.
+enum { FSEA_IN_U8H = 20 };
 
 
 template <int X> struct fsea_log2 { static const int v = 1 + fsea_log2<X / 2>::v; };
@@ -218,6 +223,44 @@ template <> struct fsea_in<FSEA_IN_F64C, double> {
     template <int N> __device__ __forceinline__ void load_staged_raw(const unsigned char*, int, double&, double&) const {}
 };
 
+// ---- one frame per unit, lanes = (even, odd) samples: element e of the packed sequence is the
+// four adjacent bytes I,Q,I,Q of samples 2e and 2e+1 ------------------------------------------
+template <> struct fsea_in<FSEA_IN_U8H, f2> {
+    const uint8_t* p;
+    const float* win;
+    uint32_t x4;
+    __device__ __forceinline__ void init(const fsea_kparams& kp, long unit, bool& live) {
+        live = unit < kp.n_seq;
+        const long s = live ? unit : kp.n_seq - 1;
+        p = (const uint8_t*)kp.in + s * kp.seq_stride * 2;
+        win = kp.window;
+        x4 = kp.xor_mask | (kp.xor_mask << 16);
+    }
+    static __device__ __forceinline__ void unpack(uint32_t w, f2& re, f2& im) {
+        re = mk2(__uint_as_float(__byte_perm(w, 0x47000000u, 0x7504)), __uint_as_float(__byte_perm(w, 0x47000000u, 0x7524)));
+        im = mk2(__uint_as_float(__byte_perm(w, 0x47000000u, 0x7514)), __uint_as_float(__byte_perm(w, 0x47000000u, 0x7534)));
+    }
+    __device__ __forceinline__ void load(int e, f2& re, f2& im) const {              // (unstaged: single-pass shapes)
+        unpack(__ldg((const uint32_t*)p + e) ^ x4, re, im);
+        const f2 off = mk2(32896.0f, 32896.0f), sc = mk2(1.0f / 256.0f, 1.0f / 256.0f);
+        re = vmul(vsub(re, off), sc); im = vmul(vsub(im, off), sc);
+    }
+    __device__ __forceinline__ f2 window(int e) const {
+        const float2 w = __ldg((const float2*)win + e);
+        return mk2(w.x, w.y);
+    }
+    template <int N, int T> __device__ __forceinline__ void prefetch(int) const {}
+    template <int N, int T> __device__ __forceinline__ void async_stage(int t, unsigned char* sm) const;   // 4 N bytes
+    template <int N> __device__ __forceinline__ void load_staged_raw(const unsigned char* sm, int e, f2& re, f2& im) const {
+        unpack(((const uint32_t*)sm)[e] ^ x4, re, im);
+    }
+    template <int N> __device__ __forceinline__ void load_staged(const unsigned char* sm, int e, f2& re, f2& im) const {
+        load_staged_raw<N>(sm, e, re, im);
+        const f2 off = mk2(32896.0f, 32896.0f);
+        re = vsub(re, off); im = vsub(im, off);
+    }
+};
+
 // ---- four-step, decimation in time (N = N1 x N2, n = N2 n1 + n2) ------------------
 // Step A is this file's transform on the N2 interleaved sub-sequences x[N2 n1 + n2] of a frame:
 // a unit is the PAIR of neighbouring sub-sequences (n2, n2+1) -- four adjacent bytes per n1,
@@ -362,6 +405,56 @@ template <int N, typename V> struct fsea_out {
     }
 };
 
+// Output side of the "half" kernels.  After the last pass a thread holds, per butterfly i, the
+// bins k = i + m M (m < R) of the even-sample transform E (lane x) and of the odd-sample
+// transform O (lane y) of ONE frame of 2 N samples.  X[k] = E[k] + W_2N^k O[k],
+// X[k + N] = E[k] - W_2N^k O[k] with W_2N^k = W_2N^i W_2R^m: the thread's own factor W_2N^i
+// comes from a table (kp.twh, M entries), the W_2R^m are the constants of fsea_cross<R>.
+// Shifted positions (src/nrf.c:611-612): bin k -> k + N, bin k + N -> k.
+template <int N> struct fsea_out_half {
+    uint8_t* row;
+    const float2* twh;
+    float pix_scale, dc;
+    __device__ __forceinline__ void init(const fsea_kparams& kp, long unit, bool unit_live, int esz) {
+        pix_scale = kp.pix_scale;
+        twh = (const float2*)kp.twh;
+        dc = kp.dc_term ? (float)N : 0.0f;                                 // N/2 (1+i) of the 2N-point frame
+        row = unit_live ? (uint8_t*)kp.out + (size_t)unit * (2 * N) * esz : (uint8_t*)kp.dump;
+    }
+    template <int OUT> __device__ __forceinline__ void put(int pos, float pwr) const {
+        if (OUT == FSEA_OUT_MAG) ((float*)row)[pos] = fsea_sqrt_approx(pwr);
+        else if (OUT == FSEA_OUT_LOGMAG) ((float*)row)[pos] = fsea_db(pwr);
+        else row[pos] = fsea_pix(fsea_db(pwr), pix_scale);
+    }
+    template <int OUT, int R, int M>
+    __device__ __forceinline__ void store_bfly(int i, f2* re, f2* im, bool dc_patch) const {
+        const float2 w = __ldg(twh + i);                                   // W_2N^i
+#pragma unroll
+        for (int m = 0; m < R; m++) {                                      // O <- W_2N^i O
+            const float br = re[m].v.y, bi = im[m].v.y;
+            re[m].v.y = fmaf(br, w.x, -bi * w.y);
+            im[m].v.y = fmaf(br, w.y, bi * w.x);
+        }
+        fsea_cross<R>(re, im);                                             // lanes: (X[k], X[k + N])
+        if (i == 0) { re[0].v.x += dc; im[0].v.x += dc; }
+#pragma unroll
+        for (int m = 0; m < R; m++) {
+            const int k = i + m * M;
+            const f2 pw = vfma2(re[m], re[m], vmul(im[m], im[m]));
+            if (!(m == 0 && dc_patch && i == 0)) put<OUT>(k + N, pw.v.x);      // bin 0 is not stored (src/nrf.c:621-622)
+            put<OUT>(k, pw.v.y);
+            if (m == R - 1 && dc_patch && i == M - 1) put<OUT>(N, pw.v.y);     // bin 2N-1 also fills the DC slot
+        }
+    }
+    template <int R, int M>
+    __device__ __forceinline__ void store_sel(int mode, int i, f2* re, f2* im, bool dc_patch) const {
+        if (mode == FSEA_OUT_MAG) store_bfly<FSEA_OUT_MAG, R, M>(i, re, im, dc_patch);
+        else if (mode == FSEA_OUT_LOGMAG) store_bfly<FSEA_OUT_LOGMAG, R, M>(i, re, im, dc_patch);
+        else store_bfly<FSEA_OUT_PIX, R, M>(i, re, im, dc_patch);
+    }
+    __device__ __forceinline__ void dc_adjust(const fsea_kparams&, int, f2&, f2&) const {}
+};
+
 // values of one bin pair in the output element type
 template <int OUT> __device__ __forceinline__ void fsea_tile_put(unsigned char* p, f2 pw, float pix_scale) {
     if (OUT == FSEA_OUT_MAG) *(float2*)p = make_float2(fsea_sqrt_approx(pw.v.x), fsea_sqrt_approx(pw.v.y));
@@ -401,6 +494,7 @@ template <int N, int N2> struct fsea_out_cplx {
 // (NTOT: the four-step factor N2 for complex rows, unused for spectra)
 template <int OK, int N, int NTOT, typename V> struct fsea_out_sel { typedef fsea_out<N, V> type; };
 template <int N, int NTOT> struct fsea_out_sel<FSEA_OK_CPLX, N, NTOT, f2> { typedef fsea_out_cplx<N, NTOT> type; };
+template <int N, int NTOT> struct fsea_out_sel<FSEA_OK_HALF, N, NTOT, f2> { typedef fsea_out_half<N> type; };
 
 // ---- group barrier ----------------------------------------------------------
 template <int T> __device__ __forceinline__ void fsea_group_sync(int group) {
@@ -430,6 +524,10 @@ template <int FMT> template <int N, int T>
 __device__ __forceinline__ void fsea_in<FMT, f2>::async_stage(int t, unsigned char* sm) const {
     fsea_async_frame<N, T>(pa, sm, t);
     fsea_async_frame<N, T>(pb, sm + 2 * N, t);
+}
+template <int N, int T>
+__device__ __forceinline__ void fsea_in<FSEA_IN_U8H, f2>::async_stage(int t, unsigned char* sm) const {
+    fsea_async_frame<2 * N, T>(p, sm, t);
 }
 
 // ---- dynamic work distribution ------------------------------------------------
@@ -476,7 +574,7 @@ __device__ __forceinline__ float fsea_transform(const fsea_kparams& kp, const fs
     constexpr int N = SH::N, R0 = SH::R0, R1 = SH::R1, R2 = SH::R2, P = SH::P, T = SH::T;
     constexpr int L0 = SH::L0, NPASS = SH::NPASS;
     constexpr bool COLS = fsea_cols_geom<FMT>::COLS;
-    constexpr bool STAGED = (FMT == FSEA_IN_U8 || COLS) && NPASS > 1 && sizeof(S) == 4;
+    constexpr bool STAGED = (FMT == FSEA_IN_U8 || FMT == FSEA_IN_U8H || COLS) && NPASS > 1 && sizeof(S) == 4;
     constexpr int XB = NPASS > 1 ? SH::UNITS * (int)sizeof(V) : 0;
     (void)tw1; (void)tw2; (void)xp; (void)raw; (void)smem_base; (void)tid; (void)more; (void)slot; (void)ring_first; (void)ring_last;
     V re[P], im[P];
@@ -680,7 +778,7 @@ fsea_fft_kernel(const fsea_kparams kp) {
     constexpr int L0 = SH::L0, NPASS = SH::NPASS;
     constexpr int LANES = fsea_vt<V>::lanes;
     constexpr bool COLS = fsea_cols_geom<FMT>::COLS;
-    constexpr bool STAGED = (FMT == FSEA_IN_U8 || COLS) && NPASS > 1 && sizeof(S) == 4;
+    constexpr bool STAGED = (FMT == FSEA_IN_U8 || FMT == FSEA_IN_U8H || COLS) && NPASS > 1 && sizeof(S) == 4;
     // four-step kernels hand out TILES of G neighbouring units per block (adjacent columns /
     // rows -> contiguous bytes across the block); the others hand out single units per group
     constexpr bool TILED = COLS;
@@ -708,7 +806,7 @@ fsea_fft_kernel(const fsea_kparams kp) {
     const bool dc_patch = (kp.flags & FSEA_FLAG_DC_PATCH) != 0;
     const int out_mode = kp.out_mode;
     const int out_esz = (out_mode == FSEA_OUT_PIX) ? 1 : (int)sizeof(S);
-    const long n_units = (kp.n_seq + LANES - 1) / LANES;
+    const long n_units = (FMT == FSEA_IN_U8H) ? kp.n_seq : (kp.n_seq + LANES - 1) / LANES;   // (half: a frame per unit)
     unsigned* ticket = kp.ticket;                                 // [0] next unit, [1] blocks finished
     FSEA_STATIC_SMEM(unsigned, fsea_slot, G > 0 ? G : 1);
     FSEA_STATIC_SMEM(unsigned, fsea_tile_slot_, 1);
@@ -943,7 +1041,7 @@ template <int OUT, int N1> struct fsea_comb<OUT, N1, 64> {
         }
         if (ARRIVE == 1) fsea_cluster_arrive_relaxed();
         fsea_dft32<f2>(re, im);
-        fsea_cross64(re, im);                                                     // lanes: (X[m], X[m+32])
+        fsea_cross<32>(re, im);                                                   // lanes: (X[m], X[m+32])
         if (kp.dc_term && k == 0) { re[0].v.x += 32.0f * (float)N1; im[0].v.x += 32.0f * (float)N1; }     // N/2 (1+i)
 #pragma unroll
         for (int m = 0; m < 32; m++) {

@@ -20,5 +20,6 @@ struct fsea_kparams {
     int n1, n2;            // four-step factors (0 otherwise)
     void* dump;            // N x 8 bytes: where sequences beyond the batch are written
     uint32_t xor_mask;     // 0x8080 for two's-complement input (FSEA_IN_S8), else 0
+    const void* twh;       // "half" kernels: W_2N^i, i < M (butterflies of the last pass), float2
     void* scratch;         // fused four-step: resident clusters x N float2 (the L2-resident intermediate)
 };

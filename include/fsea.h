@@ -52,7 +52,8 @@ enum { FSEA_WIN_NONE = 0, FSEA_WIN_HANN = 1 };
 enum { FSEA_OUT_MAG = 0, FSEA_OUT_LOGMAG = 1, FSEA_OUT_PIX = 2 };
 enum { FSEA_FLAG_DC_PATCH = 1 };
 /* arithmetic variant of the fp32 kernels (results agree to fp32 rounding) */
-enum { FSEA_ARITH_AUTO = 0, FSEA_ARITH_F32 = 1, FSEA_ARITH_F32X2 = 2 };
+enum { FSEA_ARITH_AUTO = 0, FSEA_ARITH_F32 = 1, FSEA_ARITH_F32X2 = 2,
+       FSEA_ARITH_F32X2_FRAME = 3 /* packed lanes = even / odd samples of ONE frame (N = 2048, 4096, 8192; 8-bit input) */ };
 
 enum {
     FSEA_OK = 0,

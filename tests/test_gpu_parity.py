@@ -100,6 +100,41 @@ def test_hann_overlap_logmag(fbg, n, hop):
     assert rel_err(got, ref) < MAG_TOL
 
 
+@pytest.mark.parametrize("arith", [0, 3])
+@pytest.mark.parametrize("n", [2048, 4096, 8192])
+def test_frame_per_unit_variants(fbg, n, arith):
+    """One frame per unit (packed lanes = even / odd samples, radix-2 across the lanes in the output
+    stage) and whatever FSEA_ARITH_AUTO picks for these lengths: all output modes, odd frame counts."""
+    fb = fbg
+    frames = 5
+    data = synth_u8(n * frames, seed=n + 3)
+    for flags in (fb.FLAG_DC_PATCH, 0):
+        plan = fb.Plan(n, in_format=fb.IN_U8, out_mode=fb.OUT_MAG, flags=flags, arith=arith)
+        got = plan.exec_host(data, frames)
+        ref = oracle_rows(data, n, n, frames, orc.IN_U8, orc.WIN_NONE, orc.OUT_MAG, flags=flags)
+        k = np.arange(n) != n // 2 if not flags else np.ones(n, bool)
+        assert rel_err(got[:, k], ref[:, k]) < MAG_TOL, plan.kernel_name
+        if flags:
+            assert np.array_equal(got[:, n // 2], got[:, n // 2 - 1])
+        else:
+            assert abs(got[0, n // 2] - ref[0, n // 2]) < 1e-4 * n
+    data = synth_s8(n * frames, seed=n + 4)
+    plan = fb.Plan(n, in_format=fb.IN_S8, out_mode=fb.OUT_LOGMAG, arith=arith)
+    got = plan.exec_host(data, frames).astype(np.float64)
+    ref = oracle_rows(data, n, n, frames, orc.IN_S8, orc.WIN_NONE, orc.OUT_LOGMAG)
+    lin = 10 ** (ref / 20)
+    ok = lin >= 1e-3 * np.sqrt(np.mean(lin ** 2, axis=1, keepdims=True))
+    assert np.max(np.abs(got - ref)[ok]) < 2e-3, plan.kernel_name
+    hop = n // 2
+    data = synth_u8((frames - 1) * hop + n, seed=n + 5)
+    plan = fb.Plan(n, hop=hop, in_format=fb.IN_U8, window=fb.WIN_HANN, out_mode=fb.OUT_PIX, pix_scale=5.0,
+                   flags=fb.FLAG_DC_PATCH, arith=arith)
+    got = plan.exec_host(data, frames)
+    ref = oracle_rows(data, n, hop, frames, orc.IN_U8, orc.WIN_HANN, orc.OUT_PIX, 5.0, orc.FLAG_DC_PATCH)
+    d = np.abs(got.astype(int) - ref.astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 0.005, plan.kernel_name
+
+
 @pytest.mark.parametrize("n", [16384, 32768, 65536])
 def test_four_step_sizes(fbg, n):
     """cfg4 / cfg5 sizes: N = N1 x N2 through the L2-resident intermediate."""

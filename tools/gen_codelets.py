@@ -170,20 +170,18 @@ def codelet(R, raw=False):
             f"    typedef typename fsea_vt<V>::scalar S;\n{body}\n{stores}\n}}\n"), g.ops
 
 
-def cross64():
-    """X[m] = A_m + W64^m B_m, X[m+32] = A_m - W64^m B_m on the two lanes of packed registers
-    (A in .x, B in .y -> X[m] in .x, X[m+32] in .y): the last radix-2 stage of a 64-point
-    decimation in time whose halves were transformed by one packed radix-32 codelet."""
-    L = ["// cross-lane radix-2 stage of a 64-point DIT: in (A_m, B_m), out (X[m], X[m+32]); scalar fp32",
-         "#if defined(__CUDACC__) || defined(FSEA_EMU)",
-         "FSEA_D void fsea_cross64(f2* __restrict__ re, f2* __restrict__ im) {"]
-    for m in range(32):
+def cross(R):
+    """X[m] = A_m + W_{2R}^m B_m, X[m+R] = A_m - W_{2R}^m B_m on the two lanes of R packed registers
+    (A in .x, B in .y -> X[m] in .x, X[m+R] in .y): the last radix-2 stage of a 2R-point
+    decimation in time whose halves were transformed together by one packed radix-R codelet."""
+    L = [f"template <> FSEA_D void fsea_cross<{R}>(f2* __restrict__ re, f2* __restrict__ im) {{"]
+    for m in range(R):
         L.append(f"    {{ const float ar = re[{m}].v.x, br = re[{m}].v.y, ai = im[{m}].v.x, bi = im[{m}].v.y;")
-        fr = Fraction(m, 64)
+        fr = Fraction(m, 2 * R)
         if m == 0:
             L.append("      re[0].v.x = ar + br; re[0].v.y = ar - br; im[0].v.x = ai + bi; im[0].v.y = ai - bi; }")
             continue
-        if m == 16:                                   # W = -i : W*B = (bi, -br)
+        if fr == Fraction(1, 4):                      # W = -i : W*B = (bi, -br)
             L.append(f"      re[{m}].v.x = ar + bi; re[{m}].v.y = ar - bi; im[{m}].v.x = ai - br; im[{m}].v.y = ai + br; }}")
             continue
         c, s_ = _cos_sin(fr)                          # W = c - i s ; W*B = (c br + s bi, c bi - s br)
@@ -196,8 +194,17 @@ def cross64():
         L.append(f"      re[{m}].v.x = fmaf({float(mm)!r}f, ur, ar); re[{m}].v.y = fmaf({float(-mm)!r}f, ur, ar);"
                  f" im[{m}].v.x = fmaf({float(mm)!r}f, ui, ai); im[{m}].v.y = fmaf({float(-mm)!r}f, ui, ai); }}")
     L.append("}")
-    L.append("#endif")
     return "\n".join(L) + "\n"
+
+
+def crosses():
+    out = ["// cross-lane radix-2 stage of a 2R-point DIT: in (A_m, B_m), out (X[m], X[m+R]); scalar fp32",
+           "#if defined(__CUDACC__) || defined(FSEA_EMU)",
+           "template <int R> FSEA_D void fsea_cross(f2* __restrict__ re, f2* __restrict__ im);"]
+    for R in (4, 8, 16, 32):
+        out.append(cross(R))
+    out.append("#endif")
+    return "\n".join(out) + "\n"
 
 
 def main():
@@ -212,7 +219,7 @@ def main():
     for R in (8, 16, 32, 64):
         src, ops = codelet(R, raw=True)
         out.append(src)
-    out.append(cross64())
+    out.append(crosses())
     out.append("template <int R, typename V> struct fsea_dft;\n" + "".join(
         f"template <typename V> struct fsea_dft<{R}, V> {{ static FSEA_HD void run(V* re, V* im) {{ fsea_dft{R}<V>(re, im); }} }};\n"
         for R in (1, 2, 4, 8, 16, 32, 64)))

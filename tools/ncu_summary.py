@@ -21,6 +21,16 @@ KEYS = [
     ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "L1/shared data pipe %"),
     ("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "shared-memory wavefronts"),
     ("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "shared-memory bank-conflict wavefronts"),
+    ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 (lts) throughput %"),
+    ("lts__t_bytes.sum", "L2 bytes (lts__t_bytes)"),
+    ("lts__t_sectors_op_read.sum", "L2 read sectors"),
+    ("lts__t_sectors_op_write.sum", "L2 write sectors"),
+    ("l1tex__m_xbar2l1tex_read_bytes.sum", "L2->L1 read bytes"),
+    ("l1tex__m_l1tex2xbar_write_bytes.sum", "L1->L2 write bytes"),
+    ("l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "L1/tex throughput %"),
+    ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
+    ("l1tex__lsu_writeback_active.avg.pct_of_peak_sustained_elapsed", "LSU writeback %"),
+    ("lts__t_sector_hit_rate.pct", "L2 hit rate %"),
     ("smsp__inst_executed.sum", "warp instructions"),
     ("sm__pipe_alu_cycles_active.avg.pct_of_peak_sustained_active", "ALU pipe active %"),
     ("sm__inst_executed_pipe_xu.sum", "XU (MUFU) instructions"),
