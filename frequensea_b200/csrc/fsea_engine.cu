@@ -242,7 +242,7 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
         case FSEA_IN_S8:
             p->variant = (cfg->arith == FSEA_ARITH_F32) ? FSEA_VAR_F32 : FSEA_VAR_F32X2;
             // one frame per unit where that is the faster arrangement (measured)
-            if (cfg->arith == FSEA_ARITH_F32X2_FRAME || (cfg->arith == FSEA_ARITH_AUTO && (n == 2048 || n == 8192)))
+            if (cfg->arith == FSEA_ARITH_F32X2_FRAME || (cfg->arith == FSEA_ARITH_AUTO && (n == 2048 || n == 4096 || n == 8192)))
                 p->variant = FSEA_VAR_F32X2H;
             if (cfg->window == FSEA_WIN_HANN)
                 p->variant = (p->variant == FSEA_VAR_F32) ? FSEA_VAR_F32_WIN : (p->variant == FSEA_VAR_F32X2H ? FSEA_VAR_F32X2H_WIN : FSEA_VAR_F32X2_WIN);

@@ -201,7 +201,7 @@ def crosses():
     out = ["// cross-lane radix-2 stage of a 2R-point DIT: in (A_m, B_m), out (X[m], X[m+R]); scalar fp32",
            "#if defined(__CUDACC__) || defined(FSEA_EMU)",
            "template <int R> FSEA_D void fsea_cross(f2* __restrict__ re, f2* __restrict__ im);"]
-    for R in (4, 8, 16, 32):
+    for R in (2, 4, 8, 16, 32):
         out.append(cross(R))
     out.append("#endif")
     return "\n".join(out) + "\n"
