@@ -1,0 +1,57 @@
+"""The kernel SOURCES on the CPU fiber machine (tests/emu) against the oracle -- no GPU needed.
+
+tests/emu compiles frequensea_b200/csrc/*.cu with g++ (-DFSEA_EMU) against a fake
+cuda_runtime.h: every CUDA thread is a fiber, barriers / shuffles / cluster barriers / cp.async
+have their CUDA meaning, packed f32x2 arithmetic is two scalar ops with the device's
+contraction rules.  It checks indexing, synchronisation and arithmetic of the kernels a
+reviewer reads; it says nothing about speed.  The emulated library is TEST INFRASTRUCTURE: it
+is never loaded by the product (frequensea_b200 resolves libfsea.so; FSEA_LIB is an explicit
+override used here and by tools/sweep.py A/B runs).  The -m gpu suite repeats every one of
+these comparisons on the device through the real library.
+"""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EMU = os.path.join(ROOT, "tests", "emu")
+
+
+@pytest.fixture(scope="module")
+def emu_lib():
+    r = subprocess.run(["make", "-C", EMU, "-j8"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    return os.path.join(EMU, "libfsea_emu.so")
+
+
+def run_check(emu_lib, sizes):
+    env = dict(os.environ, FSEA_LIB=emu_lib)
+    r = subprocess.run([sys.executable, os.path.join(EMU, "check.py")] + [str(n) for n in sizes],
+                       capture_output=True, text=True, env=env, timeout=900)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return json.loads(r.stdout.strip().splitlines()[-1])
+
+
+def verify(res):
+    for r in res:
+        tag = f"N={r['n']} {r['kernel']}"
+        assert r["mag_patch"] < 1e-5, tag            # the north star's 1e-5 relative bound (rms-normalised)
+        assert r["patch_dup"], tag                   # out[N/2] == out[N/2-1], src/nrf.c:621-622
+        assert r["logmag_db"] < 2e-3, tag            # dB, bins >= 1e-3 rms
+        assert r["dc_bin_db"] < 1e-3, tag            # the analytic N/2 (1+i) DC term of uncentred u8/256
+        assert r["pix_max"] <= 1 and r["pix_frac"] < 5e-3, tag   # trunc() of a float: <= 1 LSB on < 0.5 % of pixels
+
+
+def test_emulated_single_launch_sizes(emu_lib):
+    """N = 16 .. 8192: fsea_fft_kernel in every default arrangement (pairs, warp tickets, frame per unit)."""
+    verify(run_check(emu_lib, [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192]))
+
+
+def test_emulated_four_step_sizes(emu_lib):
+    """N = 16384 .. 65536: the cluster kernel (sub-spectra, cluster barrier, comb) incl. slot reuse."""
+    res = run_check(emu_lib, [16384, 32768, 65536])
+    assert all("fft4<" in r["kernel"] for r in res)
+    verify(res)
