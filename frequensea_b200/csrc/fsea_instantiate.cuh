@@ -51,6 +51,13 @@ static bool fsea_fill(fsea_kernel_info* o, const char* name) {
     return true;
 }
 
+// frame-per-unit variants: groups per block / twiddle tables in shared memory (0 / -1: derived, see fsea_cfg)
+#ifndef FSEA_HGOV
+#define FSEA_HGOV 0
+#endif
+#ifndef FSEA_HTWS
+#define FSEA_HTWS -1
+#endif
 #define FSEA_STR2(x) #x
 #define FSEA_STR(x) FSEA_STR2(x)
 // SH: shape of the packed (f32x2), float2-sample and fp64 variants; SHS: shape of the scalar fp32
@@ -65,10 +72,10 @@ static bool fsea_fill(fsea_kernel_info* o, const char* name) {
         switch (variant) {                                                                               \
             case FSEA_VAR_F32X2H:                                                                        \
                 if constexpr (H0 == 0) return false; else                                               \
-                return fsea_fill<SHH, f2, FSEA_IN_U8H, FSEA_OK_HALF>(out, "fft<" FSEA_STR(N) "=2x(" FSEA_STR(H0) "x" FSEA_STR(H1) "x" FSEA_STR(H2) "),f32x2 frame/unit>");      \
+                return fsea_fill<SHH, f2, FSEA_IN_U8H, FSEA_OK_HALF, (H0 ? N / 2 : 64), false, FSEA_HGOV, FSEA_HTWS>(out, "fft<" FSEA_STR(N) "=2x(" FSEA_STR(H0) "x" FSEA_STR(H1) "x" FSEA_STR(H2) "),f32x2 frame/unit>");      \
             case FSEA_VAR_F32X2H_WIN:                                                                    \
                 if constexpr (H0 == 0) return false; else                                               \
-                return fsea_fill<SHH, f2, FSEA_IN_U8H, FSEA_OK_HALF, N / 2, true>(out, "fft<" FSEA_STR(N) "=2x(" FSEA_STR(H0) "x" FSEA_STR(H1) "x" FSEA_STR(H2) "),f32x2 frame/unit,win>");      \
+                return fsea_fill<SHH, f2, FSEA_IN_U8H, FSEA_OK_HALF, N / 2, true, FSEA_HGOV, FSEA_HTWS>(out, "fft<" FSEA_STR(N) "=2x(" FSEA_STR(H0) "x" FSEA_STR(H1) "x" FSEA_STR(H2) "),f32x2 frame/unit,win>");      \
             case FSEA_VAR_F32:                                                                           \
                 return fsea_fill<SHS, float, FSEA_IN_U8>(out, "fft<" FSEA_SHAPE_NAME(N, S0, S1, S2) ",f32>");      \
             case FSEA_VAR_F32X2:                                                                         \

@@ -466,7 +466,11 @@ template <int OUT> __device__ __forceinline__ void fsea_tile_put(unsigned char* 
 // two float planes per frame, Yre[N2][N1] then Yim[N2][N1]: step A stores lanes of its packed
 // registers as they are and step B loads them straight into packed registers (an interleaved
 // re/im layout cost ~450 MOVs per thread of repacking in step B).
+// N2 = 64 (PAIRED): step B's lanes are the two sub-spectra (2u, 2u+1) step A produced together,
+// so the rows of a unit are stored interleaved, Yre[N2/2][N1][2]: one 8-byte store per packed
+// register here and one 8-byte load per packed register there (half the LSU instructions).
 template <int N, int N2> struct fsea_out_cplx {
+    static const bool PAIRED = (N2 == 64);
     float *ra, *rb;                                       // re rows of the unit's two sub-sequences; im at + N2 N
     __device__ __forceinline__ void init(const fsea_kparams& kp, long unit, bool unit_live, int) {
         const long f = unit / (N2 / 2);
@@ -482,10 +486,15 @@ template <int N, int N2> struct fsea_out_cplx {
     __device__ __forceinline__ void store_sel(int, int i, const f2* re, const f2* im, bool) const {
 #pragma unroll
         for (int m = 0; m < R; m++) {
-            ra[i + m * M] = re[m].v.x;
-            rb[i + m * M] = re[m].v.y;
-            ra[N2 * N + i + m * M] = im[m].v.x;
-            rb[N2 * N + i + m * M] = im[m].v.y;
+            if (PAIRED) {
+                ((float2*)ra)[i + m * M] = make_float2(re[m].v.x, re[m].v.y);
+                ((float2*)(ra + N2 * N))[i + m * M] = make_float2(im[m].v.x, im[m].v.y);
+            } else {
+                ra[i + m * M] = re[m].v.x;
+                rb[i + m * M] = re[m].v.y;
+                ra[N2 * N + i + m * M] = im[m].v.x;
+                rb[N2 * N + i + m * M] = im[m].v.y;
+            }
         }
     }
     __device__ __forceinline__ void dc_adjust(const fsea_kparams&, int, f2&, f2&) const {}
@@ -974,7 +983,7 @@ template <int OUT, int N1, int N2> struct fsea_comb {
             if (m == 0 && dc_patch && k == 0) {                              // bin 0 is not stored (src/nrf.c:621-622)
                 if (ESZ == 4) ((float*)dst)[1] = ((const float*)tmp)[1]; else dst[1] = tmp[1];
             } else if (ESZ == 4) {
-                *(float2*)dst = *(const float2*)tmp;
+                fsea_st_stream((float2*)dst, *(const float2*)tmp);
             } else {
                 *(uchar2*)dst = *(const uchar2*)tmp;
             }
@@ -1012,11 +1021,12 @@ template <int OUT, int N1> struct fsea_comb<OUT, N1, 64> {
     template <int ARRIVE>
     static __device__ __forceinline__ void run(const fsea_kparams& kp, const float* yf, int k, int, uint8_t* row, bool dc_patch) {
         f2 re[32], im[32];
-        const float* y = yf + k;
+        const float2* y = (const float2*)yf + k;                                  // rows (2j, 2j+1) interleaved (fsea_out_cplx PAIRED)
 #pragma unroll
         for (int j = 0; j < 32; j++) {
-            re[j] = mk2(__ldcg(y + (size_t)(2 * j) * N1), __ldcg(y + (size_t)(2 * j + 1) * N1));
-            im[j] = mk2(__ldcg(y + (size_t)(64 + 2 * j) * N1), __ldcg(y + (size_t)(64 + 2 * j + 1) * N1));
+            const float2 a = __ldcg(y + (size_t)j * N1);
+            const float2 b = __ldcg(y + (size_t)(32 + j) * N1);
+            re[j] = mk2(a.x, a.y); im[j] = mk2(b.x, b.y);
         }
         float bc[6], bs[6];                                                      // W^(2^r k), r < 6
 #pragma unroll
@@ -1051,9 +1061,9 @@ template <int OUT, int N1> struct fsea_comb<OUT, N1, 64> {
             uint8_t* d0 = row + ((size_t)k + (size_t)N1 * (m + 32)) * ESZ;       // bin k + N1 m        (lane x)
             uint8_t* d1 = row + ((size_t)k + (size_t)N1 * m) * ESZ;              // bin k + N1 (m + 32) (lane y)
             if (!(m == 0 && dc_patch && k == 0)) {                               // bin 0 is not stored (src/nrf.c:621-622)
-                if (ESZ == 4) *(float*)d0 = ((const float*)tmp)[0]; else d0[0] = tmp[0];
+                if (ESZ == 4) fsea_st_stream((float*)d0, ((const float*)tmp)[0]); else d0[0] = tmp[0];
             }
-            if (ESZ == 4) *(float*)d1 = ((const float*)tmp)[1]; else d1[0] = tmp[1];
+            if (ESZ == 4) fsea_st_stream((float*)d1, ((const float*)tmp)[1]); else d1[0] = tmp[1];
             if (m == 31 && dc_patch && k == N1 - 1) {                            // bin N-1 also fills the DC slot N/2
                 uint8_t* dc = row + (size_t)32 * N1 * ESZ;
                 if (ESZ == 4) *(float*)dc = ((const float*)tmp)[1]; else dc[0] = tmp[1];

@@ -34,6 +34,26 @@ __device__ __forceinline__ void fsea_prefetch_l2(const void* p) {
 #endif
 }
 
+// ---- streaming (evict-first) stores: spectra are written once and never read again by the
+// kernel, the four-step intermediate next to them in L2 is -- keep the spectra from pushing it out
+#ifndef FSEA_COMB_STREAM
+#define FSEA_COMB_STREAM 1
+#endif
+__device__ __forceinline__ void fsea_st_stream(float* p, float v) {
+#if defined(FSEA_EMU) || !FSEA_COMB_STREAM
+    *p = v;
+#else
+    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ void fsea_st_stream(float2* p, float2 v) {
+#if defined(FSEA_EMU) || !FSEA_COMB_STREAM
+    *p = v;
+#else
+    asm volatile("st.global.cs.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+#endif
+}
+
 // ---- asynchronous global -> shared copies (LDGSTS) --------------------------------------
 __device__ __forceinline__ void fsea_cp_async16(void* smem_dst, const void* gsrc) {        // 16 bytes, L2 only
 #if defined(FSEA_EMU)

@@ -2,7 +2,10 @@
 oracle on the same inputs.
 
 Tolerances (north star: spectra within 1e-5 relative of a float64 DFT):
-  MAG     max_k |y - y_ref| <= 1e-5 * rms_k(y_ref)            per frame (fp32 kernels)
+  MAG     |y - y_ref| <= 1e-5 * rms_k(y_ref) + 1e-6 * |y_ref|   every bin of every frame (fp32 kernels)
+          (atol/rtol form.  The rtol term only matters on tone bins far above the frame's rms: fp32
+          butterflies leave sigma ~ 1.1e-7 relative per bin at N = 8192 -- DESIGN.md 4 -- so a bin 52 x rms,
+          as in the cfg3 generator, cannot be promised to 1e-5 * rms = 1.6 ulp; it is held to 1e-6 of itself.)
   LOGMAG  |dB - dB_ref| <= 2e-3 dB wherever |X_ref| >= 1e-3 * rms (log of a cancelling bin is ill-conditioned)
   PIX     |pix - pix_ref| <= 1 and fewer than 0.5 % of pixels differ (trunc() of a float)
   F64     max |y - y_ref| <= 1e-11 * rms
@@ -21,9 +24,10 @@ MAG_TOL = 1e-5
 
 
 def rel_err(got, ref):
+    """max over bins of |got - ref| / (rms + 0.1 |ref|): `< 1e-5` is |d| <= 1e-5 rms + 1e-6 |ref|."""
     ref = np.asarray(ref, dtype=np.float64)
     rms = np.sqrt(np.mean(ref ** 2, axis=-1, keepdims=True))
-    return float(np.max(np.abs(got - ref) / rms))
+    return float(np.max(np.abs(got - ref) / (rms + 0.1 * np.abs(ref))))
 
 
 def oracle_rows(data, n, hop, frames, fmt, win, out, scale=10.0, flags=0):
