@@ -23,7 +23,8 @@ class FseaConfig(C.Structure):
     _fields_ = [("fft_size", C.c_int), ("hop", C.c_int), ("in_format", C.c_int),
                 ("window", C.c_int), ("out_mode", C.c_int), ("flags", C.c_int),
                 ("pix_scale", C.c_float), ("device", C.c_int), ("arith", C.c_int),
-                ("reserved", C.c_int * 7)]
+                ("log_mult", C.c_float), ("power_gain", C.c_float),
+                ("reserved", C.c_int * 5)]
 
 
 class FseaError(RuntimeError):
@@ -114,13 +115,14 @@ class Plan:
 
     def __init__(self, fft_size: int, hop: int = 0, in_format: int = IN_U8, window: int = WIN_NONE,
                  out_mode: int = OUT_MAG, flags: int = 0, pix_scale: float = 10.0, device: int = 0,
-                 arith: int = ARITH_AUTO):
+                 arith: int = ARITH_AUTO, log_mult: float = 10.0, power_gain: float = 1.0):
         L = lib()
         cfg = FseaConfig()
         L.fsea_config_default(C.byref(cfg), fft_size)
         cfg.hop = hop or fft_size
         cfg.in_format, cfg.window, cfg.out_mode, cfg.flags = in_format, window, out_mode, flags
         cfg.pix_scale, cfg.device, cfg.arith = pix_scale, device, arith
+        cfg.log_mult, cfg.power_gain = log_mult, power_gain
         self.cfg = cfg
         self.n = fft_size
         self.hop = cfg.hop

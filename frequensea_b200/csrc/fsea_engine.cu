@@ -127,6 +127,8 @@ extern "C" void fsea_config_default(fsea_config* cfg, int fft_size) {
     cfg->pix_scale = 10.0f;
     cfg->device = 0;
     cfg->arith = FSEA_ARITH_AUTO;
+    cfg->log_mult = 10.0f;
+    cfg->power_gain = 1.0f;
 }
 
 template <typename S2>
@@ -227,6 +229,7 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
     if (cfg->window != FSEA_WIN_NONE && cfg->window != FSEA_WIN_HANN) return FSEA_ERR_INVALID;
     if (cfg->out_mode < FSEA_OUT_MAG || cfg->out_mode > FSEA_OUT_PIX) return FSEA_ERR_INVALID;
     if (cfg->hop < 0) return FSEA_ERR_INVALID;
+    if (!(cfg->power_gain >= 0.0f) || !(cfg->log_mult == cfg->log_mult)) return FSEA_ERR_INVALID;   // (also rejects NaN)
     if ((cfg->in_format == FSEA_IN_U8 || cfg->in_format == FSEA_IN_S8) && (cfg->hop % 8) != 0)
         return FSEA_ERR_INVALID;          /* 8-bit frames are fetched in 16-byte pieces */
     if (fsea_device_count() <= 0) return FSEA_ERR_NO_DEVICE;
@@ -371,6 +374,12 @@ static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cu
     kp.tw2 = p->d_tw2;
     kp.window = p->d_window;
     kp.pix_scale = p->cfg.pix_scale;
+    {   // out = log_mult log10(gain P + 1e-20) = log_mult log10(2) log2(P + 1e-20 / gain) + log_mult log10(gain)
+        const double mult = p->cfg.log_mult != 0.0f ? (double)p->cfg.log_mult : 10.0;
+        const double gain = p->cfg.power_gain > 0.0f ? (double)p->cfg.power_gain : 1.0;
+        kp.lg.dmul = mult * 0.30102999566398119521; kp.lg.deps = 1.0e-20 / gain; kp.lg.dadd = gain == 1.0 ? 0.0 : mult * log10(gain);
+        kp.lg.mul = (float)kp.lg.dmul; kp.lg.eps = (float)kp.lg.deps; kp.lg.add = (float)kp.lg.dadd;
+    }
     kp.flags = p->cfg.flags;
     const bool eight_bit = p->cfg.in_format == FSEA_IN_U8 || p->cfg.in_format == FSEA_IN_S8;
     kp.dc_term = (eight_bit && p->cfg.window == FSEA_WIN_NONE && !(p->cfg.flags & FSEA_FLAG_DC_PATCH)) ? 1 : 0;

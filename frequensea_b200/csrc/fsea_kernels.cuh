@@ -69,8 +69,11 @@ struct fsea_shape {
 };
 
 // ---- scalar helpers ---------------------------------------------------------
-__device__ __forceinline__ float fsea_db(float pwr) {          // 10 log10(pwr + 1e-20)
-    return 3.010299956639812f * __log2f(pwr + 1.0e-20f);
+__device__ __forceinline__ float fsea_db(float pwr, const fsea_logp& lg) {   // mult log10(gain pwr + 1e-20); default 10 log10(pwr + 1e-20)
+    return fmaf(lg.mul, __log2f(pwr + lg.eps), lg.add);
+}
+__device__ __forceinline__ double fsea_db(double pwr, const fsea_logp& lg) {
+    return lg.dmul * log2(pwr + lg.deps) + lg.dadd;
 }
 __device__ __forceinline__ uint8_t fsea_pix(float db, float scale) {   // c/fft-batch.c:33-35,90-91
     int v = __float2int_rz(db * scale);
@@ -349,8 +352,10 @@ template <int N, typename V> struct fsea_out {
     uint8_t* row[LANES];
     bool live[LANES];
     float pix_scale;
+    fsea_logp lg;
     __device__ __forceinline__ void init(const fsea_kparams& kp, long unit, bool unit_live, int esz) {
         pix_scale = kp.pix_scale;
+        lg = kp.lg;
 #pragma unroll
         for (int l = 0; l < LANES; l++) {
             long s = unit * LANES + l;
@@ -365,14 +370,14 @@ template <int N, typename V> struct fsea_out {
             if (sizeof(S) == 8) ((double*)row[l])[pos] = sqrt((double)pwr);
             else ((float*)row[l])[pos] = fsea_sqrt_approx((float)pwr);
         } else if (OUT == FSEA_OUT_LOGMAG) {
-            if (sizeof(S) == 8) ((double*)row[l])[pos] = 10.0 * log10((double)pwr + 1.0e-20);
-            else ((float*)row[l])[pos] = fsea_db((float)pwr);
+            if (sizeof(S) == 8) ((double*)row[l])[pos] = fsea_db((double)pwr, lg);
+            else ((float*)row[l])[pos] = fsea_db((float)pwr, lg);
         } else {
             if (sizeof(S) == 8) {
-                int v = (int)(10.0 * log10((double)pwr + 1.0e-20) * (double)pix_scale);
+                int v = (int)(fsea_db((double)pwr, lg) * (double)pix_scale);
                 row[l][pos] = (uint8_t)max(0, min(255, v));
             } else {
-                row[l][pos] = fsea_pix(fsea_db((float)pwr), pix_scale);
+                row[l][pos] = fsea_pix(fsea_db((float)pwr, lg), pix_scale);
             }
         }
     }
@@ -415,16 +420,18 @@ template <int N> struct fsea_out_half {
     uint8_t* row;
     const float2* twh;
     float pix_scale, dc;
+    fsea_logp lg;
     __device__ __forceinline__ void init(const fsea_kparams& kp, long unit, bool unit_live, int esz) {
         pix_scale = kp.pix_scale;
+        lg = kp.lg;
         twh = (const float2*)kp.twh;
         dc = kp.dc_term ? (float)N : 0.0f;                                 // N/2 (1+i) of the 2N-point frame
         row = unit_live ? (uint8_t*)kp.out + (size_t)unit * (2 * N) * esz : (uint8_t*)kp.dump;
     }
     template <int OUT> __device__ __forceinline__ void put(int pos, float pwr) const {
         if (OUT == FSEA_OUT_MAG) ((float*)row)[pos] = fsea_sqrt_approx(pwr);
-        else if (OUT == FSEA_OUT_LOGMAG) ((float*)row)[pos] = fsea_db(pwr);
-        else row[pos] = fsea_pix(fsea_db(pwr), pix_scale);
+        else if (OUT == FSEA_OUT_LOGMAG) ((float*)row)[pos] = fsea_db(pwr, lg);
+        else row[pos] = fsea_pix(fsea_db(pwr, lg), pix_scale);
     }
     template <int OUT, int R, int M>
     __device__ __forceinline__ void store_bfly(int i, f2* re, f2* im, bool dc_patch) const {
@@ -456,10 +463,10 @@ template <int N> struct fsea_out_half {
 };
 
 // values of one bin pair in the output element type
-template <int OUT> __device__ __forceinline__ void fsea_tile_put(unsigned char* p, f2 pw, float pix_scale) {
+template <int OUT> __device__ __forceinline__ void fsea_tile_put(unsigned char* p, f2 pw, float pix_scale, const fsea_logp& lg) {
     if (OUT == FSEA_OUT_MAG) *(float2*)p = make_float2(fsea_sqrt_approx(pw.v.x), fsea_sqrt_approx(pw.v.y));
-    else if (OUT == FSEA_OUT_LOGMAG) *(float2*)p = make_float2(fsea_db(pw.v.x), fsea_db(pw.v.y));
-    else *(uchar2*)p = make_uchar2(fsea_pix(fsea_db(pw.v.x), pix_scale), fsea_pix(fsea_db(pw.v.y), pix_scale));
+    else if (OUT == FSEA_OUT_LOGMAG) *(float2*)p = make_float2(fsea_db(pw.v.x, lg), fsea_db(pw.v.y, lg));
+    else *(uchar2*)p = make_uchar2(fsea_pix(fsea_db(pw.v.x, lg), pix_scale), fsea_pix(fsea_db(pw.v.y, lg), pix_scale));
 }
 
 // Four-step step A: the two sub-spectra of a unit as rows of the intermediate, which is kept as
@@ -979,7 +986,7 @@ template <int OUT, int N1, int N2> struct fsea_comb {
             const f2 pw = vfma2(re[m], re[m], vmul(im[m], im[m]));
             uint8_t* dst = row + ((size_t)k + (size_t)N1 * (m ^ (N2 / 2))) * ESZ;
             __align__(8) unsigned char tmp[8];
-            fsea_tile_put<OUT>(tmp, pw, kp.pix_scale);
+            fsea_tile_put<OUT>(tmp, pw, kp.pix_scale, kp.lg);
             if (m == 0 && dc_patch && k == 0) {                              // bin 0 is not stored (src/nrf.c:621-622)
                 if (ESZ == 4) ((float*)dst)[1] = ((const float*)tmp)[1]; else dst[1] = tmp[1];
             } else if (ESZ == 4) {
@@ -1057,7 +1064,7 @@ template <int OUT, int N1> struct fsea_comb<OUT, N1, 64> {
         for (int m = 0; m < 32; m++) {
             const f2 pw = vfma2(re[m], re[m], vmul(im[m], im[m]));
             __align__(8) unsigned char tmp[8];
-            fsea_tile_put<OUT>(tmp, pw, kp.pix_scale);
+            fsea_tile_put<OUT>(tmp, pw, kp.pix_scale, kp.lg);
             uint8_t* d0 = row + ((size_t)k + (size_t)N1 * (m + 32)) * ESZ;       // bin k + N1 m        (lane x)
             uint8_t* d1 = row + ((size_t)k + (size_t)N1 * m) * ESZ;              // bin k + N1 (m + 32) (lane y)
             if (!(m == 0 && dc_patch && k == 0)) {                               // bin 0 is not stored (src/nrf.c:621-622)

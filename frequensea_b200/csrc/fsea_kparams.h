@@ -3,6 +3,10 @@
 #pragma once
 #include <stdint.h>
 
+// FSEA_OUT_LOGMAG / PIX: out = mul * log2(|X|^2 + eps) + add.  Default 10 log10(|X|^2 + 1e-20)
+// (c/fft-batch.c:88-89); log_mult / power_gain of fsea_config move the three (c/fft.c:191-196).
+struct fsea_logp { float mul, eps, add; double dmul, deps, dadd; };   // (d*: the fp64 kernels)
+
 struct fsea_kparams {
     const void* in;        // raw IQ (8-bit pairs), float2 or double2 samples
     void* out;             // float / uint8 / double rows of N
@@ -12,6 +16,7 @@ struct fsea_kparams {
     const void* tw2;       // pass-2 twiddles [j-1][k], k < R0*R1
     const float* window;   // N floats or nullptr
     float pix_scale;       // S of FSEA_OUT_PIX (c/fft-batch.c: 10, c/fft-batch-broad.c: 5)
+    fsea_logp lg;          // log-magnitude constants
     int flags;             // FSEA_FLAG_*
     int dc_term;           // 1: add N/2 (1+i) to bin k=0 (uncentred 8-bit input, no patch)
     int out_mode;          // FSEA_OUT_*

@@ -30,6 +30,8 @@
  *   X[k]   = sum_n x[n] exp(-2 pi i n k / N)                    (k = N/2 is DC)
  *   out[k] = |X[k]|                                             FSEA_OUT_MAG    (src/nrf.c:624-628)
  *          = 10 log10(|X[k]|^2 + 1e-20)                         FSEA_OUT_LOGMAG (c/fft-batch.c:88-89)
+ *            generally log_mult * log10(power_gain |X[k]|^2 + 1e-20): c/fft.c:181-197's scope row is
+ *            FSEA_IN_U8, log_mult = intensity, power_gain = (256 / (255 N))^2
  *          = clamp_u8(trunc(pix_scale * 10 log10(|X[k]|^2 + 1e-20)))   FSEA_OUT_PIX (c/fft-batch.c:89-92)
  *   FSEA_FLAG_DC_PATCH:  out[N/2] = out[N/2-1]   (src/nrf.c:621-622, c/fft-batch-broad.c:115-117)
  * Output element type: float32 (MAG/LOGMAG), uint8 (PIX), float64 for
@@ -74,7 +76,10 @@ typedef struct {
     float pix_scale;   /* S for FSEA_OUT_PIX (c/fft-batch.c: 10, c/fft-batch-broad.c: 5) */
     int device;        /* CUDA device ordinal */
     int arith;         /* FSEA_ARITH_* */
-    int reserved[7];
+    float log_mult;    /* FSEA_OUT_LOGMAG / PIX: out = log_mult * log10(power_gain * |X|^2 + 1e-20); 0 = 10 */
+    float power_gain;  /* 0 = 1.  c/fft.c:50-51,191-196 (the 512-point scope): FSEA_IN_U8, log_mult = intensity,
+                          power_gain = (256 / (255 N))^2  (samples / 255 instead of / 256, spectrum / N) */
+    int reserved[5];
 } fsea_config;
 
 typedef struct fsea_plan fsea_plan;

@@ -59,6 +59,14 @@ def check(n, frames):
     d = np.abs(got.astype(int) - ref.astype(int))
     res["pix_max"] = int(d.max())
     res["pix_frac"] = float((d > 0).mean())
+    # (4) c/fft.c's scope row: bytes / 255, spectrum / N, intensity * log10(power + 1e-20)  (c/fft.c:50-51,181-197)
+    data = synth_u8(n * 2, seed=n + 3)
+    plan = fb.Plan(n, in_format=fb.IN_U8, out_mode=fb.OUT_LOGMAG, log_mult=7.0, power_gain=(256.0 / (255.0 * n)) ** 2)
+    got = plan.exec_host(data, 2).astype(np.float64)
+    ref = np.stack([orc.scope_row(data[f * 2 * n:], n, 7.0) for f in range(2)])
+    lin = 10 ** (ref / 14)
+    ok = lin >= 1e-3 * np.sqrt(np.mean(lin ** 2, axis=1, keepdims=True))
+    res["scope_err"] = float(np.max(np.abs(got - ref)[ok]))
     return res
 
 

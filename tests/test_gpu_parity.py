@@ -211,6 +211,24 @@ def test_sweep_pixels_match_reference_tools(fbg, iq, golden):
         assert d.max() <= 1 and (d > 0).mean() < 0.005
 
 
+@pytest.mark.parametrize("n", [512, 1024, 16384])
+def test_scope_row_matches_c_fft(fbg, iq, n):
+    """c/fft.c:45-56,181-197 (the 512-point scope): raw bytes / 255 with no offset conversion,
+    half-swap fftshift, spectrum / N, intensity * log10(power + 1e-20) -- as one LOGMAG plan with
+    log_mult = intensity, power_gain = (256 / (255 N))^2."""
+    fb = fbg
+    raw = iq["rf200big4"]
+    frames, intensity = 6, 10.0
+    plan = fb.Plan(n, in_format=fb.IN_U8, out_mode=fb.OUT_LOGMAG, log_mult=intensity,
+                   power_gain=(256.0 / (255.0 * n)) ** 2)
+    got = plan.exec_host(raw, frames).astype(np.float64)
+    ref = np.stack([orc.scope_row(raw[f * 2 * n:], n, intensity) for f in range(frames)])
+    lin = 10 ** (ref / (2 * intensity))
+    ok = lin >= 1e-3 * np.sqrt(np.mean(lin ** 2, axis=1, keepdims=True))
+    assert ok.mean() > 0.95
+    assert np.max(np.abs(got - ref)[ok]) < 2e-3, plan.kernel_name
+
+
 def test_sweep_stitch(fbg, iq):
     """Sweep product: per-frequency pixel images (c/fft-batch-broad.c rows) max-blended side by side
     (c/fft-stitch-broad.c), against the oracle.  Four 'frequencies' = the four capture blocks."""
