@@ -17,6 +17,7 @@
 #include "../../include/fsea.h"
 #include "fsea_dispatch.h"
 #include "fsea_kparams.h"
+#include "fsea_ptx.cuh"
 
 // plain (non-table) kernel launches; -DFSEA_EMU (tests/emu/, test infrastructure) runs them on the CPU fiber machine
 #if defined(FSEA_EMU)
@@ -618,5 +619,133 @@ extern "C" int fsea_stitch_host(int device, const uint8_t* h_images, int n_image
     if (rc == FSEA_OK && (e = cudaMemcpy(h_out, d_out, ob, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "D2H");
     cudaFree(d_in);
     cudaFree(d_out);
+    return rc;
+}
+
+// ------------------------------------------------------------------ IQ low-pass (FIR)
+// src/nrf.c:718-724,759-768 (nrf_fir_filter_get per output of nrf_iq_filter_get_buffer):
+//   out[2i] = sum_k c[k] si[i+k],  out[2i+1] = sum_k c[k] sq[i+k],  k = 0 .. taps-1 in this order,
+// si / sq = the filter's sample line (taps-1 carried-over samples, then the new block).
+// float64, every product and every sum rounded on its own (__dmul_rn / __dadd_rn: no contraction),
+// accumulated from 0 in the reference's order: the result is bit-identical to the reference.
+#if defined(FSEA_EMU)
+static inline double __dmul_rn(double a, double b) { volatile double r = a * b; return r; }
+static inline double __dadd_rn(double a, double b) { volatile double r = a + b; return r; }
+#endif
+// A block of 256 threads produces 1024 consecutive outputs, a thread four neighbouring ones: every
+// sample is read from shared memory once per thread and feeds up to four accumulators (k = j - r),
+// each of which still sees its taps in ascending order.  The sample lines are staged
+// de-interleaved by (index mod 4), so that the 32 lanes of a load hit consecutive doubles; the
+// finished tile goes out through shared memory as coalesced 16-byte (I, Q) stores.
+#define FSEA_FIR_TPB 256
+#define FSEA_FIR_R 4
+static inline int fir_quarter(int taps) {                      // doubles per residue class, = 8 mod 16 (bank spread of the staging stores)
+    const int q = (FSEA_FIR_TPB * FSEA_FIR_R + taps - 1 + 3) / 4;
+    return ((q + 7) / 16) * 16 + 8;
+}
+__global__ void __launch_bounds__(FSEA_FIR_TPB)
+fsea_fir_iq_kernel(const double* __restrict__ coef, int taps, int quarter, const double* __restrict__ si,
+                   const double* __restrict__ sq, long length, double* __restrict__ out) {
+    FSEA_DYN_SMEM(fir_smem);
+    constexpr int TILE = FSEA_FIR_TPB * FSEA_FIR_R;
+    const int span = TILE + taps - 1;
+    double* c = (double*)fir_smem;
+    double* ti = c + ((taps + 1) & ~1);
+    double* tq = ti + 4 * quarter;
+    const int t = threadIdx.x;
+    for (int k = t; k < taps; k += FSEA_FIR_TPB) c[k] = coef[k];
+    for (long i0 = (long)blockIdx.x * TILE; i0 < length; i0 += (long)gridDim.x * TILE) {
+        __syncthreads();                                        // previous tile fully written out
+        for (int s = t; s < span; s += FSEA_FIR_TPB) {
+            const bool in = i0 + s < length + taps - 1;
+            const int q = (s & 3) * quarter + (s >> 2);
+            ti[q] = in ? si[i0 + s] : 0.0;
+            tq[q] = in ? sq[i0 + s] : 0.0;
+        }
+        __syncthreads();
+        double ai[FSEA_FIR_R], aq[FSEA_FIR_R];
+#pragma unroll
+        for (int r = 0; r < FSEA_FIR_R; r++) ai[r] = aq[r] = 0.0;
+        // sample 4t + j sits at (j & 3) quarter + t + (j >> 2); output 4t + r takes it with tap k = j - r
+        auto edge = [&](int j) {                                // first / last three samples: not every r has a tap
+            const int q = (j & 3) * quarter + t + (j >> 2);
+            const double xi = ti[q], xq = tq[q];
+#pragma unroll
+            for (int r = 0; r < FSEA_FIR_R; r++) {
+                const int k = j - r;
+                if (k >= 0 && k < taps) {
+                    ai[r] = __dadd_rn(ai[r], __dmul_rn(c[k], xi));
+                    aq[r] = __dadd_rn(aq[r], __dmul_rn(c[k], xq));
+                }
+            }
+        };
+        const int head = taps < 3 ? taps : 3;
+        for (int j = 0; j < head; j++) edge(j);
+        if (taps > 3) {
+            double c1 = c[2], c2 = c[1], c3 = c[0];
+#pragma unroll 4
+            for (int j = 3; j < taps; j++) {
+                const int q = (j & 3) * quarter + t + (j >> 2);
+                const double xi = ti[q], xq = tq[q], c0 = c[j];
+                ai[0] = __dadd_rn(ai[0], __dmul_rn(c0, xi)); aq[0] = __dadd_rn(aq[0], __dmul_rn(c0, xq));
+                ai[1] = __dadd_rn(ai[1], __dmul_rn(c1, xi)); aq[1] = __dadd_rn(aq[1], __dmul_rn(c1, xq));
+                ai[2] = __dadd_rn(ai[2], __dmul_rn(c2, xi)); aq[2] = __dadd_rn(aq[2], __dmul_rn(c2, xq));
+                ai[3] = __dadd_rn(ai[3], __dmul_rn(c3, xi)); aq[3] = __dadd_rn(aq[3], __dmul_rn(c3, xq));
+                c3 = c2; c2 = c1; c1 = c0;
+            }
+        }
+        for (int j = (taps > 3 ? taps : head); j < taps + FSEA_FIR_R - 1; j++) edge(j);
+        __syncthreads();                                        // everyone is done reading the lines
+        double2* tile = reinterpret_cast<double2*>(ti);         // 1024 x 16 bytes <= 4 quarter doubles x 2 lines
+#pragma unroll
+        for (int r = 0; r < FSEA_FIR_R; r++) tile[FSEA_FIR_R * t + r] = make_double2(ai[r], aq[r]);
+        __syncthreads();
+        for (int e = t; e < TILE; e += FSEA_FIR_TPB)
+            if (i0 + e < length) reinterpret_cast<double2*>(out)[i0 + e] = tile[e];
+    }
+}
+
+static size_t fir_smem_bytes(int taps) { return sizeof(double) * ((size_t)((taps + 1) & ~1) + 8 * (size_t)fir_quarter(taps)); }
+
+extern "C" int fsea_fir_iq_device(const double* d_coef, int taps, const double* d_si, const double* d_sq, long length,
+                                  double* d_out, void* stream) {
+    if (!d_coef || !d_si || !d_sq || !d_out || taps <= 0 || length < 0) return FSEA_ERR_INVALID;
+    if (((uintptr_t)d_out & 15) != 0) return FSEA_ERR_INVALID;
+    const size_t smem = fir_smem_bytes(taps);
+    if (smem > 200 * 1024) return FSEA_ERR_UNSUPPORTED;                  // taps <= ~10000
+    if (length == 0) return FSEA_OK;
+    const int blocks = (int)std::min<long>((length + 1023) / 1024, 148 * 8);
+    const int quarter = fir_quarter(taps);
+#if defined(FSEA_EMU)
+    fsea_emu::launch(dim3(blocks), dim3(FSEA_FIR_TPB), smem, 1, [=] { fsea_fir_iq_kernel(d_coef, taps, quarter, d_si, d_sq, length, d_out); });
+#else
+    if (smem > 48 * 1024) CU(cudaFuncSetAttribute(fsea_fir_iq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    fsea_fir_iq_kernel<<<blocks, FSEA_FIR_TPB, smem, (cudaStream_t)stream>>>(d_coef, taps, quarter, d_si, d_sq, length, d_out);
+#endif
+    CU(cudaGetLastError());
+    return FSEA_OK;
+}
+
+extern "C" int fsea_fir_iq_host(int device, const double* coef, int taps, const double* si, const double* sq, long length,
+                                double* out) {
+    if (!coef || !si || !sq || !out || taps <= 0 || length < 0) return FSEA_ERR_INVALID;
+    if (fsea_device_count() <= 0) return FSEA_ERR_NO_DEVICE;
+    if (length == 0) return FSEA_OK;
+    CU(cudaSetDevice(device));
+    const size_t line = sizeof(double) * (size_t)(length + taps - 1), ob = sizeof(double) * 2 * (size_t)length;
+    double* d = nullptr;                                           // coef | si | sq | out (out 16-byte aligned)
+    const size_t o_coef = 0, o_si = ((size_t)taps * 8 + 15) & ~(size_t)15, o_sq = o_si + ((line + 15) & ~(size_t)15),
+                 o_out = o_sq + ((line + 15) & ~(size_t)15);
+    CU(cudaMalloc(&d, o_out + ob));
+    char* b = (char*)d;
+    int rc = FSEA_OK;
+    cudaError_t e;
+    if ((e = cudaMemcpy(b + o_coef, coef, (size_t)taps * 8, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(b + o_si, si, line, cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(b + o_sq, sq, line, cudaMemcpyHostToDevice)) != cudaSuccess) rc = cuda_fail(e, "H2D");
+    if (rc == FSEA_OK) rc = fsea_fir_iq_device((const double*)(b + o_coef), taps, (const double*)(b + o_si), (const double*)(b + o_sq),
+                                               length, (double*)(b + o_out), nullptr);
+    if (rc == FSEA_OK && (e = cudaMemcpy(out, b + o_out, ob, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "D2H");
+    cudaFree(d);
     return rc;
 }

@@ -328,3 +328,111 @@ extern "C" void nrf_freq_shifter_free(nrf_freq_shifter* sh) {
     if (sh->buffer) nut_buffer_free(sh->buffer);
     free(sh);
 }
+
+// ---------------------------------------------------------------- FIR low-pass / IQ filter
+// Host side of src/nrf.c:644-776.  Windowed-sinc taps (Blackman-style window over length + 1
+// points, odd length enforced, unit DC gain), a sample line that keeps the last `length - 1`
+// samples of the previous block in front of the new one -- and the convolution itself on the device.
+static const double kTau = 2.0 * M_PI;
+
+extern "C" double* nrf_fir_get_low_pass_coefficients(int sample_rate, int half_ampl_freq, int length) {
+    if (length % 2 == 0) length++;                                   // src/nrf.c:655
+    const double f = half_ampl_freq / (double)sample_rate;
+    double* taps = (double*)calloc((size_t)length, sizeof(double));
+    const int mid = length / 2;
+    double total = 0.0;
+    for (int i = 0; i < length; i++) {
+        double v;
+        if (i == mid) {
+            v = kTau * f;
+        } else {
+            const double a = kTau * (i + 1) / (double)(length + 1);
+            v = sin(kTau * f * (i - mid)) / (double)(i - mid);
+            v *= 0.42 - 0.5 * cos(a) + 0.08 * cos(2 * a);
+        }
+        total += v;
+        taps[i] = v;
+    }
+    for (int i = 0; i < length; i++) taps[i] /= total;
+    return taps;
+}
+
+extern "C" nrf_fir_filter* nrf_fir_filter_new(int sample_rate, int half_ampl_freq, int length) {
+    nrf_fir_filter* f = (nrf_fir_filter*)calloc(1, sizeof(nrf_fir_filter));
+    f->length = length;                                              // (the even -> odd bump stays inside the
+    f->coefficients = nrf_fir_get_low_pass_coefficients(sample_rate, half_ampl_freq, length);   //  coefficient call, src/nrf.c:680-681)
+    f->offset = length - 1;
+    f->center = length / 2;
+    f->samples_length = f->offset;
+    f->samples = (double*)calloc((size_t)f->samples_length, sizeof(double));
+    return f;
+}
+
+extern "C" void nrf_fir_filter_load(nrf_fir_filter* f, double* samples, int length) {
+    const int want = length + f->offset;
+    double* line = f->samples;
+    const bool fresh = f->samples_length != want;
+    if (fresh) line = (double*)calloc((size_t)want, sizeof(double));
+    // tail of the old line first (memmove: source and destination are the same array when not fresh)
+    memmove(line, f->samples + f->samples_length - f->offset, (size_t)f->offset * sizeof(double));
+    memcpy(line + f->offset, samples, (size_t)length * sizeof(double));
+    if (fresh && f->samples_length != 0) free(f->samples);
+    f->samples = line;
+    f->samples_length = want;
+}
+
+extern "C" double nrf_fir_filter_get(nrf_fir_filter* f, int index) {
+    double v = 0;
+    for (int k = 0; k < f->length; k++) v += f->coefficients[k] * f->samples[index + k];
+    return v;
+}
+
+extern "C" void nrf_fir_filter_free(nrf_fir_filter* f) {
+    free(f->coefficients);
+    free(f->samples);
+    free(f);
+}
+
+extern "C" nrf_iq_filter* nrf_iq_filter_new(int sample_rate, int half_ampl_freq, int kernel_length) {
+    nrf_iq_filter* f = (nrf_iq_filter*)calloc(1, sizeof(nrf_iq_filter));
+    nrf_block_init(&f->block, NRF_BLOCK_GENERIC, (nrf_block_process_fn)nrf_iq_filter_process,
+                   (nrf_block_result_fn)nrf_iq_filter_get_buffer);
+    f->filter_i = nrf_fir_filter_new(sample_rate, half_ampl_freq, kernel_length);
+    f->filter_q = nrf_fir_filter_new(sample_rate, half_ampl_freq, kernel_length);
+    return f;
+}
+
+extern "C" void nrf_iq_filter_process(nrf_iq_filter* f, nut_buffer* buffer) {
+    const int length = buffer->length;
+    if (length != f->samples_length) {
+        free(f->samples_i);
+        free(f->samples_q);
+        f->samples_i = (double*)calloc((size_t)length, sizeof(double));
+        f->samples_q = (double*)calloc((size_t)length, sizeof(double));
+    }
+    f->samples_length = length;
+    for (int j = 0; j < length; j++) {                               // u8 -> /256, f64 as is (src/nut.c:129-135)
+        f->samples_i[j] = nut_buffer_get_f64(buffer, 2 * j);
+        f->samples_q[j] = nut_buffer_get_f64(buffer, 2 * j + 1);
+    }
+    nrf_fir_filter_load(f->filter_i, f->samples_i, length);
+    nrf_fir_filter_load(f->filter_q, f->samples_q, length);
+}
+
+extern "C" nut_buffer* nrf_iq_filter_get_buffer(nrf_iq_filter* f) {
+    const int length = f->samples_length;
+    nut_buffer* result = nut_buffer_new_f64(length, 2, NULL);
+    if (length <= 0) return result;
+    const int rc = fsea_fir_iq_host(0, f->filter_i->coefficients, f->filter_i->length, f->filter_i->samples,
+                                    f->filter_q->samples, length, result->data.f64);
+    if (rc != FSEA_OK) nrf_die("nrf_iq_filter_get_buffer", rc);
+    return result;
+}
+
+extern "C" void nrf_iq_filter_free(nrf_iq_filter* f) {
+    nrf_fir_filter_free(f->filter_i);
+    nrf_fir_filter_free(f->filter_q);
+    free(f->samples_i);
+    free(f->samples_q);
+    free(f);
+}

@@ -67,6 +67,11 @@ def _L():
         L.nrf_freq_shifter_process.argtypes = [vp, _NB]; L.nrf_freq_shifter_process.restype = None
         L.nrf_freq_shifter_get_buffer.argtypes = [vp]; L.nrf_freq_shifter_get_buffer.restype = _NB
         L.nrf_freq_shifter_free.argtypes = [vp]; L.nrf_freq_shifter_free.restype = None
+        L.nrf_iq_filter_new.argtypes = [i, i, i]; L.nrf_iq_filter_new.restype = vp
+        L.nrf_iq_filter_process.argtypes = [vp, _NB]; L.nrf_iq_filter_process.restype = None
+        L.nrf_iq_filter_get_buffer.argtypes = [vp]; L.nrf_iq_filter_get_buffer.restype = _NB
+        L.nrf_iq_filter_free.argtypes = [vp]; L.nrf_iq_filter_free.restype = None
+        L.nrf_fir_get_low_pass_coefficients.argtypes = [i, i, i]; L.nrf_fir_get_low_pass_coefficients.restype = C.POINTER(d)
         _ready = True
     return L
 
@@ -152,3 +157,17 @@ def freq_shifter_new(off: int, rate: int): return _L().nrf_freq_shifter_new(off,
 def freq_shifter_process(sh, b: NutBuffer): _L().nrf_freq_shifter_process(sh, b.ptr)
 def freq_shifter_get_buffer(sh) -> NutBuffer: return NutBuffer(_L().nrf_freq_shifter_get_buffer(sh))
 def freq_shifter_free(sh): _L().nrf_freq_shifter_free(sh)
+
+# lua/iq-tex-filtered.lua:43-46: filter = nrf_iq_filter_new(sample_rate, 200e3, 51); nrf_iq_filter_process(filter, samples)
+def iq_filter_new(sample_rate: int, half_ampl_freq: int, kernel_length: int): return _L().nrf_iq_filter_new(sample_rate, half_ampl_freq, kernel_length)
+def iq_filter_process(f, b: NutBuffer): _L().nrf_iq_filter_process(f, b.ptr)
+def iq_filter_get_buffer(f) -> NutBuffer: return NutBuffer(_L().nrf_iq_filter_get_buffer(f))
+def iq_filter_free(f): _L().nrf_iq_filter_free(f)
+
+
+def fir_low_pass_coefficients(sample_rate: int, half_ampl_freq: int, length: int) -> np.ndarray:
+    n = length + (length + 1) % 2
+    p = _L().nrf_fir_get_low_pass_coefficients(sample_rate, half_ampl_freq, length)
+    out = np.ctypeslib.as_array(p, shape=(n,)).copy()
+    C.CDLL(None).free(p)
+    return out

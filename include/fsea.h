@@ -132,6 +132,19 @@ int fsea_stitch_device(const uint8_t *d_images, int n_images, int rows, int widt
 int fsea_stitch_host(int device, const uint8_t *h_images, int n_images, int rows, int width, int width_step,
                      uint8_t *h_out);
 
+/* ---- IQ low-pass in front of the path ---------------- */
+
+/* The FIR evaluation of nrf_iq_filter_get_buffer (src/nrf.c:718-724,759-768):
+ *   out[2i] = sum_k coef[k] si[i+k],  out[2i+1] = sum_k coef[k] sq[i+k],  k = 0 .. taps-1,
+ * si / sq = the I and Q sample lines of length + taps - 1 doubles (taps-1
+ * carried-over samples followed by the new block), out = length interleaved
+ * (I, Q) doubles.  float64 with the reference's operation order and no
+ * contraction: bit-identical to the reference.  d_out 16-byte aligned. */
+int fsea_fir_iq_device(const double *d_coef, int taps, const double *d_si, const double *d_sq, long length,
+                       double *d_out, void *stream);
+int fsea_fir_iq_host(int device, const double *coef, int taps, const double *si, const double *sq, long length,
+                     double *out);
+
 #ifdef __cplusplus
 }
 #endif

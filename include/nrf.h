@@ -136,6 +136,40 @@ void nrf_freq_shifter_process(nrf_freq_shifter *shifter, nut_buffer *buffer);
 nut_buffer *nrf_freq_shifter_get_buffer(nrf_freq_shifter *shifter);
 void nrf_freq_shifter_free(nrf_freq_shifter *shifter);
 
+/* ---- FIR low-pass + IQ filter (src/nrf.h:144-177, src/nrf.c:644-776) ------
+ * the operator in front of the path in lua/iq-tex-filtered.lua:43-46.
+ * Coefficients, the carried-over sample line and nrf_fir_filter_get() are host code as in the
+ * reference; nrf_iq_filter_get_buffer() -- length x taps multiply-adds per block -- runs on the
+ * device (fsea_fir_iq_host) and is bit-identical to the reference's loop. */
+typedef struct {
+    int length;            /* taps */
+    double *coefficients;
+    int offset;            /* length - 1 samples carried over between blocks */
+    int center;
+    int samples_length;
+    double *samples;       /* offset carried-over samples, then the current block */
+} nrf_fir_filter;
+
+double *nrf_fir_get_low_pass_coefficients(int sample_rate, int half_ampl_freq, int length);
+nrf_fir_filter *nrf_fir_filter_new(int sample_rate, int half_ampl_freq, int length);
+void nrf_fir_filter_load(nrf_fir_filter *filter, double *samples, int length);
+double nrf_fir_filter_get(nrf_fir_filter *filter, int index);
+void nrf_fir_filter_free(nrf_fir_filter *filter);
+
+typedef struct {
+    NRF_BLOCK;
+    nrf_fir_filter *filter_i;
+    nrf_fir_filter *filter_q;
+    int samples_length;
+    double *samples_i;
+    double *samples_q;
+} nrf_iq_filter;
+
+nrf_iq_filter *nrf_iq_filter_new(int sample_rate, int half_ampl_freq, int kernel_length);
+void nrf_iq_filter_process(nrf_iq_filter *filter, nut_buffer *buffer);
+nut_buffer *nrf_iq_filter_get_buffer(nrf_iq_filter *f);
+void nrf_iq_filter_free(nrf_iq_filter *filter);
+
 #ifdef __cplusplus
 }
 #endif

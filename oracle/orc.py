@@ -213,6 +213,11 @@ def ref() -> C.CDLL:
         R.nrf_freq_shifter_new.argtypes = [i, i]; R.nrf_freq_shifter_new.restype = vp
         R.nrf_freq_shifter_process.argtypes = [vp, NB]; R.nrf_freq_shifter_process.restype = None
         R.nrf_freq_shifter_get_buffer.argtypes = [vp]; R.nrf_freq_shifter_get_buffer.restype = NB
+        R.nrf_iq_filter_new.argtypes = [i, i, i]; R.nrf_iq_filter_new.restype = vp
+        R.nrf_iq_filter_process.argtypes = [vp, NB]; R.nrf_iq_filter_process.restype = None
+        R.nrf_iq_filter_get_buffer.argtypes = [vp]; R.nrf_iq_filter_get_buffer.restype = NB
+        R.nrf_iq_filter_free.argtypes = [vp]; R.nrf_iq_filter_free.restype = None
+        R.nrf_fir_get_low_pass_coefficients.argtypes = [i, i, i]; R.nrf_fir_get_low_pass_coefficients.restype = C.POINTER(d)
         _ref = R
     return _ref
 
@@ -241,3 +246,33 @@ def ref_nrf_fft_rows(samples_u8: np.ndarray, n: int, history: int, frames) -> np
     R.nut_buffer_free(out)
     R.nrf_fft_free(fft)
     return arr
+
+
+def ref_iq_filter_blocks(blocks, sample_rate: int, half_ampl_freq: int, kernel_length: int, f64: bool = False):
+    """Run the REFERENCE nrf_iq_filter (src/nrf.c:736-776) over consecutive sample blocks (u8
+    offset-binary interleaved IQ, or float64 when f64); returns the get_buffer() result per block."""
+    R = ref()
+    flt = R.nrf_iq_filter_new(sample_rate, half_ampl_freq, kernel_length)
+    outs = []
+    for b in blocks:
+        if f64:
+            b = np.ascontiguousarray(b, dtype=np.float64)
+            nb = R.nut_buffer_new_f64(b.size // 2, 2, _p(b))
+        else:
+            b = np.ascontiguousarray(b, dtype=np.uint8)
+            nb = R.nut_buffer_new_u8(b.size // 2, 2, _p(b))
+        R.nrf_iq_filter_process(flt, nb)
+        R.nut_buffer_free(nb)
+        o = R.nrf_iq_filter_get_buffer(flt)
+        outs.append(nut_to_numpy(o))
+        R.nut_buffer_free(o)
+    R.nrf_iq_filter_free(flt)
+    return outs
+
+
+def ref_fir_coefficients(sample_rate: int, half_ampl_freq: int, length: int) -> np.ndarray:
+    n = length + (length + 1) % 2
+    p = ref().nrf_fir_get_low_pass_coefficients(sample_rate, half_ampl_freq, length)
+    out = np.ctypeslib.as_array(p, shape=(n,)).copy()
+    C.CDLL(None).free(p)
+    return out

@@ -70,9 +70,33 @@ def check(n, frames):
     return res
 
 
+def check_iq_filter():
+    """nrf_iq_filter on top of fsea_fir_iq_kernel vs the compiled reference: bit-identical, block after block."""
+    from frequensea_b200 import nrf
+    res = {"n": "iq_filter", "kernel": "fsea_fir_iq_kernel"}
+    rng = np.random.default_rng(5)
+    worst = 0.0
+    for taps, length in ((51, 1000), (50, 777), (5, 300), (3, 100), (2, 64), (1, 50), (97, 2500)):
+        blocks = [rng.integers(0, 256, size=2 * length, dtype=np.uint8) for _ in range(3)]
+        ref = orc.ref_iq_filter_blocks(blocks, 5000000, 200000, taps)
+        flt = nrf.iq_filter_new(5000000, 200000, taps)
+        for b, r in zip(blocks, ref):
+            buf = nrf.nut_buffer_new_u8(length, 2, b)
+            nrf.iq_filter_process(flt, buf)
+            got = nrf.iq_filter_get_buffer(flt).numpy()
+            worst = max(worst, float(np.max(np.abs(got - r))))
+        nrf.iq_filter_free(flt)
+        assert np.array_equal(nrf.fir_low_pass_coefficients(5000000, 200000, taps), orc.ref_fir_coefficients(5000000, 200000, taps))
+    res["max_abs_diff"] = worst
+    return res
+
+
 if __name__ == "__main__":
     assert "emu" in fb.lib_path(), "this script checks the EMULATED library only"
     out = []
+    if sys.argv[1:] == ["iq_filter"]:
+        print(json.dumps([check_iq_filter()]))
+        sys.exit(0)
     for a in sys.argv[1:]:
         n = int(a)
         out.append(check(n, 9 if n >= 8192 else 7))

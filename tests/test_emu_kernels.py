@@ -56,3 +56,15 @@ def test_emulated_four_step_sizes(emu_lib):
     res = run_check(emu_lib, [16384, 32768, 65536])
     assert all("fft4<" in r["kernel"] for r in res)
     verify(res)
+
+
+def test_emulated_iq_filter_bit_exact(emu_lib):
+    """nrf_iq_filter_* (SURVEY 8(f) rank 3): the device FIR kernel, on the fiber machine, equals the
+    compiled reference bit for bit -- odd, even and short tap counts, state carried across blocks."""
+    from oracle import orc
+    if not orc.have_ref():
+        pytest.skip("oracle/_ref/libnrf_ref.so not built")
+    env = dict(os.environ, FSEA_LIB=emu_lib)
+    r = subprocess.run([sys.executable, os.path.join(EMU, "check.py"), "iq_filter"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert json.loads(r.stdout.strip().splitlines()[-1])[0]["max_abs_diff"] == 0.0

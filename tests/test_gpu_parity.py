@@ -363,3 +363,42 @@ def test_nrf_fft_f64_chain(fbg, iq, golden):
     assert rel_err(row, golden["ref_shifted_fft_n1024"]) < 1e-11
     nrf.fft_free(fft)
     nrf.freq_shifter_free(sh)
+
+
+@pytest.mark.parametrize("taps,half_ampl", [(51, 200000), (97, 60000), (50, 100000)])
+def test_iq_filter_bit_exact_and_chain(fbg, iq, taps, half_ampl):
+    """nrf_iq_filter_* (src/nrf.c:644-776; lua/iq-tex-filtered.lua:43-46,
+    lua/dvbt.lua:37) with the FIR evaluated by fsea_fir_iq_kernel -- bit-identical to the compiled
+    reference on whole device blocks, state carried across blocks -- and chained into nrf_fft
+    (float64 samples -> fp64 kernels) against the reference's own chain."""
+    if not orc.have_ref():
+        pytest.skip("oracle/_ref/libnrf_ref.so not built")
+    from frequensea_b200 import nrf
+    rate = 5000000
+    raw = orc.device_unpack(iq["rf200big4"])                       # 4 device blocks, offset binary
+    blocks = [raw[b * BLOCK:(b + 1) * BLOCK] for b in range(3)]
+    ref = orc.ref_iq_filter_blocks(blocks, rate, half_ampl, taps)
+    flt = nrf.iq_filter_new(rate, half_ampl, taps)
+    fft = nrf.fft_new(1024, 4)
+    for b, r in zip(blocks, ref):
+        buf = nrf.nut_buffer_new_u8(BLOCK // 2, 2, b)
+        nrf.iq_filter_process(flt, buf)
+        out = nrf.iq_filter_get_buffer(flt)
+        assert out.length == BLOCK // 2 and out.channels == 2 and out.type == nrf.NUT_BUFFER_F64
+        assert np.array_equal(out.numpy(), r)
+        nrf.fft_process(fft, out)
+    hist = nrf.fft_get_buffer(fft).numpy().reshape(4, 1024)
+    # the reference's chain on its own filtered blocks (newest row first)
+    R = orc.ref()
+    rfft = R.nrf_fft_new(1024, 4)
+    for r in ref:
+        nb = R.nut_buffer_new_f64(r.size // 2, 2, r.ctypes.data_as(__import__("ctypes").c_void_p))
+        R.nrf_fft_process(rfft, nb)
+        R.nut_buffer_free(nb)
+    o = R.nrf_fft_get_buffer(rfft)
+    rhist = orc.nut_to_numpy(o).reshape(4, 1024)
+    R.nut_buffer_free(o)
+    R.nrf_fft_free(rfft)
+    assert rel_err(hist[:3], rhist[:3]) < 1e-11
+    nrf.iq_filter_free(flt)
+    nrf.fft_free(fft)
