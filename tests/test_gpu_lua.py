@@ -23,8 +23,9 @@ needs_host = pytest.mark.skipif(not os.path.exists(HOST) or not os.path.exists(o
 
 
 def run_script(name, frames, tmp_path, extra=()):
-    dump = str(tmp_path / f"{name}.dump")
-    cmd = [HOST, f"../lua/{name}.lua", "--frames", str(frames), "--step", "--dump", dump, *extra]
+    dump = str(tmp_path / f"{os.path.basename(name)}.dump")
+    path = name if os.path.isabs(name) else f"../lua/{name}.lua"
+    cmd = [HOST, path, "--frames", str(frames), "--step", "--dump", dump, *extra]
     res = subprocess.run(cmd, cwd=os.path.join(TREE, "run"), stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
     assert res.returncode == 0, res.stderr[-2000:]
     out = []
@@ -78,3 +79,30 @@ def test_retune_key_shifts_history(iq, tmp_path):
     # rows 1.. of the last frame are the previous rows 0.., shifted left by s and zero-filled
     assert np.array_equal(after[1:3, : 1024 - s], before[0:2, s:])
     assert not after[1:3, 1024 - s:].any()
+
+
+@needs_host
+def test_filter_chain_script(iq, tmp_path):
+    """tests/lua/filtered-fft.lua (ours): device -> nrf_iq_filter -> nrf_fft, the operator in front of the
+    path of lua/iq-tex-filtered.lua:43-46 -- against the compiled reference's own chain on the same blocks."""
+    if not orc.have_ref():
+        pytest.skip("oracle/_ref/libnrf_ref.so not built")
+    import ctypes as C
+    frames = 3
+    updates, stdout = run_script(os.path.join(ROOT, "tests", "lua", "filtered-fft.lua"), frames, tmp_path)
+    assert len(updates) == frames, stdout
+    blocks = [orc.device_unpack(iq["rf200big4"][b * BLOCK:(b + 1) * BLOCK]) for b in range(frames)]
+    filtered = orc.ref_iq_filter_blocks(blocks, 5000000, 200000, 51)
+    R = orc.ref()
+    rfft = R.nrf_fft_new(1024, 8)
+    for f, (frame, tex) in enumerate(updates):
+        nb = R.nut_buffer_new_f64(filtered[f].size // 2, 2, filtered[f].ctypes.data_as(C.c_void_p))
+        R.nrf_fft_process(rfft, nb)
+        R.nut_buffer_free(nb)
+        o = R.nrf_fft_get_buffer(rfft)
+        ref = orc.nut_to_numpy(o).reshape(8, 1024)
+        R.nut_buffer_free(o)
+        assert tex.shape == (8, 1024)
+        for r in range(f + 1):
+            assert rel(tex[r], ref[r]) < 1e-6, (f, r)          # float64 transform, float32 texture
+    R.nrf_fft_free(rfft)

@@ -167,6 +167,16 @@ static int l_shifter_gc(lua_State* L) { nrf_freq_shifter_free(to_shifter(L, 1));
 static int l_shifter_process(lua_State* L) { nrf_freq_shifter_process(to_shifter(L, 1), to_buffer(L, 2)); return 0; }
 static int l_shifter_get_buffer(lua_State* L) { return push_buffer(L, nrf_freq_shifter_get_buffer(to_shifter(L, 1))); }
 
+// nrf_iq_filter_* (src/main.cpp:719-747: new(sample_rate, half_ampl_freq, kernel_length), process(filter, buffer), get_buffer)
+static nrf_iq_filter* to_iq_filter(lua_State* L, int i) { return (nrf_iq_filter*)check_object(L, i, "nrf_iq_filter"); }
+static int l_iq_filter_new(lua_State* L) {
+    push_object(L, "nrf_iq_filter", nrf_iq_filter_new((int)luaL_checknumber(L, 1), (int)luaL_checknumber(L, 2), (int)luaL_checknumber(L, 3)));
+    return 1;
+}
+static int l_iq_filter_gc(lua_State* L) { nrf_iq_filter_free(to_iq_filter(L, 1)); return 0; }
+static int l_iq_filter_process(lua_State* L) { nrf_iq_filter_process(to_iq_filter(L, 1), to_buffer(L, 2)); return 0; }
+static int l_iq_filter_get_buffer(lua_State* L) { return push_buffer(L, nrf_iq_filter_get_buffer(to_iq_filter(L, 1))); }
+
 // ---------------------------------------------------------------- inert rendering / audio / osc
 static int l_nop(lua_State*) { return 0; }
 template <int K> static int l_dummy(lua_State* L) {
@@ -246,6 +256,7 @@ int main(int argc, char** argv) {
     register_type(L, "nrf_device", l_device_gc);
     register_type(L, "nrf_fft", l_fft_gc);
     register_type(L, "nrf_freq_shifter", l_shifter_gc);
+    register_type(L, "nrf_iq_filter", l_iq_filter_gc);
     for (const char* t : {"ngl_camera", "ngl_model", "ngl_shader", "ngl_texture", "ngl_skybox", "ngl_font", "nosc_server", "nrf_player"})
         register_type(L, t, nullptr);
 
@@ -268,6 +279,9 @@ int main(int argc, char** argv) {
     reg(L, "nrf_freq_shifter_new", l_shifter_new);
     reg(L, "nrf_freq_shifter_process", l_shifter_process);
     reg(L, "nrf_freq_shifter_get_buffer", l_shifter_get_buffer);
+    reg(L, "nrf_iq_filter_new", l_iq_filter_new);
+    reg(L, "nrf_iq_filter_process", l_iq_filter_process);
+    reg(L, "nrf_iq_filter_get_buffer", l_iq_filter_get_buffer);
     // out of scope: present so that the scripts run, inert
     reg(L, "ngl_camera_new", l_dummy<0>);
     reg(L, "ngl_camera_new_look_at", l_dummy<0>);
