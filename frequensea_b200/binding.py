@@ -75,6 +75,8 @@ def lib() -> C.CDLL:
     L.fsea_frames_in.argtypes = [vp, C.c_size_t]; L.fsea_frames_in.restype = l
     L.fsea_exec_device.argtypes = [vp, vp, vp, l, vp]; L.fsea_exec_device.restype = i
     L.fsea_exec_host.argtypes = [vp, vp, vp, l]; L.fsea_exec_host.restype = i
+    L.fsea_exec_file.argtypes = [vp, C.c_char_p, l, l, vp]; L.fsea_exec_file.restype = i
+    L.fsea_fir_iq_host.argtypes = [i, vp, i, vp, vp, l, vp]; L.fsea_fir_iq_host.restype = i
     L.fsea_plan_launch_count.argtypes = [vp]; L.fsea_plan_launch_count.restype = l
     L.fsea_plan_kernel_name.argtypes = [vp]; L.fsea_plan_kernel_name.restype = C.c_char_p
     L.fsea_gate_mean_host.argtypes = [vp, vp, l, C.POINTER(C.c_double)]; L.fsea_gate_mean_host.restype = i
@@ -174,6 +176,15 @@ class Plan:
         assert out.flags.c_contiguous and out.nbytes >= self.output_bytes(n_frames)
         _check(lib().fsea_exec_host(self._h, data.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p),
                                     n_frames), "fsea_exec_host")
+        return out
+
+    def exec_file(self, path: str, n_frames: int, byte_offset: int = 0, out: np.ndarray | None = None) -> np.ndarray:
+        """A capture file (raw 8-bit IQ as the SDR delivered it, c/rfcap.c / c/reader.c) through the same pipeline."""
+        if out is None:
+            out = np.empty((n_frames, self.n), dtype=self.out_dtype)
+        assert out.flags.c_contiguous and out.nbytes >= self.output_bytes(n_frames)
+        _check(lib().fsea_exec_file(self._h, os.fsencode(path), byte_offset, n_frames, out.ctypes.data_as(C.c_void_p)),
+               "fsea_exec_file")
         return out
 
     def exec_host_ptr(self, h_in: int, h_out: int, n_frames: int) -> None:

@@ -11,6 +11,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <algorithm>
 #include <vector>
 
@@ -475,11 +479,14 @@ static int ensure_stages(fsea_plan* p, long want_frames, bool staging) {
     return FSEA_OK;
 }
 
-extern "C" int fsea_exec_host(fsea_plan* p, const void* h_in, void* h_out, long n_frames) {
-    if (!p || n_frames < 0 || (n_frames > 0 && (!h_in || !h_out))) return FSEA_ERR_INVALID;
-    if (n_frames == 0) return FSEA_OK;
+// `fill` (may be empty) loads the raw bytes of frames [first, first + nf) into a pinned slot;
+// without it the bytes come from h_in (directly when that is page-locked).
+template <class FILL>
+static int exec_pipeline(fsea_plan* p, const void* h_in, void* h_out, long n_frames, bool from_source, FILL fill) {
     CU(cudaSetDevice(p->cfg.device));
-    const bool direct = is_pinned_host(h_in) && is_pinned_host(h_out);
+    const bool out_pinned = is_pinned_host(h_out);
+    const bool direct = !from_source && is_pinned_host(h_in) && out_pinned;     // no staging copy on either side
+    const bool stage_out = from_source ? !out_pinned : !direct;                 // spectra return through the slot's pinned buffer
     int rc = ensure_stages(p, n_frames, !direct);
     if (rc != FSEA_OK) return rc;
     const size_t in_frame_stride = (size_t)p->hop * p->sample_bytes;
@@ -493,7 +500,7 @@ extern "C" int fsea_exec_host(fsea_plan* p, const void* h_in, void* h_out, long 
         if (!pending[s]) return FSEA_OK;
         fsea_stage& st = p->stage[s];
         CU(cudaEventSynchronize(st.done));
-        if (!direct)
+        if (stage_out)
             memcpy((uint8_t*)h_out + (size_t)pending_first[s] * out_per, st.h_out, (size_t)pending[s] * out_per);
         pending[s] = 0;
         return FSEA_OK;
@@ -505,7 +512,13 @@ extern "C" int fsea_exec_host(fsea_plan* p, const void* h_in, void* h_out, long 
         const size_t ib = fsea_input_bytes(p, nf);
         const uint8_t* src = (const uint8_t*)h_in + (size_t)issued * in_frame_stride;
         uint8_t* dst = (uint8_t*)h_out + (size_t)issued * out_per;
-        if (!direct) { memcpy(st.h_in, src, ib); src = (const uint8_t*)st.h_in; dst = (uint8_t*)st.h_out; }
+        if (from_source) {
+            if ((rc = fill(st.h_in, issued, nf, ib)) != FSEA_OK) break;
+            src = (const uint8_t*)st.h_in;
+            if (stage_out) dst = (uint8_t*)st.h_out;
+        } else if (!direct) {
+            memcpy(st.h_in, src, ib); src = (const uint8_t*)st.h_in; dst = (uint8_t*)st.h_out;
+        }
         CU(cudaMemcpyAsync(st.d_in, src, ib, cudaMemcpyHostToDevice, st.stream));
         if ((rc = launch(p, st.d_in, st.d_out, nf, st.stream, 1 + slot)) != FSEA_OK) return rc;
         CU(cudaMemcpyAsync(dst, st.d_out, (size_t)nf * out_per, cudaMemcpyDeviceToHost, st.stream));
@@ -516,9 +529,42 @@ extern "C" int fsea_exec_host(fsea_plan* p, const void* h_in, void* h_out, long 
         slot = (slot + 1) % fsea_plan::NSTAGE;
     }
     for (int s = 0; s < fsea_plan::NSTAGE; s++) {
-        if ((rc = drain((slot + s) % fsea_plan::NSTAGE)) != FSEA_OK) return rc;
+        const int rd = drain((slot + s) % fsea_plan::NSTAGE);
+        if (rc == FSEA_OK) rc = rd;
     }
-    return FSEA_OK;
+    return rc;
+}
+
+extern "C" int fsea_exec_host(fsea_plan* p, const void* h_in, void* h_out, long n_frames) {
+    if (!p || n_frames < 0 || (n_frames > 0 && (!h_in || !h_out))) return FSEA_ERR_INVALID;
+    if (n_frames == 0) return FSEA_OK;
+    return exec_pipeline(p, h_in, h_out, n_frames, false, [](void*, long, long, size_t) { return (int)FSEA_OK; });
+}
+
+// Capture files are the bytes the SDR delivered, block after block (c/rfcap.c:26-41 one file per
+// block, c/reader.c:25-49 one file per run; src/nrf.c:256-284 replays them): no header, interleaved
+// 8-bit I,Q.  pread() fills the pinned slot of the pipeline while the other slots are in flight.
+extern "C" int fsea_exec_file(fsea_plan* p, const char* path, long byte_offset, long n_frames, void* h_out) {
+    if (!p || !path || byte_offset < 0 || n_frames < 0 || (n_frames > 0 && !h_out)) return FSEA_ERR_INVALID;
+    if (p->cfg.in_format != FSEA_IN_U8 && p->cfg.in_format != FSEA_IN_S8) return FSEA_ERR_INVALID;
+    if (byte_offset & 15) return FSEA_ERR_INVALID;                  // frames are fetched in 16-byte pieces
+    if (n_frames == 0) return FSEA_OK;
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return FSEA_ERR_INVALID;
+    struct stat sb;
+    if (fstat(fd, &sb) != 0 || (size_t)sb.st_size < (size_t)byte_offset + fsea_input_bytes(p, n_frames)) { close(fd); return FSEA_ERR_INVALID; }
+    const size_t stride = (size_t)p->hop * p->sample_bytes;
+    const int rc = exec_pipeline(p, nullptr, h_out, n_frames, true, [&](void* dst, long first, long, size_t bytes) {
+        size_t got = 0;
+        while (got < bytes) {
+            const ssize_t r = pread(fd, (char*)dst + got, bytes - got, (off_t)(byte_offset + first * stride + got));
+            if (r <= 0) return (int)FSEA_ERR_INVALID;
+            got += (size_t)r;
+        }
+        return (int)FSEA_OK;
+    });
+    close(fd);
+    return rc;
 }
 
 // ------------------------------------------------------------------ sweep gate

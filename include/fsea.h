@@ -110,6 +110,13 @@ int fsea_exec_device(fsea_plan *plan, const void *d_in, void *d_out, long n_fram
  * the nrf_fft shim and bench.py's `e2e` use. */
 int fsea_exec_host(fsea_plan *plan, const void *h_in, void *h_out, long n_frames);
 
+/* The same pipeline fed from a capture file: the raw bytes an SDR delivered, block after block,
+ * no header (c/rfcap.c:26-41, c/reader.c:25-49; replayed by src/nrf.c:256-284).  Frames
+ * [0, n_frames) start at byte_offset (a multiple of 16) + f * hop * 2; pread() fills the pinned
+ * slots while earlier slots cross PCIe and compute.  8-bit input formats only.
+ * FSEA_ERR_INVALID when the file is missing or shorter than the frames asked for. */
+int fsea_exec_file(fsea_plan *plan, const char *path, long byte_offset, long n_frames, void *h_out);
+
 /* Number of kernel launches issued by this plan so far (bench gpu_launches). */
 long fsea_plan_launch_count(const fsea_plan *plan);
 /* Name of the kernel variant the plan dispatches to, e.g. "fft<1024:32x32x1,f32x2>". */

@@ -70,6 +70,32 @@ def check(n, frames):
     return res
 
 
+def check_file_feed():
+    """fsea_exec_file == fsea_exec_host on the same bytes: offsets, overlap, short files."""
+    import tempfile
+    res = {"n": "file", "kernel": "fsea_exec_file"}
+    data = synth_s8(40000, seed=11)
+    with tempfile.NamedTemporaryFile(suffix=".raw", delete=False) as f:
+        f.write(data.tobytes())
+        path = f.name
+    ok = True
+    for n, hop, off_bytes, frames in ((1024, 1024, 0, 30), (1024, 512, 4096, 50), (256, 128, 16, 100), (16384, 16384, 0, 2)):
+        plan = fb.Plan(n, hop=hop, in_format=fb.IN_S8, out_mode=fb.OUT_MAG, flags=fb.FLAG_DC_PATCH)
+        a = plan.exec_file(path, frames, off_bytes)
+        b = plan.exec_host(data[off_bytes:], frames)
+        ok = ok and np.array_equal(a, b)
+    plan = fb.Plan(1024, in_format=fb.IN_S8)
+    for bad in (lambda: plan.exec_file(path, 40), lambda: plan.exec_file(path + ".missing", 1), lambda: plan.exec_file(path, 1, 8)):
+        try:
+            bad()
+            ok = False
+        except RuntimeError:
+            pass
+    os.unlink(path)
+    res["identical"] = bool(ok)
+    return res
+
+
 def check_iq_filter():
     """nrf_iq_filter on top of fsea_fir_iq_kernel vs the compiled reference: bit-identical, block after block."""
     from frequensea_b200 import nrf
@@ -96,6 +122,9 @@ if __name__ == "__main__":
     out = []
     if sys.argv[1:] == ["iq_filter"]:
         print(json.dumps([check_iq_filter()]))
+        sys.exit(0)
+    if sys.argv[1:] == ["file"]:
+        print(json.dumps([check_file_feed()]))
         sys.exit(0)
     for a in sys.argv[1:]:
         n = int(a)

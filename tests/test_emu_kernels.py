@@ -68,3 +68,12 @@ def test_emulated_iq_filter_bit_exact(emu_lib):
     r = subprocess.run([sys.executable, os.path.join(EMU, "check.py"), "iq_filter"], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
     assert json.loads(r.stdout.strip().splitlines()[-1])[0]["max_abs_diff"] == 0.0
+
+
+def test_emulated_capture_file_feed(emu_lib):
+    """fsea_exec_file: pread-fed pipeline == host-buffer pipeline, byte offsets,
+    overlapping frames, several slots in flight; short / missing / misaligned files are refused."""
+    env = dict(os.environ, FSEA_LIB=emu_lib)
+    r = subprocess.run([sys.executable, os.path.join(EMU, "check.py"), "file"], capture_output=True, text=True, env=env, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    assert json.loads(r.stdout.strip().splitlines()[-1])[0]["identical"] is True

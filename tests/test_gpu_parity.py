@@ -402,3 +402,33 @@ def test_iq_filter_bit_exact_and_chain(fbg, iq, taps, half_ampl):
     assert rel_err(hist[:3], rhist[:3]) < 1e-11
     nrf.iq_filter_free(flt)
     nrf.fft_free(fft)
+
+
+def test_capture_file_feed(fbg, iq, tmp_path):
+    """a capture file as c/reader.c:25-49 writes it (raw int8 IQ, block after block)
+    streamed through fsea_exec_file -- same rows as the host-buffer path and as the oracle; the
+    reference replays such files block-wise (src/nrf.c:256-284)."""
+    fb = fbg
+    raw = iq["rf200big4"]                                  # 4 capture blocks
+    path = str(tmp_path / "rf-200.500.raw")
+    raw.tofile(path)
+    n = 1024
+    frames = raw.size // (2 * n)
+    plan = fb.Plan(n, in_format=fb.IN_S8, out_mode=fb.OUT_MAG, flags=fb.FLAG_DC_PATCH)
+    got = plan.exec_file(path, frames)
+    assert np.array_equal(got, plan.exec_host(raw, frames))
+    ref = oracle_rows(raw, n, n, 16, orc.IN_S8, orc.WIN_NONE, orc.OUT_MAG, flags=orc.FLAG_DC_PATCH)
+    assert rel_err(got[:16], ref) < MAG_TOL
+    # second block only, overlapping frames, pixels
+    plan = fb.Plan(n, hop=512, in_format=fb.IN_S8, out_mode=fb.OUT_PIX, pix_scale=5.0, flags=fb.FLAG_DC_PATCH)
+    got = plan.exec_file(path, 200, byte_offset=BLOCK)
+    assert np.array_equal(got, plan.exec_host(raw[BLOCK:], 200))
+    # many slots in flight: 65536-point frames from a larger file
+    big = np.tile(raw, 8)
+    bpath = str(tmp_path / "big.raw")
+    big.tofile(bpath)
+    plan = fb.Plan(65536, in_format=fb.IN_S8, out_mode=fb.OUT_LOGMAG)
+    got = plan.exec_file(bpath, 64)
+    assert np.array_equal(got, plan.exec_host(big, 64))
+    with pytest.raises(RuntimeError):
+        plan.exec_file(bpath, 65)                          # file too short
