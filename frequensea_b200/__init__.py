@@ -18,5 +18,6 @@ from .binding import (  # noqa: F401
     ARITH_AUTO, ARITH_F32, ARITH_F32X2, ARITH_F32X2_FRAME,
 )
 from . import nrf  # noqa: F401
+from . import shard, sweep  # noqa: F401
 
 __all__ = ["FseaError", "Plan", "build", "device_count", "lib", "lib_path", "nrf"]

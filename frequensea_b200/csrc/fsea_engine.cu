@@ -570,11 +570,21 @@ extern "C" int fsea_exec_file(fsea_plan* p, const char* path, long byte_offset, 
 // ------------------------------------------------------------------ sweep gate
 // c/fft-batch-broad.c:80-98: mean |X| over the first `rows` rows.  The rows'
 // magnitudes are produced by the MAG kernel and summed in fp64 on the device.
-__global__ void fsea_sum_kernel(const float* __restrict__ x, long n, double* __restrict__ acc) {
+// Deterministic: every block leaves ONE partial sum (lanes by shuffle, warps in index order), the
+// host adds the 256 partials in block order -- the same bits on every run and on every rank.
+#define FSEA_SUM_BLOCKS 256
+__global__ void fsea_sum_kernel(const float* __restrict__ x, long n, double* __restrict__ partial) {
+    FSEA_STATIC_SMEM(double, warp_sum, 8);
     double s = 0.0;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) s += (double)x[i];
     for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) atomicAdd(acc, s);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++) t += warp_sum[w];
+        partial[blockIdx.x] = t;
+    }
 }
 
 extern "C" int fsea_gate_mean_host(fsea_plan* p, const void* h_in, long rows, double* mean_out) {
@@ -583,20 +593,20 @@ extern "C" int fsea_gate_mean_host(fsea_plan* p, const void* h_in, long rows, do
     CU(cudaSetDevice(p->cfg.device));
     const size_t ib = fsea_input_bytes(p, rows), ob = fsea_output_bytes(p, rows);
     void *d_in = nullptr, *d_out = nullptr;
-    if (!p->d_gate) CU(cudaMalloc(&p->d_gate, sizeof(double)));
+    if (!p->d_gate) CU(cudaMalloc(&p->d_gate, sizeof(double) * FSEA_SUM_BLOCKS));
     CU(cudaMalloc(&d_in, ib));
     cudaError_t e = cudaMalloc(&d_out, ob);
     if (e != cudaSuccess) { cudaFree(d_in); return cuda_fail(e, "cudaMalloc"); }
     int rc = FSEA_OK;
     do {
         if ((e = cudaMemcpy(d_in, h_in, ib, cudaMemcpyHostToDevice)) != cudaSuccess) { rc = cuda_fail(e, "H2D"); break; }
-        if ((e = cudaMemset(p->d_gate, 0, sizeof(double))) != cudaSuccess) { rc = cuda_fail(e, "memset"); break; }
         if ((rc = launch(p, d_in, d_out, rows, 0)) != FSEA_OK) break;
         const long n = rows * p->cfg.fft_size;
-        FSEA_LAUNCH(fsea_sum_kernel, 256, 256, (cudaStream_t)0, (const float*)d_out, n, p->d_gate);
+        FSEA_LAUNCH(fsea_sum_kernel, FSEA_SUM_BLOCKS, 256, (cudaStream_t)0, (const float*)d_out, n, p->d_gate);
         p->launches++;
-        double total = 0;
-        if ((e = cudaMemcpy(&total, p->d_gate, sizeof(double), cudaMemcpyDeviceToHost)) != cudaSuccess) { rc = cuda_fail(e, "D2H"); break; }
+        double part[FSEA_SUM_BLOCKS], total = 0;
+        if ((e = cudaMemcpy(part, p->d_gate, sizeof(part), cudaMemcpyDeviceToHost)) != cudaSuccess) { rc = cuda_fail(e, "D2H"); break; }
+        for (int b = 0; b < FSEA_SUM_BLOCKS; b++) total += part[b];
         *mean_out = total / (double)n;
     } while (0);
     cudaFree(d_in);

@@ -432,3 +432,22 @@ def test_capture_file_feed(fbg, iq, tmp_path):
     assert np.array_equal(got, plan.exec_host(big, 64))
     with pytest.raises(RuntimeError):
         plan.exec_file(bpath, 65)                          # file too short
+
+
+def test_sweep_workflow_single_gpu(fbg):
+    """BASELINE cfg4 as a job (frequensea_b200/sweep.py): gate (c/fft-batch-broad.c:80-98), pixel rows
+    (:108-118), stitch (c/fft-stitch-broad.c) on the engine == the same job on the oracle; quiet
+    frequencies are gated off.  The N > 1 form of it runs over gloo in tests/test_shard_gloo.py and
+    over NCCL in tools/sweep_demo.py."""
+    from frequensea_b200 import sweep
+    from test_shard_gloo import OracleOps
+    n_freqs, n, rows, step = 6, 1024, 16, 400
+    stream = lambda f: sweep.synth_frequency(f, n, rows, quiet_every=3)
+    got = sweep.sweep(sweep.EngineOps(n), n_freqs, stream, n, rows, step, gate_rows=8)
+    ref = sweep.sweep(OracleOps(n), n_freqs, stream, n, rows, step, gate_rows=8)
+    assert got["keep"].tolist() == ref["keep"].tolist() == [f % 3 != 2 for f in range(n_freqs)]
+    np.testing.assert_allclose(got["means"], ref["means"], rtol=1e-5)
+    d = np.abs(got["images"].astype(int) - ref["images"].astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 0.005
+    assert np.array_equal(got["stitched"], orc.stitch(got["images"], step))     # stitch itself is bit-exact
+    assert got["stitched"].shape == (rows, n + (n_freqs - 1) * step)

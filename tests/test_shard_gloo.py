@@ -61,3 +61,58 @@ def test_two_rank_scatter_transform_gather(n, hop, n_frames):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert ok
+
+
+class OracleOps:
+    """Stand-in for sweep.EngineOps in this CPU suite only (no GPU here): the oracle's arithmetic."""
+    device = 0
+
+    def __init__(self, n):
+        self.n = n
+
+    def gate_mean(self, raw, rows):
+        from oracle import orc
+        return float(orc.engine_batch(raw, self.n, self.n, rows, orc.IN_S8, orc.WIN_NONE, orc.OUT_MAG).astype(np.float64).mean())
+
+    def pixel_rows(self, raw, rows):
+        from oracle import orc
+        return orc.engine_batch(raw, self.n, self.n, rows, orc.IN_S8, orc.WIN_NONE, orc.OUT_PIX, 5.0, flags=orc.FLAG_DC_PATCH)
+
+    def stitch(self, images, step):
+        from oracle import orc
+        return orc.stitch(images, step)
+
+
+def _sweep_worker(rank, world, port, n_freqs, n, rows, step, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from frequensea_b200 import sweep
+    stream = lambda f: sweep.synth_frequency(f, n, rows, quiet_every=4)
+    res = sweep.sweep(OracleOps(n), n_freqs, stream, n, rows, step, rank=rank, world=world, gate_rows=8)
+    if rank == 0:
+        one = sweep.sweep(OracleOps(n), n_freqs, stream, n, rows, step, gate_rows=8)      # the same job on one rank
+        same = all(np.array_equal(res[k], one[k]) for k in ("means", "keep", "images", "stitched"))
+        q.put((bool(same), res["keep"].tolist(), res["stitched"].shape))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sweep_gate_and_stitch():
+    """cfg4 workflow (c/fft-batch-broad.c gate + pixels, c/fft-stitch-broad.c): frequency f -> rank f mod 2,
+    images and gate decisions gathered on rank 0 and stitched == the one-rank job; every 4th frequency
+    is noise-only and must be gated off, the others kept."""
+    n_freqs, n, rows, step = 7, 256, 12, 100
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29850 + (os.getpid() % 100)
+    procs = [ctx.Process(target=_sweep_worker, args=(r, 2, port, n_freqs, n, rows, step, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    same, keep, shape = q.get(timeout=180)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert same
+    assert keep == [f % 4 != 3 for f in range(n_freqs)]
+    assert tuple(shape) == (rows, n + (n_freqs - 1) * step)
