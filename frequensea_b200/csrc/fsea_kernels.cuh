@@ -1079,22 +1079,6 @@ template <int OUT, int N1> struct fsea_comb<OUT, N1, 64> {
     }
 };
 
-// two-launch form of step B (N2 = 32)
-template <int OUT, int N1>
-__global__ void __launch_bounds__(128, 3)
-fsea_comb32_kernel(const fsea_kparams kp) {
-    constexpr int hp = N1 >> 1;                            // bin pairs per frame
-    const long pairs = kp.n_seq;
-    const bool dc_patch = (kp.flags & FSEA_FLAG_DC_PATCH) != 0;
-    constexpr int ESZ = (OUT == FSEA_OUT_PIX) ? 1 : 4;
-    for (long u = (long)blockIdx.x * blockDim.x + threadIdx.x; u < pairs; u += (long)gridDim.x * blockDim.x) {
-        const long f = u / hp;
-        const int p = (int)(u - f * hp);
-        fsea_comb<OUT, N1, 32>::template run<0>(kp, (const float*)kp.in + (size_t)f * 64 * N1, p, 0,
-                                                (uint8_t*)kp.out + (size_t)f * 32 * N1 * ESZ, dc_patch);
-    }
-}
-
 // ---- four-step, both steps in one kernel: a thread-block CLUSTER per frame -------------------
 // The CS blocks of a cluster transform the sub-sequences of one frame (one tile each, step A),
 // meet at the cluster barrier, and each combs its share of the frame's bins (step B).  The
