@@ -15,12 +15,22 @@ ncu --set full --clock-control none --import-source on -k regex:fsea_fft -s 3 -c
 python tools/ncu_summary.py $O/prof_n1024.ncu-rep > $O/ncu_full_n1024_f32x2.txt 2>&1
 # one full capture per other kernel family: frame-per-unit 2048 / 4096 / 8192(+Hann), cluster four-step 16384 / 32768 / 65536
 SWEEP_STEPS=1 SWEEP_WARMUP=1 timeout 900 ncu --set full --clock-control none -k regex:fsea_ -c 14 -o $O/prof_family \
-   python tools/sweep.py n2048 n4096 n8192 cfg3 n16384 n32768 n65536 > $O/ncu_family.log 2>&1
+   python tools/sweep.py n2048 n4096 n8192 cfg3 n16384 > $O/ncu_family.log 2>&1
 python tools/ncu_summary.py $O/prof_family.ncu-rep > $O/ncu_full_family.txt 2>&1
 rm -f $O/prof_family.ncu-rep
+SWEEP_STEPS=1 SWEEP_WARMUP=1 timeout 600 ncu --set full --clock-control none -k regex:fsea_ -c 6 -o $O/prof_four \
+   python tools/sweep.py n32768 n65536 > $O/ncu_four.log 2>&1
+python tools/ncu_summary.py $O/prof_four.ncu-rep > $O/ncu_full_four_step_32768_65536.txt 2>&1
+rm -f $O/prof_four.ncu-rep
 sz=$(stat -c %s $O/prof_n1024.ncu-rep 2>/dev/null || echo 0); if [ $sz -gt 30000000 ]; then rm $O/prof_n1024.ncu-rep; fi
 for w in n128 n256 n512 n2048 n4096 n8192 n16384 n32768 n65536 cfg3 cfg4 cfg5; do
   timeout 150 python bench.py --workload $w --steps 5 --warmup 3 > $O/bench_$w.json 2> $O/bench_$w.err
+done
+python tools/bench_fir.py --taps 51 > $O/bench_fir_51.json 2> $O/bench_fir_51.err
+python tools/bench_fir.py --taps 97 > $O/bench_fir_97.json 2> $O/bench_fir_97.err
+python tools/bench_operator.py > $O/bench_operator_per_draw.json 2> $O/bench_operator.err
+for tool in memcheck racecheck synccheck; do
+  timeout 400 compute-sanitizer --tool $tool python tools/sanitize.py > $O/compute_sanitizer_$tool.txt 2>&1; echo "$tool rc=$?" >> $O/compute_sanitizer_$tool.txt
 done
 python - <<'PY'
 import json, glob
