@@ -14,7 +14,7 @@ IN_U8, IN_S8, IN_F32C, IN_F64C = 0, 1, 2, 3
 WIN_NONE, WIN_HANN = 0, 1
 OUT_MAG, OUT_LOGMAG, OUT_PIX = 0, 1, 2
 FLAG_DC_PATCH = 1
-ARITH_AUTO, ARITH_F32, ARITH_F32X2, ARITH_F32X2_FRAME = 0, 1, 2, 3
+ARITH_AUTO, ARITH_F32, ARITH_F32X2, ARITH_F32X2_FRAME, ARITH_F32X2_RADIX64 = 0, 1, 2, 3, 4
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM = 0, -1, -2, -3, -4, -5
 

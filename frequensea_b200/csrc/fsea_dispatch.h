@@ -13,7 +13,8 @@ enum {
     FSEA_VAR_F32X2_WIN = 5,
     FSEA_VAR_F32X2H = 6,     // 8-bit IQ, ONE frame per group: lanes = even / odd samples, radix-2 across the lanes at the end
     FSEA_VAR_F32X2H_WIN = 7,
-    FSEA_VAR_COUNT = 8
+    FSEA_VAR_F32X2X = 8,     // 8-bit IQ, N = 4096 = 64 x 64: ONE frame per group of 64 threads, 64 points per thread (fsea_k64.cuh)
+    FSEA_VAR_COUNT = 9
 };
 
 struct fsea_kernel_info {
@@ -26,6 +27,7 @@ struct fsea_kernel_info {
     int tw1, tw2;        // twiddle table entries
     int scalar_bytes;    // 4 or 8
     int half;            // 1: n, r0.. describe the (N/2)-point transform of a "half" kernel
+    int x64;             // 1: fsea_fft4096x_kernel (its twiddle table goes where the half kernels keep theirs)
     const char* name;
 };
 

@@ -55,7 +55,8 @@ enum { FSEA_OUT_MAG = 0, FSEA_OUT_LOGMAG = 1, FSEA_OUT_PIX = 2 };
 enum { FSEA_FLAG_DC_PATCH = 1 };
 /* arithmetic variant of the fp32 kernels (results agree to fp32 rounding) */
 enum { FSEA_ARITH_AUTO = 0, FSEA_ARITH_F32 = 1, FSEA_ARITH_F32X2 = 2,
-       FSEA_ARITH_F32X2_FRAME = 3 /* packed lanes = even / odd samples of ONE frame (N = 2048, 4096, 8192; 8-bit input) */ };
+       FSEA_ARITH_F32X2_FRAME = 3 /* packed lanes = even / odd samples of ONE frame (N = 2048, 4096, 8192; 8-bit input) */,
+       FSEA_ARITH_F32X2_RADIX64 = 4 /* N = 4096 = 64 x 64, 64 points per thread, one exchange (8-bit input, no window) */ };
 
 enum {
     FSEA_OK = 0,

@@ -30,11 +30,11 @@ def rows(data, n, hop, frames, fmt, win, out, scale=10.0, flags=0):
     return np.stack([orc.engine_frame(data[f * hop * 2:], n, fmt, win, out, scale, flags) for f in range(frames)])
 
 
-def check(n, frames):
+def check(n, frames, arith=0):
     res = {"n": n}
     # (1) two's-complement input, magnitude, DC patch (nrf_fft semantics); more frames than clusters in flight
     data = synth_s8(n * frames, seed=n)
-    plan = fb.Plan(n, in_format=fb.IN_S8, out_mode=fb.OUT_MAG, flags=fb.FLAG_DC_PATCH)
+    plan = fb.Plan(n, in_format=fb.IN_S8, out_mode=fb.OUT_MAG, flags=fb.FLAG_DC_PATCH, arith=arith)
     res["kernel"] = plan.kernel_name
     got = plan.exec_host(data, frames)
     ref = rows(data, n, n, frames, orc.IN_S8, orc.WIN_NONE, orc.OUT_MAG, flags=orc.FLAG_DC_PATCH)
@@ -42,7 +42,7 @@ def check(n, frames):
     res["patch_dup"] = bool(np.array_equal(got[:, n // 2], got[:, n // 2 - 1]))
     # (2) offset-binary input, uncentred DC kept, log-magnitude
     data = synth_u8(n * 3, seed=n + 1)
-    plan = fb.Plan(n, in_format=fb.IN_U8, out_mode=fb.OUT_LOGMAG)
+    plan = fb.Plan(n, in_format=fb.IN_U8, out_mode=fb.OUT_LOGMAG, arith=arith)
     got = plan.exec_host(data, 3).astype(np.float64)
     ref = rows(data, n, n, 3, orc.IN_U8, orc.WIN_NONE, orc.OUT_LOGMAG)
     lin = 10 ** (ref / 20)
@@ -53,7 +53,7 @@ def check(n, frames):
     hop = n // 2
     data = synth_u8(2 * hop + n, seed=n + 2)
     plan = fb.Plan(n, hop=hop, in_format=fb.IN_U8, window=fb.WIN_HANN, out_mode=fb.OUT_PIX, pix_scale=5.0,
-                   flags=fb.FLAG_DC_PATCH)
+                   flags=fb.FLAG_DC_PATCH, arith=arith)
     got = plan.exec_host(data, 3)
     ref = rows(data, n, hop, 3, orc.IN_U8, orc.WIN_HANN, orc.OUT_PIX, 5.0, orc.FLAG_DC_PATCH)
     d = np.abs(got.astype(int) - ref.astype(int))
@@ -61,7 +61,7 @@ def check(n, frames):
     res["pix_frac"] = float((d > 0).mean())
     # (4) c/fft.c's scope row: bytes / 255, spectrum / N, intensity * log10(power + 1e-20)  (c/fft.c:50-51,181-197)
     data = synth_u8(n * 2, seed=n + 3)
-    plan = fb.Plan(n, in_format=fb.IN_U8, out_mode=fb.OUT_LOGMAG, log_mult=7.0, power_gain=(256.0 / (255.0 * n)) ** 2)
+    plan = fb.Plan(n, in_format=fb.IN_U8, out_mode=fb.OUT_LOGMAG, log_mult=7.0, power_gain=(256.0 / (255.0 * n)) ** 2, arith=arith)
     got = plan.exec_host(data, 2).astype(np.float64)
     ref = np.stack([orc.scope_row(data[f * 2 * n:], n, 7.0) for f in range(2)])
     lin = 10 ** (ref / 14)
@@ -126,7 +126,8 @@ if __name__ == "__main__":
     if sys.argv[1:] == ["file"]:
         print(json.dumps([check_file_feed()]))
         sys.exit(0)
-    for a in sys.argv[1:]:
-        n = int(a)
-        out.append(check(n, 9 if n >= 8192 else 7))
+    for a in sys.argv[1:]:                                   # N or N:arith
+        n, _, ar = a.partition(":")
+        n = int(n)
+        out.append(check(n, 9 if n >= 8192 else 7, int(ar or 0)))
     print(json.dumps(out))

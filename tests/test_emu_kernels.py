@@ -51,6 +51,14 @@ def test_emulated_single_launch_sizes(emu_lib):
     verify(run_check(emu_lib, [16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192]))
 
 
+def test_emulated_alternative_arrangements(emu_lib):
+    """The arrangements FSEA_ARITH_AUTO does not pick: frame pairs (2), frame per unit (3) at 2048 ... 8192,
+    scalar fp32 (1)."""
+    res = run_check(emu_lib, ["2048:2", "4096:2", "4096:3", "8192:2", "1024:1", "4096:1"])
+    assert "64x64" not in res[2]["kernel"] and "frame/unit" in res[2]["kernel"]
+    verify(res)
+
+
 def test_emulated_four_step_sizes(emu_lib):
     """N = 16384 .. 65536: the cluster kernel (sub-spectra, cluster barrier, comb) incl. slot reuse."""
     res = run_check(emu_lib, [16384, 32768, 65536])

@@ -108,7 +108,8 @@ def test_hann_overlap_logmag(fbg, n, hop):
 @pytest.mark.parametrize("n", [2048, 4096, 8192])
 def test_frame_per_unit_variants(fbg, n, arith):
     """One frame per unit (packed lanes = even / odd samples, radix-2 across the lanes in the output
-    stage) and whatever FSEA_ARITH_AUTO picks for these lengths: all output modes, odd frame counts."""
+    stage) and whatever FSEA_ARITH_AUTO picks for these lengths (N = 4096 without a window: 64 x 64
+    with 64 points per thread, fsea_k64.cuh): all output modes, odd frame counts."""
     fb = fbg
     frames = 5
     data = synth_u8(n * frames, seed=n + 3)

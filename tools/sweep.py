@@ -62,7 +62,7 @@ def run(item, steps=int(os.environ.get("SWEEP_STEPS", "5")), warmup=int(os.envir
     cfg.out_mode = {"mag": B.OUT_MAG, "logmag": B.OUT_LOGMAG, "pix": B.OUT_PIX}[w["out"]]
     cfg.flags = B.FLAG_DC_PATCH if w["patch"] else 0
     cfg.pix_scale = w.get("scale", 10.0)
-    cfg.arith = {"auto": 0, "f32": 1, "f32x2": 2, "f32x2h": 3}[arith]
+    cfg.arith = {"auto": 0, "f32": 1, "f32x2": 2, "f32x2h": 3, "r64": 4}[arith]
     h = C.c_void_p()
     rc = L.fsea_plan_create(C.byref(cfg), C.byref(h))
     if rc:
