@@ -146,6 +146,7 @@ def device_step(dev): _L().nrf_device_step(dev)
 def device_get_samples_buffer(dev): return NutBuffer(_L().nrf_device_get_samples_buffer(dev))
 def device_free(dev): _L().nrf_device_free(dev)
 def block_connect(a, b): _L().nrf_block_connect(a, b)
+def block_process(block, b: NutBuffer): _L().nrf_block_process(block, b.ptr)
 
 def fft_new(fft_size: int, fft_history_size: int): return _L().nrf_fft_new(fft_size, fft_history_size)
 def fft_shift(fft, d: float): _L().nrf_fft_shift(fft, d)

@@ -452,3 +452,24 @@ def test_sweep_workflow_single_gpu(fbg):
     assert d.max() <= 1 and (d > 0).mean() < 0.005
     assert np.array_equal(got["stitched"], orc.stitch(got["images"], step))     # stitch itself is bit-exact
     assert got["stitched"].shape == (rows, n + (n_freqs - 1) * step)
+
+
+def test_block_graph_filter_into_fft(fbg, iq):
+    """nrf_block_connect / nrf_block_process (src/nrf.c:24-50): pushing a buffer into a filter block
+    runs the filter, hands its result to the connected nrf_fft and frees it -- same history as calling
+    the two operators by hand."""
+    from frequensea_b200 import nrf
+    raw = orc.device_unpack(iq["rf200big4"])
+    blocks = [raw[b * BLOCK:(b + 1) * BLOCK] for b in range(2)]
+    flt_a, fft_a = nrf.iq_filter_new(5000000, 150000, 33), nrf.fft_new(256, 4)
+    flt_b, fft_b = nrf.iq_filter_new(5000000, 150000, 33), nrf.fft_new(256, 4)
+    nrf.block_connect(flt_a, fft_a)                 # NRF_BLOCK is the first member of both objects
+    for b in blocks:
+        buf = nrf.nut_buffer_new_u8(BLOCK // 2, 2, b)
+        nrf.block_process(flt_a, buf)
+        nrf.iq_filter_process(flt_b, buf)
+        nrf.fft_process(fft_b, nrf.iq_filter_get_buffer(flt_b))
+    a, b_ = nrf.fft_get_buffer(fft_a).numpy(), nrf.fft_get_buffer(fft_b).numpy()
+    assert a.any() and np.array_equal(a, b_)
+    for o, free in ((flt_a, nrf.iq_filter_free), (flt_b, nrf.iq_filter_free), (fft_a, nrf.fft_free), (fft_b, nrf.fft_free)):
+        free(o)
