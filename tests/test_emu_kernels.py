@@ -85,3 +85,16 @@ def test_emulated_capture_file_feed(emu_lib):
     r = subprocess.run([sys.executable, os.path.join(EMU, "check.py"), "file"], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
     assert json.loads(r.stdout.strip().splitlines()[-1])[0]["identical"] is True
+
+
+def test_gpu_suite_on_the_fiber_machine(emu_lib, tmp_path):
+    """The -m gpu parity tests themselves (C ABI, operator mirror, sweep job, the reference's Lua
+    scripts on tools/_ref/fsea-lua) with the emulated library in libfsea.so's place: the test logic
+    and every kernel source are exercised before a GPU minute is spent.  Left out: the two tests that
+    allocate device memory through torch.  On the B200 box the same tests run against the real library."""
+    os.symlink(emu_lib, tmp_path / "libfsea.so")                     # for the Lua host's DT_NEEDED libfsea.so
+    env = dict(os.environ, FSEA_LIB=emu_lib, LD_LIBRARY_PATH=str(tmp_path) + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"),
+                        os.path.join(ROOT, "tests", "test_gpu_lua.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
+                        "-k", "not many_frames and not large_batch"], capture_output=True, text=True, env=env, cwd=ROOT, timeout=1500)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]
