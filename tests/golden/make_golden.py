@@ -13,7 +13,7 @@ Contents
                     np_*  : numpy (pocketfft) restatement of SURVEY.md 8(a)
                     ref_* : the compiled reference itself (nrf_fft_new/process/
                             get_buffer, nrf_fft_shift, nrf_freq_shifter_*,
-                            nut_buffer_*), FFTW role stubbed by oracle/stubs
+                            nut_buffer_*, nrf_iq_filter_*), FFTW role stubbed by oracle/stubs
 """
 import os
 import sys
@@ -112,6 +112,15 @@ def main():
         for b in (nb, sb, clip, hb):
             R.nut_buffer_free(b)
         R.nrf_fft_free(fft)
+        # nrf_iq_filter over the first 3 device blocks (lua/iq-tex-filtered.lua:43-46: 200 kHz, 51 taps; lua/dvbt.lua:37:
+        # 60 kHz, 97 taps; an even tap count, where the reference keeps length + 1 coefficients but uses length)
+        blocks = [ubig[b * BLOCK:(b + 1) * BLOCK] for b in range(3)]
+        for taps, half in ((51, 200000), (97, 60000), (50, 100000)):
+            outs = orc.ref_iq_filter_blocks(blocks, 5000000, half, taps)
+            out[f"ref_fir_coef_t{taps}_f{half}"] = orc.ref_fir_coefficients(5000000, half, taps)
+            out[f"ref_iq_filter_t{taps}_f{half}_head"] = np.stack([o[:4096] for o in outs])         # first 2048 samples of each block
+            out[f"ref_iq_filter_t{taps}_f{half}_tail"] = np.stack([o[-4096:] for o in outs])
+            out[f"ref_iq_filter_t{taps}_f{half}_sum"] = np.array([o.sum() for o in outs])
     np.savez_compressed(os.path.join(HERE, "golden_ref.npz"), **out)
     for k, v in out.items():
         print(k, getattr(v, "shape", None))

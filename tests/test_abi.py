@@ -145,3 +145,14 @@ def test_device_file_replay_semantics(fb, iq, tmp_path):
     assert len(seen) >= 3
     assert nrf.device_set_frequency(dev, 123.4) == 123.4
     nrf.device_free(dev)
+
+
+def test_fir_coefficients_match_reference_golden(fb, golden):
+    """nrf_fir_get_low_pass_coefficients (src/nrf.c:654-676): host code, no device needed -- bit-identical to
+    the coefficients recorded from the compiled reference, odd and even lengths."""
+    from frequensea_b200 import nrf
+    for taps, half in ((51, 200000), (97, 60000), (50, 100000)):
+        got = nrf.fir_low_pass_coefficients(5000000, half, taps)
+        ref = golden[f"ref_fir_coef_t{taps}_f{half}"]
+        assert got.shape == ref.shape and np.array_equal(got, ref)
+        assert abs(got.sum() - 1.0) < 1e-12                       # unit DC gain

@@ -367,6 +367,24 @@ def test_nrf_fft_f64_chain(fbg, iq, golden):
 
 
 @pytest.mark.parametrize("taps,half_ampl", [(51, 200000), (97, 60000), (50, 100000)])
+def test_iq_filter_matches_committed_golden(fbg, iq, golden, taps, half_ampl):
+    """The same operator against vectors recorded from the compiled reference (tests/golden/make_golden.py):
+    does not need oracle/_ref at run time."""
+    from frequensea_b200 import nrf
+    raw = orc.device_unpack(iq["rf200big4"])
+    flt = nrf.iq_filter_new(5000000, half_ampl, taps)
+    key = f"ref_iq_filter_t{taps}_f{half_ampl}"
+    for b in range(3):
+        buf = nrf.nut_buffer_new_u8(BLOCK // 2, 2, raw[b * BLOCK:(b + 1) * BLOCK])
+        nrf.iq_filter_process(flt, buf)
+        out = nrf.iq_filter_get_buffer(flt).numpy()
+        assert np.array_equal(out[:4096], golden[key + "_head"][b])
+        assert np.array_equal(out[-4096:], golden[key + "_tail"][b])
+        assert out.sum() == golden[key + "_sum"][b]
+    nrf.iq_filter_free(flt)
+
+
+@pytest.mark.parametrize("taps,half_ampl", [(51, 200000), (97, 60000), (50, 100000)])
 def test_iq_filter_bit_exact_and_chain(fbg, iq, taps, half_ampl):
     """nrf_iq_filter_* (src/nrf.c:644-776; lua/iq-tex-filtered.lua:43-46,
     lua/dvbt.lua:37) with the FIR evaluated by fsea_fir_iq_kernel -- bit-identical to the compiled
