@@ -52,6 +52,7 @@ FSEA_DECL_SIZE(8192)
 struct fsea_kernel_info4 {
     const void* fn;          // __global__ entry
     int cs;                  // blocks per cluster (1: plain launch, one block per frame)
+    int ws;                  // 1: fsea_ws4_kernel (no L2 intermediate, one block per SM)
     int threads;             // block size
     size_t smem;             // dynamic shared memory per block
     int n1, n2;              // sub-spectrum length, sub-sequences
@@ -61,3 +62,5 @@ struct fsea_kernel_info4 {
 };
 // alt: 0 = the shipped configuration of this length, 1.. = alternatives kept for A/B runs (FSEA_FOUR_ALT)
 bool fsea_get_kernel4(int n, bool window, int out_mode, int alt, fsea_kernel_info4* out);
+// warp-specialised block-per-frame kernel with the intermediate in shared memory (fsea_ws4.cuh)
+bool fsea_get_kernel_ws4(int n, bool window, int out_mode, fsea_kernel_info4* out);

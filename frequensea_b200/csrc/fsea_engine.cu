@@ -12,16 +12,19 @@
 #include <string.h>
 
 #include <fcntl.h>
+#include <sched.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
 #include <algorithm>
+#include <mutex>
 #include <vector>
 
 #include "../../include/fsea.h"
 #include "fsea_dispatch.h"
 #include "fsea_kparams.h"
 #include "fsea_ptx.cuh"
+#include "fsea_internal.h"
 
 // plain (non-table) kernel launches; -DFSEA_EMU (tests/emu/, test infrastructure) runs them on the CPU fiber machine
 #if defined(FSEA_EMU)
@@ -103,6 +106,14 @@ struct fsea_plan {
     void* d_tw4 = nullptr;                       // comb twiddles: W_N^{2^r k}, r < log2 N2, as cos / sin planes
     static const int SCRATCH_SLOTS = 4;           // slot 0: fsea_exec_device, 1..3: host pipeline stages
     void* d_cscratch[SCRATCH_SLOTS] = {nullptr, nullptr, nullptr, nullptr};   // max_clusters x N float2 each (L2-resident)
+    // A scratch slot is written and read back by every launch that uses it: launches of one slot
+    // that go to DIFFERENT streams are ordered by an event (same stream: stream order does it).
+    cudaEvent_t scratch_done[SCRATCH_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaStream_t scratch_stream[SCRATCH_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    bool scratch_used[SCRATCH_SLOTS] = {false, false, false, false};
+    // gate (fsea_gate_mean_host): grow-only device buffers, no allocation per call
+    void* d_gate_in = nullptr; size_t gate_in_bytes = 0;
+    void* d_gate_out = nullptr; size_t gate_out_bytes = 0;
 };
 
 static fsea_get_kernel_fn size_table(int n) {
@@ -178,7 +189,12 @@ extern "C" int fsea_plan_destroy(fsea_plan* p) {
     if (p->d_tickets) cudaFree(p->d_tickets);
     if (p->d_dump) cudaFree(p->d_dump);
     if (p->d_tw4) cudaFree(p->d_tw4);
-    for (int q = 0; q < fsea_plan::SCRATCH_SLOTS; q++) if (p->d_cscratch[q]) cudaFree(p->d_cscratch[q]);
+    for (int q = 0; q < fsea_plan::SCRATCH_SLOTS; q++) {
+        if (p->d_cscratch[q]) cudaFree(p->d_cscratch[q]);
+        if (p->scratch_done[q]) cudaEventDestroy(p->scratch_done[q]);
+    }
+    if (p->d_gate_in) cudaFree(p->d_gate_in);
+    if (p->d_gate_out) cudaFree(p->d_gate_out);
     delete p;
     return FSEA_OK;
 }
@@ -228,7 +244,16 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
     // N >= 16384 always runs four-step; N = 8192 can (FSEA_8192_FOUR, A/B runs: measured slower
     // than the single-kernel transform)
     bool want4 = !get || (n == 8192 && eight && cfg->arith == FSEA_ARITH_AUTO && getenv("FSEA_8192_FOUR"));
-    const bool four = want4 && eight && fsea_get_kernel4(n, cfg->window == FSEA_WIN_HANN, cfg->out_mode, alt, &k4);
+    // alt 0: the warp-specialised block-per-frame kernel where it exists (fsea_ws4.cuh), else the cluster kernel
+    bool four = false;
+    int ws_env = -1;
+    if (const char* ev = getenv("FSEA_WS")) ws_env = atoi(ev);                       // A/B runs: 0 = never, 1 = wherever it exists
+    const bool ws_default = (n == 16384);
+    if (eight && cfg->arith == FSEA_ARITH_AUTO && alt == 0 && (ws_env < 0 ? ws_default : ws_env != 0) && (n == 4096 || n == 8192 || n == 16384)) {
+        four = fsea_get_kernel_ws4(n, cfg->window == FSEA_WIN_HANN, cfg->out_mode, &k4);
+        if (four) want4 = true;
+    }
+    if (!four) four = want4 && eight && fsea_get_kernel4(n, cfg->window == FSEA_WIN_HANN, cfg->out_mode, alt == 9 ? 0 : alt, &k4);
     if (!get && !four) return FSEA_ERR_UNSUPPORTED;
     if (cfg->in_format < FSEA_IN_U8 || cfg->in_format > FSEA_IN_F64C) return FSEA_ERR_INVALID;
     if (cfg->window != FSEA_WIN_NONE && cfg->window != FSEA_WIN_HANN) return FSEA_ERR_INVALID;
@@ -349,6 +374,14 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
             } else {
                 p->max_clusters = p->max_blocks;
             }
+            // the intermediate of every slot is allocated here, not at the first launch: a lazy
+            // cudaMalloc would synchronise the device and break stream capture
+            bool bad = false;
+            for (int q = 0; q < fsea_plan::SCRATCH_SLOTS && !bad && !p->k4.ws; q++) {       // (ws: the intermediate lives in shared memory)
+                if ((e = cudaMalloc(&p->d_cscratch[q], (size_t)p->max_clusters * n * sizeof(float2))) != cudaSuccess ||
+                    (e = cudaEventCreateWithFlags(&p->scratch_done[q], cudaEventDisableTiming)) != cudaSuccess) { rc = cuda_fail(e, "four-step intermediate"); bad = true; }
+            }
+            if (bad) break;
         }
         if ((e = cudaMalloc(&p->d_tickets, sizeof(unsigned) * 2 * fsea_plan::TICKET_SLOTS)) != cudaSuccess ||
             (e = cudaMemset(p->d_tickets, 0, sizeof(unsigned) * 2 * fsea_plan::TICKET_SLOTS)) != cudaSuccess) {
@@ -386,7 +419,7 @@ extern "C" long fsea_plan_launch_count(const fsea_plan* p) { return p ? p->launc
 extern "C" const char* fsea_plan_kernel_name(const fsea_plan* p) { return p ? p->ki.name : ""; }
 
 
-static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cudaStream_t stream, int slot = 0) {
+static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cudaStream_t stream, int slot = 0, long out_stride = 0) {
     if (n_frames <= 0) return FSEA_OK;
     fsea_kparams kp;
     kp.in = d_in;
@@ -413,14 +446,16 @@ static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cu
     kp.twh = p->d_twh;
     kp.n1 = kp.n2 = 0;
     kp.scratch = nullptr;
+    kp.out_stride = out_stride > 0 ? out_stride : (long)p->cfg.fft_size * p->out_elem_bytes;
     if (p->four) {
         // one launch: a cluster per frame, the intermediate lives in the clusters' L2-resident slots
         const int n = p->cfg.fft_size;
         kp.n1 = p->k4.n1; kp.n2 = p->k4.n2;
-        if (!p->d_cscratch[slot]) CU(cudaMalloc(&p->d_cscratch[slot], (size_t)p->max_clusters * n * sizeof(float2)));
+        (void)n;
+        if (!p->k4.ws && p->scratch_used[slot] && p->scratch_stream[slot] != stream) CU(cudaStreamWaitEvent(stream, p->scratch_done[slot], 0));
         kp.scratch = p->d_cscratch[slot];
         kp.ticket = nullptr;
-        const long nc = std::min<long>(n_frames, p->max_clusters);
+        const long nc = p->k4.ws ? std::min<long>((n_frames + p->k4.ws - 1) / p->k4.ws, p->max_clusters) : std::min<long>(n_frames, p->max_clusters);
         void* af[] = {&kp};
         if (p->k4.cs > 1) {
             cudaLaunchConfig_t lc;
@@ -433,6 +468,11 @@ static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cu
             CU(cudaLaunchKernelExC(&lc, p->k4.fn, af));
         } else {
             CU(cudaLaunchKernel(p->k4.fn, dim3((unsigned)nc), dim3((unsigned)p->k4.threads), af, p->k4.smem, stream));
+        }
+        if (!p->k4.ws) {
+            CU(cudaEventRecord(p->scratch_done[slot], stream));
+            p->scratch_stream[slot] = stream;
+            p->scratch_used[slot] = true;
         }
         p->launches++;
         return FSEA_OK;
@@ -452,6 +492,57 @@ extern "C" int fsea_exec_device(fsea_plan* p, const void* d_in, void* d_out, lon
     if (((uintptr_t)d_in & 15) != 0) return FSEA_ERR_INVALID;
     CU(cudaSetDevice(p->cfg.device));
     return launch(p, d_in, d_out, n_frames, (cudaStream_t)stream);
+}
+
+extern "C" int fsea_exec_device_strided(fsea_plan* p, const void* d_in, void* d_out, long out_row_stride_bytes, long n_frames, void* stream) {
+    if (!p || n_frames < 0 || (n_frames > 0 && (!d_in || !d_out))) return FSEA_ERR_INVALID;
+    if (((uintptr_t)d_in & 15) != 0) return FSEA_ERR_INVALID;
+    const long packed = (long)p->cfg.fft_size * p->out_elem_bytes;
+    if (out_row_stride_bytes < packed || (out_row_stride_bytes % (p->out_elem_bytes == 1 ? 4 : p->out_elem_bytes)) != 0 ||
+        ((uintptr_t)d_out % (p->out_elem_bytes == 1 ? 4 : 8)) != 0) return FSEA_ERR_INVALID;
+    CU(cudaSetDevice(p->cfg.device));
+    return launch(p, d_in, d_out, n_frames, (cudaStream_t)stream, 0, out_row_stride_bytes);
+}
+
+// the sweep engine (fsea_sweep.cu) launches plans on its own stream
+int fsea_launch_internal(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cudaStream_t stream, long out_stride) {
+    return launch(p, d_in, d_out, n_frames, stream, 0, out_stride);
+}
+int fsea_fail_cuda_internal(cudaError_t e, const char* what) { return cuda_fail(e, what); }
+int fsea_plan_elem_bytes_internal(const fsea_plan* p) { return p->out_elem_bytes; }
+void fsea_count_launch_internal(fsea_plan* p) { p->launches++; }
+
+// ------------------------------------------------------------------ host placement
+// A rank's pinned buffers and the thread that feeds its copy engines belong on the NUMA node
+// its GPU hangs off: sysfs names the CPUs local to the device's PCI function.
+extern "C" int fsea_host_bind_near_device(int device) {
+#if defined(FSEA_EMU)
+    (void)device; return 0;
+#else
+    char bus[32] = "";
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return FSEA_ERR_INVALID; }
+    for (char* c = bus; *c; c++) if (*c >= 'A' && *c <= 'F') *c = (char)(*c - 'A' + 'a');
+    char path[128];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bus);
+    FILE* fp = fopen(path, "r");
+    if (!fp) return 0;
+    char list[1024] = "";
+    const bool ok = fgets(list, sizeof(list), fp) != nullptr;
+    fclose(fp);
+    if (!ok) return 0;
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    int n_cpus = 0;
+    for (char* tok = strtok(list, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+        int a = 0, b = 0;
+        const int got = sscanf(tok, "%d-%d", &a, &b);
+        if (got == 1) b = a;
+        if (got >= 1) for (int c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET(c, &set); n_cpus++; }
+    }
+    if (n_cpus == 0) return 0;
+    if (sched_setaffinity(0, sizeof(set), &set) != 0) return 0;           // (a cgroup may forbid the CPUs: leave things as they are)
+    return n_cpus;
+#endif
 }
 
 // ------------------------------------------------------------------ host pipeline
@@ -500,7 +591,7 @@ static int ensure_stages(fsea_plan* p, long want_frames, bool staging) {
 // `fill` (may be empty) loads the raw bytes of frames [first, first + nf) into a pinned slot;
 // without it the bytes come from h_in (directly when that is page-locked).
 template <class FILL>
-static int exec_pipeline(fsea_plan* p, const void* h_in, void* h_out, long n_frames, bool from_source, FILL fill) {
+static int exec_pipeline(fsea_plan* p, const void* h_in, void* h_out, long n_frames, bool from_source, FILL fill, bool copy_only = false) {
     CU(cudaSetDevice(p->cfg.device));
     const bool out_pinned = is_pinned_host(h_out);
     const bool direct = !from_source && is_pinned_host(h_in) && out_pinned;     // no staging copy on either side
@@ -525,7 +616,7 @@ static int exec_pipeline(fsea_plan* p, const void* h_in, void* h_out, long n_fra
     };
     while (issued < n_frames) {
         fsea_stage& st = p->stage[slot];
-        if ((rc = drain(slot)) != FSEA_OK) return rc;
+        if ((rc = drain(slot)) != FSEA_OK) break;
         const long nf = std::min(sf, n_frames - issued);
         const size_t ib = fsea_input_bytes(p, nf);
         const uint8_t* src = (const uint8_t*)h_in + (size_t)issued * in_frame_stride;
@@ -537,20 +628,31 @@ static int exec_pipeline(fsea_plan* p, const void* h_in, void* h_out, long n_fra
         } else if (!direct) {
             memcpy(st.h_in, src, ib); src = (const uint8_t*)st.h_in; dst = (uint8_t*)st.h_out;
         }
-        CU(cudaMemcpyAsync(st.d_in, src, ib, cudaMemcpyHostToDevice, st.stream));
-        if ((rc = launch(p, st.d_in, st.d_out, nf, st.stream, 1 + slot)) != FSEA_OK) return rc;
-        CU(cudaMemcpyAsync(dst, st.d_out, (size_t)nf * out_per, cudaMemcpyDeviceToHost, st.stream));
-        CU(cudaEventRecord(st.done, st.stream));
+        cudaError_t ce;
+        if ((ce = cudaMemcpyAsync(st.d_in, src, ib, cudaMemcpyHostToDevice, st.stream)) != cudaSuccess) { rc = cuda_fail(ce, "H2D"); break; }
+        if (!copy_only && (rc = launch(p, st.d_in, st.d_out, nf, st.stream, 1 + slot)) != FSEA_OK) break;
+        if ((ce = cudaMemcpyAsync(dst, st.d_out, (size_t)nf * out_per, cudaMemcpyDeviceToHost, st.stream)) != cudaSuccess ||
+            (ce = cudaEventRecord(st.done, st.stream)) != cudaSuccess) { rc = cuda_fail(ce, "D2H"); break; }
         pending[slot] = nf;
         pending_first[slot] = issued;
         issued += nf;
         slot = (slot + 1) % fsea_plan::NSTAGE;
     }
+    // (also on an error: copies already in flight land in caller memory before this returns)
     for (int s = 0; s < fsea_plan::NSTAGE; s++) {
         const int rd = drain((slot + s) % fsea_plan::NSTAGE);
         if (rc == FSEA_OK) rc = rd;
     }
     return rc;
+}
+
+// The same chunks over the same three streams with the kernel left out: what the box's PCIe
+// links allow for this job (bench.py reports e2e as a fraction of it).  h_out receives the
+// (stale) contents of the device slots.
+extern "C" int fsea_copy_only_host(fsea_plan* p, const void* h_in, void* h_out, long n_frames) {
+    if (!p || n_frames < 0 || (n_frames > 0 && (!h_in || !h_out))) return FSEA_ERR_INVALID;
+    if (n_frames == 0) return FSEA_OK;
+    return exec_pipeline(p, h_in, h_out, n_frames, false, [](void*, long, long, size_t) { return (int)FSEA_OK; }, true);
 }
 
 extern "C" int fsea_exec_host(fsea_plan* p, const void* h_in, void* h_out, long n_frames) {
@@ -590,7 +692,6 @@ extern "C" int fsea_exec_file(fsea_plan* p, const char* path, long byte_offset, 
 // magnitudes are produced by the MAG kernel and summed in fp64 on the device.
 // Deterministic: every block leaves ONE partial sum (lanes by shuffle, warps in index order), the
 // host adds the 256 partials in block order -- the same bits on every run and on every rank.
-#define FSEA_SUM_BLOCKS 256
 __global__ void fsea_sum_kernel(const float* __restrict__ x, long n, double* __restrict__ partial) {
     FSEA_STATIC_SMEM(double, warp_sum, 8);
     double s = 0.0;
@@ -610,11 +711,21 @@ extern "C" int fsea_gate_mean_host(fsea_plan* p, const void* h_in, long rows, do
     if (p->cfg.out_mode != FSEA_OUT_MAG || p->ki.scalar_bytes != 4) return FSEA_ERR_INVALID;
     CU(cudaSetDevice(p->cfg.device));
     const size_t ib = fsea_input_bytes(p, rows), ob = fsea_output_bytes(p, rows);
-    void *d_in = nullptr, *d_out = nullptr;
     if (!p->d_gate) CU(cudaMalloc(&p->d_gate, sizeof(double) * FSEA_SUM_BLOCKS));
-    CU(cudaMalloc(&d_in, ib));
-    cudaError_t e = cudaMalloc(&d_out, ob);
-    if (e != cudaSuccess) { cudaFree(d_in); return cuda_fail(e, "cudaMalloc"); }
+    if (p->gate_in_bytes < ib) {                                   // grow-only: nothing is allocated per call once warm
+        if (p->d_gate_in) cudaFree(p->d_gate_in);
+        p->d_gate_in = nullptr; p->gate_in_bytes = 0;
+        CU(cudaMalloc(&p->d_gate_in, ib));
+        p->gate_in_bytes = ib;
+    }
+    if (p->gate_out_bytes < ob) {
+        if (p->d_gate_out) cudaFree(p->d_gate_out);
+        p->d_gate_out = nullptr; p->gate_out_bytes = 0;
+        CU(cudaMalloc(&p->d_gate_out, ob));
+        p->gate_out_bytes = ob;
+    }
+    void *d_in = p->d_gate_in, *d_out = p->d_gate_out;
+    cudaError_t e;
     int rc = FSEA_OK;
     do {
         if ((e = cudaMemcpy(d_in, h_in, ib, cudaMemcpyHostToDevice)) != cudaSuccess) { rc = cuda_fail(e, "H2D"); break; }
@@ -627,8 +738,6 @@ extern "C" int fsea_gate_mean_host(fsea_plan* p, const void* h_in, long rows, do
         for (int b = 0; b < FSEA_SUM_BLOCKS; b++) total += part[b];
         *mean_out = total / (double)n;
     } while (0);
-    cudaFree(d_in);
-    cudaFree(d_out);
     return rc;
 }
 
@@ -677,22 +786,38 @@ extern "C" int fsea_stitch_device(const uint8_t* d_images, int n_images, int row
     return FSEA_OK;
 }
 
+// Device scratch of the *_host convenience calls (stitch, FIR): one grow-only buffer per device
+// and purpose, so that a call allocates nothing once warm.  The lock is held for the whole call.
+static std::mutex g_scratch_mu;
+static void* g_scratch[64][2];
+static size_t g_scratch_bytes[64][2];
+static int scratch_get(int device, int which, size_t bytes, void** out) {
+    if (device < 0 || device >= 64) return FSEA_ERR_INVALID;
+    if (g_scratch_bytes[device][which] < bytes) {
+        if (g_scratch[device][which]) cudaFree(g_scratch[device][which]);
+        g_scratch[device][which] = nullptr; g_scratch_bytes[device][which] = 0;
+        CU(cudaMalloc(&g_scratch[device][which], bytes));
+        g_scratch_bytes[device][which] = bytes;
+    }
+    *out = g_scratch[device][which];
+    return FSEA_OK;
+}
+
 extern "C" int fsea_stitch_host(int device, const uint8_t* h_images, int n_images, int rows, int width, int width_step,
                                 uint8_t* h_out) {
     if (!h_images || !h_out || n_images <= 0 || rows <= 0 || width <= 0 || width_step <= 0) return FSEA_ERR_INVALID;
     if (fsea_device_count() <= 0) return FSEA_ERR_NO_DEVICE;
     CU(cudaSetDevice(device));
     const size_t ib = (size_t)n_images * rows * width, ob = (size_t)rows * (width + (size_t)(n_images - 1) * width_step);
+    std::lock_guard<std::mutex> lock(g_scratch_mu);
     uint8_t *d_in = nullptr, *d_out = nullptr;
-    CU(cudaMalloc(&d_in, ib));
-    cudaError_t e = cudaMalloc(&d_out, ob);
-    if (e != cudaSuccess) { cudaFree(d_in); return cuda_fail(e, "cudaMalloc"); }
-    int rc = FSEA_OK;
+    int rc = scratch_get(device, 0, ib, (void**)&d_in);
+    if (rc == FSEA_OK) rc = scratch_get(device, 1, ob, (void**)&d_out);
+    if (rc != FSEA_OK) return rc;
+    cudaError_t e;
     if ((e = cudaMemcpy(d_in, h_images, ib, cudaMemcpyHostToDevice)) != cudaSuccess) rc = cuda_fail(e, "H2D");
     if (rc == FSEA_OK) rc = fsea_stitch_device(d_in, n_images, rows, width, width_step, d_out, nullptr);
     if (rc == FSEA_OK && (e = cudaMemcpy(h_out, d_out, ob, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "D2H");
-    cudaFree(d_in);
-    cudaFree(d_out);
     return rc;
 }
 
@@ -810,9 +935,10 @@ extern "C" int fsea_fir_iq_host(int device, const double* coef, int taps, const 
     double* d = nullptr;                                           // coef | si | sq | out (out 16-byte aligned)
     const size_t o_coef = 0, o_si = ((size_t)taps * 8 + 15) & ~(size_t)15, o_sq = o_si + ((line + 15) & ~(size_t)15),
                  o_out = o_sq + ((line + 15) & ~(size_t)15);
-    CU(cudaMalloc(&d, o_out + ob));
+    std::lock_guard<std::mutex> lock(g_scratch_mu);
+    int rc = scratch_get(device, 0, o_out + ob, (void**)&d);
+    if (rc != FSEA_OK) return rc;
     char* b = (char*)d;
-    int rc = FSEA_OK;
     cudaError_t e;
     if ((e = cudaMemcpy(b + o_coef, coef, (size_t)taps * 8, cudaMemcpyHostToDevice)) != cudaSuccess ||
         (e = cudaMemcpy(b + o_si, si, line, cudaMemcpyHostToDevice)) != cudaSuccess ||
@@ -820,6 +946,5 @@ extern "C" int fsea_fir_iq_host(int device, const double* coef, int taps, const 
     if (rc == FSEA_OK) rc = fsea_fir_iq_device((const double*)(b + o_coef), taps, (const double*)(b + o_si), (const double*)(b + o_sq),
                                                length, (double*)(b + o_out), nullptr);
     if (rc == FSEA_OK && (e = cudaMemcpy(out, b + o_out, ob, cudaMemcpyDeviceToHost)) != cudaSuccess) rc = cuda_fail(e, "D2H");
-    cudaFree(d);
     return rc;
 }

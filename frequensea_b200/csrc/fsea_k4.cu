@@ -15,6 +15,7 @@ static bool fill_fused(fsea_kernel_info4* o, bool window, int out_mode, const ch
                    : (out_mode == FSEA_OUT_MAG ? FSEA_FUSED(false, FSEA_OUT_MAG) : out_mode == FSEA_OUT_LOGMAG ? FSEA_FUSED(false, FSEA_OUT_LOGMAG) : FSEA_FUSED(false, FSEA_OUT_PIX));
 #undef FSEA_FUSED
     o->cs = CS;
+    o->ws = 0;
     o->threads = SHA::T * C::G;
     o->smem = C::SMEM;
     o->n1 = SHA::N; o->n2 = N2;

@@ -1,0 +1,29 @@
+// fsea_k_ws4.cu -- instantiations of the warp-specialised block-per-frame kernel (fsea_ws4.cuh)
+#include "fsea_instantiate.cuh"
+#include "fsea_ws4.cuh"
+
+template <int N2>
+static bool fill_ws(fsea_kernel_info4* o, bool window, int out_mode, const char* name) {
+#define FSEA_WS(W, O) (const void*)&fsea_ws4_kernel<N2, O, W>
+    o->fn = window ? (out_mode == FSEA_OUT_MAG ? FSEA_WS(true, FSEA_OUT_MAG) : out_mode == FSEA_OUT_LOGMAG ? FSEA_WS(true, FSEA_OUT_LOGMAG) : FSEA_WS(true, FSEA_OUT_PIX))
+                   : (out_mode == FSEA_OUT_MAG ? FSEA_WS(false, FSEA_OUT_MAG) : out_mode == FSEA_OUT_LOGMAG ? FSEA_WS(false, FSEA_OUT_LOGMAG) : FSEA_WS(false, FSEA_OUT_PIX));
+#undef FSEA_WS
+    o->cs = 1;
+    o->ws = 16 / N2;                       // frames per block iteration
+    o->threads = FSEA_WS_THREADS;
+    o->smem = FSEA_WS_SMEM;
+    o->n1 = 1024; o->n2 = N2;
+    o->r0 = 32; o->r1 = 32; o->r2 = 1;
+    o->tw1 = 31 * 32; o->tw2 = 0;
+    o->name = name;
+    return true;
+}
+
+bool fsea_get_kernel_ws4(int n, bool window, int out_mode, fsea_kernel_info4* o) {
+    switch (n) {
+        case 4096: return fill_ws<4>(o, window, out_mode, "ws4<4096=1024x4: 8 transform + 4 comb warps, 4 frames per block, intermediate in shared memory, f32x2>");
+        case 8192: return fill_ws<8>(o, window, out_mode, "ws4<8192=1024x8: 8 transform + 4 comb warps, 2 frames per block, intermediate in shared memory, f32x2>");
+        case 16384: return fill_ws<16>(o, window, out_mode, "ws4<16384=1024x16: 8 transform + 4 comb warps per frame, intermediate in shared memory, f32x2>");
+    }
+    return false;
+}

@@ -27,4 +27,6 @@ struct fsea_kparams {
     uint32_t xor_mask;     // 0x8080 for two's-complement input (FSEA_IN_S8), else 0
     const void* twh;       // "half" kernels: W_2N^i, i < M (butterflies of the last pass), float2
     void* scratch;         // fused four-step: resident clusters x N float2 (the L2-resident intermediate)
+    long out_stride;       // bytes between the starts of consecutive output rows (N x element size when rows are packed;
+                           // larger when the rows land inside a wider picture, e.g. a sweep's stitched canvas)
 };

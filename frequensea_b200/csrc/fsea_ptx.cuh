@@ -100,6 +100,22 @@ template <int COUNT> __device__ __forceinline__ void fsea_bar_sync(int id) {    
     asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(COUNT) : "memory");
 #endif
 }
+// producer / consumer form of the named barriers (warp-specialised kernels): the barrier completes
+// when `count` threads have arrived, by either instruction; only bar.sync waits
+__device__ __forceinline__ void fsea_named_sync(int id, int count) {
+#if defined(FSEA_EMU)
+    fsea_emu::sync_named(id, count);
+#else
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory");
+#endif
+}
+__device__ __forceinline__ void fsea_named_arrive(int id, int count) {
+#if defined(FSEA_EMU)
+    fsea_emu::arrive_named(id, count);
+#else
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory");
+#endif
+}
 __device__ __forceinline__ void fsea_cluster_arrive_release() {
 #if defined(FSEA_EMU)
     fsea_emu::cluster_arrive();

@@ -1,0 +1,199 @@
+// fsea_ws4.cuh -- N = 1024 x N2 (N2 = 4, 8, 16: N = 4096, 8192, 16384) with BOTH four-step phases
+// inside one block and the intermediate in SHARED memory: a warp-specialised kernel.
+//
+// Decimation in time as in fsea_fused4_kernel (n = N2 n1 + n2): step A = 1024-point transforms
+// of the N2 interleaved sub-sequences of a frame, step B = twiddle + radix-N2 across the
+// sub-spectra.  There the intermediate Y[n2][k] made a round trip through L2 (8 + 8 bytes per
+// point through the LSU, a release/acquire cluster barrier, 4-byte global stores: ncu showed the
+// kernel waiting on exactly those -- STG 10 %, ERRBAR 8 %, UCGABAR 5 %, LDG 6 % of all stall
+// samples, nothing saturated).  Here a block of 12 warps owns FPB = 16 / N2 frames at a time:
+//
+//   warps 0..7  (A)  one unit each = the PAIR of sub-sequences (2u, 2u+1) of one frame, the two
+//                    packed lanes: raw words -> radix-32 -> a warp-private exchange plane (no
+//                    block barrier) -> twiddle -> radix-32, i.e. the 32 x 32 warp-synchronous
+//                    transform of the 1024-point kernel; the finished sub-spectra go to
+//                    Y[frame][n2][k] in shared memory.  The unit's raw words (4 bytes per n1,
+//                    2 N2 bytes apart in the frame) are loaded by the warp itself straight into
+//                    registers (32 LDG.32 gathers; the comb warps have pulled the frame into L2
+//                    an iteration earlier, the 8 units of a frame share its lines in L1): no
+//                    staging in shared memory -- a cp.async gather costs one shared-memory
+//                    wavefront per 128-byte line it touches, 8 x the data (ncu: 29 % of all
+//                    wavefronts of the kernel);
+//   warps 8..11 (B)  comb: per bin pair (k, k+1) 2 N2 conflict-free LDS.64 of Y, the four-step
+//                    twiddles, one packed radix-N2 codelet, magnitude / log / pixel epilogue and
+//                    coalesced stores of the spectrum.
+//
+// A computes frames f+1 while B combs frames f: all 12 warps run at once, as in the 1024-point
+// kernel, and the only waits are named barriers (producer: bar.arrive, consumer: bar.sync):
+// Y_FULL (all A -> B) and one Y_FREE per transform warp (B -> that warp; a warp holds its finished
+// unit in registers until the comb has read the previous frames out of Y) -- per warp, so that
+// the transform warps never wait for EACH OTHER and drift apart into different phases (load /
+// arithmetic / exchange) the way the independent warps of the 1024-point kernel do.
+// Shared memory: 8 exchange planes (66 KB) + Y (128 KB) + the pass-1 twiddle table (8 KB): one
+// block per SM, 384 threads at 168 registers.
+//
+// What replaces what: as fsea_kernels.cuh (src/nrf.c:598-631, c/fft-batch-broad.c:63-118).
+#pragma once
+#include "fsea_kernels.cuh"
+
+#define FSEA_WS_NA 8
+#define FSEA_WS_NB 4
+#define FSEA_WS_THREADS ((FSEA_WS_NA + FSEA_WS_NB) * 32)
+#define FSEA_WS_PLANE (1056 * 8)
+#define FSEA_WS_Y (2 * 16 * 1024 * 4)
+#define FSEA_WS_TW (31 * 32 * 8)
+#define FSEA_WS_SMEM (FSEA_WS_NA * FSEA_WS_PLANE + FSEA_WS_Y + FSEA_WS_TW)
+
+enum { FSEA_WS_BAR_Y_FULL = 1, FSEA_WS_BAR_Y_FREE = 2 /* + transform warp: 2 .. 9 */ };
+
+
+// step B loads: one bin pair of all N2 sub-spectra from Y in shared memory (rows of 1024 floats)
+template <int N2>
+__device__ __forceinline__ void fsea_ws_comb_load(const float* y, int k, f2* re, f2* im) {
+#pragma unroll
+    for (int j = 0; j < N2; j++) {
+        const float2 a = *(const float2*)(y + j * 1024 + k);
+        const float2 b = *(const float2*)(y + (N2 + j) * 1024 + k);
+        re[j] = mk2(a.x, a.y); im[j] = mk2(b.x, b.y);
+    }
+}
+
+template <int N2, int OUT, bool WIN>
+__global__ void __launch_bounds__(FSEA_WS_THREADS, 1)
+fsea_ws4_kernel(const fsea_kparams kp) {
+    constexpr int N1 = 1024;
+    constexpr int FPB = 16 / N2;                            // frames a block works on at a time
+    constexpr int UPF = N2 / 2;                             // units (= transform warps) per frame
+    typedef fsea_comb<OUT, N1, N2> COMB;
+    constexpr int U = COMB::U > 4 ? 4 : COMB::U;            // bin pairs per comb call (64 points; 32 for N2 = 4: registers)
+    constexpr int TB = FSEA_WS_NB * 32;
+    constexpr int CPF = (N1 / 2) / U;                       // comb calls per frame
+    constexpr int BIT = FPB * CPF / TB;
+    static_assert(FPB * UPF == FSEA_WS_NA, "one unit per transform warp");
+    static_assert(BIT * TB == FPB * CPF && BIT >= 1, "the comb must divide over its warps");
+
+    FSEA_DYN_SMEM(fsea_smem);
+    const int tid = threadIdx.x;
+    const int w = tid >> 5, t = tid & 31;
+    float* Y = reinterpret_cast<float*>(fsea_smem + FSEA_WS_NA * FSEA_WS_PLANE);       // [frame][re | im][n2][1024]
+    float2* stw = reinterpret_cast<float2*>(fsea_smem + FSEA_WS_NA * FSEA_WS_PLANE + FSEA_WS_Y);
+    const long frames = kp.n_seq;
+    const long groups = (frames + FPB - 1) / FPB;           // block iterations in the batch
+    const long step = gridDim.x;
+    const size_t frame_bytes = (size_t)kp.seq_stride * 2;
+    const uint32_t x4 = kp.xor_mask | (kp.xor_mask << 16);
+
+    for (int q = tid; q < 31 * 32; q += FSEA_WS_THREADS) stw[q] = ((const float2*)kp.tw1)[q];
+    __syncthreads();
+
+    if (w < FSEA_WS_NA) {
+        // ------------------------------------------------ A: transform warps
+        const int fi = w / UPF, u = w - fi * UPF;           // frame of the group, unit of the frame
+        f2* xp = reinterpret_cast<f2*>(fsea_smem + (size_t)w * FSEA_WS_PLANE);
+        float* yre = Y + (size_t)fi * (2 * N2 * 1024) + (2 * u) * 1024 + t;
+        float* yim = yre + N2 * 1024;
+        auto unit_src = [&](long g) {                       // frames past the end of the batch: transform the last one again (never stored)
+            long f = g * FPB + fi;
+            if (f >= frames) f = frames - 1;
+            return (const uint8_t*)kp.in + (size_t)f * frame_bytes + 4 * u;
+        };
+        for (long g = blockIdx.x; g < groups; g += step) {
+            f2 re[32], im[32];
+            const uint8_t* src = unit_src(g) + (size_t)t * (2 * N2);
+            uint32_t raw[32];
+#pragma unroll
+            for (int j = 0; j < 32; j++) raw[j] = __ldg((const uint32_t*)(src + (size_t)j * (32 * 2 * N2)));
+            const float* wsrc = WIN ? kp.window + (size_t)N2 * t + 2 * u : nullptr;    // sample n = N2 n1 + 2u (+1), n1 = t + 32 j
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const uint32_t v = raw[j] ^ x4;
+                re[j] = mk2(__uint_as_float(__byte_perm(v, 0x47000000u, 0x7504)), __uint_as_float(__byte_perm(v, 0x47000000u, 0x7524)));
+                im[j] = mk2(__uint_as_float(__byte_perm(v, 0x47000000u, 0x7514)), __uint_as_float(__byte_perm(v, 0x47000000u, 0x7534)));
+                if (WIN) {
+                    const float2 wv = __ldg((const float2*)(wsrc + (size_t)N2 * 32 * j));
+                    const f2 w2 = mk2(wv.x, wv.y), off = mk2(32896.0f, 32896.0f);
+                    re[j] = vmul(vsub(re[j], off), w2);
+                    im[j] = vmul(vsub(im[j], off), w2);
+                }
+            }
+            if (WIN) fsea_dft32<f2>(re, im);
+            else fsea_dft32_raw<f2>(re, im);
+            // exchange (fsea_kernels.cuh): write a' = t 33 + m, read a' = t + 33 j; re plane, then im plane
+            {
+                f2* wp = xp + t * 33;
+#pragma unroll
+                for (int m = 0; m < 32; m++) wp[m] = re[m];
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 32; j++) re[j] = xp[t + 33 * j];
+                __syncwarp();
+#pragma unroll
+                for (int m = 0; m < 32; m++) wp[m] = im[m];
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 32; j++) im[j] = xp[t + 33 * j];
+                __syncwarp();
+            }
+            re[0] = vmuls(re[0], 1.0f / 256.0f);
+            im[0] = vmuls(im[0], 1.0f / 256.0f);
+#pragma unroll
+            for (int j = 1; j < 32; j++) {
+                const float2 tw = stw[(j - 1) * 32 + t];
+                vcmul(re[j], im[j], tw.x, tw.y);
+            }
+            fsea_dft32<f2>(re, im);
+            fsea_named_sync(FSEA_WS_BAR_Y_FREE + w, 32 + FSEA_WS_NB * 32);   // the comb has read the previous frames
+#pragma unroll
+            for (int m = 0; m < 32; m++) {
+                yre[32 * m] = re[m].v.x;
+                yre[1024 + 32 * m] = re[m].v.y;
+                yim[32 * m] = im[m].v.x;
+                yim[1024 + 32 * m] = im[m].v.y;
+            }
+            fsea_named_arrive(FSEA_WS_BAR_Y_FULL, FSEA_WS_THREADS);
+        }
+    } else {
+        // ------------------------------------------------ B: comb warps
+        const int bt = tid - FSEA_WS_NA * 32;
+        const bool dc_patch = (kp.flags & FSEA_FLAG_DC_PATCH) != 0;
+        long g = blockIdx.x;
+        auto free_y = [&]() {
+#pragma unroll
+            for (int a = 0; a < FSEA_WS_NA; a++) fsea_named_arrive(FSEA_WS_BAR_Y_FREE + a, 32 + FSEA_WS_NB * 32);
+        };
+        // the raw bytes of a group (FPB frames of 2 N bytes = 256 lines), pulled into L2 two iterations ahead
+        auto prefetch = [&](long gg) {
+            if (gg >= groups) return;
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const int line = bt + TB * q;                              // 256 lines: frame line / (256 / FPB)
+                const int pf = line / (256 / FPB), pl = line - pf * (256 / FPB);
+                long f = gg * FPB + pf;
+                if (f >= frames) f = frames - 1;
+                fsea_prefetch_l2((const uint8_t*)kp.in + (size_t)f * frame_bytes + (size_t)pl * 128);
+            }
+        };
+        if (g < groups) { free_y(); prefetch(g + step); }                  // Y starts out free
+        for (; g < groups; g += step) {
+            const bool more = g + step < groups;
+            prefetch(g + 2 * step);
+            fsea_named_sync(FSEA_WS_BAR_Y_FULL, FSEA_WS_THREADS);      // the sub-spectra of this group are in Y
+#pragma unroll 1
+            for (int it = 0; it < BIT; it++) {
+                const int c = it * TB + bt;                            // comb call: frame c / CPF, pairs (c % CPF) + uu CPF
+                const int fi = c / CPF, p0 = c - fi * CPF;
+                const long f = g * FPB + fi;
+                const float* yf = Y + (size_t)fi * (2 * N2 * 1024);
+                uint8_t* row = f < frames ? (uint8_t*)kp.out + (size_t)f * (size_t)kp.out_stride : (uint8_t*)kp.dump;
+                f2 re[U][N2], im[U][N2];
+#pragma unroll
+                for (int uu = 0; uu < U; uu++) fsea_ws_comb_load<N2>(yf, 2 * (p0 + uu * CPF), re[uu], im[uu]);
+#pragma unroll
+                for (int uu = 0; uu < U; uu++) COMB::twiddle(kp, 2 * (p0 + uu * CPF), re[uu], im[uu]);
+                if (it == BIT - 1 && more) free_y();                   // Y has been read
+#pragma unroll
+                for (int uu = 0; uu < U; uu++) COMB::finish(kp, 2 * (p0 + uu * CPF), row, dc_patch, re[uu], im[uu]);
+            }
+        }
+    }
+}

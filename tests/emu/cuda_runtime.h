@@ -31,6 +31,8 @@ struct float4 { float x, y, z, w; };
 struct double2 { double x, y; };
 struct uchar2 { unsigned char x, y; };
 struct uint3 { unsigned x, y, z; };
+struct uint4 { unsigned x, y, z, w; };
+struct uchar4 { unsigned char x, y, z, w; };
 struct dim3 {
     unsigned x, y, z;
     dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
@@ -60,6 +62,7 @@ unsigned char* dyn_smem();                            // this block's dynamic sh
 void* static_smem(int key, size_t bytes);             // this block's named static shared variable
 void sync_block();                                    // __syncthreads
 void sync_named(int id, int count);                   // bar.sync id, count
+void arrive_named(int id, int count);                 // bar.arrive id, count
 void sync_warp();                                     // __syncwarp (full mask)
 unsigned shfl_idx(unsigned v, int src_lane);          // shfl.sync.idx, full mask
 double shfl_down_f64(double v, int delta);
@@ -151,6 +154,7 @@ static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSucce
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventCreateWithFlags(cudaEvent_t* e, int) { *e = (void*)1; return cudaSuccess; }
 static inline cudaError_t cudaEventRecord(cudaEvent_t, cudaStream_t) { return cudaSuccess; }
+static inline cudaError_t cudaStreamWaitEvent(cudaStream_t, cudaEvent_t, int) { return cudaSuccess; }
 static inline cudaError_t cudaEventSynchronize(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaEventDestroy(cudaEvent_t) { return cudaSuccess; }
 static inline cudaError_t cudaPointerGetAttributes(cudaPointerAttributes* a, const void*) { a->type = cudaMemoryTypeUnregistered; return cudaSuccess; }

@@ -74,6 +74,11 @@ void* static_smem(int key, size_t bytes) {
 }
 void sync_block() { Block& b = myblock(); barrier_wait(b.block_bar, b.threads); }
 void sync_named(int id, int count) { barrier_wait(myblock().named[id & 15], count); }
+void arrive_named(int id, int count) {
+    Barrier& b = myblock().named[id & 15];
+    progress++;
+    if (++b.arrived == count) { b.arrived = 0; b.gen++; }
+}
 void sync_warp() { Block& b = myblock(); barrier_wait(b.warp_bar[cur->tid.x >> 5], 32); }
 unsigned shfl_idx(unsigned v, int src_lane) {
     Block& b = myblock();

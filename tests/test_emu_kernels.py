@@ -27,8 +27,8 @@ def emu_lib():
     return os.path.join(EMU, "libfsea_emu.so")
 
 
-def run_check(emu_lib, sizes):
-    env = dict(os.environ, FSEA_LIB=emu_lib)
+def run_check(emu_lib, sizes, **extra_env):
+    env = dict(os.environ, FSEA_LIB=emu_lib, **extra_env)
     r = subprocess.run([sys.executable, os.path.join(EMU, "check.py")] + [str(n) for n in sizes],
                        capture_output=True, text=True, env=env, timeout=900)
     assert r.returncode == 0, r.stderr[-3000:]
@@ -60,9 +60,22 @@ def test_emulated_alternative_arrangements(emu_lib):
 
 
 def test_emulated_four_step_sizes(emu_lib):
-    """N = 16384 .. 65536: the cluster kernel (sub-spectra, cluster barrier, comb) incl. slot reuse."""
+    """N = 16384 .. 65536: the defaults -- the warp-specialised block-per-frame kernel (16384) and the
+    cluster kernel (sub-spectra, cluster barrier, comb) incl. slot reuse."""
     res = run_check(emu_lib, [16384, 32768, 65536])
-    assert all("fft4<" in r["kernel"] for r in res)
+    assert "ws4<" in res[0]["kernel"] and all("fft4<" in r["kernel"] for r in res[1:])
+    verify(res)
+
+
+def test_emulated_warp_specialised_and_cluster_alternatives(emu_lib):
+    """fsea_ws4_kernel at every length it exists for (FSEA_WS=1: 4, 2 and 1 frames per block iteration; named
+    barriers between transform and comb warps, register gathers, frames past the end of the batch), and
+    the cluster kernel at 16384 (FSEA_FOUR_ALT=9), which the default no longer picks."""
+    res = run_check(emu_lib, [4096, 8192, 16384], FSEA_WS="1")
+    assert all("ws4<" in r["kernel"] for r in res)
+    verify(res)
+    res = run_check(emu_lib, [16384], FSEA_FOUR_ALT="9")
+    assert "fft4<" in res[0]["kernel"]
     verify(res)
 
 

@@ -1,0 +1,7 @@
+O=gpurun_out/r02d; mkdir -p $O
+python tools/sweep.py n16384 cfg4 n8192:::FSEA_WS=1 n8192:::FSEA_WS=0 cfg3:::FSEA_WS=1 cfg3:::FSEA_WS=0 n4096:::FSEA_WS=1 n4096:::FSEA_WS=0 n16384@296 > $O/sweep.txt 2>&1; cat $O/sweep.txt
+SWEEP_STEPS=1 SWEEP_WARMUP=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fsea_ -s 1 -c 1 -o $O/prof python tools/sweep.py n16384@8192 > $O/ncu.log 2>&1
+python tools/ncu_summary.py $O/prof.ncu-rep > $O/ncu_full.txt 2>&1; python tools/ncu_ops.py $O/prof.ncu-rep > $O/ncu_ops.txt 2>&1
+ncu -i $O/prof.ncu-rep --page source --csv 2>/dev/null | gzip > $O/ncu_source.csv.gz
+rm -f $O/prof.ncu-rep
+cat $O/ncu_full.txt
