@@ -1,34 +1,43 @@
 #!/usr/bin/env python3
-"""bench.py -- headline benchmark of the IQ -> spectrum hot path.
+"""bench.py -- benchmark of the IQ -> spectrum hot path (BASELINE.json).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-Workload (BASELINE.json configs[1]): the nrf_fft path --
-1024-point FFT of every frame of rfdata/rf-433.000.raw (two's-complement int8
-IQ, 128 frames per 262144-byte block), float32 magnitude with the reference's
-DC patch -- with the capture block replayed R times so that one step's input
-(512 MiB) and output (1 GiB) are far larger than L2 (126 MB).  One "step" =
-one pass of the hot path over that batch.  Metric: frames/s (whole job).
+Headline workload (BASELINE.json configs[1], cfg2): the nrf_fft path -- 1024-point FFT of every
+frame of rfdata/rf-433.000.raw (two's-complement int8 IQ, 128 frames per 262144-byte block),
+float32 magnitude with the reference's DC patch -- the capture block replayed to 2^18 frames
+(512 MiB in, 1 GiB out: far larger than the 126 MB L2).  A STEP is R passes of the hot path over
+that batch, R chosen so that the K timed steps last >= ~1.2 s (the clock sampler then sees the
+kernel under sustained load); `burst` is the same kernel timed alone over K single launches, as in
+round 1.  Metric: frames/s (whole job).
 
-  value     device-resident batch (fsea_exec_device), CUDA-event timed, max over ranks
-  e2e       same batch through the C ABI with HOST buffers (fsea_exec_host):
-            pinned host -> H2D -> kernel -> D2H -> pinned host, wall clock
-  roofline  algorithmic bytes (2*hop + 4*N per frame) / kernel time
-            against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
-  cpu_baseline  the reference's own nrf_fft_* (oracle/_ref) or the oracle port,
-            timed on this box's host cores on a bounded sample of the same frames
+  value       device-resident (fsea_exec_device), CUDA events on the launching stream, max over ranks
+  burst       K single launches (7 ms): the kernel at boost clocks
+  e2e         the same batch through the C ABI with HOST buffers (fsea_exec_host): pinned host ->
+              H2D -> kernel -> D2H -> pinned host; next to it the same copies WITHOUT the kernel
+              (`copy_only`: what the box's PCIe links allow) and the u8-pixel form (3N bytes/frame)
+  roofline    algorithmic bytes (2*hop + 4*N per frame) / kernel time against the
+              measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  secondary   every other BASELINE configuration and the size ladder, measured the same way:
+              cfg3 (8192 Hann 50 % overlap, the 8(d) tone source), cfg4 (16384-pt sweep rows -> u8
+              pixels), cfg5 (65536), n128 .. n65536; `sustained` = cfg5 over a resident ring of
+              4096 frames for >= 5 s; `sweep` = the cfg4 JOB (1000 centre frequencies x 512 rows,
+              gate + pixels + stitched picture, device-resident engines, f -> rank f mod N)
+  cpu_baseline  the reference's own nrf_fft_* (oracle/_ref) or the oracle port, timed on this box's
+              host cores on a bounded sample of the same frames
 
-Multi-GPU (torchrun, one rank per GPU): frames are independent, so each rank
-transforms its own shard -- no data-path collective; weak scaling.
+Multi-GPU (torchrun, one rank per GPU): frames are independent, so each rank transforms its own
+shard -- no data-path collective; weak scaling.  The sweep job's only exchange is
+the u8 pictures (NCCL gather, or peer stores straight into the destination's canvas).
 """
 import argparse
 import ctypes as C
+import datetime
 import json
 import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 import numpy as np
@@ -40,31 +49,30 @@ N = 1024
 HOP = 1024
 FRAMES_PER_BLOCK = 128
 BLOCK = 262144
-DEFAULT_FRAMES = 1 << 18          # per GPU per step: 512 MiB in, 1 GiB out
+DEFAULT_FRAMES = 1 << 18          # per GPU per launch: 512 MiB in, 1 GiB out
 METRIC = "fft_frames_per_s"
 UNIT = "frames/s"
 
-# Secondary workloads; the headline line is always cfg2.  Synthetic IQ is
-# drawn on the device (uniform bytes): throughput does not depend on the sample values and
-# the parity gate checks the very frames that are timed.
+
 def _size_workload(n):
-    frames = max(256, (1 << 28) // n)            # 512 MiB of raw IQ per step
-    return dict(n=n, hop=n, fmt="s8", window=False, out="mag", patch=True, frames=frames,
+    frames = max(256, (1 << 28) // n)            # 512 MiB of raw IQ per launch
+    return dict(n=n, hop=n, fmt="s8", window=False, out="mag", patch=True, frames=frames, source="uniform",
                 desc=f"size ladder: {n}-pt FFT, int8 IQ -> f32 magnitude + DC patch")
 
 
 WORKLOADS = {
-    "cfg2": dict(n=1024, hop=1024, fmt="s8", window=False, out="mag", patch=True, frames=1 << 18,
+    "cfg2": dict(n=1024, hop=1024, fmt="s8", window=False, out="mag", patch=True, frames=1 << 18, source="uniform",
                  desc="cfg2 nrf_fft path: 1024-pt FFT, all frames of rf-433.000.raw, int8 IQ -> f32 magnitude + DC patch"),
-    "cfg3": dict(n=8192, hop=4096, fmt="u8", window=True, out="logmag", patch=False, frames=65535,
-                 desc="cfg3: 8192-pt FFT, Hann, 50% overlap, synthetic uint8 IQ -> f32 log-magnitude"),
-    "cfg4": dict(n=16384, hop=16384, fmt="s8", window=False, out="pix", patch=True, frames=1 << 14, scale=5.0,
+    "cfg3": dict(n=8192, hop=4096, fmt="u8", window=True, out="logmag", patch=False, frames=65535, source="cfg3",
+                 desc="cfg3: 8192-pt FFT, Hann, 50% overlap, synthetic 2.4 MS/s uint8 IQ (3 tones + noise, SURVEY 8(d)) -> f32 log-magnitude"),
+    "cfg4": dict(n=16384, hop=16384, fmt="s8", window=False, out="pix", patch=True, frames=1 << 14, scale=5.0, source="uniform",
                  desc="cfg4 sweep rows: 16384-pt FFT, int8 IQ -> u8 pixels (S=5, DC patch)"),
-    "cfg5": dict(n=65536, hop=65536, fmt="s8", window=False, out="logmag", patch=False, frames=4096,
-                 desc="cfg5: 65536-pt FFT, synthetic int8 HackRF IQ -> f32 log-magnitude"),
+    "cfg5": dict(n=65536, hop=65536, fmt="s8", window=False, out="logmag", patch=False, frames=4096, source="cfg5",
+                 desc="cfg5: 65536-pt FFT, synthetic 20 MS/s int8 HackRF IQ (noise + chirp, SURVEY 8(d)) -> f32 log-magnitude"),
 }
 for _n in (128, 256, 512, 2048, 4096, 8192, 16384, 32768, 65536):
     WORKLOADS[f"n{_n}"] = _size_workload(_n)
+SECONDARY_ORDER = ["cfg3", "cfg4", "cfg5", "n2048", "n4096", "n8192", "n16384", "n32768", "n65536", "n512", "n256", "n128"]
 
 
 def load_capture():
@@ -83,43 +91,48 @@ def peak_hbm():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    """nvidia-smi clocks / throttle reasons DURING the timed regions (B200_PROFILING.md): one sampler runs
+    for the whole bench, every timed region reads back the samples that fall inside it."""
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index=0):
+    def __init__(self, gpu_index=0, period_ms=50):
         self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.proc = None
-        self.idx = gpu_index
-
-    def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=self.tmp, stderr=subprocess.DEVNULL)
+            import shutil
+            cmd = ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", str(period_ms), "-i", str(gpu_index)]
+            if shutil.which("stdbuf"):
+                cmd = ["stdbuf", "-oL"] + cmd                  # line-buffered: a region reads its samples while the sampler runs
+            self.proc = subprocess.Popen(cmd, stdout=self.tmp, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
 
-    def stop(self):
+    @staticmethod
+    def now():
+        return datetime.datetime.now()
+
+    def region(self, t0, t1):
+        """summary of the samples taken between the datetimes t0 and t1 (a little slack on both sides)"""
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         if not self.proc:
             return out
-        time.sleep(0.15)
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
+        time.sleep(0.06)
         self.tmp.flush()
-        rows = [r.strip().split(",") for r in open(self.tmp.name) if r.strip()]
-        os.unlink(self.tmp.name)
         sm, mx, power, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in rows:
+        slack = datetime.timedelta(milliseconds=20)
+        for line in open(self.tmp.name):
+            r = [x.strip() for x in line.strip().split(",")]
+            if len(r) < 10:
+                continue
             try:
-                r = [x.strip() for x in r]
-                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
-                for nm, v in zip(names, r[5:9]):
+                ts = datetime.datetime.strptime(r[0], "%Y/%m/%d %H:%M:%S.%f")
+                if ts < t0 - slack or ts > t1 + slack:
+                    continue
+                sm.append(float(r[2])); mx.append(float(r[3])); power.append(float(r[4]))
+                for nm, v in zip(names, r[6:10]):
                     if v.lower().startswith("active"):
                         reasons.add(nm)
             except Exception:
@@ -127,8 +140,21 @@ class ClockSampler:
         if sm:
             hot = [s for s, p in zip(sm, power) if p >= 0.6 * max(power)] or sm
             out.update(sm_mhz=float(np.median(hot)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
-                       samples=len(sm), power_w_max=float(max(power)))
+                       samples=len(sm), power_w_max=float(max(power)), power_w_median=float(np.median(power)))
         return out
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+            try:
+                os.unlink(self.tmp.name)
+            except OSError:
+                pass
+            self.proc = None
 
 
 def dist_setup(gpus):
@@ -145,7 +171,7 @@ def dist_setup(gpus):
     return rank, world, local
 
 
-def cpu_reference_rate(raw, threads, target_s=12.0, impl_only=False):
+def cpu_reference_rate(raw, threads, target_s=12.0):
     """Reference arm / CPU baseline: the reference's own nrf_fft_* (oracle/_ref) when
     it was compiled, else the oracle port, on a bounded sample of the workload."""
     from oracle import orc
@@ -172,147 +198,298 @@ def cpu_reference_rate(raw, threads, target_s=12.0, impl_only=False):
     return kind, frames, run
 
 
-def secondary(args):
-    """Device-resident throughput + roofline of a secondary workload; under torchrun every
-    rank runs the same per-GPU batch on its own device (independent frames / sweep
-    frequencies: no collective, weak scaling), time = max over ranks."""
-    import torch
-    import frequensea_b200 as fb
+# ----------------------------------------------------------------------------------------- helpers
+class Ctx:
+    """what every leg needs: rank / world, device, stream, barrier, the clock sampler"""
+
+    def __init__(self, args):
+        import torch
+        self.torch = torch
+        self.args = args
+        self.rank, self.world, self.local = dist_setup(args.gpus)
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.stream = torch.cuda.current_stream()
+        self.clocks = ClockSampler(self.local) if self.rank == 0 else None
+        self.t_start = time.perf_counter()
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, *vals):
+        t = self.torch.tensor(list(vals), dtype=self.torch.float64, device=self.dev)
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def elapsed(self):
+        return time.perf_counter() - self.t_start
+
+
+def oracle_check(w, d_in, d_out, frames, frame_ids):
+    """parity gate on the data that is timed: oracle on a few frames.  Returns (worst, ok, what)."""
     from oracle import orc
-    rank, world, local = dist_setup(args.gpus)
-    torch.cuda.set_device(local)
-    w = WORKLOADS[args.workload]
-    n, hop, frames = w["n"], w["hop"], w["frames"]
-    if args.frames != DEFAULT_FRAMES:
-        frames = args.frames
-    fmt = fb.IN_S8 if w["fmt"] == "s8" else fb.IN_U8
-    out_mode = {"mag": fb.OUT_MAG, "logmag": fb.OUT_LOGMAG, "pix": fb.OUT_PIX}[w["out"]]
-    flags = fb.FLAG_DC_PATCH if w["patch"] else 0
-    arith = {"auto": fb.ARITH_AUTO, "f32": fb.ARITH_F32, "f32x2": fb.ARITH_F32X2}[args.arith]
-    plan = fb.Plan(n, hop=hop, in_format=fmt, window=fb.WIN_HANN if w["window"] else fb.WIN_NONE,
-                   out_mode=out_mode, flags=flags, pix_scale=w.get("scale", 10.0), arith=arith, device=local)
-    dev = torch.device("cuda", local)
-    g = torch.Generator(device=dev).manual_seed(20260925 + rank)
-    d_in = torch.randint(0, 256, (plan.input_bytes(frames),), dtype=torch.uint8, device=dev, generator=g)
-    d_out = torch.empty((frames, n), dtype=torch.uint8 if out_mode == fb.OUT_PIX else torch.float32, device=dev)
-    stream = torch.cuda.current_stream()
-    plan.exec_device(d_in.data_ptr(), d_out.data_ptr(), frames, stream.cuda_stream)
-    torch.cuda.synchronize()
-    # parity gate on the timed data
-    chk = [0, 1, frames // 2, frames - 1]
-    worst = 0.0
-    for f in chk:
+    n, hop = w["n"], w["hop"]
+    fmt = orc.IN_S8 if w["fmt"] == "s8" else orc.IN_U8
+    win = orc.WIN_HANN if w["window"] else orc.WIN_NONE
+    out = {"mag": orc.OUT_MAG, "logmag": orc.OUT_LOGMAG, "pix": orc.OUT_PIX}[w["out"]]
+    worst, strict, ndiff, total = 0.0, 0.0, 0, 0
+    for f in frame_ids:
         raw = d_in[f * hop * 2:f * hop * 2 + 2 * n].cpu().numpy()
-        ref = orc.engine_frame(raw, n, orc.IN_S8 if w["fmt"] == "s8" else orc.IN_U8,
-                               orc.WIN_HANN if w["window"] else orc.WIN_NONE,
-                               {"mag": orc.OUT_MAG, "logmag": orc.OUT_LOGMAG, "pix": orc.OUT_PIX}[w["out"]],
-                               w.get("scale", 10.0), orc.FLAG_DC_PATCH if w["patch"] else 0).astype(np.float64)
+        ref = orc.engine_frame(raw, n, fmt, win, out, w.get("scale", 10.0), orc.FLAG_DC_PATCH if w["patch"] else 0).astype(np.float64)
         got = d_out[f].cpu().numpy().astype(np.float64)
         if w["out"] == "mag":
-            worst = max(worst, float(np.max(np.abs(got - ref)) / np.sqrt(np.mean(ref ** 2))))
-            ok = worst < 1e-5
+            rms = np.sqrt(np.mean(ref ** 2))
+            worst = max(worst, float(np.max(np.abs(got - ref) / (rms + 0.1 * np.abs(ref)))))     # |d| <= 1e-5 rms + 1e-6 |ref|
+            strict = max(strict, float(np.max(np.abs(got - ref)) / rms))                          # SURVEY 7: max|d| / rms
         elif w["out"] == "logmag":
             lin = 10 ** (ref / 20)
             m = lin >= 1e-3 * np.sqrt(np.mean(lin ** 2))
             worst = max(worst, float(np.max(np.abs(got - ref)[m])))
-            ok = worst < 2e-3
         else:
-            worst = max(worst, float(np.max(np.abs(got - ref))))
-            ok = worst <= 1
-        if not ok:
-            raise SystemExit(f"bench.py: parity gate failed on {args.workload} ({worst})")
-    for _ in range(args.warmup):
-        plan.exec_device(d_in.data_ptr(), d_out.data_ptr(), frames, stream.cuda_stream)
-    def barrier():
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-        torch.cuda.synchronize()
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    l0 = plan.launches
+            d = np.abs(got - ref)
+            worst = max(worst, float(d.max()))
+            ndiff += int((d > 0).sum()); total += d.size
+    if w["out"] == "mag":
+        return {"max_err_over_rms_plus_0.1ref": worst, "strict_max_err_over_rms": strict, "bound": 1e-5, "frames": len(frame_ids)}, worst < 1e-5
+    if w["out"] == "logmag":
+        return {"max_db_err_bins_above_1e-3_rms": worst, "bound_db": 2e-3, "frames": len(frame_ids)}, worst < 2e-3
+    return {"max_pixel_diff": worst, "pixels_differing": ndiff / max(total, 1), "bound": "<= 1 LSB", "frames": len(frame_ids)}, worst <= 1
+
+
+def make_plan(fb, w, local, arith=0):
+    fmt = fb.IN_S8 if w["fmt"] == "s8" else fb.IN_U8
+    out_mode = {"mag": fb.OUT_MAG, "logmag": fb.OUT_LOGMAG, "pix": fb.OUT_PIX}[w["out"]]
+    return fb.Plan(w["n"], hop=w["hop"], in_format=fmt, window=fb.WIN_HANN if w["window"] else fb.WIN_NONE, out_mode=out_mode,
+                   flags=fb.FLAG_DC_PATCH if w["patch"] else 0, pix_scale=w.get("scale", 10.0), arith=arith, device=local)
+
+
+def make_input(ctx, w, plan, frames):
+    torch = ctx.torch
+    nbytes = plan.input_bytes(frames)
+    if w["source"] == "cfg3":
+        from frequensea_b200 import synth
+        return synth.synth_u8_cfg3(nbytes // 2, ctx.dev, seed=20260925 + ctx.rank), "SURVEY 8(d) cfg3 source drawn on the device (3 tones + N(0, 20^2), offset-binary uint8)"
+    if w["source"] == "cfg5":
+        from frequensea_b200 import synth
+        return synth.synth_s8_cfg5(nbytes // 2, ctx.dev, seed=7 + ctx.rank), "SURVEY 8(d) cfg5 source drawn on the device (sigma-24 noise + chirp, int8)"
+    g = torch.Generator(device=ctx.dev).manual_seed(20260925 + ctx.rank)
+    return torch.randint(0, 256, (nbytes,), dtype=torch.uint8, device=ctx.dev, generator=g), "uniform random bytes drawn on the device"
+
+
+def timed_launches(ctx, plan, d_in, d_out, frames, steps, inner):
+    """`steps` timed steps of `inner` launches each; CUDA events on the launching stream around every step.
+    -> (total ms between the outer events, [ms per step], wall datetimes of the region)"""
+    torch = ctx.torch
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for _ in range(args.steps):
-        plan.exec_device(d_in.data_ptr(), d_out.data_ptr(), frames, stream.cuda_stream)
-    e1.record(stream)
-    barrier()
-    tms = torch.tensor([e0.elapsed_time(e1) / args.steps], dtype=torch.float64, device=dev)
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms = float(tms[0])
-    clocks = sampler.stop() if rank == 0 else None
-    if rank != 0:
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-            dist.destroy_process_group()
-        return 0
+    s = ctx.stream.cuda_stream
+    ip, op = d_in.data_ptr(), d_out.data_ptr()
+    ctx.barrier()
+    t0 = ClockSampler.now()
+    e0.record(ctx.stream)
+    for a, b in ev:
+        a.record(ctx.stream)
+        for _ in range(inner):
+            plan.exec_device(ip, op, frames, s)
+        b.record(ctx.stream)
+    e1.record(ctx.stream)
+    ctx.barrier()
+    t1 = ClockSampler.now()
+    return e0.elapsed_time(e1), [a.elapsed_time(b) for a, b in ev], (t0, t1)
+
+
+def measure_workload(ctx, fb, name, frames_override=None, min_region_s=0.35, arith=0):
+    """one secondary entry: device-resident throughput + roofline of workload `name`, parity-gated"""
+    torch = ctx.torch
+    w = WORKLOADS[name]
+    n, hop = w["n"], w["hop"]
+    frames = frames_override or w["frames"]
+    plan = make_plan(fb, w, ctx.local, arith)
+    d_in, data_desc = make_input(ctx, w, plan, frames)
+    pix = w["out"] == "pix"
+    d_out = torch.empty((frames, n), dtype=torch.uint8 if pix else torch.float32, device=ctx.dev)
+    s = ctx.stream.cuda_stream
+    plan.exec_device(d_in.data_ptr(), d_out.data_ptr(), frames, s)
+    torch.cuda.synchronize()
+    gate, ok = oracle_check(w, d_in, d_out, frames, [0, 1, frames // 2, frames - 1])
+    if not ok:
+        raise RuntimeError(f"parity gate failed on {name}: {gate}")
+    for _ in range(max(ctx.args.warmup, 3)):
+        plan.exec_device(d_in.data_ptr(), d_out.data_ptr(), frames, s)
+    torch.cuda.synchronize()
+    # size the steps so that the timed region lasts >= min_region_s
+    _, probe, _ = timed_launches(ctx, plan, d_in, d_out, frames, 2, 1)
+    steps = max(ctx.args.steps, 5)
+    inner = max(1, int(np.ceil(min_region_s * 1e3 / (steps * max(min(probe), 1e-3)))))
+    l0 = plan.launches
+    total_ms, per_step, (t0, t1) = timed_launches(ctx, plan, d_in, d_out, frames, steps, inner)
+    launches = plan.launches - l0
+    ms_launch = ctx.max_over_ranks(total_ms / (steps * inner))[0]
     peak, peak_src = peak_hbm()
-    out_b = 1 if w["out"] == "pix" else 4
-    alg = frames * (2 * hop + out_b * n)
-    achieved = alg / (ms * 1e-3) / 1e9
-    # end to end from a capture FILE (raw 8-bit IQ as c/rfcap.c / c/reader.c write it): pread -> pinned
-    # slots -> H2D -> kernels -> D2H, through fsea_exec_file (SURVEY 8(f) rank 4); rank 0, N = 1 only
-    file_ingest = None
-    if world == 1 and not args.no_e2e:
+    alg = frames * (2 * hop + (1 if pix else 4) * n)
+    achieved = alg / (ms_launch * 1e-3) / 1e9
+    entry = {
+        "workload": w["desc"], "value": ctx.world * frames / (ms_launch * 1e-3), "unit": UNIT, "ms_per_step": ms_launch * inner,
+        "ms_per_launch": ms_launch, "launches_per_step": inner, "steps": steps, "frames_per_gpu_per_launch": frames,
+        "iq_gsps": ctx.world * frames * hop / (ms_launch * 1e-3) / 1e9, "kernel": plan.kernel_name, "parity_gate": gate,
+        "gpu_launches": launches, "data": data_desc,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "algorithmic_bytes_per_launch": alg, "peak_source": peak_src},
+        "clocks": ctx.clocks.region(t0, t1) if ctx.clocks else None,
+    }
+    del d_in, d_out, plan
+    torch.cuda.empty_cache()
+    return entry
+
+
+def sustained_cfg5(ctx, fb, seconds=5.0):
+    """a resident ring of 4096 frames of 65536 points, transformed over and over for >= 5 s
+    after warm-up: steady-state frames/s, GS/s, GB/s and x real time against 20 MS/s (305 frames/s)."""
+    torch = ctx.torch
+    w = WORKLOADS["cfg5"]
+    n, frames = w["n"], 4096
+    plan = make_plan(fb, w, ctx.local)
+    d_in, data_desc = make_input(ctx, w, plan, frames)
+    d_out = torch.empty((frames, n), dtype=torch.float32, device=ctx.dev)
+    s = ctx.stream.cuda_stream
+    for _ in range(3):
+        plan.exec_device(d_in.data_ptr(), d_out.data_ptr(), frames, s)
+    torch.cuda.synchronize()
+    gate, ok = oracle_check(w, d_in, d_out, frames, [0, frames - 1])
+    if not ok:
+        raise RuntimeError(f"parity gate failed on sustained cfg5: {gate}")
+    _, probe, _ = timed_launches(ctx, plan, d_in, d_out, frames, 2, 1)
+    passes = max(8, int(np.ceil(seconds * 1e3 / max(min(probe), 1e-3))))
+    steps = 8
+    inner = (passes + steps - 1) // steps
+    total_ms, per_step, (t0, t1) = timed_launches(ctx, plan, d_in, d_out, frames, steps, inner)
+    total_ms = ctx.max_over_ranks(total_ms)[0]
+    fps = ctx.world * frames * steps * inner / (total_ms * 1e-3)
+    peak, _ = peak_hbm()
+    gbs = fps / ctx.world * 6 * n / 1e9
+    out = {"workload": "cfg5 sustained: resident ring of 4096 frames x 65536 points per GPU, int8 -> f32 log-magnitude",
+           "seconds": total_ms * 1e-3, "passes_over_ring": steps * inner, "value": fps, "unit": UNIT, "iq_gsps": fps * n / 1e9,
+           "gbs_per_gpu": gbs, "roofline_frac": gbs / peak, "x_real_time_at_20MSps": fps * n / 20e6,
+           "first_vs_last_step_ms": [per_step[0], per_step[-1]], "kernel": plan.kernel_name, "parity_gate": gate, "data": data_desc,
+           "clocks": ctx.clocks.region(t0, t1) if ctx.clocks else None}
+    del d_in, d_out, plan
+    torch.cuda.empty_cache()
+    return out
+
+
+def sweep_job(ctx, fb, n_freqs=1000, rows=512, n=16384):
+    """The cfg4 JOB (c/fft-batch-broad.c:56-129,189-209 + c/fft-stitch-broad.c:66-88): 1000 centre frequencies x 512
+    rows x 16384 points, frequency f -> rank f mod N, raw IQ resident per rank (drawn on the device, untimed), then
+    timed: gate rows + decisions, pixel rows of the kept frequencies, the stitched picture on rank 0."""
+    torch = ctx.torch
+    from frequensea_b200 import sweep
+    per = (n_freqs + ctx.world - 1) // ctx.world
+    eng = sweep.DeviceEngine(n, rows, per, device=ctx.local)
+    mine = list(range(ctx.rank, n_freqs, ctx.world))
+    out = {"workload": f"cfg4 sweep job: {n_freqs} centre frequencies x {rows} rows x {n}-pt, int8 -> gate + u8 pixels (S=5, DC patch) + stitched picture",
+           "n_freqs": n_freqs, "rows": rows, "fft_size": n, "partition": f"frequency f -> rank f mod {ctx.world}",
+           "data": "SURVEY 8(d) cfg4 source drawn on the device per frequency (noise + tone at bin (37 f + 11) mod N; every 10th frequency quiet)"}
+    # parity sample: a few of this rank's frequencies against the oracle (rank 0 only)
+    for j, f in enumerate(mine):
+        eng.submit(j, f)
+    eng.eng.sync()
+    modes = {}
+    for mode in ("p2p", "gather"):
         try:
-            fframes = min(frames, max(2, (1 << 29) // (2 * hop)))            # <= 512 MiB of capture
-            shm = "/dev/shm" if os.path.isdir("/dev/shm") else tempfile.gettempdir()
-            path = os.path.join(shm, f"fsea_bench_{os.getpid()}.raw")
-            d_in[:plan.input_bytes(fframes)].cpu().numpy().tofile(path)
-            t_out = torch.empty((fframes, n), dtype=torch.uint8 if out_mode == fb.OUT_PIX else torch.float32).pin_memory()
-            h_out = t_out.numpy()
-            plan.exec_file(path, fframes, 0, out=h_out)                       # warm-up (page cache, staging slots)
-            assert np.array_equal(h_out[fframes - 1], d_out[fframes - 1].cpu().numpy()), "file path differs from device path"
+            ctx.barrier()
+            l0 = eng.launches
             t0 = time.perf_counter()
-            reps = 3
-            for _ in range(reps):
-                plan.exec_file(path, fframes, 0, out=h_out)
-            dt = (time.perf_counter() - t0) / reps
-            os.unlink(path)
-            file_ingest = {"value": fframes / dt, "unit": UNIT, "msps": fframes * hop / dt / 1e6, "file_bytes": plan.input_bytes(fframes),
-                           "d2h_bytes": int(h_out.nbytes), "source": f"capture file on {shm} (page cache), pinned result buffer",
-                           "matches_device_path": True}
-        except Exception as e:                                                # never fail the bench line over the extra leg
-            file_ingest = {"error": str(e)[:200]}
-    print(json.dumps({
-        "metric": METRIC, "value": world * frames / (ms * 1e-3), "file_ingest": file_ingest, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic uniform 8-bit IQ drawn on the device",
-        "config": {"workload": w["desc"], "fft_size": n, "hop": hop, "frames_per_gpu_per_step": frames, "kernel": plan.kernel_name,
-                   "parallelism": f"frames / sweep frequencies sharded over {world} GPU(s), no collective",
-                   "l2": f"inputs larger than L2: {plan.input_bytes(frames) >> 20} MiB in + {plan.output_bytes(frames) >> 20} MiB out per step"},
-        "iq_gsps": world * frames * hop / (ms * 1e-3) / 1e9, "parity_gate": worst, "gpu_launches": plan.launches - l0, "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": plan.kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "algorithmic_bytes_per_step": alg, "peak_source": peak_src,
-                     "note": "per GPU, per step (all launches of the step)"},
-    }))
-    if world > 1:
-        import torch.distributed as dist
-        dist.barrier()
-        dist.destroy_process_group()
-    return 0
+            res = sweep.sweep(_Resident(eng, len(mine)), n_freqs, n, rows, n, rank=ctx.rank, world=ctx.world, mode=mode, keep_images=False)
+            torch.cuda.synchronize()
+            dt = ctx.max_over_ranks(time.perf_counter() - t0)[0]
+            launches = eng.launches - l0
+            if ctx.rank == 0:
+                kept = int(res["keep"].sum())
+                import hashlib
+                pic = res["stitched"]
+                # a cheap fingerprint of the 8 GB picture: column sums of every 64th row
+                fp = hashlib.sha256(pic[::64].to(torch.int64).sum(dim=0).cpu().numpy().tobytes()).hexdigest()[:16]
+                modes[mode] = {"seconds": dt, "rows_per_s": kept * rows / dt, "kept": kept, "gated_off": n_freqs - kept,
+                               "picture_shape": list(pic.shape), "picture_fingerprint": fp, "gpu_launches_rank0": launches}
+                if mode == "gather" and "p2p" in modes:
+                    modes[mode]["same_picture_as_p2p"] = modes["p2p"]["picture_fingerprint"] == fp
+                if "parity" not in out:
+                    out["parity"] = _sweep_parity(eng, res, mine, n, rows)
+            del res
+            torch.cuda.empty_cache()
+        except Exception as e:                                    # never lose the bench line over this leg
+            modes[mode] = {"error": str(e)[:300]}
+    out["modes"] = modes
+    best = max((m for m in modes.values() if "rows_per_s" in m), key=lambda m: m["rows_per_s"], default=None)
+    if best:
+        out["value"] = best["rows_per_s"]
+        out["unit"] = "rows/s"
+    del eng
+    torch.cuda.empty_cache()
+    return out
 
 
+class _Resident:
+    """sweep.sweep() over an engine whose raw IQ is already resident (bench: the source is drawn untimed)"""
+
+    def __init__(self, eng, n_slots):
+        self._e = eng
+        self.tdev = eng.tdev
+
+    def submit(self, *a, **k):
+        pass
+
+    def __getattr__(self, name):
+        return getattr(self._e, name)
+
+
+def _sweep_parity(eng, res, mine, n, rows):
+    """rank 0: gate mean and pixel rows of two of its frequencies against the oracle on the bytes the device drew"""
+    from oracle import orc
+    out = {}
+    try:
+        worst_mean, worst_pix, ndiff, total = 0.0, 0, 0, 0
+        for j in (0, min(9, len(mine) - 1)):
+            f = mine[j]
+            raw = eng.eng.read_raw(j)
+            gr = min(100, rows)
+            ref_mean = float(orc.engine_batch(raw, n, n, gr, orc.IN_S8, orc.WIN_NONE, orc.OUT_MAG).astype(np.float64).mean())
+            worst_mean = max(worst_mean, abs(float(res["means"][f]) - ref_mean) / ref_mean)
+            ref_keep = not (ref_mean < 1.1)
+            assert bool(res["keep"][f]) == ref_keep
+            sample_rows = [0, 1, rows // 2, rows - 1]
+            got = res["stitched"][sample_rows, f * n:(f + 1) * n].cpu().numpy().astype(int)
+            for k, r in enumerate(sample_rows):
+                ref = orc.engine_frame(raw[r * 2 * n:], n, orc.IN_S8, orc.WIN_NONE, orc.OUT_PIX, 5.0, orc.FLAG_DC_PATCH).astype(int) if ref_keep else np.zeros(n, int)
+                d = np.abs(got[k] - ref)
+                worst_pix = max(worst_pix, int(d.max())); ndiff += int((d > 0).sum()); total += d.size
+        out = {"gate_mean_rel_err": worst_mean, "max_pixel_diff": worst_pix, "pixels_differing": ndiff / max(total, 1), "frequencies_checked": 2}
+        assert worst_mean < 1e-5 and worst_pix <= 1
+    except AssertionError:
+        raise RuntimeError(f"sweep parity failed: {out}")
+    return out
+
+
+# ----------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--frames", type=int, default=DEFAULT_FRAMES, help="frames per GPU per step")
+    ap.add_argument("--frames", type=int, default=DEFAULT_FRAMES, help="frames per GPU per launch")
     ap.add_argument("--arith", default="auto", choices=["auto", "f32", "f32x2"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-secondary", action="store_true", help="headline only")
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS), help="only this workload, as a line of its own (development)")
+    ap.add_argument("--budget-s", type=float, default=240.0, help="secondary legs are skipped once the run is this old")
     args = ap.parse_args()
-    if args.workload != "cfg2":
-        return secondary(args)
     args.warmup = max(args.warmup, 3)
     raw = load_capture()
     threads = os.cpu_count() or 1
@@ -346,11 +523,29 @@ def main():
     # ------------------------------------------------------------ our arm
     import torch
     import frequensea_b200 as fb
-    rank, world, local = dist_setup(args.gpus)
+    ctx = Ctx(args)
+    rank, world, local, dev = ctx.rank, ctx.world, ctx.local, ctx.dev
     if fb.device_count() <= 0:
         raise SystemExit("bench.py: no CUDA device -- the engine has no CPU fallback")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
+    numa_cpus = fb.binding.host_bind_near_device(local)          # this rank's host thread + pinned buffers next to its GPU
+
+    if args.workload != "cfg2":                                   # development: one workload as its own line
+        e = measure_workload(ctx, fb, args.workload, frames_override=None if args.frames == DEFAULT_FRAMES else args.frames,
+                             arith={"auto": fb.ARITH_AUTO, "f32": fb.ARITH_F32, "f32x2": fb.ARITH_F32X2}[args.arith])
+        if rank == 0:
+            w = WORKLOADS[args.workload]
+            print(json.dumps({"metric": METRIC, "value": e["value"], "unit": UNIT, "n_gpus": world, "steps": e["steps"], "warmup": args.warmup,
+                              "ms_per_step": e["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                              "data": e["data"], "config": {"workload": w["desc"], "fft_size": w["n"], "hop": w["hop"], "kernel": e["kernel"],
+                                                           "frames_per_gpu_per_step": e["frames_per_gpu_per_launch"] * e["launches_per_step"]},
+                              "parity_gate": e["parity_gate"], "gpu_launches": e["gpu_launches"], "clocks": e["clocks"], "roofline": e["roofline"]}))
+        if ctx.clocks:
+            ctx.clocks.stop()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier(); dist.destroy_process_group()
+        return 0
+
     frames = args.frames - args.frames % FRAMES_PER_BLOCK
     arith = {"auto": fb.ARITH_AUTO, "f32": fb.ARITH_F32, "f32x2": fb.ARITH_F32X2}[args.arith]
     plan = fb.Plan(N, hop=HOP, in_format=fb.IN_S8, out_mode=fb.OUT_MAG, flags=fb.FLAG_DC_PATCH, device=local, arith=arith)
@@ -363,75 +558,99 @@ def main():
     h_out = torch.empty((frames, N), dtype=torch.float32, pin_memory=True)
     d_in = h_in.to(dev, non_blocking=False)
     d_out = torch.empty((frames, N), dtype=torch.float32, device=dev)
-    stream = torch.cuda.current_stream()
-
-    def barrier():
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-        torch.cuda.synchronize()
+    stream = ctx.stream
 
     # parity gate before any timing (same build, same data): oracle on a few frames
-    from oracle import orc
     plan.exec_device(d_in.data_ptr(), d_out.data_ptr(), frames, stream.cuda_stream)
     torch.cuda.synchronize()
     chk = [0, 1, 77, frames - 1]
-    got = d_out[chk].cpu().numpy().astype(np.float64)
-    hin = h_in.numpy()
-    ref = np.stack([orc.engine_frame(hin[f * 2 * N:], N, orc.IN_S8, orc.WIN_NONE, orc.OUT_MAG, flags=orc.FLAG_DC_PATCH) for f in chk])
-    perr = float(np.max(np.abs(got - ref) / np.sqrt(np.mean(ref ** 2, axis=1, keepdims=True))))
-    if not perr < 1e-5:
-        raise SystemExit(f"bench.py: parity gate failed (max rel err {perr:.3e}) -- refusing to time")
+    gate, ok = oracle_check(WORKLOADS["cfg2"], d_in, d_out, frames, chk)
+    perr = gate["strict_max_err_over_rms"]
+    if not ok or not perr < 1e-5:
+        raise SystemExit(f"bench.py: parity gate failed ({gate}) -- refusing to time")
 
-    # ---- value: device-resident, CUDA events on the launching stream
+    # ---- burst: K single launches, the kernel timed alone (round-1 definition)
     for _ in range(args.warmup):
         plan.exec_device(d_in.data_ptr(), d_out.data_ptr(), frames, stream.cuda_stream)
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    launches0 = plan.launches
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    e0.record(stream)
-    for a, b in ev:
-        a.record(stream)
+    b_total, b_steps, (bt0, bt1) = timed_launches(ctx, plan, d_in, d_out, frames, args.steps, 1)
+    b_total, b_kernel = ctx.max_over_ranks(b_total, float(np.mean(b_steps)))
+    # ---- value: K steps of R launches, >= ~1.2 s under load
+    inner = max(1, int(np.ceil(1200.0 / (args.steps * max(b_kernel, 1e-3)))))
+    for _ in range(args.warmup):
         plan.exec_device(d_in.data_ptr(), d_out.data_ptr(), frames, stream.cuda_stream)
-        b.record(stream)
-    e1.record(stream)
-    barrier()
-    total_ms = e0.elapsed_time(e1)
-    kernel_ms = float(np.mean([a.elapsed_time(b) for a, b in ev]))
+    launches0 = plan.launches
+    total_ms, step_ms, (t0, t1) = timed_launches(ctx, plan, d_in, d_out, frames, args.steps, inner)
     launches = plan.launches - launches0
-    clocks = sampler.stop() if rank == 0 else None
-    t = torch.tensor([total_ms, kernel_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        import torch.distributed as dist
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, kernel_ms_max = float(t[0]), float(t[1])
-    value = world * frames * args.steps / (total_ms * 1e-3)
+    clocks = ctx.clocks.region(t0, t1) if ctx.clocks else None
+    burst_clocks = ctx.clocks.region(bt0, bt1) if ctx.clocks else None
+    total_ms, kernel_ms = ctx.max_over_ranks(total_ms, float(np.mean(step_ms)) / inner)
+    value = world * frames * inner * args.steps / (total_ms * 1e-3)
 
     # ---- e2e: host buffers through the C ABI (H2D + kernel + D2H inside the timed region)
     e2e = None
     if not args.no_e2e:
         e2e_steps = max(3, min(args.steps, 10))
-        for _ in range(2):
-            plan.exec_host_ptr(h_in.data_ptr(), h_out.data_ptr(), frames)
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            plan.exec_host_ptr(h_in.data_ptr(), h_out.data_ptr(), frames)
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        t = torch.tensor([dt], dtype=torch.float64, device=dev)
-        if world > 1:
-            import torch.distributed as dist
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+
+        def wall(fn, steps):
+            for _ in range(2):
+                fn()
+            ctx.barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                fn()
+            torch.cuda.synchronize()
+            return ctx.max_over_ranks(time.perf_counter() - t0)[0]
+
+        dt = wall(lambda: plan.exec_host_ptr(h_in.data_ptr(), h_out.data_ptr(), frames), e2e_steps)
         e2e_ok = bool(torch.equal(h_out[chk], d_out[chk].cpu()))
-        e2e = {"value": world * frames * e2e_steps / float(t[0]), "unit": UNIT,
-               "h2d_bytes_per_step": world * plan.input_bytes(frames), "d2h_bytes_per_step": world * plan.output_bytes(frames),
-               "steps": e2e_steps, "host_memory": "pinned", "matches_device_path": e2e_ok}
+        dt_copy = wall(lambda: plan.copy_only_host_ptr(h_in.data_ptr(), h_out.data_ptr(), frames), e2e_steps)
+        ib, ob = plan.input_bytes(frames), plan.output_bytes(frames)
+        e2e = {"value": world * frames * e2e_steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": world * ib, "d2h_bytes_per_step": world * ob,
+               "steps": e2e_steps, "host_memory": "pinned", "matches_device_path": e2e_ok,
+               "gbs_h2d_plus_d2h": world * (ib + ob) * e2e_steps / dt / 1e9,
+               "copy_only": {"value": world * frames * e2e_steps / dt_copy, "unit": UNIT, "gbs_h2d_plus_d2h": world * (ib + ob) * e2e_steps / dt_copy / 1e9,
+                             "note": "fsea_copy_only_host: the same chunks over the same three streams, kernel left out -- the PCIe / host-memory ceiling of this job on this box"},
+               "frac_of_copy_only": dt_copy / dt,
+               "numa": f"rank thread + pinned buffers bound to the GPU's node ({numa_cpus} CPUs)" if numa_cpus > 0 else "topology unknown: not bound"}
+        # the sweep's product form: u8 pixels out (3N bytes per frame instead of 6N)
+        try:
+            pplan = fb.Plan(N, hop=HOP, in_format=fb.IN_S8, out_mode=fb.OUT_PIX, pix_scale=10.0, device=local)
+            hp = torch.empty((frames, N), dtype=torch.uint8, pin_memory=True)
+            dtp = wall(lambda: pplan.exec_host_ptr(h_in.data_ptr(), hp.data_ptr(), frames), e2e_steps)
+            e2e["pix_u8"] = {"value": world * frames * e2e_steps / dtp, "unit": UNIT, "d2h_bytes_per_step": world * frames * N,
+                             "gbs_h2d_plus_d2h": world * (ib + frames * N) * e2e_steps / dtp / 1e9}
+            del pplan, hp
+        except Exception as e:
+            e2e["pix_u8"] = {"error": str(e)[:200]}
+
+    del h_out, d_out, d_in, h_in
+    torch.cuda.empty_cache()
+
+    # ---- secondary workloads (every rank measures; rank 0 reports)
+    secondary, sustained, sweep_res = {}, None, None
+    if not args.no_secondary:
+        names = SECONDARY_ORDER if world == 1 else ["cfg5", "cfg3", "cfg4"]
+        for name in names:
+            if ctx.max_over_ranks(ctx.elapsed())[0] > args.budget_s:
+                secondary[name] = {"skipped": "time budget"}
+                continue
+            try:
+                secondary[name] = measure_workload(ctx, fb, name)
+            except Exception as e:
+                secondary[name] = {"error": str(e)[:300]}
+        if ctx.max_over_ranks(ctx.elapsed())[0] <= args.budget_s:
+            try:
+                sustained = sustained_cfg5(ctx, fb, seconds=5.0)
+            except Exception as e:
+                sustained = {"error": str(e)[:300]}
+        if ctx.max_over_ranks(ctx.elapsed())[0] <= args.budget_s + 30:
+            try:
+                sweep_res = sweep_job(ctx, fb)
+            except Exception as e:
+                sweep_res = {"error": str(e)[:300]}
+        secondary["sustained"] = sustained
+        secondary["sweep"] = sweep_res
 
     if rank != 0:
         if world > 1:
@@ -443,7 +662,8 @@ def main():
     # ---- roofline of the (single) kernel
     peak, peak_src = peak_hbm()
     alg_bytes = frames * (2 * HOP + 4 * N)
-    achieved = alg_bytes / (kernel_ms_max * 1e-3) / 1e9
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+    burst_achieved = alg_bytes / (b_kernel * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     if os.path.exists(tp):
@@ -454,8 +674,10 @@ def main():
         except Exception:
             pass
     roofline = {"bound": "hbm", "kernel": plan.kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes,
-                "kernel_ms": kernel_ms_max, "peak_source": peak_src}
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": "profiles/ncu_traffic.json (one ncu --set full capture of this kernel and batch, not this run)" if traffic else None,
+                "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kernel_ms, "peak_source": peak_src,
+                "burst_frac": burst_achieved / peak, "burst_kernel_ms": b_kernel,
+                "note": "frac: average launch inside the >= 1.2 s timed region; burst_frac: K single launches (7 ms), the kernel timed alone"}
 
     # ---- cpu baseline (rank 0, N=1 only): bounded sample of the same frames
     cpu = None
@@ -471,13 +693,19 @@ def main():
         "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "rfdata/rf-433.000.raw capture block (committed fixture) replayed to batch size",
         "config": {"workload": "cfg2 nrf_fft path: 1024-pt FFT, all frames of rf-433.000.raw, int8 IQ -> f32 magnitude + DC patch",
-                   "fft_size": N, "hop": HOP, "frames_per_gpu_per_step": frames, "parallelism": f"frames sharded over {world} GPU(s), no collective",
-                   "l2": "inputs larger than L2: 512 MiB in + 1 GiB out per step per GPU" if frames >= (1 << 17) else "WARNING: batch smaller than L2",
+                   "fft_size": N, "hop": HOP, "frames_per_gpu_per_step": frames * inner, "launches_per_step": inner, "frames_per_gpu_per_launch": frames,
+                   "parallelism": f"frames sharded over {world} GPU(s), no collective",
+                   "l2": "inputs larger than L2: 512 MiB in + 1 GiB out per launch per GPU" if frames >= (1 << 17) else "WARNING: batch smaller than L2",
                    "kernel": plan.kernel_name, "arith": args.arith},
-        "iq_gsps": value * HOP / 1e9, "parity_max_rel_err": perr,
+        "iq_gsps": value * HOP / 1e9, "parity_max_rel_err": perr, "parity_gate": gate,
+        "burst": {"value": world * frames * args.steps / (b_total * 1e-3), "unit": UNIT, "ms_per_launch": b_kernel, "launches": args.steps, "clocks": burst_clocks},
         "e2e": e2e, "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+        "secondary": secondary if not args.no_secondary else None,
+        "bench_seconds": ctx.elapsed(),
     }
     print(json.dumps(line))
+    if ctx.clocks:
+        ctx.clocks.stop()
     if world > 1:
         import torch.distributed as dist
         dist.barrier()

@@ -8,7 +8,16 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.environ.get("FSEA_LIB") or os.path.join(_HERE, "libfsea.so")   # FSEA_LIB: A/B builds
+_LIB_PATH = os.path.join(_HERE, "libfsea.so")
+
+
+def _use_library(path: str) -> None:
+    """Test / tooling hook (tests/emu, tools/sweep.py A/B builds): bind this module to another build of
+    the library BEFORE the first call.  The product never calls it: frequensea_b200 resolves its own
+    libfsea.so and nothing else -- no environment variable can point it at a CPU build."""
+    global _LIB_PATH, _lib
+    _LIB_PATH = path
+    _lib = None
 
 IN_U8, IN_S8, IN_F32C, IN_F64C = 0, 1, 2, 3
 WIN_NONE, WIN_HANN = 0, 1
@@ -25,6 +34,12 @@ class FseaConfig(C.Structure):
                 ("pix_scale", C.c_float), ("device", C.c_int), ("arith", C.c_int),
                 ("log_mult", C.c_float), ("power_gain", C.c_float),
                 ("reserved", C.c_int * 5)]
+
+
+class FseaSweepConfig(C.Structure):
+    _fields_ = [("fft_size", C.c_int), ("rows", C.c_int), ("gate_rows", C.c_int), ("gate_threshold", C.c_double),
+                ("pix_scale", C.c_float), ("in_format", C.c_int), ("device", C.c_int), ("capacity", C.c_int),
+                ("own_raw", C.c_int), ("own_images", C.c_int), ("reserved", C.c_int * 4)]
 
 
 class FseaError(RuntimeError):
@@ -82,6 +97,27 @@ def lib() -> C.CDLL:
     L.fsea_gate_mean_host.argtypes = [vp, vp, l, C.POINTER(C.c_double)]; L.fsea_gate_mean_host.restype = i
     L.fsea_stitch_host.argtypes = [i, vp, i, i, i, i, vp]; L.fsea_stitch_host.restype = i
     L.fsea_stitch_device.argtypes = [vp, i, i, i, i, vp, vp]; L.fsea_stitch_device.restype = i
+    L.fsea_stitch_sharded_device.argtypes = [vp, i, i, i, i, i, i, vp, vp]; L.fsea_stitch_sharded_device.restype = i
+    L.fsea_exec_device_strided.argtypes = [vp, vp, vp, l, l, vp]; L.fsea_exec_device_strided.restype = i
+    L.fsea_copy_only_host.argtypes = [vp, vp, vp, l]; L.fsea_copy_only_host.restype = i
+    L.fsea_host_bind_near_device.argtypes = [i]; L.fsea_host_bind_near_device.restype = i
+    PS = C.POINTER(FseaSweepConfig)
+    L.fsea_sweep_create.argtypes = [PS, C.POINTER(vp)]; L.fsea_sweep_create.restype = i
+    L.fsea_sweep_destroy.argtypes = [vp]; L.fsea_sweep_destroy.restype = i
+    L.fsea_sweep_submit_host.argtypes = [vp, i, vp]; L.fsea_sweep_submit_host.restype = i
+    L.fsea_sweep_submit_device.argtypes = [vp, i, vp]; L.fsea_sweep_submit_device.restype = i
+    L.fsea_sweep_submit_synth.argtypes = [vp, i, i, i]; L.fsea_sweep_submit_synth.restype = i
+    L.fsea_sweep_gate.argtypes = [vp, i, vp, vp]; L.fsea_sweep_gate.restype = i
+    L.fsea_sweep_gate_begin.argtypes = [vp, i]; L.fsea_sweep_gate_begin.restype = i
+    L.fsea_sweep_gate_end.argtypes = [vp, i, vp, vp]; L.fsea_sweep_gate_end.restype = i
+    L.fsea_sweep_render.argtypes = [vp, i, vp, l, l, l]; L.fsea_sweep_render.restype = i
+    L.fsea_sweep_sync.argtypes = [vp]; L.fsea_sweep_sync.restype = i
+    L.fsea_sweep_read_images.argtypes = [vp, i, i, vp]; L.fsea_sweep_read_images.restype = i
+    L.fsea_sweep_read_raw.argtypes = [vp, i, vp]; L.fsea_sweep_read_raw.restype = i
+    L.fsea_sweep_images.argtypes = [vp]; L.fsea_sweep_images.restype = vp
+    L.fsea_sweep_raw.argtypes = [vp, i]; L.fsea_sweep_raw.restype = vp
+    L.fsea_sweep_stream.argtypes = [vp]; L.fsea_sweep_stream.restype = vp
+    L.fsea_sweep_launch_count.argtypes = [vp]; L.fsea_sweep_launch_count.restype = l
     _lib = L
     return L
 
@@ -162,6 +198,15 @@ class Plan:
         _check(lib().fsea_exec_device(self._h, C.c_void_p(d_in), C.c_void_p(d_out), n_frames,
                                       C.c_void_p(stream)), "fsea_exec_device")
 
+    def exec_device_strided(self, d_in: int, d_out: int, out_row_stride_bytes: int, n_frames: int, stream: int = 0) -> None:
+        """As exec_device with the output rows `out_row_stride_bytes` apart (rows inside a wider picture)."""
+        _check(lib().fsea_exec_device_strided(self._h, C.c_void_p(d_in), C.c_void_p(d_out), out_row_stride_bytes, n_frames,
+                                              C.c_void_p(stream)), "fsea_exec_device_strided")
+
+    def copy_only_host_ptr(self, h_in: int, h_out: int, n_frames: int) -> None:
+        """exec_host_ptr's copies without the kernel (the PCIe ceiling of the same job)."""
+        _check(lib().fsea_copy_only_host(self._h, C.c_void_p(h_in), C.c_void_p(h_out), n_frames), "fsea_copy_only_host")
+
     def exec_host(self, data: np.ndarray, n_frames: int | None = None, out: np.ndarray | None = None) -> np.ndarray:
         """Host buffers through the pinned H2D -> kernel -> D2H pipeline."""
         data = np.ascontiguousarray(data, dtype=_IN_NP[self.in_format]).ravel()
@@ -193,6 +238,8 @@ class Plan:
 
     def gate_mean(self, data: np.ndarray, rows: int) -> float:
         data = np.ascontiguousarray(data, dtype=_IN_NP[self.in_format]).ravel()
+        if data.nbytes < self.input_bytes(rows):
+            raise ValueError(f"input too short: {data.nbytes} < {self.input_bytes(rows)} bytes for {rows} rows")
         m = C.c_double()
         _check(lib().fsea_gate_mean_host(self._h, data.ctypes.data_as(C.c_void_p), rows, C.byref(m)),
                "fsea_gate_mean_host")
@@ -201,6 +248,85 @@ class Plan:
     def close(self) -> None:
         if self._h:
             lib().fsea_plan_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def host_bind_near_device(device: int = 0) -> int:
+    """Pin this thread (and the pinned buffers it allocates next) to the GPU's NUMA node; CPUs bound, 0 = unknown topology."""
+    return int(lib().fsea_host_bind_near_device(device))
+
+
+class Sweep:
+    """The device-resident sweep engine of one GPU (fsea_sweep): raw IQ of `capacity` centre frequencies
+    -> gate decisions -> u8 pixel rows, nothing crossing the host in between (c/fft-batch-broad.c:56-129)."""
+
+    def __init__(self, fft_size: int, rows: int, capacity: int, gate_rows: int = 100, gate_threshold: float = 1.1,
+                 pix_scale: float = 5.0, in_format: int = IN_S8, device: int = 0, own_raw: bool = True, own_images: bool = False):
+        cfg = FseaSweepConfig(fft_size=fft_size, rows=rows, gate_rows=gate_rows, gate_threshold=gate_threshold,
+                              pix_scale=pix_scale, in_format=in_format, device=device, capacity=capacity,
+                              own_raw=int(own_raw), own_images=int(own_images))
+        self.n, self.rows, self.capacity, self.device = fft_size, rows, capacity, device
+        self._h = C.c_void_p()
+        _check(lib().fsea_sweep_create(C.byref(cfg), C.byref(self._h)), "fsea_sweep_create")
+
+    def submit_host(self, slot: int, raw: np.ndarray) -> None:
+        raw = np.ascontiguousarray(raw, dtype=np.uint8).ravel()
+        if raw.nbytes < 2 * self.n * self.rows:
+            raise ValueError("raw IQ of a frequency must hold rows * N complex samples")
+        _check(lib().fsea_sweep_submit_host(self._h, slot, raw.ctypes.data_as(C.c_void_p)), "fsea_sweep_submit_host")
+        lib().fsea_sweep_sync(self._h)                        # (pageable source: the copy must be over before `raw` may go away)
+
+    def submit_device(self, slot: int, d_raw: int) -> None:
+        _check(lib().fsea_sweep_submit_device(self._h, slot, C.c_void_p(d_raw)), "fsea_sweep_submit_device")
+
+    def submit_synth(self, slot: int, freq_idx: int, quiet_every: int = 10) -> None:
+        _check(lib().fsea_sweep_submit_synth(self._h, slot, freq_idx, quiet_every), "fsea_sweep_submit_synth")
+
+    def gate(self, n_slots: int):
+        means = np.zeros(n_slots, dtype=np.float64)
+        keep = np.zeros(n_slots, dtype=np.uint8)
+        if n_slots > 0:
+            _check(lib().fsea_sweep_gate(self._h, n_slots, means.ctypes.data_as(C.c_void_p), keep.ctypes.data_as(C.c_void_p)), "fsea_sweep_gate")
+        return means, keep.astype(bool)
+
+    def render(self, n_slots: int, d_canvas: int = 0, canvas_stride: int = 0, col0: int = 0, col_step: int = 0) -> None:
+        if n_slots > 0:
+            _check(lib().fsea_sweep_render(self._h, n_slots, C.c_void_p(d_canvas) if d_canvas else None, canvas_stride, col0, col_step),
+                   "fsea_sweep_render")
+
+    def sync(self) -> None:
+        _check(lib().fsea_sweep_sync(self._h), "fsea_sweep_sync")
+
+    def read_images(self, first: int, count: int) -> np.ndarray:
+        out = np.empty((count, self.rows, self.n), dtype=np.uint8)
+        _check(lib().fsea_sweep_read_images(self._h, first, count, out.ctypes.data_as(C.c_void_p)), "fsea_sweep_read_images")
+        return out
+
+    def read_raw(self, slot: int) -> np.ndarray:
+        out = np.empty(2 * self.rows * self.n, dtype=np.uint8)
+        _check(lib().fsea_sweep_read_raw(self._h, slot, out.ctypes.data_as(C.c_void_p)), "fsea_sweep_read_raw")
+        return out
+
+    def raw_ptr(self, slot: int) -> int:
+        return int(lib().fsea_sweep_raw(self._h, slot) or 0)
+
+    @property
+    def stream(self) -> int:
+        return int(lib().fsea_sweep_stream(self._h) or 0)
+
+    @property
+    def launches(self) -> int:
+        return int(lib().fsea_sweep_launch_count(self._h))
+
+    def close(self) -> None:
+        if self._h:
+            lib().fsea_sweep_destroy(self._h)
             self._h = C.c_void_p()
 
     def __del__(self):

@@ -26,12 +26,6 @@
 #include "fsea_ptx.cuh"
 #include "fsea_internal.h"
 
-// plain (non-table) kernel launches; -DFSEA_EMU (tests/emu/, test infrastructure) runs them on the CPU fiber machine
-#if defined(FSEA_EMU)
-#define FSEA_LAUNCH(kernel, grid, block, stream, ...) fsea_emu::launch(dim3(grid), dim3(block), 0, 1, [=] { kernel(__VA_ARGS__); })
-#else
-#define FSEA_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
-#endif
 
 // ------------------------------------------------------------------ errors
 static thread_local char g_cuda_err[256] = "";
@@ -746,8 +740,10 @@ extern "C" int fsea_gate_mean_host(fsea_plan* p, const void* h_in, long rows, do
 // pixel images of a sweep are max-blended side by side, image i at column i * width_step,
 // into one picture of width  width + (n_images - 1) * width_step  (zero where nothing lands).
 // One thread per 4 output pixels; every source pixel is read once per output it covers.
+// (world, per: the images as a sharded sweep gathers them -- frequency i is image i / world of
+// rank i % world, ranks `per` images apart; world = 1: plain frequency order)
 __global__ void fsea_stitch_kernel(const uint8_t* __restrict__ img, int n_images, int rows, int width, int step,
-                                   int out_width, uint8_t* __restrict__ out) {
+                                   int out_width, uint8_t* __restrict__ out, int world, int per) {
     const long quads_per_row = (out_width + 3) / 4;
     const long total = (long)rows * quads_per_row;
     for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long)gridDim.x * blockDim.x) {
@@ -765,7 +761,8 @@ __global__ void fsea_stitch_kernel(const uint8_t* __restrict__ img, int n_images
             if (x - width + 1 <= 0) lo = 0;
             uint8_t m = 0;
             for (int i = lo; i <= hi; i++) {
-                const uint8_t s = img[((size_t)i * rows + y) * width + (x - i * step)];
+                const size_t at = (world == 1) ? (size_t)i : (size_t)(i % world) * per + (size_t)(i / world);
+                const uint8_t s = img[(at * rows + y) * width + (x - i * step)];
                 m = s > m ? s : m;
             }
             v[k] = m;
@@ -781,7 +778,18 @@ extern "C" int fsea_stitch_device(const uint8_t* d_images, int n_images, int row
     const int out_width = width + (n_images - 1) * width_step;
     const long quads = (long)rows * ((out_width + 3) / 4);
     const int blocks = (int)std::min<long>((quads + 255) / 256, 148 * 16);
-    FSEA_LAUNCH(fsea_stitch_kernel, blocks, 256, (cudaStream_t)stream, d_images, n_images, rows, width, width_step, out_width, d_out);
+    FSEA_LAUNCH(fsea_stitch_kernel, blocks, 256, (cudaStream_t)stream, d_images, n_images, rows, width, width_step, out_width, d_out, 1, n_images);
+    CU(cudaGetLastError());
+    return FSEA_OK;
+}
+
+extern "C" int fsea_stitch_sharded_device(const uint8_t* d_images, int n_images, int world, int per_rank, int rows, int width, int width_step,
+                                          uint8_t* d_out, void* stream) {
+    if (!d_images || !d_out || n_images <= 0 || rows <= 0 || width <= 0 || width_step <= 0 || world <= 0 || per_rank * world < n_images) return FSEA_ERR_INVALID;
+    const int out_width = width + (n_images - 1) * width_step;
+    const long quads = (long)rows * ((out_width + 3) / 4);
+    const int blocks = (int)std::min<long>((quads + 255) / 256, 148 * 16);
+    FSEA_LAUNCH(fsea_stitch_kernel, blocks, 256, (cudaStream_t)stream, d_images, n_images, rows, width, width_step, out_width, d_out, world, per_rank);
     CU(cudaGetLastError());
     return FSEA_OK;
 }

@@ -2,6 +2,14 @@
 #pragma once
 #include <cuda_runtime.h>
 #include "../../include/fsea.h"
+#include "fsea_ptx.cuh"
+
+// plain (non-table) kernel launches; -DFSEA_EMU (tests/emu/, test infrastructure) runs them on the CPU fiber machine
+#if defined(FSEA_EMU)
+#define FSEA_LAUNCH(kernel, grid, block, stream, ...) fsea_emu::launch(dim3(grid), dim3(block), 0, 1, [=] { kernel(__VA_ARGS__); })
+#else
+#define FSEA_LAUNCH(kernel, grid, block, stream, ...) kernel<<<(grid), (block), 0, (stream)>>>(__VA_ARGS__)
+#endif
 
 // launch a plan on `stream` (no device switch, no argument checks); out_stride = bytes between
 // output rows (0: packed)

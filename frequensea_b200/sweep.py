@@ -1,4 +1,4 @@
-"""The multi-centre-frequency sweep (BASELINE cfg4) as one sharded job.
+"""The multi-centre-frequency sweep (BASELINE cfg4) as one sharded, device-resident job.
 
 What the reference does per centre frequency (c/fft-batch-broad.c:56-129,189-209): retune, take
 rows of an N-point spectrum, after GATE_ROWS rows look at the mean magnitude and give the
@@ -6,15 +6,24 @@ frequency up if nothing is there (:80-98), otherwise finish HEIGHT rows of u8 pi
 (S = 5, DC patch, :108-118) -- one image per frequency; c/fft-stitch-broad.c:28-36,66-88 then
 max-blends the images side by side, image i at column i * WIDTH_STEP.
 
-Here centre frequency f belongs to rank f mod world; every rank gates and
-transforms its own frequencies on its own GPU with no collective in the data path; the u8 images
-(4x less traffic than float32 spectra) and the gate decisions are gathered on one rank, which
-stitches them on its device.  `ops` is the per-rank arithmetic: EngineOps (the CUDA engine) in the
-product, a stand-in only where a test says so.
+Here centre frequency f belongs to rank f mod world.  Every rank owns a
+device-resident engine (fsea_sweep_*, include/fsea.h): the raw IQ of a frequency is uploaded (or
+drawn on the device) once, the gate sum is reduced on the device, the keep flags cross to the host
+in one small copy, and the pixel rows never leave device memory.  Getting them to the rank that
+owns the stitched picture is the job's only exchange, in one of two ways:
+
+  mode="gather"  NCCL gather of the u8 images (device -> device over NVLink; 4x less traffic than
+                 float32 spectra), max-blend stitch on the destination's device;
+  mode="p2p"     (WIDTH_STEP == N: the images tile the picture) the destination shares its canvas
+                 over CUDA IPC and every rank's transform kernel stores its pixel rows straight
+                 into it -- the kernel's stores ARE the gather (NVLink peer writes), there is no
+                 collective and no stitch pass.
+
+`engine` is DeviceEngine in the product; the CPU test-suite passes a stand-in with the same methods.
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, List, Optional
+from typing import Callable, Dict, Optional
 
 import numpy as np
 
@@ -48,79 +57,143 @@ def synth_frequency(freq_idx: int, n: int, rows: int, quiet_every: int = 10) -> 
     return out.view(np.uint8)
 
 
-class EngineOps:
-    """The engine on this rank's GPU: gate mean (fsea_gate_mean_host), pixel rows, stitch."""
+class DeviceEngine:
+    """This rank's GPU: fsea_sweep (raw -> gate -> pixel rows, device-resident) + stitch."""
 
-    def __init__(self, n: int, device: int = 0, pix_scale: float = PIX_SCALE):
-        from . import binding as B
-        self._B = B
-        self.device = device
-        self.pix = B.Plan(n, in_format=B.IN_S8, out_mode=B.OUT_PIX, pix_scale=pix_scale, flags=B.FLAG_DC_PATCH, device=device)
-        self.mag = B.Plan(n, in_format=B.IN_S8, out_mode=B.OUT_MAG, device=device)      # |X| incl. the DC bin, as :84-90 sums it
-
-    def gate_mean(self, raw: np.ndarray, rows: int) -> float:
-        return self.mag.gate_mean(raw, rows)
-
-    def pixel_rows(self, raw: np.ndarray, rows: int) -> np.ndarray:
-        return self.pix.exec_host(raw, rows)
-
-    def stitch(self, images: np.ndarray, width_step: int) -> np.ndarray:
-        return self._B.stitch(images, width_step, self.device)
-
-
-def sweep_local(ops, freqs: List[int], stream: Callable[[int], np.ndarray], n: int, rows: int,
-                gate_rows: int = GATE_ROWS, gate_threshold: float = GATE_THRESHOLD):
-    """This rank's frequencies: (means, keep flags, images[len(freqs), rows, n] with zeros where gated off)."""
-    means = np.zeros(len(freqs), dtype=np.float64)
-    keep = np.zeros(len(freqs), dtype=bool)
-    images = np.zeros((len(freqs), rows, n), dtype=np.uint8)
-    for j, f in enumerate(freqs):
-        raw = stream(f)
-        means[j] = ops.gate_mean(raw, min(gate_rows, rows))
-        keep[j] = not (means[j] < gate_threshold)                  # "interesting", c/fft-batch-broad.c:93-97
-        if keep[j]:
-            images[j] = ops.pixel_rows(raw, rows)
-    return means, keep, images
-
-
-def sweep(ops, n_freqs: int, stream: Callable[[int], np.ndarray], n: int, rows: int, width_step: int,
-          rank: int = 0, world: int = 1, dst: int = 0, group=None,
-          gate_rows: int = GATE_ROWS, gate_threshold: float = GATE_THRESHOLD) -> Optional[Dict[str, np.ndarray]]:
-    """The whole sweep.  On `dst`: {"means", "keep", "images" (frequency order), "stitched"}; None elsewhere."""
-    mine = shard.sweep_shard(n_freqs, rank, world)
-    means, keep, images = sweep_local(ops, mine, stream, n, rows, gate_rows, gate_threshold)
-    if world == 1:
-        all_means, all_keep, all_images = means, keep, images
-    else:
+    def __init__(self, n: int, rows: int, capacity: int, device: int = 0, gate_rows: int = GATE_ROWS,
+                 gate_threshold: float = GATE_THRESHOLD, pix_scale: float = PIX_SCALE):
         import torch
-        import torch.distributed as dist
-        per = (n_freqs + world - 1) // world                         # pad every shard to the same length
-        # NCCL moves device memory (u8 pixel images over NVLink); gloo, in the CPU tests, host memory
-        dev = torch.device("cuda", getattr(ops, "device", 0)) if dist.get_backend(group) == "nccl" else torch.device("cpu")
-        pad_i = torch.zeros((per, rows, n), dtype=torch.uint8, device=dev)
-        pad_m = torch.zeros(per, dtype=torch.float64, device=dev)
-        pad_k = torch.zeros(per, dtype=torch.uint8, device=dev)
-        pad_i[: len(mine)] = torch.from_numpy(images).to(dev)
-        pad_m[: len(mine)] = torch.from_numpy(means).to(dev)
-        pad_k[: len(mine)] = torch.from_numpy(keep.astype(np.uint8)).to(dev)
-        if rank == dst:
-            gi = [torch.empty_like(pad_i) for _ in range(world)]
-            gm = [torch.empty_like(pad_m) for _ in range(world)]
-            gk = [torch.empty_like(pad_k) for _ in range(world)]
+        from . import binding as B
+        self._B, self._torch = B, torch
+        self.n, self.rows, self.capacity, self.device = n, rows, capacity, device
+        self.tdev = torch.device("cuda", device)
+        self.eng = B.Sweep(n, rows, capacity, gate_rows=gate_rows, gate_threshold=gate_threshold, pix_scale=pix_scale,
+                           in_format=B.IN_S8, device=device, own_raw=True, own_images=False)
+
+    def submit(self, slot: int, freq_idx: int, raw: Optional[np.ndarray] = None, quiet_every: int = 10) -> None:
+        """raw IQ of a frequency: host bytes (uploaded once) or, with raw=None, the 8(d) source drawn on the device"""
+        if raw is None:
+            self.eng.submit_synth(slot, freq_idx, quiet_every)
         else:
-            gi = gm = gk = None
-        dist.gather(pad_i, gi, dst=dst, group=group)
-        dist.gather(pad_m, gm, dst=dst, group=group)
-        dist.gather(pad_k, gk, dst=dst, group=group)
-        if rank != dst:
-            return None
-        all_images = np.zeros((n_freqs, rows, n), dtype=np.uint8)
-        all_means = np.zeros(n_freqs, dtype=np.float64)
-        all_keep = np.zeros(n_freqs, dtype=bool)
-        for r in range(world):
-            fr = shard.sweep_shard(n_freqs, r, world)
-            all_images[fr] = gi[r][: len(fr)].cpu().numpy()
-            all_means[fr] = gm[r][: len(fr)].cpu().numpy()
-            all_keep[fr] = gk[r][: len(fr)].cpu().numpy().astype(bool)
-    stitched = ops.stitch(all_images, width_step)
-    return {"means": all_means, "keep": all_keep, "images": all_images, "stitched": stitched}
+            self.eng.submit_host(slot, raw)
+
+    def gate(self, n_slots: int):
+        return self.eng.gate(n_slots)
+
+    def render_images(self, n_slots: int, per: int):
+        """[per, rows, n] u8 on the device (slots >= n_slots zero): what a gather moves"""
+        torch = self._torch
+        img = torch.zeros((per, self.rows, self.n), dtype=torch.uint8, device=self.tdev)
+        torch.cuda.current_stream(self.tdev).synchronize()          # the zero fill ran on torch's stream
+        self.eng.render(n_slots, img.data_ptr(), self.n, 0, self.rows * self.n)
+        self.eng.sync()
+        return img
+
+    def render_into(self, n_slots: int, ptr: int, stride: int, col0: int, col_step: int) -> None:
+        self.eng.render(n_slots, ptr, stride, col0, col_step)
+        self.eng.sync()
+
+    def new_canvas(self, rows: int, width: int):
+        return self._torch.zeros((rows, width), dtype=self._torch.uint8, device=self.tdev)
+
+    def stitch(self, gathered, n_freqs: int, world: int, per: int, width_step: int):
+        """gathered: [world * per, rows, n] u8 on this device, rank-major as dist.gather delivers it"""
+        torch, B = self._torch, self._B
+        out = torch.empty((self.rows, self.n + (n_freqs - 1) * width_step), dtype=torch.uint8, device=self.tdev)
+        stream = torch.cuda.current_stream(self.tdev)
+        B._check(B.lib().fsea_stitch_sharded_device(gathered.data_ptr(), n_freqs, world, per, self.rows, self.n, width_step,
+                                                    out.data_ptr(), stream.cuda_stream), "fsea_stitch_sharded_device")
+        stream.synchronize()
+        return out
+
+    @property
+    def launches(self) -> int:
+        return self.eng.launches
+
+
+def _share_canvas(engine, rows: int, width: int, rank: int, dst: int, group):
+    """The destination's canvas as a device pointer every rank of the box can store through
+    (CUDA IPC under torch's allocator; peer access over NVLink).  Returns (canvas or None, pointer, keep-alive)."""
+    import torch
+    import torch.distributed as dist
+    canvas, handle = None, [None]
+    if rank == dst:
+        canvas = engine.new_canvas(rows, width)
+        torch.cuda.synchronize(engine.tdev)
+        handle = [canvas.untyped_storage()._share_cuda_()]
+    dist.broadcast_object_list(handle, src=dst, group=group)
+    if rank == dst:
+        return canvas, canvas.data_ptr(), None
+    h = handle[0]
+    storage = torch.UntypedStorage._new_shared_cuda(*h)
+    return None, storage.data_ptr() + int(h[3]), storage
+
+
+def sweep(engine, n_freqs: int, n: int, rows: int, width_step: int,
+          source: Optional[Callable[[int], np.ndarray]] = None, rank: int = 0, world: int = 1, dst: int = 0, group=None,
+          mode: str = "gather", quiet_every: int = 10, keep_images: bool = True) -> Optional[Dict]:
+    """The whole sweep.  On `dst`: {"means", "keep" (numpy, frequency order), "stitched" (tensor on the engine's
+    device, or numpy for a host stand-in), "images" (frequency order, when keep_images and mode == "gather")};
+    None elsewhere.  source(f) -> the raw bytes of frequency f; None = the device-drawn 8(d) source."""
+    import torch
+    mine = shard.sweep_shard(n_freqs, rank, world)
+    per = (n_freqs + world - 1) // world                             # every shard padded to the same length
+    for j, f in enumerate(mine):
+        engine.submit(j, f, None if source is None else source(f), quiet_every)
+    means, keep = engine.gate(len(mine))
+    out_width = n + (n_freqs - 1) * width_step
+    pad_m = np.zeros(per, dtype=np.float64); pad_m[: len(mine)] = means
+    pad_k = np.zeros(per, dtype=np.uint8); pad_k[: len(mine)] = keep
+
+    if world == 1:
+        all_means, all_keep = means, np.asarray(keep, dtype=bool)
+        if mode == "p2p" and width_step == n:
+            canvas = engine.new_canvas(rows, out_width)
+            torch.cuda.synchronize()
+            engine.render_into(len(mine), canvas.data_ptr(), out_width, 0, n)
+            return {"means": all_means, "keep": all_keep, "stitched": canvas}
+        img = engine.render_images(len(mine), per)
+        res = {"means": all_means, "keep": all_keep, "stitched": engine.stitch(img, n_freqs, 1, per, width_step)}
+        if keep_images:
+            res["images"] = img[:n_freqs]
+        return res
+
+    import torch.distributed as dist
+    nccl = dist.get_backend(group) == "nccl"
+    dev = engine.tdev if nccl else torch.device("cpu")
+    t_m = torch.from_numpy(pad_m).to(dev)
+    t_k = torch.from_numpy(pad_k).to(dev)
+    gm = [torch.empty_like(t_m) for _ in range(world)] if rank == dst else None
+    gk = [torch.empty_like(t_k) for _ in range(world)] if rank == dst else None
+    dist.gather(t_m, gm, dst=dst, group=group)
+    dist.gather(t_k, gk, dst=dst, group=group)
+
+    res = None
+    if mode == "p2p" and width_step == n and nccl:
+        canvas, ptr, alive = _share_canvas(engine, rows, out_width, rank, dst, group)
+        engine.render_into(len(mine), ptr, out_width, rank * n, world * n)        # frequency j * world + rank at column (j world + rank) N
+        dist.barrier(group=group)                                                 # every rank's stores have landed (render_into synchronised its stream)
+        del alive
+        if rank == dst:
+            res = {"stitched": canvas}
+    else:
+        img = engine.render_images(len(mine), per)
+        if rank == dst:
+            gathered = torch.empty((world * per, rows, n), dtype=torch.uint8, device=img.device)
+            dist.gather(img, list(gathered.view(world, per, rows, n).unbind(0)), dst=dst, group=group)
+            res = {"stitched": engine.stitch(gathered, n_freqs, world, per, width_step)}
+            if keep_images:
+                order = [(f % world) * per + f // world for f in range(n_freqs)]
+                res["images"] = gathered[torch.as_tensor(order, device=gathered.device)]
+        else:
+            dist.gather(img, None, dst=dst, group=group)
+    if rank != dst:
+        return None
+    all_means = np.zeros(n_freqs, dtype=np.float64)
+    all_keep = np.zeros(n_freqs, dtype=bool)
+    for r in range(world):
+        fr = shard.sweep_shard(n_freqs, r, world)
+        all_means[fr] = gm[r][: len(fr)].cpu().numpy()
+        all_keep[fr] = gk[r][: len(fr)].cpu().numpy().astype(bool)
+    res["means"], res["keep"] = all_means, all_keep
+    return res

@@ -106,10 +106,26 @@ long fsea_frames_in(const fsea_plan *plan, size_t n_samples);
  * default stream).  This is what bench.py's `value` times. */
 int fsea_exec_device(fsea_plan *plan, const void *d_in, void *d_out, long n_frames, void *stream);
 
+/* The same, with the output rows out_row_stride_bytes apart (>= N * element size, a multiple of 4):
+ * rows that land inside a wider picture -- frame f of a sweep frequency goes to row f of the
+ * stitched canvas (c/fft-stitch-broad.c:28-36), possibly in a PEER device's memory (the stores of
+ * the transform kernel then cross NVLink and no gather or stitch pass is left). */
+int fsea_exec_device_strided(fsea_plan *plan, const void *d_in, void *d_out, long out_row_stride_bytes,
+                             long n_frames, void *stream);
+
 /* Host buffers: chunked, double-buffered H2D -> kernel -> D2H through pinned
  * staging on three streams (page-locked caller memory is used directly); returns when h_out is complete.  This is the call
  * the nrf_fft shim and bench.py's `e2e` use. */
 int fsea_exec_host(fsea_plan *plan, const void *h_in, void *h_out, long n_frames);
+
+/* fsea_exec_host's chunks over the same streams with the kernel left out: what the box's PCIe
+ * links allow for this job (bench.py reports e2e as a fraction of it).  h_out receives stale bytes. */
+int fsea_copy_only_host(fsea_plan *plan, const void *h_in, void *h_out, long n_frames);
+
+/* Pin the calling thread (and so the first-touch placement of the pinned buffers it allocates
+ * next) to the CPUs of the NUMA node `device` hangs off (sysfs local_cpulist of its PCI function).
+ * Returns the number of CPUs bound to, 0 if the topology is unknown (nothing changed), < 0 on error. */
+int fsea_host_bind_near_device(int device);
 
 /* The same pipeline fed from a capture file: the raw bytes an SDR delivered, block after block,
  * no header (c/rfcap.c:26-41, c/reader.c:25-49; replayed by src/nrf.c:256-284).  Frames
@@ -137,8 +153,64 @@ int fsea_gate_mean_host(fsea_plan *plan, const void *h_in, long rows, double *me
  * out = max(out, image), zero where no image lands. */
 int fsea_stitch_device(const uint8_t *d_images, int n_images, int rows, int width, int width_step,
                        uint8_t *d_out, void *stream);
+/* The same from the layout a sharded sweep gathers (frequency f -> rank f mod world):
+ * d_images = [world][per_rank][rows][width], frequency i = image i / world of rank i % world. */
+int fsea_stitch_sharded_device(const uint8_t *d_images, int n_images, int world, int per_rank, int rows, int width,
+                               int width_step, uint8_t *d_out, void *stream);
 int fsea_stitch_host(int device, const uint8_t *h_images, int n_images, int rows, int width, int width_step,
                      uint8_t *h_out);
+
+/* ---- the multi-centre-frequency sweep as a device-resident engine (BASELINE cfg4) ----------
+ * What c/fft-batch-broad.c:56-129,189-209 does per centre frequency -- rows of an N-point
+ * spectrum; after gate_rows rows the mean |X| decides whether anything is there (:80-98); if so
+ * `rows` rows of u8 pixels (S = pix_scale, DC patch, :108-118), one image per frequency -- for the
+ * `capacity` frequencies of one GPU, with nothing crossing the host between raw IQ and images:
+ *   submit   raw IQ of a frequency (rows * N complex int8 samples) becomes resident, once
+ *   gate     the gate rows of everything submitted are transformed and summed (deterministically,
+ *            as fsea_gate_mean_host); means and keep flags in one small D2H, the job's only sync
+ *   render   pixel rows of the kept frequencies, zeros for the others, into the engine's
+ *            images [slot][rows][N] or straight into a stitched canvas (row stride = canvas width,
+ *            possibly peer memory: c/fft-stitch-broad.c:28-36,66-88 with WIDTH_STEP = N)
+ * No allocation after create. */
+typedef struct fsea_sweep fsea_sweep;
+typedef struct {
+    int fft_size;          /* N */
+    int rows;              /* HEIGHT, c/fft-batch-broad.c:15 */
+    int gate_rows;         /* 100, :80 (clamped to rows) */
+    double gate_threshold; /* 1.1, :93 */
+    float pix_scale;       /* 5, :112-113 */
+    int in_format;         /* FSEA_IN_S8 (HackRF captures) or FSEA_IN_U8 */
+    int device;
+    int capacity;          /* frequencies held at once */
+    int own_raw;           /* 1: the engine keeps the raw IQ (needed by submit_host / submit_synth) */
+    int own_images;        /* 1: the engine keeps images [capacity][rows][N] */
+    int reserved[4];
+} fsea_sweep_config;
+int fsea_sweep_create(const fsea_sweep_config *cfg, fsea_sweep **out);
+int fsea_sweep_destroy(fsea_sweep *s);
+/* raw IQ of slot `slot`: from host memory (H2D on the engine's stream), from device memory (used in
+ * place: must stay valid until render), or the SURVEY 8(d) cfg4 synthetic source of centre
+ * frequency freq_idx drawn on the device (noise + one tone whose bin depends on freq_idx; every
+ * quiet_every-th frequency noise-only below the gate).  Asynchronous. */
+int fsea_sweep_submit_host(fsea_sweep *s, int slot, const void *h_raw);
+int fsea_sweep_submit_device(fsea_sweep *s, int slot, const void *d_raw);
+int fsea_sweep_submit_synth(fsea_sweep *s, int slot, int freq_idx, int quiet_every);
+/* gate decisions of slots [0, n_slots): means[n_slots], keep[n_slots] (host); synchronises the engine's stream */
+int fsea_sweep_gate(fsea_sweep *s, int n_slots, double *means, uint8_t *keep);
+/* the same in two halves (one host thread driving several devices): begin queues the work, end waits for it */
+int fsea_sweep_gate_begin(fsea_sweep *s, int n_slots);
+int fsea_sweep_gate_end(fsea_sweep *s, int n_slots, double *means, uint8_t *keep);
+/* pixel rows of slots [0, n_slots).  d_canvas == NULL: into the engine's images.  Otherwise image of
+ * slot j goes to d_canvas + canvas_col0 + j * canvas_col_step, rows canvas_stride bytes apart.  Asynchronous. */
+int fsea_sweep_render(fsea_sweep *s, int n_slots, uint8_t *d_canvas, long canvas_stride, long canvas_col0, long canvas_col_step);
+int fsea_sweep_sync(fsea_sweep *s);
+/* back on the host (tests, small jobs): images of slots [first, first + count) (own_images); raw IQ of a slot */
+int fsea_sweep_read_images(fsea_sweep *s, int first, int count, uint8_t *h_out);
+int fsea_sweep_read_raw(fsea_sweep *s, int slot, uint8_t *h_out);
+uint8_t *fsea_sweep_images(fsea_sweep *s);        /* device pointer, capacity x rows x N (own_images) */
+const void *fsea_sweep_raw(fsea_sweep *s, int slot);   /* device pointer of the slot's raw IQ */
+void *fsea_sweep_stream(fsea_sweep *s);           /* the engine's cudaStream_t */
+long fsea_sweep_launch_count(const fsea_sweep *s);
 
 /* ---- IQ low-pass in front of the path ---------------- */
 

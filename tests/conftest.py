@@ -8,6 +8,13 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+# The CPU suite re-runs the -m gpu tests against the fiber-machine build of the kernel sources
+# (tests/emu, test infrastructure): FSEA_TEST_LIB is read HERE, by the tests -- the product package
+# has no such switch (frequensea_b200.binding resolves its own libfsea.so only).
+if os.environ.get("FSEA_TEST_LIB"):
+    from frequensea_b200 import binding as _binding
+    _binding._use_library(os.environ["FSEA_TEST_LIB"])
+
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 BLOCK = 262144
 
@@ -25,8 +32,17 @@ def _has_gpu() -> bool:
 
 
 def pytest_collection_modifyitems(config, items):
-    # -m gpu on a box without a device must fail loudly, not skip: the product has no CPU path.
-    pass
+    """Plain `pytest tests` on a box without a GPU runs the CPU suite and SKIPS the gpu-marked tests;
+    an explicit `-m gpu` there still fails loudly (the product has no CPU path, and a silent skip of
+    everything would look like a pass)."""
+    if "gpu" in (config.getoption("-m") or ""):
+        return
+    if _has_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device (run with -m gpu on the B200 box)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
 
 
 @pytest.fixture(scope="session")
@@ -74,3 +90,44 @@ def synth_s8(n_samples: int, seed: int = 7) -> np.ndarray:
     out[0::2] = np.clip(np.round(i), -128, 127)
     out[1::2] = np.clip(np.round(q), -128, 127)
     return out.view(np.uint8)
+
+
+class OracleEngine:
+    """TEST stand-in for frequensea_b200.sweep.DeviceEngine (same methods, CPU, the oracle's arithmetic):
+    what the gloo world-2 test runs per rank, and what the GPU job test compares the device engine with."""
+
+    def __init__(self, n, rows, capacity, gate_rows=100, gate_threshold=1.1, pix_scale=5.0):
+        import torch
+        self.n, self.rows, self.capacity = n, rows, capacity
+        self.gate_rows, self.thr, self.scale = min(gate_rows, rows), gate_threshold, pix_scale
+        self.tdev = torch.device("cpu")
+        self.raw = {}
+        self.keep = None
+
+    def submit(self, slot, freq_idx, raw=None, quiet_every=10):
+        assert raw is not None, "the CPU stand-in needs the bytes"
+        self.raw[slot] = np.asarray(raw, dtype=np.uint8)
+
+    def gate(self, n_slots):
+        from oracle import orc
+        means = np.array([orc.engine_batch(self.raw[j], self.n, self.n, self.gate_rows, orc.IN_S8, orc.WIN_NONE, orc.OUT_MAG)
+                          .astype(np.float64).mean() for j in range(n_slots)], dtype=np.float64)
+        self.keep = ~(means < self.thr)
+        return means, self.keep
+
+    def render_images(self, n_slots, per):
+        import torch
+        from oracle import orc
+        img = np.zeros((per, self.rows, self.n), dtype=np.uint8)
+        for j in range(n_slots):
+            if self.keep[j]:
+                img[j] = orc.engine_batch(self.raw[j], self.n, self.n, self.rows, orc.IN_S8, orc.WIN_NONE, orc.OUT_PIX, self.scale,
+                                          flags=orc.FLAG_DC_PATCH)
+        return torch.from_numpy(img)
+
+    def stitch(self, gathered, n_freqs, world, per, width_step):
+        import torch
+        from oracle import orc
+        g = gathered.numpy()
+        images = np.stack([g[(f % world) * per + f // world] for f in range(n_freqs)])
+        return torch.from_numpy(orc.stitch(images, width_step))

@@ -1,8 +1,8 @@
 """TEST INFRASTRUCTURE: parity of the kernel SOURCE, executed on the CPU fiber machine
 (tests/emu/libfsea_emu.so), against the oracle.  Run as a subprocess by
-tests/test_emu_kernels.py with FSEA_LIB pointing at the emulated library.
+tests/test_emu_kernels.py with FSEA_TEST_LIB pointing at the emulated library.
 
-    FSEA_LIB=tests/emu/libfsea_emu.so python tests/emu/check.py <n> [<n> ...]
+    FSEA_TEST_LIB=tests/emu/libfsea_emu.so python tests/emu/check.py <n> [<n> ...]
 """
 import json
 import os
@@ -15,6 +15,8 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import numpy as np  # noqa: E402
 
+from frequensea_b200 import binding as _binding  # noqa: E402
+_binding._use_library(os.environ["FSEA_TEST_LIB"])      # the emulated build, explicitly (the product has no such switch)
 import frequensea_b200 as fb  # noqa: E402
 from conftest import synth_s8, synth_u8  # noqa: E402
 from oracle import orc  # noqa: E402

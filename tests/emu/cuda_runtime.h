@@ -5,7 +5,7 @@
 // source runs on the CPU, every CUDA thread a cooperative fiber (ucontext), so the index
 // arithmetic, barrier placement, shared-memory layout and cp.async discipline of a kernel
 // can be checked against the oracle in the GPU-less authoring container.  It is loaded only
-// by tests/test_emu_kernels.py (through FSEA_LIB-style explicit paths); the product library
+// by tests/test_emu_kernels.py (through an explicit path); the product library
 // (libfsea.so, nvcc, sm_100a) never sees this header and has no CPU path.
 //
 // Semantics worth knowing:
@@ -149,6 +149,11 @@ static inline cudaError_t cudaFreeHost(void* p) { free(p); return cudaSuccess; }
 static inline cudaError_t cudaMemcpy(void* d, const void* s, size_t n, cudaMemcpyKind) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemcpyAsync(void* d, const void* s, size_t n, cudaMemcpyKind, cudaStream_t) { memcpy(d, s, n); return cudaSuccess; }
 static inline cudaError_t cudaMemset(void* d, int v, size_t n) { memset(d, v, n); return cudaSuccess; }
+static inline cudaError_t cudaMemsetAsync(void* d, int v, size_t n, cudaStream_t) { memset(d, v, n); return cudaSuccess; }
+static inline cudaError_t cudaMemset2DAsync(void* d, size_t pitch, int v, size_t w, size_t h, cudaStream_t) {
+    for (size_t y = 0; y < h; y++) memset((char*)d + y * pitch, v, w);
+    return cudaSuccess;
+}
 static inline cudaError_t cudaStreamCreateWithFlags(cudaStream_t* s, int) { *s = (void*)1; return cudaSuccess; }
 static inline cudaError_t cudaStreamSynchronize(cudaStream_t) { return cudaSuccess; }
 static inline cudaError_t cudaStreamDestroy(cudaStream_t) { return cudaSuccess; }

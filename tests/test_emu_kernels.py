@@ -5,8 +5,8 @@ cuda_runtime.h: every CUDA thread is a fiber, barriers / shuffles / cluster barr
 have their CUDA meaning, packed f32x2 arithmetic is two scalar ops with the device's
 contraction rules.  It checks indexing, synchronisation and arithmetic of the kernels a
 reviewer reads; it says nothing about speed.  The emulated library is TEST INFRASTRUCTURE: it
-is never loaded by the product (frequensea_b200 resolves libfsea.so; FSEA_LIB is an explicit
-override used here and by tools/sweep.py A/B runs).  The -m gpu suite repeats every one of
+is never loaded by the product (frequensea_b200 resolves its own libfsea.so; FSEA_TEST_LIB is read by
+tests/conftest.py and tests/emu/check.py, which bind the package to the emulated build explicitly).  The -m gpu suite repeats every one of
 these comparisons on the device through the real library.
 """
 import json
@@ -28,7 +28,7 @@ def emu_lib():
 
 
 def run_check(emu_lib, sizes, **extra_env):
-    env = dict(os.environ, FSEA_LIB=emu_lib, **extra_env)
+    env = dict(os.environ, FSEA_TEST_LIB=emu_lib, **extra_env)
     r = subprocess.run([sys.executable, os.path.join(EMU, "check.py")] + [str(n) for n in sizes],
                        capture_output=True, text=True, env=env, timeout=900)
     assert r.returncode == 0, r.stderr[-3000:]
@@ -85,7 +85,7 @@ def test_emulated_iq_filter_bit_exact(emu_lib):
     from oracle import orc
     if not orc.have_ref():
         pytest.skip("oracle/_ref/libnrf_ref.so not built")
-    env = dict(os.environ, FSEA_LIB=emu_lib)
+    env = dict(os.environ, FSEA_TEST_LIB=emu_lib)
     r = subprocess.run([sys.executable, os.path.join(EMU, "check.py"), "iq_filter"], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
     assert json.loads(r.stdout.strip().splitlines()[-1])[0]["max_abs_diff"] == 0.0
@@ -94,7 +94,7 @@ def test_emulated_iq_filter_bit_exact(emu_lib):
 def test_emulated_capture_file_feed(emu_lib):
     """fsea_exec_file: pread-fed pipeline == host-buffer pipeline, byte offsets,
     overlapping frames, several slots in flight; short / missing / misaligned files are refused."""
-    env = dict(os.environ, FSEA_LIB=emu_lib)
+    env = dict(os.environ, FSEA_TEST_LIB=emu_lib)
     r = subprocess.run([sys.executable, os.path.join(EMU, "check.py"), "file"], capture_output=True, text=True, env=env, timeout=600)
     assert r.returncode == 0, r.stderr[-3000:]
     assert json.loads(r.stdout.strip().splitlines()[-1])[0]["identical"] is True
@@ -106,8 +106,8 @@ def test_gpu_suite_on_the_fiber_machine(emu_lib, tmp_path):
     and every kernel source are exercised before a GPU minute is spent.  Left out: the two tests that
     allocate device memory through torch.  On the B200 box the same tests run against the real library."""
     os.symlink(emu_lib, tmp_path / "libfsea.so")                     # for the Lua host's DT_NEEDED libfsea.so
-    env = dict(os.environ, FSEA_LIB=emu_lib, LD_LIBRARY_PATH=str(tmp_path) + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
+    env = dict(os.environ, FSEA_TEST_LIB=emu_lib, LD_LIBRARY_PATH=str(tmp_path) + os.pathsep + os.environ.get("LD_LIBRARY_PATH", ""))
     r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"),
                         os.path.join(ROOT, "tests", "test_gpu_lua.py"), "-m", "gpu", "-q", "-x", "-p", "no:cacheprovider",
-                        "-k", "not many_frames and not large_batch"], capture_output=True, text=True, env=env, cwd=ROOT, timeout=1500)
+                        "-k", "not many_frames and not large_batch and not sweep_job and not mgpu"], capture_output=True, text=True, env=env, cwd=ROOT, timeout=1500)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-1000:]

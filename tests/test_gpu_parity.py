@@ -453,23 +453,94 @@ def test_capture_file_feed(fbg, iq, tmp_path):
         plan.exec_file(bpath, 65)                          # file too short
 
 
-def test_sweep_workflow_single_gpu(fbg):
-    """BASELINE cfg4 as a job (frequensea_b200/sweep.py): gate (c/fft-batch-broad.c:80-98), pixel rows
-    (:108-118), stitch (c/fft-stitch-broad.c) on the engine == the same job on the oracle; quiet
-    frequencies are gated off.  The N > 1 form of it runs over gloo in tests/test_shard_gloo.py and
-    over NCCL in tools/sweep_demo.py."""
+def test_sweep_engine_device_resident(fbg):
+    """fsea_sweep_* (BASELINE cfg4 per GPU): raw IQ resident once, gate sum on the device
+    (c/fft-batch-broad.c:80-98), pixel rows of the kept frequencies (:108-118), zeros for the others --
+    against the oracle on the same bytes; host-fed and device-drawn (SURVEY 8(d) cfg4 source) frequencies,
+    images in the engine's own store and placed in a stitched canvas (c/fft-stitch-broad.c, WIDTH_STEP = N)."""
+    fb = fbg
     from frequensea_b200 import sweep
-    from test_shard_gloo import OracleOps
+    from frequensea_b200.binding import Sweep
+    n, rows, nf = 1024, 16, 6
+    eng = Sweep(n, rows, nf, gate_rows=8, own_images=True)
+    raws = []
+    for f in range(nf):
+        if f < 3:
+            raw = sweep.synth_frequency(f, n, rows, quiet_every=3)
+            eng.submit_host(f, raw)
+        else:
+            eng.submit_synth(f, f, 3)                       # drawn on the device: read the bytes back for the oracle
+            raw = eng.read_raw(f)
+        raws.append(raw)
+    means, keep = eng.gate(nf)
+    ref_means = np.array([orc.engine_batch(r, n, n, 8, orc.IN_S8, orc.WIN_NONE, orc.OUT_MAG).astype(np.float64).mean() for r in raws])
+    np.testing.assert_allclose(means, ref_means, rtol=1e-5)
+    assert keep.tolist() == [f % 3 != 2 for f in range(nf)]
+    # the device-drawn source: quiet frequencies really are noise-only, the others carry their tone at bin (37 f + 11) mod N
+    for f in (3, 4):
+        mag = orc.engine_batch(raws[f], n, n, 1, orc.IN_S8, orc.WIN_NONE, orc.OUT_MAG, flags=orc.FLAG_DC_PATCH)[0]
+        assert int(np.argmax(mag)) == (37 * f + 11) % n
+    eng.render(nf)
+    images = eng.read_images(0, nf)
+    for f in range(nf):
+        if not keep[f]:
+            assert not images[f].any()
+            continue
+        ref = orc.engine_batch(raws[f], n, n, rows, orc.IN_S8, orc.WIN_NONE, orc.OUT_PIX, 5.0, flags=orc.FLAG_DC_PATCH)
+        d = np.abs(images[f].astype(int) - ref.astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 0.005
+    # deterministic: a second engine fed the same bytes through submit_device / submit_host agrees bit for bit
+    eng2 = Sweep(n, rows, nf, gate_rows=8, own_images=True)
+    for f in range(nf):
+        eng2.submit_host(f, raws[f])
+    means2, keep2 = eng2.gate(nf)
+    assert np.array_equal(means, means2) and np.array_equal(keep, keep2)
+    eng2.render(nf)
+    assert np.array_equal(eng2.read_images(0, nf), images)
+
+
+def test_sweep_job_single_gpu(fbg):
+    """The job (frequensea_b200/sweep.py) on one GPU: device engine == oracle stand-in; the canvas form
+    (pixel rows stored straight into the stitched picture, what mode="p2p" does across GPUs) == gather + stitch.
+    The N > 1 form runs over gloo in tests/test_shard_gloo.py and over NCCL in tools/sweep_demo.py / bench.py."""
+    import torch
+    from frequensea_b200 import sweep
+    from conftest import OracleEngine
     n_freqs, n, rows, step = 6, 1024, 16, 400
     stream = lambda f: sweep.synth_frequency(f, n, rows, quiet_every=3)
-    got = sweep.sweep(sweep.EngineOps(n), n_freqs, stream, n, rows, step, gate_rows=8)
-    ref = sweep.sweep(OracleOps(n), n_freqs, stream, n, rows, step, gate_rows=8)
+    got = sweep.sweep(sweep.DeviceEngine(n, rows, n_freqs, gate_rows=8), n_freqs, n, rows, step, source=stream)
+    ref = sweep.sweep(OracleEngine(n, rows, n_freqs, gate_rows=8), n_freqs, n, rows, step, source=stream)
     assert got["keep"].tolist() == ref["keep"].tolist() == [f % 3 != 2 for f in range(n_freqs)]
     np.testing.assert_allclose(got["means"], ref["means"], rtol=1e-5)
-    d = np.abs(got["images"].astype(int) - ref["images"].astype(int))
+    gi, ri = got["images"].cpu().numpy(), ref["images"].numpy()
+    d = np.abs(gi.astype(int) - ri.astype(int))
     assert d.max() <= 1 and (d > 0).mean() < 0.005
-    assert np.array_equal(got["stitched"], orc.stitch(got["images"], step))     # stitch itself is bit-exact
-    assert got["stitched"].shape == (rows, n + (n_freqs - 1) * step)
+    assert np.array_equal(got["stitched"].cpu().numpy(), orc.stitch(gi, step))     # stitch itself is bit-exact
+    assert tuple(got["stitched"].shape) == (rows, n + (n_freqs - 1) * step)
+    # WIDTH_STEP = N (c/fft-stitch-broad.c with SAMPLE_RATE = FREQUENCY_STEP): canvas stores == gather + stitch
+    a = sweep.sweep(sweep.DeviceEngine(n, rows, n_freqs, gate_rows=8), n_freqs, n, rows, n, source=stream, mode="p2p")
+    b = sweep.sweep(sweep.DeviceEngine(n, rows, n_freqs, gate_rows=8), n_freqs, n, rows, n, source=stream, mode="gather")
+    assert torch.equal(a["stitched"], b["stitched"])
+
+
+def test_mgpu_driver_one_process(fbg):
+    """libfsea_mgpu.so (one process, ncclCommInitAll over the GPUs of the box): the cfg4 job on
+    all visible GPUs (at most 2 here) == the same job on one GPU, bit for bit, in gather mode and with the
+    pixel rows stored straight into device 0's canvas; and == the Python-driven engine.  Runs in a subprocess
+    without torch (the driver links the system NCCL)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    g = min(2, fbg.device_count())
+    for mode in ("gather", "p2p"):
+        r = subprocess.run([sys.executable, os.path.join(root, "tools", "sweep_mgpu.py"), "--gpus", str(g), "--freqs", "10", "--rows", "24",
+                            "--fft-size", "4096", "--mode", mode, "--check", "--f32-gather-mib", "0"], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        res = json.loads(r.stdout.strip().splitlines()[-1])
+        assert res["kept"] == 9 and res["rows_rendered"] == 9 * 24          # frequency 9 is the quiet one (every 10th): gated off
+        if g > 1:
+            assert res["equals_one_gpu_job"]
 
 
 def test_block_graph_filter_into_fft(fbg, iq):

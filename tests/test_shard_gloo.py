@@ -63,37 +63,19 @@ def test_two_rank_scatter_transform_gather(n, hop, n_frames):
     assert ok
 
 
-class OracleOps:
-    """Stand-in for sweep.EngineOps in this CPU suite only (no GPU here): the oracle's arithmetic."""
-    device = 0
-
-    def __init__(self, n):
-        self.n = n
-
-    def gate_mean(self, raw, rows):
-        from oracle import orc
-        return float(orc.engine_batch(raw, self.n, self.n, rows, orc.IN_S8, orc.WIN_NONE, orc.OUT_MAG).astype(np.float64).mean())
-
-    def pixel_rows(self, raw, rows):
-        from oracle import orc
-        return orc.engine_batch(raw, self.n, self.n, rows, orc.IN_S8, orc.WIN_NONE, orc.OUT_PIX, 5.0, flags=orc.FLAG_DC_PATCH)
-
-    def stitch(self, images, step):
-        from oracle import orc
-        return orc.stitch(images, step)
-
-
 def _sweep_worker(rank, world, port, n_freqs, n, rows, step, q):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from frequensea_b200 import sweep
+    from conftest import OracleEngine
     stream = lambda f: sweep.synth_frequency(f, n, rows, quiet_every=4)
-    res = sweep.sweep(OracleOps(n), n_freqs, stream, n, rows, step, rank=rank, world=world, gate_rows=8)
+    per = (n_freqs + world - 1) // world
+    res = sweep.sweep(OracleEngine(n, rows, per, gate_rows=8), n_freqs, n, rows, step, source=stream, rank=rank, world=world)
     if rank == 0:
-        one = sweep.sweep(OracleOps(n), n_freqs, stream, n, rows, step, gate_rows=8)      # the same job on one rank
-        same = all(np.array_equal(res[k], one[k]) for k in ("means", "keep", "images", "stitched"))
-        q.put((bool(same), res["keep"].tolist(), res["stitched"].shape))
+        one = sweep.sweep(OracleEngine(n, rows, n_freqs, gate_rows=8), n_freqs, n, rows, step, source=stream)   # the same job on one rank
+        same = all(np.array_equal(np.asarray(res[k]), np.asarray(one[k])) for k in ("means", "keep", "images", "stitched"))
+        q.put((bool(same), res["keep"].tolist(), tuple(res["stitched"].shape)))
     dist.barrier()
     dist.destroy_process_group()
 
