@@ -399,12 +399,17 @@ def sweep_job(ctx, fb, n_freqs=1000, rows=512, n=16384):
         eng.submit(j, f)
     eng.eng.sync()
     modes = {}
-    for mode in ("p2p", "gather"):
+    resident = _Resident(eng, len(mine))
+    for mode in ("gather", "p2p"):
         try:
+            canvas = sweep.prepare_canvas(eng, n_freqs, n, rows, ctx.rank, ctx.world) if (mode == "p2p" and ctx.world > 1) else None
+            # set-up run (connections, allocator), then the timed one
+            res = sweep.sweep(resident, n_freqs, n, rows, n, rank=ctx.rank, world=ctx.world, mode=mode, keep_images=False, canvas=canvas)
+            del res
             ctx.barrier()
             l0 = eng.launches
             t0 = time.perf_counter()
-            res = sweep.sweep(_Resident(eng, len(mine)), n_freqs, n, rows, n, rank=ctx.rank, world=ctx.world, mode=mode, keep_images=False)
+            res = sweep.sweep(resident, n_freqs, n, rows, n, rank=ctx.rank, world=ctx.world, mode=mode, keep_images=False, canvas=canvas)
             torch.cuda.synchronize()
             dt = ctx.max_over_ranks(time.perf_counter() - t0)[0]
             launches = eng.launches - l0
@@ -415,12 +420,18 @@ def sweep_job(ctx, fb, n_freqs=1000, rows=512, n=16384):
                 # a cheap fingerprint of the 8 GB picture: column sums of every 64th row
                 fp = hashlib.sha256(pic[::64].to(torch.int64).sum(dim=0).cpu().numpy().tobytes()).hexdigest()[:16]
                 modes[mode] = {"seconds": dt, "rows_per_s": kept * rows / dt, "kept": kept, "gated_off": n_freqs - kept,
-                               "picture_shape": list(pic.shape), "picture_fingerprint": fp, "gpu_launches_rank0": launches}
-                if mode == "gather" and "p2p" in modes:
-                    modes[mode]["same_picture_as_p2p"] = modes["p2p"]["picture_fingerprint"] == fp
+                               "picture_shape": list(pic.shape), "picture_fingerprint": fp, "gpu_launches_rank0": launches,
+                               "exchange": ("NCCL gather of u8 images to rank 0 + max-blend stitch there" if mode == "gather" else
+                                            "none: every rank's transform kernel stores its pixel rows into rank 0's canvas (CUDA IPC, NVLink peer stores)")
+                                           if ctx.world > 1 else "one GPU: no exchange"}
+                if mode == "p2p" and "gather" in modes and "picture_fingerprint" in modes["gather"]:
+                    modes[mode]["same_picture_as_gather"] = modes["gather"]["picture_fingerprint"] == fp
                 if "parity" not in out:
                     out["parity"] = _sweep_parity(eng, res, mine, n, rows)
             del res
+            if canvas is not None:
+                canvas[2].close()
+            canvas = None
             torch.cuda.empty_cache()
         except Exception as e:                                    # never lose the bench line over this leg
             modes[mode] = {"error": str(e)[:300]}

@@ -101,6 +101,10 @@ def lib() -> C.CDLL:
     L.fsea_exec_device_strided.argtypes = [vp, vp, vp, l, l, vp]; L.fsea_exec_device_strided.restype = i
     L.fsea_copy_only_host.argtypes = [vp, vp, vp, l]; L.fsea_copy_only_host.restype = i
     L.fsea_host_bind_near_device.argtypes = [i]; L.fsea_host_bind_near_device.restype = i
+    L.fsea_ipc_alloc.argtypes = [i, C.c_size_t, C.POINTER(vp), C.c_char_p]; L.fsea_ipc_alloc.restype = i
+    L.fsea_ipc_open.argtypes = [i, C.c_char_p, C.POINTER(vp)]; L.fsea_ipc_open.restype = i
+    L.fsea_ipc_close.argtypes = [vp]; L.fsea_ipc_close.restype = i
+    L.fsea_ipc_free.argtypes = [vp]; L.fsea_ipc_free.restype = i
     PS = C.POINTER(FseaSweepConfig)
     L.fsea_sweep_create.argtypes = [PS, C.POINTER(vp)]; L.fsea_sweep_create.restype = i
     L.fsea_sweep_destroy.argtypes = [vp]; L.fsea_sweep_destroy.restype = i
@@ -328,6 +332,41 @@ class Sweep:
         if self._h:
             lib().fsea_sweep_destroy(self._h)
             self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class SharedDeviceBuffer:
+    """Device memory another process of the box can store into (fsea_ipc_*): owner side `alloc`, peer side `open`."""
+
+    def __init__(self, ptr: int, nbytes: int, owner: bool, handle: bytes = b""):
+        self.ptr, self.nbytes, self.owner, self.handle = ptr, nbytes, owner, handle
+
+    @classmethod
+    def alloc(cls, device: int, nbytes: int) -> "SharedDeviceBuffer":
+        p = C.c_void_p()
+        h = C.create_string_buffer(64)
+        _check(lib().fsea_ipc_alloc(device, nbytes, C.byref(p), h), "fsea_ipc_alloc")
+        return cls(int(p.value), nbytes, True, h.raw)
+
+    @classmethod
+    def open(cls, device: int, handle: bytes, nbytes: int) -> "SharedDeviceBuffer":
+        p = C.c_void_p()
+        _check(lib().fsea_ipc_open(device, C.create_string_buffer(handle, 64), C.byref(p)), "fsea_ipc_open")
+        return cls(int(p.value), nbytes, False)
+
+    @property
+    def __cuda_array_interface__(self):
+        return {"shape": (self.nbytes,), "typestr": "|u1", "data": (self.ptr, False), "version": 2, "strides": None}
+
+    def close(self) -> None:
+        if self.ptr:
+            (lib().fsea_ipc_free if self.owner else lib().fsea_ipc_close)(C.c_void_p(self.ptr))
+            self.ptr = 0
 
     def __del__(self):
         try:

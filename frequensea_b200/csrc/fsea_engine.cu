@@ -413,7 +413,8 @@ extern "C" long fsea_plan_launch_count(const fsea_plan* p) { return p ? p->launc
 extern "C" const char* fsea_plan_kernel_name(const fsea_plan* p) { return p ? p->ki.name : ""; }
 
 
-static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cudaStream_t stream, int slot = 0, long out_stride = 0) {
+static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cudaStream_t stream, int slot = 0, long out_stride = 0,
+                  long out_group = 0, long out_group_stride = 0) {
     if (n_frames <= 0) return FSEA_OK;
     fsea_kparams kp;
     kp.in = d_in;
@@ -441,6 +442,8 @@ static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cu
     kp.n1 = kp.n2 = 0;
     kp.scratch = nullptr;
     kp.out_stride = out_stride > 0 ? out_stride : (long)p->cfg.fft_size * p->out_elem_bytes;
+    kp.out_group = out_group;
+    kp.out_group_stride = out_group_stride;
     if (p->four) {
         // one launch: a cluster per frame, the intermediate lives in the clusters' L2-resident slots
         const int n = p->cfg.fft_size;
@@ -499,8 +502,9 @@ extern "C" int fsea_exec_device_strided(fsea_plan* p, const void* d_in, void* d_
 }
 
 // the sweep engine (fsea_sweep.cu) launches plans on its own stream
-int fsea_launch_internal(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cudaStream_t stream, long out_stride) {
-    return launch(p, d_in, d_out, n_frames, stream, 0, out_stride);
+int fsea_launch_internal(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cudaStream_t stream, long out_stride, int scratch_slot,
+                         long out_group, long out_group_stride) {
+    return launch(p, d_in, d_out, n_frames, stream, scratch_slot, out_stride, out_group, out_group_stride);
 }
 int fsea_fail_cuda_internal(cudaError_t e, const char* what) { return cuda_fail(e, what); }
 int fsea_plan_elem_bytes_internal(const fsea_plan* p) { return p->out_elem_bytes; }
@@ -772,25 +776,97 @@ __global__ void fsea_stitch_kernel(const uint8_t* __restrict__ img, int n_images
     }
 }
 
+// 16 pixels per thread (one 128-bit load per image that covers them, bytewise max in 4 VMAX.U8x4): the form
+// every real sweep has -- width, step and both buffers multiples of 16
+__global__ void fsea_stitch16_kernel(const uint4* __restrict__ img, int n_images, int rows, int width16, int step16,
+                                     int out_width16, uint4* __restrict__ out, int world, int per) {
+    const long total = (long)rows * out_width16;
+    for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long)gridDim.x * blockDim.x) {
+        const long y = q / out_width16;
+        const int x = (int)(q - y * out_width16);
+        int hi = x / step16;
+        if (hi > n_images - 1) hi = n_images - 1;
+        const int lo = (x - width16 + 1 <= 0) ? 0 : (x - width16 + step16) / step16;
+        uint4 acc = make_uint4(0u, 0u, 0u, 0u);
+        for (int i = lo; i <= hi; i++) {
+            const size_t at = (world == 1) ? (size_t)i : (size_t)(i % world) * per + (size_t)(i / world);
+            const uint4 v = img[(at * rows + y) * width16 + (x - i * step16)];
+            acc.x = __vmaxu4(acc.x, v.x); acc.y = __vmaxu4(acc.y, v.y); acc.z = __vmaxu4(acc.z, v.z); acc.w = __vmaxu4(acc.w, v.w);
+        }
+        out[q] = acc;
+    }
+}
+
+static int stitch_launch(const uint8_t* d_images, int n_images, int world, int per, int rows, int width, int width_step,
+                         uint8_t* d_out, cudaStream_t stream) {
+    const int out_width = width + (n_images - 1) * width_step;
+    if ((width % 16) == 0 && (width_step % 16) == 0 && (((uintptr_t)d_images | (uintptr_t)d_out) & 15) == 0) {
+        const long items = (long)rows * (out_width / 16);
+        const int blocks = (int)std::min<long>((items + 255) / 256, 148 * 32);
+        FSEA_LAUNCH(fsea_stitch16_kernel, blocks, 256, stream, (const uint4*)d_images, n_images, rows, width / 16, width_step / 16,
+                    out_width / 16, (uint4*)d_out, world, per);
+    } else {
+        const long quads = (long)rows * ((out_width + 3) / 4);
+        const int blocks = (int)std::min<long>((quads + 255) / 256, 148 * 16);
+        FSEA_LAUNCH(fsea_stitch_kernel, blocks, 256, stream, d_images, n_images, rows, width, width_step, out_width, d_out, world, per);
+    }
+    CU(cudaGetLastError());
+    return FSEA_OK;
+}
+
 extern "C" int fsea_stitch_device(const uint8_t* d_images, int n_images, int rows, int width, int width_step,
                                   uint8_t* d_out, void* stream) {
     if (!d_images || !d_out || n_images <= 0 || rows <= 0 || width <= 0 || width_step <= 0) return FSEA_ERR_INVALID;
-    const int out_width = width + (n_images - 1) * width_step;
-    const long quads = (long)rows * ((out_width + 3) / 4);
-    const int blocks = (int)std::min<long>((quads + 255) / 256, 148 * 16);
-    FSEA_LAUNCH(fsea_stitch_kernel, blocks, 256, (cudaStream_t)stream, d_images, n_images, rows, width, width_step, out_width, d_out, 1, n_images);
-    CU(cudaGetLastError());
-    return FSEA_OK;
+    return stitch_launch(d_images, n_images, 1, n_images, rows, width, width_step, d_out, (cudaStream_t)stream);
 }
 
 extern "C" int fsea_stitch_sharded_device(const uint8_t* d_images, int n_images, int world, int per_rank, int rows, int width, int width_step,
                                           uint8_t* d_out, void* stream) {
     if (!d_images || !d_out || n_images <= 0 || rows <= 0 || width <= 0 || width_step <= 0 || world <= 0 || per_rank * world < n_images) return FSEA_ERR_INVALID;
-    const int out_width = width + (n_images - 1) * width_step;
-    const long quads = (long)rows * ((out_width + 3) / 4);
-    const int blocks = (int)std::min<long>((quads + 255) / 256, 148 * 16);
-    FSEA_LAUNCH(fsea_stitch_kernel, blocks, 256, (cudaStream_t)stream, d_images, n_images, rows, width, width_step, out_width, d_out, world, per_rank);
-    CU(cudaGetLastError());
+    return stitch_launch(d_images, n_images, world, per_rank, rows, width, width_step, d_out, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ device memory another process of the box can store into
+// A sweep's stitched canvas lives on one GPU; with one process per GPU (torchrun) the other ranks reach it through
+// CUDA IPC: the owner allocates and exports, the others open the 64-byte handle and get a pointer their kernels can
+// store through (peer access over NVLink).
+extern "C" int fsea_ipc_alloc(int device, size_t bytes, void** d_ptr, unsigned char handle[64]) {
+    if (!d_ptr || !handle || bytes == 0) return FSEA_ERR_INVALID;
+#if defined(FSEA_EMU)
+    (void)device; return FSEA_ERR_UNSUPPORTED;
+#else
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    CU(cudaSetDevice(device));
+    CU(cudaMalloc(d_ptr, bytes));
+    cudaIpcMemHandle_t h;
+    cudaError_t e = cudaIpcGetMemHandle(&h, *d_ptr);
+    if (e != cudaSuccess) { cudaFree(*d_ptr); *d_ptr = nullptr; return cuda_fail(e, "cudaIpcGetMemHandle"); }
+    memcpy(handle, &h, 64);
+    return FSEA_OK;
+#endif
+}
+extern "C" int fsea_ipc_open(int device, const unsigned char handle[64], void** d_ptr) {
+    if (!d_ptr || !handle) return FSEA_ERR_INVALID;
+#if defined(FSEA_EMU)
+    (void)device; return FSEA_ERR_UNSUPPORTED;
+#else
+    CU(cudaSetDevice(device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CU(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return FSEA_OK;
+#endif
+}
+extern "C" int fsea_ipc_close(void* d_ptr) {
+#if defined(FSEA_EMU)
+    (void)d_ptr; return FSEA_OK;
+#else
+    if (d_ptr) CU(cudaIpcCloseMemHandle(d_ptr));
+    return FSEA_OK;
+#endif
+}
+extern "C" int fsea_ipc_free(void* d_ptr) {
+    if (d_ptr) CU(cudaFree(d_ptr));
     return FSEA_OK;
 }
 

@@ -122,7 +122,7 @@ fsea_fft4096x_kernel(const fsea_kparams kp) {
         fsea_dft32<f2>(re, im);
         fsea_cross<32>(re, im);                                        // X[t + 64 m] (x), X[t + 64 (m + 32)] (y)
         if (kp.dc_term && t == 0) { re[0].v.x += (float)(N / 2); im[0].v.x += (float)(N / 2); }   // N/2 (1+i) in FFT bin 0
-        uint8_t* row = (uint8_t*)kp.out + (size_t)f * (size_t)kp.out_stride;
+        uint8_t* row = (uint8_t*)kp.out + fsea_out_row(kp, f);
         if (kp.out_mode == FSEA_OUT_MAG) fsea_k64_store<FSEA_OUT_MAG>(kp, row, t, re, im, dc_patch);
         else if (kp.out_mode == FSEA_OUT_LOGMAG) fsea_k64_store<FSEA_OUT_LOGMAG>(kp, row, t, re, im, dc_patch);
         else fsea_k64_store<FSEA_OUT_PIX>(kp, row, t, re, im, dc_patch);

@@ -362,7 +362,7 @@ template <int N, typename V> struct fsea_out {
             live[l] = unit_live && s < kp.n_seq;
             // sequences past the end of the batch (odd tail, idle group) write to a dump row:
             // the stores themselves stay unconditional
-            row[l] = live[l] ? (uint8_t*)kp.out + (size_t)s * (size_t)kp.out_stride : (uint8_t*)kp.dump;
+            row[l] = live[l] ? (uint8_t*)kp.out + fsea_out_row(kp, s) : (uint8_t*)kp.dump;
         }
     }
     template <int OUT> __device__ __forceinline__ void put(int l, int pos, S pwr) const {
@@ -426,7 +426,7 @@ template <int N> struct fsea_out_half {
         lg = kp.lg;
         twh = (const float2*)kp.twh;
         dc = kp.dc_term ? (float)N : 0.0f;                                 // N/2 (1+i) of the 2N-point frame
-        row = unit_live ? (uint8_t*)kp.out + (size_t)unit * (size_t)kp.out_stride : (uint8_t*)kp.dump;
+        row = unit_live ? (uint8_t*)kp.out + fsea_out_row(kp, unit) : (uint8_t*)kp.dump;
     }
     template <int OUT> __device__ __forceinline__ void put(int pos, float pwr) const {
         if (OUT == FSEA_OUT_MAG) ((float*)row)[pos] = fsea_sqrt_approx(pwr);
@@ -1167,7 +1167,7 @@ fsea_fused4_kernel(const fsea_kparams kp) {
         } else {
             __syncthreads();
         }
-        uint8_t* row = (uint8_t*)kp.out + (size_t)f * (size_t)kp.out_stride;
+        uint8_t* row = (uint8_t*)kp.out + fsea_out_row(kp, f);
 #pragma unroll 1
         for (int it = 0; it < BIT; it++) {
             // the block's thread-calls of this pass: first index and stride between a thread's U items

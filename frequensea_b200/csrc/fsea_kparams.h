@@ -7,6 +7,13 @@
 // (c/fft-batch.c:88-89); log_mult / power_gain of fsea_config move the three (c/fft.c:191-196).
 struct fsea_logp { float mul, eps, add; double dmul, deps, dadd; };   // (d*: the fp64 kernels)
 
+struct fsea_kparams;
+// byte offset of output row `f` (frame index) from kparams.out
+#if defined(__CUDACC__) || defined(FSEA_EMU)
+#define FSEA_KP_HD __host__ __device__ inline
+#else
+#define FSEA_KP_HD inline
+#endif
 struct fsea_kparams {
     const void* in;        // raw IQ (8-bit pairs), float2 or double2 samples
     void* out;             // float / uint8 / double rows of N
@@ -27,6 +34,16 @@ struct fsea_kparams {
     uint32_t xor_mask;     // 0x8080 for two's-complement input (FSEA_IN_S8), else 0
     const void* twh;       // "half" kernels: W_2N^i, i < M (butterflies of the last pass), float2
     void* scratch;         // fused four-step: resident clusters x N float2 (the L2-resident intermediate)
+    long out_group;        // > 0: output rows come in groups of this many frames (a sweep frequency's image), group g starting
+    long out_group_stride; //      g * out_group_stride bytes into `out` (images side by side in a stitched canvas); 0: one run of rows
     long out_stride;       // bytes between the starts of consecutive output rows (N x element size when rows are packed;
                            // larger when the rows land inside a wider picture, e.g. a sweep's stitched canvas)
 };
+
+FSEA_KP_HD size_t fsea_out_row(const fsea_kparams& kp, long f) {
+    if (kp.out_group > 0) {
+        const long g = f / kp.out_group;
+        return (size_t)g * (size_t)kp.out_group_stride + (size_t)(f - g * kp.out_group) * (size_t)kp.out_stride;
+    }
+    return (size_t)f * (size_t)kp.out_stride;
+}

@@ -76,6 +76,15 @@ extern "C" int fsea_mgpu_sweep(const fsea_mgpu_sweep_config* cfg, uint8_t* h_sti
     }
     CU(cudaSetDevice(0));
     if (gather) CU(cudaMalloc(&d_gathered, (size_t)G * per * img));
+    if (gather && G > 1) {
+        // first use of a send / recv pair sets up the NVLink connection (100s of ms): do that outside the timed region
+        NC(ncclGroupStart());
+        for (int g = 1; g < G; g++) {
+            NC(ncclSend(fsea_sweep_images(eng[g]), 256, ncclUint8, 0, comm[g], (cudaStream_t)fsea_sweep_stream(eng[g])));
+            NC(ncclRecv(d_gathered + (size_t)g * per * img, 256, ncclUint8, g, comm[0], (cudaStream_t)fsea_sweep_stream(eng[0])));
+        }
+        NC(ncclGroupEnd());
+    }
     if (gather || p2p) {
         CU(cudaMalloc(&d_canvas, (size_t)rows * out_w));
         CU(cudaMemset(d_canvas, 0, (size_t)rows * out_w));

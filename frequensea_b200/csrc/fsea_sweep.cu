@@ -31,11 +31,16 @@ struct fsea_sweep {
     fsea_sweep_config cfg;
     fsea_plan* mag = nullptr;                   // |X| of the gate rows, DC bin included (c/fft-batch-broad.c:84-90 sums every bin)
     fsea_plan* pix = nullptr;                   // pixel rows, S = pix_scale, DC patch
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;              // the engine's stream: submits, decisions, what callers order against
+    // A frequency is a small launch (gate: 100 frames, pixels: 512 frames on 148 SMs): slots are dealt to NS
+    // side streams so that the tails of neighbouring launches overlap; events fork them from / join them to `stream`.
+    static const int NS = 4;
+    cudaStream_t side[NS] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t fork = nullptr, join[NS] = {nullptr, nullptr, nullptr, nullptr};
     size_t raw_bytes = 0, img_bytes = 0;        // per frequency
     uint8_t* d_raw = nullptr;                   // [capacity][raw_bytes]   (own_raw)
     std::vector<const void*> raw_ptr;           // where each slot's raw IQ lives
-    float* d_gate_mag = nullptr;                // gate_rows x N
+    float* d_gate_mag = nullptr;                // NS x gate_rows x N
     double* d_partials = nullptr;               // [capacity][FSEA_SUM_BLOCKS]
     double* d_means = nullptr;
     uint8_t* d_keep = nullptr;
@@ -105,6 +110,11 @@ extern "C" int fsea_sweep_destroy(fsea_sweep* s) {
     if (s->h_means) cudaFreeHost(s->h_means);
     if (s->h_keep) cudaFreeHost(s->h_keep);
     if (s->d_images) cudaFree(s->d_images);
+    for (int k = 0; k < fsea_sweep::NS; k++) {
+        if (s->side[k]) { cudaStreamSynchronize(s->side[k]); cudaStreamDestroy(s->side[k]); }
+        if (s->join[k]) cudaEventDestroy(s->join[k]);
+    }
+    if (s->fork) cudaEventDestroy(s->fork);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
     return FSEA_OK;
@@ -125,11 +135,16 @@ static int sweep_setup(fsea_sweep* s) {
     if ((rc = fsea_plan_create(&pc, &s->pix)) != FSEA_OK) return rc;
     CU(cudaSetDevice(c.device));
     CU(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&s->fork, cudaEventDisableTiming));
+    for (int k = 0; k < fsea_sweep::NS; k++) {
+        CU(cudaStreamCreateWithFlags(&s->side[k], cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&s->join[k], cudaEventDisableTiming));
+    }
     s->raw_bytes = (size_t)c.rows * c.fft_size * 2;
     s->img_bytes = (size_t)c.rows * c.fft_size;
     if (c.own_raw) CU(cudaMalloc(&s->d_raw, s->raw_bytes * c.capacity));
     if (c.own_images) CU(cudaMalloc(&s->d_images, s->img_bytes * c.capacity));
-    CU(cudaMalloc(&s->d_gate_mag, sizeof(float) * (size_t)c.gate_rows * c.fft_size));
+    CU(cudaMalloc(&s->d_gate_mag, sizeof(float) * fsea_sweep::NS * (size_t)c.gate_rows * c.fft_size));
     CU(cudaMalloc(&s->d_partials, sizeof(double) * FSEA_SUM_BLOCKS * (size_t)c.capacity));
     CU(cudaMalloc(&s->d_means, sizeof(double) * c.capacity));
     CU(cudaMalloc(&s->d_keep, (size_t)c.capacity));
@@ -156,11 +171,26 @@ extern "C" int fsea_sweep_create(const fsea_sweep_config* cfg, fsea_sweep** out)
 }
 
 // the gate rows of a slot whose raw IQ is in place: |X| of the first gate_rows rows, summed per block
+static int sweep_fork(fsea_sweep* s) {                       // side streams start behind everything queued on `stream`
+    CU(cudaEventRecord(s->fork, s->stream));
+    for (int k = 0; k < fsea_sweep::NS; k++) CU(cudaStreamWaitEvent(s->side[k], s->fork, 0));
+    return FSEA_OK;
+}
+static int sweep_join(fsea_sweep* s) {                       // ... and `stream` continues behind the side streams
+    for (int k = 0; k < fsea_sweep::NS; k++) {
+        CU(cudaEventRecord(s->join[k], s->side[k]));
+        CU(cudaStreamWaitEvent(s->stream, s->join[k], 0));
+    }
+    return FSEA_OK;
+}
+
 static int sweep_gate_rows(fsea_sweep* s, int slot) {
-    int rc = fsea_launch_internal(s->mag, s->raw_ptr[slot], s->d_gate_mag, s->cfg.gate_rows, s->stream, 0);
-    if (rc != FSEA_OK) return rc;
+    const int k = slot % fsea_sweep::NS;
     const long n = (long)s->cfg.gate_rows * s->cfg.fft_size;
-    FSEA_LAUNCH(fsea_sum_kernel, FSEA_SUM_BLOCKS, 256, s->stream, (const float*)s->d_gate_mag, n, s->d_partials + (size_t)slot * FSEA_SUM_BLOCKS);
+    float* mag = s->d_gate_mag + (size_t)k * n;
+    int rc = fsea_launch_internal(s->mag, s->raw_ptr[slot], mag, s->cfg.gate_rows, s->side[k], 0, k);
+    if (rc != FSEA_OK) return rc;
+    FSEA_LAUNCH(fsea_sum_kernel, FSEA_SUM_BLOCKS, 256, s->side[k], (const float*)mag, n, s->d_partials + (size_t)slot * FSEA_SUM_BLOCKS);
     CU(cudaGetLastError());
     s->launches += 2;
     return FSEA_OK;
@@ -203,10 +233,10 @@ extern "C" int fsea_sweep_gate_begin(fsea_sweep* s, int n_slots) {
     if (!s || n_slots <= 0 || n_slots > s->cfg.capacity) return FSEA_ERR_INVALID;
     for (int j = 0; j < n_slots; j++) if (!s->raw_ptr[j]) return FSEA_ERR_INVALID;
     CU(cudaSetDevice(s->cfg.device));
-    for (int j = 0; j < n_slots; j++) {
-        const int rc = sweep_gate_rows(s, j);
-        if (rc != FSEA_OK) return rc;
-    }
+    int rc = sweep_fork(s);
+    for (int j = 0; j < n_slots && rc == FSEA_OK; j++) rc = sweep_gate_rows(s, j);
+    if (rc == FSEA_OK) rc = sweep_join(s);
+    if (rc != FSEA_OK) return rc;
     const double count = (double)s->cfg.gate_rows * (double)s->cfg.fft_size;
     FSEA_LAUNCH(fsea_gate_decide_kernel, (n_slots + 127) / 128, 128, s->stream, (const double*)s->d_partials, n_slots, count,
                 s->cfg.gate_threshold, s->d_means, s->d_keep);
@@ -239,18 +269,32 @@ extern "C" int fsea_sweep_render(fsea_sweep* s, int n_slots, uint8_t* d_canvas, 
     if (!d_canvas && !s->d_images) return FSEA_ERR_INVALID;
     if (d_canvas && (canvas_stride < n || (canvas_stride & 3) || (canvas_col0 & 3) || (canvas_col_step & 3) || ((uintptr_t)d_canvas & 3))) return FSEA_ERR_INVALID;
     CU(cudaSetDevice(s->cfg.device));
-    for (int j = 0; j < n_slots; j++) {
+    int rc = sweep_fork(s);
+    if (rc != FSEA_OK) return rc;
+    // A run of consecutive kept slots whose raw IQ is contiguous is ONE launch of run x rows frames: the rows of
+    // slot j + q start q * col_step bytes further on (images one after the other, or side by side in a canvas).
+    const long col_step = d_canvas ? canvas_col_step : (long)s->img_bytes;
+    int launches = 0;
+    for (int j = 0; j < n_slots;) {
         uint8_t* dst = d_canvas ? d_canvas + canvas_col0 + (size_t)j * canvas_col_step : s->d_images + (size_t)j * s->img_bytes;
         const long stride = d_canvas ? canvas_stride : (long)n;
-        if (s->keep[j]) {
-            const int rc = fsea_launch_internal(s->pix, s->raw_ptr[j], dst, s->cfg.rows, s->stream, stride);
-            if (rc != FSEA_OK) return rc;
-            s->launches++;
-        } else {
-            CU(cudaMemset2DAsync(dst, (size_t)stride, 0, (size_t)n, (size_t)s->cfg.rows, s->stream));
+        cudaStream_t st = s->side[launches % fsea_sweep::NS];
+        if (!s->keep[j]) {
+            CU(cudaMemset2DAsync(dst, (size_t)stride, 0, (size_t)n, (size_t)s->cfg.rows, st));
+            j++;
+            continue;
         }
+        int run = 1;
+        while (j + run < n_slots && s->keep[j + run] &&
+               (const uint8_t*)s->raw_ptr[j + run] == (const uint8_t*)s->raw_ptr[j] + (size_t)run * s->raw_bytes) run++;
+        rc = fsea_launch_internal(s->pix, s->raw_ptr[j], dst, (long)run * s->cfg.rows, st, stride, launches % fsea_sweep::NS,
+                                  run > 1 ? (long)s->cfg.rows : 0, col_step);
+        if (rc != FSEA_OK) return rc;
+        s->launches++;
+        launches++;
+        j += run;
     }
-    return FSEA_OK;
+    return sweep_join(s);
 }
 
 extern "C" int fsea_sweep_sync(fsea_sweep* s) {

@@ -184,7 +184,7 @@ fsea_ws4_kernel(const fsea_kparams kp) {
                 const int fi = c / CPF, p0 = c - fi * CPF;
                 const long f = g * FPB + fi;
                 const float* yf = Y + (size_t)fi * (2 * N2 * 1024);
-                uint8_t* row = f < frames ? (uint8_t*)kp.out + (size_t)f * (size_t)kp.out_stride : (uint8_t*)kp.dump;
+                uint8_t* row = f < frames ? (uint8_t*)kp.out + fsea_out_row(kp, f) : (uint8_t*)kp.dump;
                 f2 re[U][N2], im[U][N2];
 #pragma unroll
                 for (int uu = 0; uu < U; uu++) fsea_ws_comb_load<N2>(yf, 2 * (p0 + uu * CPF), re[uu], im[uu]);

@@ -112,26 +112,37 @@ class DeviceEngine:
 
 
 def _share_canvas(engine, rows: int, width: int, rank: int, dst: int, group):
-    """The destination's canvas as a device pointer every rank of the box can store through
-    (CUDA IPC under torch's allocator; peer access over NVLink).  Returns (canvas or None, pointer, keep-alive)."""
+    """The destination's canvas as a device pointer every rank of the box can store through (fsea_ipc_*: CUDA IPC,
+    peer access over NVLink).  Returns (canvas tensor on dst or None, pointer, the buffer object to keep alive)."""
     import torch
     import torch.distributed as dist
-    canvas, handle = None, [None]
+    from .binding import SharedDeviceBuffer
+    nbytes = rows * width
+    buf, handle = None, [None]
     if rank == dst:
-        canvas = engine.new_canvas(rows, width)
-        torch.cuda.synchronize(engine.tdev)
-        handle = [canvas.untyped_storage()._share_cuda_()]
+        buf = SharedDeviceBuffer.alloc(engine.device, nbytes)
+        handle = [buf.handle]
     dist.broadcast_object_list(handle, src=dst, group=group)
     if rank == dst:
-        return canvas, canvas.data_ptr(), None
-    h = handle[0]
-    storage = torch.UntypedStorage._new_shared_cuda(*h)
-    return None, storage.data_ptr() + int(h[3]), storage
+        canvas = torch.as_tensor(buf, device=engine.tdev).view(rows, width)     # zero-copy view of the shared allocation
+        canvas.zero_()
+        torch.cuda.synchronize(engine.tdev)
+        dist.barrier(group=group)                                               # nobody stores before the canvas is clear
+        return canvas, buf.ptr, buf
+    buf = SharedDeviceBuffer.open(engine.device, handle[0], nbytes)
+    dist.barrier(group=group)
+    return None, buf.ptr, buf
+
+
+def prepare_canvas(engine, n_freqs: int, n: int, rows: int, rank: int = 0, world: int = 1, dst: int = 0, group=None):
+    """mode="p2p" across ranks: allocate the destination's canvas and share it ONCE (the allocation, the clear and the
+    handle exchange are set-up, not part of a sweep); pass the result to sweep(canvas=...) as often as wanted."""
+    return _share_canvas(engine, rows, n * n_freqs, rank, dst, group)
 
 
 def sweep(engine, n_freqs: int, n: int, rows: int, width_step: int,
           source: Optional[Callable[[int], np.ndarray]] = None, rank: int = 0, world: int = 1, dst: int = 0, group=None,
-          mode: str = "gather", quiet_every: int = 10, keep_images: bool = True) -> Optional[Dict]:
+          mode: str = "gather", quiet_every: int = 10, keep_images: bool = True, canvas=None) -> Optional[Dict]:
     """The whole sweep.  On `dst`: {"means", "keep" (numpy, frequency order), "stitched" (tensor on the engine's
     device, or numpy for a host stand-in), "images" (frequency order, when keep_images and mode == "gather")};
     None elsewhere.  source(f) -> the raw bytes of frequency f; None = the device-drawn 8(d) source."""
@@ -170,12 +181,14 @@ def sweep(engine, n_freqs: int, n: int, rows: int, width_step: int,
 
     res = None
     if mode == "p2p" and width_step == n and nccl:
-        canvas, ptr, alive = _share_canvas(engine, rows, out_width, rank, dst, group)
+        own = canvas is None
+        cv, ptr, alive = _share_canvas(engine, rows, out_width, rank, dst, group) if own else canvas
         engine.render_into(len(mine), ptr, out_width, rank * n, world * n)        # frequency j * world + rank at column (j world + rank) N
         dist.barrier(group=group)                                                 # every rank's stores have landed (render_into synchronised its stream)
-        del alive
         if rank == dst:
-            res = {"stitched": canvas}
+            res = {"stitched": cv, "_shared": alive}                              # (the picture lives in the shared allocation: keep it)
+        elif own:
+            alive.close()
     else:
         img = engine.render_images(len(mine), per)
         if rank == dst:

@@ -212,6 +212,15 @@ const void *fsea_sweep_raw(fsea_sweep *s, int slot);   /* device pointer of the 
 void *fsea_sweep_stream(fsea_sweep *s);           /* the engine's cudaStream_t */
 long fsea_sweep_launch_count(const fsea_sweep *s);
 
+/* Device memory the other processes of the box can store into (one process per GPU: the stitched canvas of a
+ * sweep lives on one rank, the others' transform kernels write their pixel rows into it over NVLink).  alloc:
+ * cudaMalloc + the 64-byte CUDA IPC handle to pass around; open: a pointer valid for kernels of `device` in the
+ * calling process; close / free when done.  FSEA_ERR_UNSUPPORTED where there is no CUDA IPC. */
+int fsea_ipc_alloc(int device, size_t bytes, void **d_ptr, unsigned char handle[64]);
+int fsea_ipc_open(int device, const unsigned char handle[64], void **d_ptr);
+int fsea_ipc_close(void *d_ptr);
+int fsea_ipc_free(void *d_ptr);
+
 /* ---- IQ low-pass in front of the path ---------------- */
 
 /* The FIR evaluation of nrf_iq_filter_get_buffer (src/nrf.c:718-724,759-768):

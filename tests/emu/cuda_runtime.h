@@ -37,6 +37,12 @@ struct dim3 {
     unsigned x, y, z;
     dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
+static inline uint4 make_uint4(unsigned a, unsigned b, unsigned c, unsigned d) { uint4 r; r.x = a; r.y = b; r.z = c; r.w = d; return r; }
+static inline unsigned __vmaxu4(unsigned a, unsigned b) {
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) { const unsigned x = (a >> (8 * i)) & 255u, y = (b >> (8 * i)) & 255u; r |= (x > y ? x : y) << (8 * i); }
+    return r;
+}
 static inline float2 make_float2(float a, float b) { float2 r; r.x = a; r.y = b; return r; }
 static inline float4 make_float4(float a, float b, float c, float d) { float4 r; r.x = a; r.y = b; r.z = c; r.w = d; return r; }
 static inline double2 make_double2(double a, double b) { double2 r; r.x = a; r.y = b; return r; }
