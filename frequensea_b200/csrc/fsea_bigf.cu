@@ -1,0 +1,139 @@
+// fsea_bigf.cu -- float-sample frames longer than 8192 points (FSEA_IN_F32C / FSEA_IN_F64C, N = 16384 .. 65536).
+//
+// The reference's float64 branch (src/nrf.c:607-609: raw doubles from a frequency shifter or an IQ filter)
+// has no length limit below its 131072-sample block.  The fast kernels of this engine take 8-bit IQ above
+// 8192 points; a float frame that long is one spectrum row per device block for a script such as
+// lua/fft-shifted.lua, not a throughput case -- it gets a plain, exact path: a radix-2 Stockham autosort
+// transform in fp64, one launch per stage through two work buffers in global memory (L2-resident for the
+// one-frame use), samples widened on load, |X| / log / pixel and the fftshift rotation in a last launch.
+#include <cuda_runtime.h>
+
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "../../include/fsea.h"
+#include "fsea_internal.h"
+#include "fsea_kparams.h"
+
+#define CU(call)                                                        \
+    do {                                                                \
+        cudaError_t e__ = (call);                                       \
+        if (e__ != cudaSuccess) return fsea_fail_cuda_internal(e__, #call); \
+    } while (0)
+
+struct fsea_bigf {
+    int n = 0, in_format = 0, out_mode = 0, flags = 0;
+    long chunk = 1;                     // frames per pass through the work buffers
+    double2* d_tw = nullptr;            // exp(-2 pi i j / N), j < N/2
+    double2* d_work[2] = {nullptr, nullptr};
+};
+
+// x[n] = w[n] * sample[n]  (src/nrf.c:607-612; the (-1)^n is the output rotation of the last launch)
+__global__ void fsea_bigf_load_kernel(const void* __restrict__ in, int f32, long seq_stride, int n, const float* __restrict__ win,
+                                      double2* __restrict__ out, int gx) {
+    const long f = blockIdx.x / gx;                            // (one-dimensional grid: gx blocks per frame)
+    for (int i = (blockIdx.x % gx) * blockDim.x + threadIdx.x; i < n; i += gx * blockDim.x) {
+        double re, im;
+        if (f32) { const float2 v = ((const float2*)in)[f * seq_stride + i]; re = v.x; im = v.y; }
+        else { const double2 v = ((const double2*)in)[f * seq_stride + i]; re = v.x; im = v.y; }
+        if (win) { const double w = (double)win[i]; re *= w; im *= w; }
+        out[f * n + i] = make_double2(re, im);
+    }
+}
+
+// one radix-2 Stockham stage: ns = 1, 2, 4 .. N/2 sub-transform length going in
+__global__ void fsea_bigf_stage_kernel(const double2* __restrict__ in, double2* __restrict__ out, const double2* __restrict__ tw,
+                                       int n, int ns, int gx) {
+    const long f = blockIdx.x / gx;
+    const int half = n >> 1;
+    for (int j = (blockIdx.x % gx) * blockDim.x + threadIdx.x; j < half; j += gx * blockDim.x) {
+        const int k = j & (ns - 1);
+        const double2 w = tw[(size_t)k * (half / ns)];                 // exp(-2 pi i k / (2 ns))
+        const double2 a = in[f * n + j], b0 = in[f * n + j + half];
+        const double2 b = make_double2(b0.x * w.x - b0.y * w.y, b0.x * w.y + b0.y * w.x);
+        const size_t o = (size_t)f * n + (size_t)(j - k) * 2 + k;
+        out[o] = make_double2(a.x + b.x, a.y + b.y);
+        out[o + ns] = make_double2(a.x - b.x, a.y - b.y);
+    }
+}
+
+// bin k -> position (k + N/2) mod N; magnitude / log / pixel; out[N/2] = out[N/2 - 1] with the DC patch
+__global__ void fsea_bigf_finish_kernel(const double2* __restrict__ x, int n, fsea_kparams kp, int out_f64, long frame0, int gx) {
+    const long f = blockIdx.x / gx;
+    uint8_t* row = (uint8_t*)kp.out + fsea_out_row(kp, frame0 + f);
+    const bool patch = (kp.flags & FSEA_FLAG_DC_PATCH) != 0;
+    for (int p = (blockIdx.x % gx) * blockDim.x + threadIdx.x; p < n; p += gx * blockDim.x) {
+        const int src_pos = (patch && p == n / 2) ? n / 2 - 1 : p;     // src/nrf.c:621-622
+        const int k = (src_pos + n / 2) & (n - 1);
+        const double2 v = x[f * n + k];
+        const double pw = v.x * v.x + v.y * v.y;
+        double val;
+        if (kp.out_mode == FSEA_OUT_MAG) val = sqrt(pw);
+        else val = kp.lg.dmul * log2(pw + kp.lg.deps) + kp.lg.dadd;
+        if (kp.out_mode == FSEA_OUT_PIX) {
+            int q = (int)(val * (double)kp.pix_scale);
+            q = q < 0 ? 0 : (q > 255 ? 255 : q);
+            row[p] = (uint8_t)q;
+        } else if (out_f64) {
+            ((double*)row)[p] = val;
+        } else {
+            ((float*)row)[p] = (float)val;
+        }
+    }
+}
+
+int fsea_bigf_destroy(fsea_bigf* b) {
+    if (!b) return FSEA_OK;
+    if (b->d_tw) cudaFree(b->d_tw);
+    if (b->d_work[0]) cudaFree(b->d_work[0]);
+    if (b->d_work[1]) cudaFree(b->d_work[1]);
+    delete b;
+    return FSEA_OK;
+}
+
+int fsea_bigf_create(int n, int in_format, fsea_bigf** out) {
+    fsea_bigf* b = new fsea_bigf();
+    b->n = n;
+    b->in_format = in_format;
+    b->chunk = std::max<long>(1, (1L << 21) / n);
+    std::vector<double2> tw((size_t)n / 2);
+    const long double PI2 = 6.283185307179586476925286766559005768L;
+    for (int j = 0; j < n / 2; j++) {
+        const long double a = -PI2 * (long double)j / (long double)n;
+        tw[j].x = (double)cosl(a); tw[j].y = (double)sinl(a);
+    }
+    cudaError_t e;
+    if ((e = cudaMalloc(&b->d_tw, tw.size() * sizeof(double2))) != cudaSuccess ||
+        (e = cudaMemcpy(b->d_tw, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMalloc(&b->d_work[0], (size_t)b->chunk * n * sizeof(double2))) != cudaSuccess ||
+        (e = cudaMalloc(&b->d_work[1], (size_t)b->chunk * n * sizeof(double2))) != cudaSuccess) {
+        fsea_bigf_destroy(b);
+        return fsea_fail_cuda_internal(e, "float-frame work buffers");
+    }
+    *out = b;
+    return FSEA_OK;
+}
+
+// kp: the launch's argument block as fsea_engine.cu fills it (in / out / strides / log constants / flags)
+int fsea_bigf_launch(fsea_bigf* b, const fsea_kparams& kp, long n_frames, cudaStream_t stream, long* launches) {
+    const int n = b->n;
+    const int f32 = b->in_format == FSEA_IN_F32C;
+    const int gx = std::min(n / 2 / 256, 32);
+    for (long f0 = 0; f0 < n_frames; f0 += b->chunk) {
+        const long nf = std::min(b->chunk, n_frames - f0);
+        const void* in = f32 ? (const void*)((const float2*)kp.in + f0 * kp.seq_stride) : (const void*)((const double2*)kp.in + f0 * kp.seq_stride);
+        FSEA_LAUNCH(fsea_bigf_load_kernel, (unsigned)(gx * nf), 256, stream, in, f32, kp.seq_stride, n, kp.window, b->d_work[0], gx);
+        int cur = 0;
+        for (int ns = 1; ns < n; ns <<= 1) {
+            FSEA_LAUNCH(fsea_bigf_stage_kernel, (unsigned)(gx * nf), 256, stream, (const double2*)b->d_work[cur], b->d_work[cur ^ 1], (const double2*)b->d_tw, n, ns, gx);
+            cur ^= 1;
+            (*launches)++;
+        }
+        FSEA_LAUNCH(fsea_bigf_finish_kernel, (unsigned)(gx * nf), 256, stream, (const double2*)b->d_work[cur], n, kp, f32 ? 0 : 1, f0, gx);
+        (*launches) += 2;
+        CU(cudaGetLastError());
+    }
+    return FSEA_OK;
+}

@@ -94,6 +94,7 @@ struct fsea_plan {
     static const int TICKET_SLOTS = 64;
     void* d_dump = nullptr;
     // four-step (N = N1 x N2 >= 8192, 8-bit input): both steps in one cluster kernel
+    fsea_bigf* bigf = nullptr;                   // float frames longer than 8192 points (fsea_bigf.cu)
     bool four = false;
     int max_clusters = 0;                        // clusters (frames in flight) resident at once
     fsea_kernel_info4 k4;
@@ -183,6 +184,7 @@ extern "C" int fsea_plan_destroy(fsea_plan* p) {
     if (p->d_tickets) cudaFree(p->d_tickets);
     if (p->d_dump) cudaFree(p->d_dump);
     if (p->d_tw4) cudaFree(p->d_tw4);
+    fsea_bigf_destroy(p->bigf);
     for (int q = 0; q < fsea_plan::SCRATCH_SLOTS; q++) {
         if (p->d_cscratch[q]) cudaFree(p->d_cscratch[q]);
         if (p->scratch_done[q]) cudaEventDestroy(p->scratch_done[q]);
@@ -248,7 +250,8 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
         if (four) want4 = true;
     }
     if (!four) four = want4 && eight && fsea_get_kernel4(n, cfg->window == FSEA_WIN_HANN, cfg->out_mode, alt == 9 ? 0 : alt, &k4);
-    if (!get && !four) return FSEA_ERR_UNSUPPORTED;
+    const bool bigf = !get && !four && !eight && (cfg->in_format == FSEA_IN_F32C || cfg->in_format == FSEA_IN_F64C);   // float frames > 8192 points: fsea_bigf.cu
+    if (!get && !four && !bigf) return FSEA_ERR_UNSUPPORTED;
     if (cfg->in_format < FSEA_IN_U8 || cfg->in_format > FSEA_IN_F64C) return FSEA_ERR_INVALID;
     if (cfg->window != FSEA_WIN_NONE && cfg->window != FSEA_WIN_HANN) return FSEA_ERR_INVALID;
     if (cfg->out_mode < FSEA_OUT_MAG || cfg->out_mode > FSEA_OUT_PIX) return FSEA_ERR_INVALID;
@@ -281,7 +284,12 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
         case FSEA_IN_F32C: p->variant = FSEA_VAR_F32C; p->sample_bytes = 8; break;
         default: p->variant = FSEA_VAR_F64; p->sample_bytes = 16; break;
     }
-    if (four) {
+    if (bigf) {
+        memset(&p->ki, 0, sizeof(p->ki));
+        p->ki.n = n; p->ki.lanes = 1; p->ki.groups = 1; p->ki.threads = 256;
+        p->ki.scalar_bytes = cfg->in_format == FSEA_IN_F64C ? 8 : 4;
+        p->ki.name = cfg->in_format == FSEA_IN_F64C ? "bigf<radix-2 Stockham, fp64, one launch per stage, f64 samples>" : "bigf<radix-2 Stockham, fp64, one launch per stage, f32 samples>";
+    } else if (four) {
         p->four = true;
         p->k4 = k4;
         memset(&p->ki, 0, sizeof(p->ki));   // the step-A transform's shape: tables, lanes, names
@@ -298,6 +306,9 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
     int rc = FSEA_OK;
     do {
         cudaError_t e;
+        if (bigf) {
+            if ((rc = fsea_bigf_create(n, cfg->in_format, &p->bigf)) != FSEA_OK) break;
+        } else {
         if ((rc = setup_kernel(p->ki, cfg->device, &p->max_blocks)) != FSEA_OK) break;
         // staged 8-bit kernels transform integer-scaled samples (b - 128): the 1/256 of
         // src/nrf.c:605-606 rides on the pass-1 twiddles
@@ -377,6 +388,7 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
             }
             if (bad) break;
         }
+        }
         if ((e = cudaMalloc(&p->d_tickets, sizeof(unsigned) * 2 * fsea_plan::TICKET_SLOTS)) != cudaSuccess ||
             (e = cudaMemset(p->d_tickets, 0, sizeof(unsigned) * 2 * fsea_plan::TICKET_SLOTS)) != cudaSuccess) {
             rc = cuda_fail(e, "ticket counters"); break;
@@ -444,6 +456,7 @@ static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cu
     kp.out_stride = out_stride > 0 ? out_stride : (long)p->cfg.fft_size * p->out_elem_bytes;
     kp.out_group = out_group;
     kp.out_group_stride = out_group_stride;
+    if (p->bigf) return fsea_bigf_launch(p->bigf, kp, n_frames, stream, &p->launches);
     if (p->four) {
         // one launch: a cluster per frame, the intermediate lives in the clusters' L2-resident slots
         const int n = p->cfg.fft_size;
@@ -824,6 +837,45 @@ extern "C" int fsea_stitch_sharded_device(const uint8_t* d_images, int n_images,
                                           uint8_t* d_out, void* stream) {
     if (!d_images || !d_out || n_images <= 0 || rows <= 0 || width <= 0 || width_step <= 0 || world <= 0 || per_rank * world < n_images) return FSEA_ERR_INVALID;
     return stitch_launch(d_images, n_images, world, per_rank, rows, width, width_step, d_out, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------ history image on the device
+// nrf_fft keeps H rows of N magnitudes, newest first; the reference scrolls the whole image by one row per frame
+// (src/nrf.c:617, 8 MiB at 1024 x 1024) and, on a retune, every row sideways (src/nrf.c:569-596).  Here the image
+// is a ring of float64 rows in device memory: a new spectrum is ONE row written in place (widened from the fp32
+// kernels' output), the retune scroll is one kernel.
+__global__ void fsea_history_put_kernel(const void* __restrict__ row, int row_is_f64, double* __restrict__ dst, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        dst[i] = row_is_f64 ? ((const double*)row)[i] : (double)((const float*)row)[i];
+}
+// every row scrolled by s bins: s > 0 left (row[i] = old[i + s]), s < 0 right, vacated bins zero (src/nrf.c:580-595)
+__global__ void fsea_history_shift_kernel(const double* __restrict__ src, double* __restrict__ dst, int n, int rows, int s) {
+    const long total = (long)n * rows;
+    for (long q = (long)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (long)gridDim.x * blockDim.x) {
+        const int i = (int)(q % n);
+        const int from = i + s;
+        dst[q] = (from >= 0 && from < n) ? src[q + s] : 0.0;
+    }
+}
+
+extern "C" int fsea_history_put_device(const void* d_row, int row_is_f64, double* d_ring_row, int n, void* stream) {
+    if (!d_row || !d_ring_row || n <= 0) return FSEA_ERR_INVALID;
+    FSEA_LAUNCH(fsea_history_put_kernel, (n + 255) / 256 < 64 ? (n + 255) / 256 : 64, 256, (cudaStream_t)stream, d_row, row_is_f64, d_ring_row, n);
+    CU(cudaGetLastError());
+    return FSEA_OK;
+}
+
+extern "C" int fsea_history_shift_device(const double* d_src, double* d_dst, int n, int rows, int s, void* stream) {
+    if (!d_src || !d_dst || d_src == d_dst || n <= 0 || rows <= 0) return FSEA_ERR_INVALID;
+    if (s >= n || s <= -n) {                                            // everything scrolls out: clear (src/nrf.c:574-577)
+        CU(cudaMemsetAsync(d_dst, 0, sizeof(double) * (size_t)n * rows, (cudaStream_t)stream));
+        return FSEA_OK;
+    }
+    const long total = (long)n * rows;
+    const int blocks = (int)std::min<long>((total + 255) / 256, 148 * 8);
+    FSEA_LAUNCH(fsea_history_shift_kernel, blocks, 256, (cudaStream_t)stream, d_src, d_dst, n, rows, s);
+    CU(cudaGetLastError());
+    return FSEA_OK;
 }
 
 // ------------------------------------------------------------------ device memory another process of the box can store into

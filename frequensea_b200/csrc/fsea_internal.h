@@ -22,3 +22,10 @@ void fsea_count_launch_internal(fsea_plan* p);
 
 #define FSEA_SUM_BLOCKS 256
 __global__ void fsea_sum_kernel(const float* __restrict__ x, long n, double* __restrict__ partial);
+
+// float-sample frames longer than 8192 points (fsea_bigf.cu)
+struct fsea_bigf;
+struct fsea_kparams;
+int fsea_bigf_create(int n, int in_format, fsea_bigf** out);
+int fsea_bigf_destroy(fsea_bigf* b);
+int fsea_bigf_launch(fsea_bigf* b, const fsea_kparams& kp, long n_frames, cudaStream_t stream, long* launches);

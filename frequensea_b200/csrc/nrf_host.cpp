@@ -21,6 +21,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <cuda_runtime.h>
+
+#include <mutex>
+
 #include "fsea.h"
 
 // ---------------------------------------------------------------- fail-stop
@@ -62,19 +66,23 @@ static const int kReplaySampleRate = 5000000;     // what the reference reports 
 // offset-binary u8 convention of nut buffers, publish, run the graph (src/nrf.c:95-131).
 static void device_ingest_block(nrf_device* dev, const uint8_t* raw) {
     if (!dev->receiving) return;
+    // one thread at a time publishes a block and walks the graph behind it: the 60 Hz replay thread and a
+    // caller of nrf_device_publish_now would otherwise both drive the same nrf_fft / filter objects
+    pthread_mutex_lock(&dev->graph_mutex);
     pthread_mutex_lock(&dev->data_mutex);
     const bool flip = dev->device_type != NRF_DEVICE_RTLSDR;
     for (int i = 0; i < NRF_BUFFER_SIZE_BYTES; i++) dev->samples[i] = flip ? (uint8_t)(raw[i] ^ 0x80u) : raw[i];
     pthread_mutex_unlock(&dev->data_mutex);
     if (dev->decode_cb_fn) dev->decode_cb_fn(dev, dev->decode_cb_ctx);
-    if (!dev->receiving) return;
-    nrf_block_process(&dev->block, NULL);
+    if (dev->receiving) nrf_block_process(&dev->block, NULL);
+    pthread_mutex_unlock(&dev->graph_mutex);
 }
 
 static void* device_replay_thread(void* arg) {
     nrf_device* dev = (nrf_device*)arg;
     while (dev->receiving) {
-        device_ingest_block(dev, dev->receive_buffer + (size_t)dev->dummy_block_index * NRF_BUFFER_SIZE_BYTES);
+        // (manual: the caller publishes blocks itself with nrf_device_publish_now -- deterministic replay)
+        if (!dev->manual) device_ingest_block(dev, dev->receive_buffer + (size_t)dev->dummy_block_index * NRF_BUFFER_SIZE_BYTES);
         if (!dev->paused) {                       // src/nrf.c:153-160
             if (++dev->dummy_block_index >= dev->dummy_block_length) dev->dummy_block_index = 0;
         }
@@ -87,6 +95,7 @@ extern "C" nrf_device* nrf_device_new_with_config(const nrf_device_config config
     nrf_device* dev = (nrf_device*)calloc(1, sizeof(nrf_device));
     nrf_block_init(&dev->block, NRF_BLOCK_SOURCE, NULL, (nrf_block_result_fn)nrf_device_get_samples_buffer);
     pthread_mutex_init(&dev->data_mutex, NULL);
+    pthread_mutex_init(&dev->graph_mutex, NULL);
     dev->device_type = NRF_DEVICE_DUMMY;          // no USB SDR drivers in this build
     dev->sample_rate = kReplaySampleRate;
     const char* path = config.data_file;
@@ -147,6 +156,7 @@ extern "C" void nrf_device_step(nrf_device* device) {
 // paused device (nrf_device_set_paused + nrf_device_step, src/nrf.c:341-350) can be replayed
 // block by block without waiting for the 60 Hz producer thread.  Used by tools/fsea-lua --step.
 extern "C" void nrf_device_publish_now(nrf_device* device) {
+    device->manual = 1;                               // from now on only the caller publishes: the replay thread idles
     device_ingest_block(device, device->receive_buffer + (size_t)device->dummy_block_index * NRF_BUFFER_SIZE_BYTES);
 }
 
@@ -162,28 +172,47 @@ extern "C" void nrf_device_free(nrf_device* device) {
     pthread_join(device->receive_thread, NULL);
     free(device->receive_buffer);
     pthread_mutex_destroy(&device->data_mutex);
+    pthread_mutex_destroy(&device->graph_mutex);
     free(device);
 }
 
 // ---------------------------------------------------------------- FFT block
-// Engine state behind nrf_fft::engine.  The staging arrays play the role of
-// the reference's persistent fft_in: a buffer shorter than N samples leaves
-// the tail of the previous call in place (src/nrf.c:599-614 only writes
-// size/2 entries); buffers longer than the reference's 131072-sample fft_in
-// (lua/fft-shifted.lua produces one) are clamped instead of overflowing.
+// Engine state behind nrf_fft::engine.
+//
+// History.  The reference scrolls its whole N x H image by one row on every
+// frame (an 8 MiB memmove at 1024 x 1024, src/nrf.c:617) and on a retune scrolls every row sideways
+// (src/nrf.c:569-596).  Here the image is a RING of float64 rows in DEVICE memory: nrf_fft_process
+// uploads the N samples that matter, the transform writes its row on the device and one small kernel
+// puts it in place of the oldest row -- nothing comes back and nothing is waited for; nrf_fft_shift
+// is one kernel over the ring.  The host keeps a mirror of the ring (fft->buffer) that
+// nrf_fft_get_buffer brings up to date by copying only the rows written since the last call, before
+// it unrolls the ring into the reference's layout (row 0 newest) for the caller's fresh copy.
+//
+// The staging arrays play the role of the reference's persistent fft_in: a buffer shorter than N
+// samples leaves the tail of the previous call in place (src/nrf.c:599-614 only writes size/2
+// entries); buffers longer than the reference's 131072-sample fft_in (lua/fft-shifted.lua produces
+// one) are clamped instead of overflowing.
 struct nrf_fft_engine {
-    // The history image is a RING of rows in fft->buffer: `head` is the row that holds the
-    // newest spectrum.  The reference scrolls the whole N x H image by one row on every frame
-    // (an 8 MiB memmove at 1024 x 1024, src/nrf.c:617); here a frame costs one row write, and
-    // nrf_fft_get_buffer() unrolls the ring into the reference's layout (row 0 newest).
-    int head = 0;
+    std::mutex mu;                   // process / shift / get_buffer may come from the device's producer thread and the script's thread
+    int head = 0;                    // ring row that holds the newest spectrum
+    int dirty = 0;                   // rows written on the device since the host mirror was last brought up to date
     fsea_plan* plan_u8 = nullptr;
     fsea_plan* plan_f64 = nullptr;
-    uint8_t* stage_u8 = nullptr;     // 2N bytes
-    double* stage_f64 = nullptr;     // 2N doubles
-    float* row_f32 = nullptr;        // N
-    double* row_f64 = nullptr;       // N
+    cudaStream_t stream = nullptr;
+    cudaEvent_t staged = nullptr;    // the last upload has left the pinned staging arrays
+    uint8_t* stage_u8 = nullptr;     // 2N bytes, pinned
+    double* stage_f64 = nullptr;     // 2N doubles, pinned
+    void* d_in = nullptr;            // 2N doubles' worth
+    void* d_row = nullptr;           // N doubles' worth: the transform's output row
+    double* d_ring = nullptr;        // H x N, the history
+    double* d_ring_alt = nullptr;    // second buffer of the retune scroll
 };
+
+static void cu_die(cudaError_t e, const char* what) {
+    if (e == cudaSuccess) return;
+    fprintf(stderr, "NRF fatal error: %s: %s\n", what, cudaGetErrorString(e));
+    exit(EXIT_FAILURE);
+}
 
 static fsea_plan* make_plan(int n, int in_format) {
     fsea_config cfg;
@@ -203,47 +232,81 @@ extern "C" nrf_fft* nrf_fft_new(int fft_size, int fft_history_size) {
                    (nrf_block_result_fn)nrf_fft_get_buffer);
     fft->fft_size = fft_size;
     fft->fft_history_size = fft_history_size;
-    fft->buffer = (double*)calloc((size_t)fft_size * (size_t)fft_history_size, sizeof(double));
+    const size_t n = (size_t)fft_size, rows = (size_t)(fft_history_size > 0 ? fft_history_size : 1);
+    fft->buffer = (double*)calloc(n * rows, sizeof(double));
     nrf_fft_engine* eng = new nrf_fft_engine();
-    eng->plan_u8 = make_plan(fft_size, FSEA_IN_U8);
-    eng->stage_u8 = (uint8_t*)calloc(2 * (size_t)fft_size, 1);
-    eng->row_f32 = (float*)calloc((size_t)fft_size, sizeof(float));
+    eng->plan_u8 = make_plan(fft_size, FSEA_IN_U8);          // (fails loudly here for a size the engine does not have)
+    cu_die(cudaStreamCreateWithFlags(&eng->stream, cudaStreamNonBlocking), "nrf_fft_new: stream");
+    cu_die(cudaEventCreateWithFlags(&eng->staged, cudaEventDisableTiming), "nrf_fft_new: event");
+    cu_die(cudaMallocHost((void**)&eng->stage_u8, 2 * n), "nrf_fft_new: staging");
+    cu_die(cudaMallocHost((void**)&eng->stage_f64, 2 * n * sizeof(double)), "nrf_fft_new: staging");
+    memset(eng->stage_u8, 0, 2 * n);
+    memset(eng->stage_f64, 0, 2 * n * sizeof(double));
+    cu_die(cudaMalloc(&eng->d_in, 2 * n * sizeof(double)), "nrf_fft_new: device input");
+    cu_die(cudaMalloc(&eng->d_row, n * sizeof(double)), "nrf_fft_new: device row");
+    cu_die(cudaMalloc((void**)&eng->d_ring, n * rows * sizeof(double)), "nrf_fft_new: history");
+    cu_die(cudaMalloc((void**)&eng->d_ring_alt, n * rows * sizeof(double)), "nrf_fft_new: history");
+    cu_die(cudaMemset(eng->d_ring, 0, n * rows * sizeof(double)), "nrf_fft_new: history");
     fft->engine = eng;
     return fft;
 }
 
 extern "C" void nrf_fft_process(nrf_fft* fft, nut_buffer* buffer) {
     nrf_fft_engine* eng = (nrf_fft_engine*)fft->engine;
+    std::lock_guard<std::mutex> lock(eng->mu);
     const int n = fft->fft_size;
     const size_t have = (size_t)buffer->length * (size_t)buffer->channels / 2;   // complex samples offered
     const size_t take = have < (size_t)n ? have : (size_t)n;                      // only the first N matter
     const int rows = fft->fft_history_size > 0 ? fft->fft_history_size : 1;
     eng->head = (eng->head + rows - 1) % rows;                   // newest row moves "up" by one
-    double* row0 = fft->buffer + (size_t)eng->head * n;
+    double* ring_row = eng->d_ring + (size_t)eng->head * n;
+    cu_die(cudaEventSynchronize(eng->staged), "nrf_fft_process");             // (long since true: the previous upload has left the staging arrays)
     int rc;
     if (buffer->type == NUT_BUFFER_U8) {
         memcpy(eng->stage_u8, buffer->data.u8, 2 * take);
-        rc = fsea_exec_host(eng->plan_u8, eng->stage_u8, eng->row_f32, 1);
-        if (rc != FSEA_OK) nrf_die("nrf_fft_process", rc);
-        for (int i = 0; i < n; i++) row0[i] = (double)eng->row_f32[i];       // D2H moved this one row only
+        cu_die(cudaMemcpyAsync(eng->d_in, eng->stage_u8, 2 * (size_t)n, cudaMemcpyHostToDevice, eng->stream), "nrf_fft_process: upload");
+        cu_die(cudaEventRecord(eng->staged, eng->stream), "nrf_fft_process");
+        rc = fsea_exec_device(eng->plan_u8, eng->d_in, eng->d_row, 1, eng->stream);
+        if (rc == FSEA_OK) rc = fsea_history_put_device(eng->d_row, 0, ring_row, n, eng->stream);
     } else {
-        if (!eng->plan_f64) {
-            eng->plan_f64 = make_plan(n, FSEA_IN_F64C);
-            eng->stage_f64 = (double*)calloc(2 * (size_t)n, sizeof(double));
-            eng->row_f64 = (double*)calloc((size_t)n, sizeof(double));
-        }
+        if (!eng->plan_f64) eng->plan_f64 = make_plan(n, FSEA_IN_F64C);
         memcpy(eng->stage_f64, buffer->data.f64, 2 * take * sizeof(double));
-        rc = fsea_exec_host(eng->plan_f64, eng->stage_f64, eng->row_f64, 1);
-        if (rc != FSEA_OK) nrf_die("nrf_fft_process", rc);
-        memcpy(row0, eng->row_f64, (size_t)n * sizeof(double));
+        cu_die(cudaMemcpyAsync(eng->d_in, eng->stage_f64, 2 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, eng->stream), "nrf_fft_process: upload");
+        cu_die(cudaEventRecord(eng->staged, eng->stream), "nrf_fft_process");
+        rc = fsea_exec_device(eng->plan_f64, eng->d_in, eng->d_row, 1, eng->stream);
+        if (rc == FSEA_OK) rc = fsea_history_put_device(eng->d_row, 1, ring_row, n, eng->stream);
     }
+    if (rc != FSEA_OK) nrf_die("nrf_fft_process", rc);
+    if (eng->dirty < rows) eng->dirty++;
 }
 
-// horizontal scroll of every history row after a retune (src/nrf.c:569-596)
+// the rows written on the device since the last call -> the host mirror (ring order, like the device's)
+static void fft_flush_to_host(nrf_fft* fft, nrf_fft_engine* eng) {
+    const size_t n = (size_t)fft->fft_size, rows = (size_t)(fft->fft_history_size > 0 ? fft->fft_history_size : 1);
+    if (eng->dirty > 0) {
+        // dirty rows are head, head+1, .. (mod rows): at most two contiguous pieces of the ring
+        const size_t first = (size_t)eng->head, count = (size_t)eng->dirty;
+        const size_t a = count < rows - first ? count : rows - first;
+        cu_die(cudaMemcpyAsync(fft->buffer + first * n, eng->d_ring + first * n, a * n * sizeof(double), cudaMemcpyDeviceToHost, eng->stream), "nrf_fft: history download");
+        if (count > a)
+            cu_die(cudaMemcpyAsync(fft->buffer, eng->d_ring, (count - a) * n * sizeof(double), cudaMemcpyDeviceToHost, eng->stream), "nrf_fft: history download");
+        eng->dirty = 0;
+    }
+    cu_die(cudaStreamSynchronize(eng->stream), "nrf_fft: history download");
+}
+
+// horizontal scroll of every history row after a retune (src/nrf.c:569-596): one kernel over the device
+// ring, and the same scroll on the host mirror (which is brought up to date first)
 extern "C" void nrf_fft_shift(nrf_fft* fft, double d) {
-    const int n = fft->fft_size, rows = fft->fft_history_size;
+    nrf_fft_engine* eng = (nrf_fft_engine*)fft->engine;
+    std::lock_guard<std::mutex> lock(eng->mu);
+    const int n = fft->fft_size, rows = fft->fft_history_size > 0 ? fft->fft_history_size : 1;
     const int s = (int)round(n / d);
     if (s == 0) return;
+    fft_flush_to_host(fft, eng);
+    const int rc = fsea_history_shift_device(eng->d_ring, eng->d_ring_alt, n, rows, s, eng->stream);
+    if (rc != FSEA_OK) nrf_die("nrf_fft_shift", rc);
+    double* t = eng->d_ring; eng->d_ring = eng->d_ring_alt; eng->d_ring_alt = t;
     if (abs(s) >= n) {
         memset(fft->buffer, 0, (size_t)n * rows * sizeof(double));
         return;
@@ -262,23 +325,41 @@ extern "C" void nrf_fft_shift(nrf_fft* fft, double d) {
 
 extern "C" nut_buffer* nrf_fft_get_buffer(nrf_fft* fft) {
     nrf_fft_engine* eng = (nrf_fft_engine*)fft->engine;
-    const size_t n = (size_t)fft->fft_size, rows = (size_t)fft->fft_history_size;
+    const size_t n = (size_t)fft->fft_size, rows = (size_t)(fft->fft_history_size > 0 ? fft->fft_history_size : 1);
     nut_buffer* out = nut_buffer_new_f64((int)(n * rows), 1, NULL);
+    std::lock_guard<std::mutex> lock(eng->mu);
+    fft_flush_to_host(fft, eng);
     const size_t head = (size_t)eng->head;
     memcpy(out->data.f64, fft->buffer + head * n, (rows - head) * n * sizeof(double));          // rows head .. H-1
     if (head) memcpy(out->data.f64 + (rows - head) * n, fft->buffer, head * n * sizeof(double)); // rows 0 .. head-1
     return out;
 }
 
+// Extension (not in the reference): the history where it lives.  *d_ring = H x N float64 rows in device memory,
+// ring order; *head = the row holding the newest spectrum (row (head + k) mod H is k frames old).  Valid until the
+// next nrf_fft_shift / nrf_fft_free; work queued by nrf_fft_process is complete when this returns.
+extern "C" void nrf_fft_get_history_device(nrf_fft* fft, const double** d_ring, int* head) {
+    nrf_fft_engine* eng = (nrf_fft_engine*)fft->engine;
+    std::lock_guard<std::mutex> lock(eng->mu);
+    cu_die(cudaStreamSynchronize(eng->stream), "nrf_fft_get_history_device");
+    if (d_ring) *d_ring = eng->d_ring;
+    if (head) *head = eng->head;
+}
+
 extern "C" void nrf_fft_free(nrf_fft* fft) {
     nrf_fft_engine* eng = (nrf_fft_engine*)fft->engine;
     if (eng) {
+        if (eng->stream) cudaStreamSynchronize(eng->stream);
         fsea_plan_destroy(eng->plan_u8);
         fsea_plan_destroy(eng->plan_f64);
-        free(eng->stage_u8);
-        free(eng->stage_f64);
-        free(eng->row_f32);
-        free(eng->row_f64);
+        if (eng->stage_u8) cudaFreeHost(eng->stage_u8);
+        if (eng->stage_f64) cudaFreeHost(eng->stage_f64);
+        if (eng->d_in) cudaFree(eng->d_in);
+        if (eng->d_row) cudaFree(eng->d_row);
+        if (eng->d_ring) cudaFree(eng->d_ring);
+        if (eng->d_ring_alt) cudaFree(eng->d_ring_alt);
+        if (eng->staged) cudaEventDestroy(eng->staged);
+        if (eng->stream) cudaStreamDestroy(eng->stream);
         delete eng;
     }
     free(fft->buffer);          // the reference leaks this (src/nrf.c:637-642)

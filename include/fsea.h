@@ -212,6 +212,14 @@ const void *fsea_sweep_raw(fsea_sweep *s, int slot);   /* device pointer of the 
 void *fsea_sweep_stream(fsea_sweep *s);           /* the engine's cudaStream_t */
 long fsea_sweep_launch_count(const fsea_sweep *s);
 
+/* ---- the history image on the device ----------------
+ * nrf_fft's N x H image (src/nrf.c:617,633-635) as a ring of float64 rows in device memory: put = one new row
+ * (a float32 or float64 spectrum row already on the device) written in place of the oldest; shift = the retune
+ * scroll of every row by s bins, zero fill (src/nrf.c:569-596), from d_src into d_dst (two buffers, swapped by the
+ * caller).  include/nrf.h's nrf_fft_* keep their history this way and copy to the host only in nrf_fft_get_buffer. */
+int fsea_history_put_device(const void *d_row, int row_is_f64, double *d_ring_row, int n, void *stream);
+int fsea_history_shift_device(const double *d_src, double *d_dst, int n, int rows, int s, void *stream);
+
 /* Device memory the other processes of the box can store into (one process per GPU: the stitched canvas of a
  * sweep lives on one rank, the others' transform kernels write their pixel rows into it over NVLink).  alloc:
  * cudaMalloc + the 64-byte CUDA IPC handle to pass around; open: a pointer valid for kernels of `device` in the

@@ -12,8 +12,8 @@
  * follow the reference, so its Lua binding (src/main.cpp:616-717,775-811) and
  * its lua/fft*.lua scripts work against this header unchanged.
  *
- * Out of scope (not declared): live RTL-SDR / HackRF USB drivers, FIR / IQ
- * filter, interpolator, IQ drawing, demodulators, OpenAL player.
+ * Out of scope (not declared): live RTL-SDR / HackRF USB drivers, downsampler,
+ * interpolator, IQ drawing, signal detector, demodulators, OpenAL player.
  */
 #ifndef NRF_H
 #define NRF_H
@@ -92,6 +92,9 @@ struct nrf_device {
     int dummy_block_length;          /* file size / NRF_BUFFER_SIZE_BYTES */
     int dummy_block_index;
     uint8_t samples[NRF_BUFFER_SIZE_BYTES];   /* current block, offset-binary u8 */
+    /* (not in the reference; appended, the layout above is the reference's) */
+    pthread_mutex_t graph_mutex;     /* one thread at a time publishes a block and walks the graph behind it */
+    int manual;                      /* set by nrf_device_publish_now: the replay thread stops publishing */
 };
 
 nrf_device *nrf_device_new(double freq_mhz, const char *data_file);
@@ -102,7 +105,8 @@ void nrf_device_set_paused(nrf_device *device, int paused);
 void nrf_device_step(nrf_device *device);
 nut_buffer *nrf_device_get_samples_buffer(nrf_device *device);
 void nrf_device_free(nrf_device *device);
-/* extension: publish the current block now (deterministic replay of a paused device) */
+/* extension: publish the current block now, on the caller's thread; from the first call on the 60 Hz replay
+ * thread no longer publishes (deterministic replay of a paused device: nrf_device_set_paused + nrf_device_step) */
 void nrf_device_publish_now(nrf_device *device);
 
 /* ---- FFT analysis (src/nrf.h:126-142) ----------------------------------- */
@@ -110,7 +114,9 @@ typedef struct {
     NRF_BLOCK;
     int fft_size;
     int fft_history_size;
-    double *buffer;      /* fft_size x fft_history_size magnitudes, row 0 newest */
+    double *buffer;      /* OPAQUE here: the host mirror of a device-resident RING of fft_history_size rows (not the
+                            reference's "row 0 newest" image, and only as fresh as the last nrf_fft_get_buffer).
+                            Read the history through nrf_fft_get_buffer, which returns the reference's layout. */
     void *engine;        /* opaque; stands where the reference kept
                             fftw_complex *fft_in, *fft_out; fftw_plan fft_plan */
 } nrf_fft;
@@ -120,6 +126,9 @@ void nrf_fft_shift(nrf_fft *fft, double d);
 void nrf_fft_process(nrf_fft *fft, nut_buffer *buffer);
 nut_buffer *nrf_fft_get_buffer(nrf_fft *fft);
 void nrf_fft_free(nrf_fft *fft);
+/* extension: the history where it lives -- fft_history_size x fft_size float64 rows in DEVICE memory, ring order;
+ * *head = the row of the newest spectrum.  Valid until the next nrf_fft_shift / nrf_fft_free. */
+void nrf_fft_get_history_device(nrf_fft *fft, const double **d_ring, int *head);
 
 /* ---- frequency shifter (src/nrf.h:206-221): host pass-through ------------ */
 typedef struct {

@@ -15,6 +15,7 @@ Contents
                             get_buffer, nrf_fft_shift, nrf_freq_shifter_*,
                             nut_buffer_*, nrf_iq_filter_*), FFTW role stubbed by oracle/stubs
 """
+import hashlib
 import os
 import sys
 
@@ -122,6 +123,15 @@ def main():
             out[f"ref_iq_filter_t{taps}_f{half}_tail"] = np.stack([o[-4096:] for o in outs])
             out[f"ref_iq_filter_t{taps}_f{half}_sum"] = np.array([o.sum() for o in outs])
     np.savez_compressed(os.path.join(HERE, "golden_ref.npz"), **out)
+    # BASELINE cfg1 (c/fft-batch.c over rf-200.500-big.raw): the reference transforms the first 1024 samples of every
+    # 262144-byte block -- those 2048 bytes of each of the 100 blocks, and the pixel rows c/fft-batch.c:61-92 makes of
+    # them (oracle restatement: S = 10, no DC patch), so that the 100 rows run where the 26 MB capture is not at hand
+    full = np.fromfile(os.path.join(REF, "rf-200.500-big.raw"), dtype=np.uint8)
+    assert hashlib.sha256(full.tobytes()).hexdigest().startswith("b7318ed7e926eacf")
+    heads = np.ascontiguousarray(full.reshape(100, BLOCK)[:, :2048])
+    ref_pix = np.stack([orc.engine_frame(h, 1024, orc.IN_S8, orc.WIN_NONE, orc.OUT_PIX, 10.0, 0) for h in heads]).astype(np.uint8)
+    np.savez_compressed(os.path.join(HERE, "cfg1_block_heads.npz"), heads=heads, ref_pix=ref_pix)
+    print("cfg1_block_heads", heads.shape, ref_pix.shape, int(ref_pix[0].sum()), int(ref_pix[0, 512]))
     for k, v in out.items():
         print(k, getattr(v, "shape", None))
 

@@ -147,6 +147,42 @@ def test_device_file_replay_semantics(fb, iq, tmp_path):
     nrf.device_free(dev)
 
 
+def test_device_short_capture_file_is_padded_to_one_block(fb, iq, tmp_path):
+    """rfdata/rf-433.000-short.raw is 172144 bytes, less than one 262144-byte block: the reference computes
+    dummy_block_length = size / 262144 = 0 and reads out of bounds (src/nrf.c:268,162-166).  Here the file is
+    padded with silence to one block: the bytes that exist are published ((b+128)%256), the rest is 0x80."""
+    nrf = fb.nrf
+    short = iq["rf433"][:172144]
+    p = tmp_path / "rf-433.000-short.raw"
+    short.tofile(p)
+    dev = nrf.device_new(433.0, str(p))
+    nrf.device_set_paused(dev, True)
+    import time
+    for _ in range(100):                                   # the 60 Hz producer thread publishes the block
+        got = nrf.device_get_samples_buffer(dev).numpy()
+        if got[:64].any():
+            break
+        time.sleep(0.02)
+    assert got.size == 262144
+    assert np.array_equal(got[:172144], orc.device_unpack(short))
+    assert np.all(got[172144:] == 0x80)
+    nrf.device_step(dev)                                   # one block only: stepping wraps to the same block
+    time.sleep(0.05)
+    assert np.array_equal(nrf.device_get_samples_buffer(dev).numpy()[:172144], orc.device_unpack(short))
+    nrf.device_free(dev)
+
+
+def test_mgpu_library_exports_every_declared_symbol(fb):
+    """include/fsea_mgpu.h <-> libfsea_mgpu.so (the one-process NCCL driver): load + symbols, no compute."""
+    path = os.path.join(ROOT, "frequensea_b200", "libfsea_mgpu.so")
+    if not os.path.exists(path):
+        fb.build()
+    fb.lib()                                               # libfsea.so first (DT_NEEDED by rpath too)
+    L = C.CDLL(path)
+    for name in sorted(_declared("fsea_mgpu.h")):
+        assert hasattr(L, name), name
+
+
 def test_fir_coefficients_match_reference_golden(fb, golden):
     """nrf_fir_get_low_pass_coefficients (src/nrf.c:654-676): host code, no device needed -- bit-identical to
     the coefficients recorded from the compiled reference, odd and even lengths."""

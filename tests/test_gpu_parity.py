@@ -230,6 +230,82 @@ def test_scope_row_matches_c_fft(fbg, iq, n):
     assert np.max(np.abs(got - ref)[ok]) < 2e-3, plan.kernel_name
 
 
+def test_glsl_log_power_consumer_constants(fbg, iq):
+    """the fragment shader of lua/fft-shifted.lua:19-35 turns the two texture channels into
+    v = 10 ln(r^2 + g^2 + 1e-20) * 0.02.  With the spectrum's re / im as the channels that is LOGMAG with
+    log_mult = 0.2 ln 10 and power_gain = 1: checked at exactly those constants against float64."""
+    fb = fbg
+    raw = iq["rf433"]
+    n, frames = 1024, 16
+    plan = fb.Plan(n, in_format=fb.IN_S8, out_mode=fb.OUT_LOGMAG, log_mult=0.2 * np.log(10.0), power_gain=1.0)
+    got = plan.exec_host(raw, frames).astype(np.float64)
+    mag = oracle_rows(raw, n, n, frames, orc.IN_S8, orc.WIN_NONE, orc.OUT_MAG).astype(np.float64)
+    ref = 10.0 * np.log(mag ** 2 + 1.0e-20) * 0.02
+    ok = mag >= 1e-3 * np.sqrt(np.mean(mag ** 2, axis=1, keepdims=True))
+    assert ok.mean() > 0.95
+    assert np.max(np.abs(got - ref)[ok]) < 0.2 * np.log(10.0) / 10.0 * 2e-3     # the 2e-3 dB bound in the shader's units
+
+
+@pytest.mark.parametrize("n", [16384, 65536])
+def test_float_frames_above_8192_points(fbg, n):
+    """FSEA_IN_F64C / F32C above 8192 points (the reference's float64 branch, src/nrf.c:607-609, has no such
+    limit below its 131072-sample block): the plain fp64 path of fsea_bigf.cu, to 1e-11 of the oracle; and the
+    nrf_fft operator at that size fed by a float64 buffer, as lua/fft-shifted.lua feeds it."""
+    fb = fbg
+    rng = np.random.default_rng(n)
+    x = rng.normal(0, 1, 2 * 2 * n) + 0.5
+    plan = fb.Plan(n, in_format=fb.IN_F64C, out_mode=fb.OUT_MAG, flags=fb.FLAG_DC_PATCH)
+    got = plan.exec_host(x, 2)
+    ref = np.stack([orc.engine_frame(x[f * 2 * n:], n, orc.IN_F64C, orc.WIN_NONE, orc.OUT_MAG, flags=orc.FLAG_DC_PATCH) for f in range(2)])
+    assert got.dtype == np.float64 and np.max(np.abs(got - ref)) < 1e-11 * np.sqrt(np.mean(ref ** 2))
+    assert np.array_equal(got[:, n // 2], got[:, n // 2 - 1])
+    xf = x.astype(np.float32)
+    plan = fb.Plan(n, in_format=fb.IN_F32C, window=fb.WIN_HANN, out_mode=fb.OUT_LOGMAG)
+    got = plan.exec_host(xf, 2).astype(np.float64)
+    ref = np.stack([orc.engine_frame(xf[f * 2 * n:], n, orc.IN_F32C, orc.WIN_HANN, orc.OUT_LOGMAG) for f in range(2)])
+    assert np.max(np.abs(got - ref)) < 2e-3
+    nrf = fb.nrf
+    fft = nrf.fft_new(n, 2)
+    buf = nrf.nut_buffer_new_f64(n, 2, x[:2 * n])
+    nrf.fft_process(fft, buf)
+    row = nrf.fft_get_buffer(fft).numpy()[:n]
+    ref = orc.engine_frame(x, n, orc.IN_F64C, orc.WIN_NONE, orc.OUT_MAG, flags=orc.FLAG_DC_PATCH)
+    assert np.max(np.abs(row - ref)) < 1e-11 * np.sqrt(np.mean(ref ** 2))
+    nrf.fft_free(fft)
+
+
+def test_fft_batch_all_blocks_of_the_big_capture(fbg):
+    """BASELINE cfg1 (c/fft-batch.c over rfdata/rf-200.500-big.raw): ALL 100 blocks of the capture, where the file is
+    at hand (the authoring container; its sha256 is checked) -- the reference's semantics (one 1024-point row
+    per 262144-byte block, first 1024 samples, S = 10, no DC patch, c/fft-batch.c:54-102) and every one of the
+    12800 non-overlapping frames -- against the oracle.  Elsewhere the committed fixture holds the first frame of
+    every block (tests/golden/cfg1_block_heads.npz), so the 100 reference rows run on the GPU box too."""
+    import hashlib
+    fb = fbg
+    n = 1024
+    big = "/root/reference/rfdata/rf-200.500-big.raw"
+    heads = np.load(os.path.join(os.path.dirname(__file__), "golden", "cfg1_block_heads.npz"))
+    plan = fb.Plan(n, hop=n, in_format=fb.IN_S8, out_mode=fb.OUT_PIX, pix_scale=10.0)
+    got = plan.exec_host(heads["heads"].reshape(-1), 100)                     # 100 blocks x first 1024 samples
+    d = np.abs(got.astype(int) - heads["ref_pix"].astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 0.005
+    assert got[0, 512] == 255 and int(heads["ref_pix"][0].sum()) == 23772       # SURVEY 8(c) goldens: block 0
+    if not os.path.exists(big):
+        return
+    raw = np.fromfile(big, dtype=np.uint8)
+    assert hashlib.sha256(raw.tobytes()).hexdigest().startswith("b7318ed7e926eacf") and raw.size == 100 * BLOCK
+    assert np.array_equal(raw.reshape(100, BLOCK)[:, :2 * n], heads["heads"])
+    frames = raw.size // (2 * n)
+    assert frames == 12800
+    mag = fb.Plan(n, hop=n, in_format=fb.IN_S8, out_mode=fb.OUT_MAG).exec_host(raw, frames)
+    ref = orc.engine_batch(raw, n, n, frames, orc.IN_S8, orc.WIN_NONE, orc.OUT_MAG).astype(np.float64)
+    assert rel_err(mag.astype(np.float64), ref) < MAG_TOL
+    pix = plan.exec_host(raw, frames)
+    refp = orc.engine_batch(raw, n, n, frames, orc.IN_S8, orc.WIN_NONE, orc.OUT_PIX, 10.0)
+    d = np.abs(pix.astype(int) - refp.astype(int))
+    assert d.max() <= 1 and (d > 0).mean() < 0.005
+
+
 def test_sweep_stitch(fbg, iq):
     """Sweep product: per-frequency pixel images (c/fft-batch-broad.c rows) max-blended side by side
     (c/fft-stitch-broad.c), against the oracle.  Four 'frequencies' = the four capture blocks."""
