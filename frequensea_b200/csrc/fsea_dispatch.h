@@ -52,7 +52,8 @@ FSEA_DECL_SIZE(8192)
 struct fsea_kernel_info4 {
     const void* fn;          // __global__ entry
     int cs;                  // blocks per cluster (1: plain launch, one block per frame)
-    int ws;                  // 1: fsea_ws4_kernel (no L2 intermediate, one block per SM)
+    int ws;                  // > 0: warp-specialised kernel (no L2 intermediate, one block per SM), frames per block iteration
+    int tma;                 // 1: fsea_wsc_kernel -- takes a tensor map of the input as its second argument
     int threads;             // block size
     size_t smem;             // dynamic shared memory per block
     int n1, n2;              // sub-spectrum length, sub-sequences
@@ -64,3 +65,5 @@ struct fsea_kernel_info4 {
 bool fsea_get_kernel4(int n, bool window, int out_mode, int alt, fsea_kernel_info4* out);
 // warp-specialised block-per-frame kernel with the intermediate in shared memory (fsea_ws4.cuh)
 bool fsea_get_kernel_ws4(int n, bool window, int out_mode, fsea_kernel_info4* out);
+// ... spread over a cluster, intermediate in distributed shared memory, raw tiles by TMA (fsea_wsc.cuh): N = 32768, 65536
+bool fsea_get_kernel_wsc(int n, bool window, int out_mode, fsea_kernel_info4* out);

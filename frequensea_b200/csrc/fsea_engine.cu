@@ -244,9 +244,10 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
     bool four = false;
     int ws_env = -1;
     if (const char* ev = getenv("FSEA_WS")) ws_env = atoi(ev);                       // A/B runs: 0 = never, 1 = wherever it exists
-    const bool ws_default = (n == 16384);
-    if (eight && cfg->arith == FSEA_ARITH_AUTO && alt == 0 && (ws_env < 0 ? ws_default : ws_env != 0) && (n == 4096 || n == 8192 || n == 16384)) {
-        four = fsea_get_kernel_ws4(n, cfg->window == FSEA_WIN_HANN, cfg->out_mode, &k4);
+    const bool ws_default = (n == 16384 || n == 32768);      // measured: DESIGN.md 3.3 (65536: the L2 cluster kernel is still ahead, 3.68 vs 3.40 M frames/s)
+    if (eight && cfg->arith == FSEA_ARITH_AUTO && alt == 0 && (ws_env < 0 ? ws_default : ws_env != 0) && n >= 4096) {
+        four = n <= 16384 ? fsea_get_kernel_ws4(n, cfg->window == FSEA_WIN_HANN, cfg->out_mode, &k4)
+                          : fsea_get_kernel_wsc(n, cfg->window == FSEA_WIN_HANN, cfg->out_mode, &k4);
         if (four) want4 = true;
     }
     if (!four) four = want4 && eight && fsea_get_kernel4(n, cfg->window == FSEA_WIN_HANN, cfg->out_mode, alt == 9 ? 0 : alt, &k4);
@@ -425,6 +426,45 @@ extern "C" long fsea_plan_launch_count(const fsea_plan* p) { return p ? p->launc
 extern "C" const char* fsea_plan_kernel_name(const fsea_plan* p) { return p ? p->ki.name : ""; }
 
 
+// The input of a launch as a 3-d TMA tensor of bytes: [frame][row n1 of 2 N2 bytes][byte], box = 16 bytes x 256 rows
+// (fsea_wsc.cuh fetches a block's 32-byte column slice of a frame with 8 such boxes).  cuTensorMapEncodeTiled comes
+// from the driver through the runtime's entry-point query: libfsea.so does not link libcuda.
+#if !defined(FSEA_EMU)
+typedef CUresult (*fsea_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+#endif
+static int make_input_tmap(fsea_tmap* tm, const void* d_in, int n2, long hop, long n_frames) {
+#if defined(FSEA_EMU)
+    tm->base = (const unsigned char*)d_in;
+    tm->dim[0] = 2ull * n2; tm->dim[1] = 1024; tm->dim[2] = (unsigned long long)n_frames;
+    tm->stride[0] = 1; tm->stride[1] = 2ull * n2; tm->stride[2] = 2ull * hop;
+    tm->box[0] = 16; tm->box[1] = 256; tm->box[2] = 1;
+    return FSEA_OK;
+#else
+    static fsea_encode_tiled_fn encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        CU(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
+        if (!fn || qr != cudaDriverEntryPointSuccess) return FSEA_ERR_UNSUPPORTED;
+        encode = (fsea_encode_tiled_fn)fn;
+    }
+    const cuuint64_t dims[3] = {(cuuint64_t)(2 * n2), 1024, (cuuint64_t)n_frames};
+    const cuuint64_t strides[2] = {(cuuint64_t)(2 * n2), (cuuint64_t)(2 * hop)};          // bytes, dimensions 1 and 2
+    const cuuint32_t box[3] = {16, 256, 1};
+    const cuuint32_t estr[3] = {1, 1, 1};
+    const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, const_cast<void*>(d_in), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return FSEA_ERR_CUDA;
+    }
+    return FSEA_OK;
+#endif
+}
+
 static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cudaStream_t stream, int slot = 0, long out_stride = 0,
                   long out_group = 0, long out_group_stride = 0) {
     if (n_frames <= 0) return FSEA_OK;
@@ -466,7 +506,12 @@ static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cu
         kp.scratch = p->d_cscratch[slot];
         kp.ticket = nullptr;
         const long nc = p->k4.ws ? std::min<long>((n_frames + p->k4.ws - 1) / p->k4.ws, p->max_clusters) : std::min<long>(n_frames, p->max_clusters);
-        void* af[] = {&kp};
+        fsea_tmap tmap;
+        void* af[] = {&kp, &tmap};
+        if (p->k4.tma) {
+            const int trc = make_input_tmap(&tmap, d_in, p->k4.n2, p->hop, n_frames);
+            if (trc != FSEA_OK) return trc;
+        }
         if (p->k4.cs > 1) {
             cudaLaunchConfig_t lc;
             memset(&lc, 0, sizeof(lc));

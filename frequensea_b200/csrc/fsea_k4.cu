@@ -16,6 +16,7 @@ static bool fill_fused(fsea_kernel_info4* o, bool window, int out_mode, const ch
 #undef FSEA_FUSED
     o->cs = CS;
     o->ws = 0;
+    o->tma = 0;
     o->threads = SHA::T * C::G;
     o->smem = C::SMEM;
     o->n1 = SHA::N; o->n2 = N2;

@@ -1021,6 +1021,54 @@ template <int OUT, int N1, int N2> struct fsea_comb {
 // X[m] = A_m + W64^m B_m, X[m+32] = A_m - W64^m B_m across the lanes (fsea_cross64, scalar).
 // Twiddle pairs w[j] = (W^{2j k}, W^{(2j+1) k}) = w[j - low] * W^{2 low k}: the chain runs on
 // packed registers with a broadcast scalar factor.
+// (twiddle and finish as free functions: fsea_wsc.cuh feeds them from shared memory)
+__device__ __forceinline__ void fsea_comb64_twiddle(const fsea_kparams& kp, int N1, int k, f2* re, f2* im) {
+    float bc[6], bs[6];                                                      // W^(2^r k), r < 6
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+        bc[r] = __ldg((const float*)kp.tw4 + (size_t)(2 * r) * N1 + k);
+        bs[r] = __ldg((const float*)kp.tw4 + (size_t)(2 * r + 1) * N1 + k);
+    }
+    f2 wr[32], wi[32];
+    wr[0] = mk2(1.0f, bc[0]); wi[0] = mk2(0.0f, bs[0]);
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+        if (j > 0) {
+            const int low = j & -j;
+            const int r = (low == 1) ? 1 : (low == 2) ? 2 : (low == 4) ? 3 : (low == 8) ? 4 : 5;   // W^{2 low k}
+            const int q = j - low;
+            wr[j] = vfnmas(wi[q], bs[r], vmuls(wr[q], bc[r]));               // wr c - wi s
+            wi[j] = vfmas(wr[q], bs[r], vmuls(wi[q], bc[r]));                // wr s + wi c
+        }
+        const f2 a = vsub(vmul(re[j], wr[j]), vmul(im[j], wi[j]));
+        im[j] = vfma2(re[j], wi[j], vmul(im[j], wr[j]));
+        re[j] = a;
+    }
+}
+template <int OUT, int N1>
+__device__ __forceinline__ void fsea_comb64_finish(const fsea_kparams& kp, int k, uint8_t* row, bool dc_patch, f2* re, f2* im) {
+    constexpr int ESZ = (OUT == FSEA_OUT_PIX) ? 1 : 4;
+    fsea_dft32<f2>(re, im);
+    fsea_cross<32>(re, im);                                                   // lanes: (X[m], X[m+32])
+    if (kp.dc_term && k == 0) { re[0].v.x += 32.0f * (float)N1; im[0].v.x += 32.0f * (float)N1; }     // N/2 (1+i)
+#pragma unroll
+    for (int m = 0; m < 32; m++) {
+        const f2 pw = vfma2(re[m], re[m], vmul(im[m], im[m]));
+        __align__(8) unsigned char tmp[8];
+        fsea_tile_put<OUT>(tmp, pw, kp.pix_scale, kp.lg);
+        uint8_t* d0 = row + ((size_t)k + (size_t)N1 * (m + 32)) * ESZ;       // bin k + N1 m        (lane x)
+        uint8_t* d1 = row + ((size_t)k + (size_t)N1 * m) * ESZ;              // bin k + N1 (m + 32) (lane y)
+        if (!(m == 0 && dc_patch && k == 0)) {                               // bin 0 is not stored (src/nrf.c:621-622)
+            if (ESZ == 4) fsea_st_stream((float*)d0, ((const float*)tmp)[0]); else d0[0] = tmp[0];
+        }
+        if (ESZ == 4) fsea_st_stream((float*)d1, ((const float*)tmp)[1]); else d1[0] = tmp[1];
+        if (m == 31 && dc_patch && k == N1 - 1) {                            // bin N-1 also fills the DC slot N/2
+            uint8_t* dc = row + (size_t)32 * N1 * ESZ;
+            if (ESZ == 4) *(float*)dc = ((const float*)tmp)[1]; else dc[0] = tmp[1];
+        }
+    }
+}
+
 template <int OUT, int N1> struct fsea_comb<OUT, N1, 64> {
     static const int ESZ = (OUT == FSEA_OUT_PIX) ? 1 : 4;
     static const int U = 1;
@@ -1035,47 +1083,9 @@ template <int OUT, int N1> struct fsea_comb<OUT, N1, 64> {
             const float2 b = __ldcg(y + (size_t)(32 + j) * N1);
             re[j] = mk2(a.x, a.y); im[j] = mk2(b.x, b.y);
         }
-        float bc[6], bs[6];                                                      // W^(2^r k), r < 6
-#pragma unroll
-        for (int r = 0; r < 6; r++) {
-            bc[r] = __ldg((const float*)kp.tw4 + (size_t)(2 * r) * N1 + k);
-            bs[r] = __ldg((const float*)kp.tw4 + (size_t)(2 * r + 1) * N1 + k);
-        }
-        f2 wr[32], wi[32];
-        wr[0] = mk2(1.0f, bc[0]); wi[0] = mk2(0.0f, bs[0]);
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-            if (j > 0) {
-                const int low = j & -j;
-                const int r = (low == 1) ? 1 : (low == 2) ? 2 : (low == 4) ? 3 : (low == 8) ? 4 : 5;   // W^{2 low k}
-                const int q = j - low;
-                wr[j] = vfnmas(wi[q], bs[r], vmuls(wr[q], bc[r]));               // wr c - wi s
-                wi[j] = vfmas(wr[q], bs[r], vmuls(wi[q], bc[r]));                // wr s + wi c
-            }
-            const f2 a = vsub(vmul(re[j], wr[j]), vmul(im[j], wi[j]));
-            im[j] = vfma2(re[j], wi[j], vmul(im[j], wr[j]));
-            re[j] = a;
-        }
+        fsea_comb64_twiddle(kp, N1, k, re, im);
         if (ARRIVE == 1) fsea_cluster_arrive_relaxed();
-        fsea_dft32<f2>(re, im);
-        fsea_cross<32>(re, im);                                                   // lanes: (X[m], X[m+32])
-        if (kp.dc_term && k == 0) { re[0].v.x += 32.0f * (float)N1; im[0].v.x += 32.0f * (float)N1; }     // N/2 (1+i)
-#pragma unroll
-        for (int m = 0; m < 32; m++) {
-            const f2 pw = vfma2(re[m], re[m], vmul(im[m], im[m]));
-            __align__(8) unsigned char tmp[8];
-            fsea_tile_put<OUT>(tmp, pw, kp.pix_scale, kp.lg);
-            uint8_t* d0 = row + ((size_t)k + (size_t)N1 * (m + 32)) * ESZ;       // bin k + N1 m        (lane x)
-            uint8_t* d1 = row + ((size_t)k + (size_t)N1 * m) * ESZ;              // bin k + N1 (m + 32) (lane y)
-            if (!(m == 0 && dc_patch && k == 0)) {                               // bin 0 is not stored (src/nrf.c:621-622)
-                if (ESZ == 4) fsea_st_stream((float*)d0, ((const float*)tmp)[0]); else d0[0] = tmp[0];
-            }
-            if (ESZ == 4) fsea_st_stream((float*)d1, ((const float*)tmp)[1]); else d1[0] = tmp[1];
-            if (m == 31 && dc_patch && k == N1 - 1) {                            // bin N-1 also fills the DC slot N/2
-                uint8_t* dc = row + (size_t)32 * N1 * ESZ;
-                if (ESZ == 4) *(float*)dc = ((const float*)tmp)[1]; else dc[0] = tmp[1];
-            }
-        }
+        fsea_comb64_finish<OUT, N1>(kp, k, row, dc_patch, re, im);
     }
 };
 

@@ -183,3 +183,187 @@ __device__ __forceinline__ unsigned fsea_shfl_idx(unsigned v, int src_lane) {   
     return r;
 #endif
 }
+
+
+// ---- distributed shared memory, mbarriers, TMA (the cluster kernel of fsea_wsc.cuh) -------------------
+// fsea_cptr: an address in the shared memory of a block of this cluster (shared::cluster window).
+#if defined(FSEA_EMU)
+typedef unsigned char* fsea_cptr;
+struct fsea_tmap { const unsigned char* base; unsigned long long dim[3], stride[3]; unsigned box[3]; };   // stand-in for CUtensorMap
+#else
+#include <cuda.h>
+typedef uint32_t fsea_cptr;
+typedef CUtensorMap fsea_tmap;
+#endif
+
+__device__ __forceinline__ fsea_cptr fsea_mapa(const void* local_smem, unsigned cta_rank) {
+#if defined(FSEA_EMU)
+    return fsea_emu::map_cluster((unsigned char*)local_smem, cta_rank);
+#else
+    uint32_t r;
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(local_smem);
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(cta_rank));
+    return r;
+#endif
+}
+__device__ __forceinline__ void fsea_st_cluster(fsea_cptr p, int byte_off, float v) {
+#if defined(FSEA_EMU)
+    *(float*)(p + byte_off) = v;
+#else
+    asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(p + (uint32_t)byte_off), "f"(v) : "memory");
+#endif
+}
+__device__ __forceinline__ void fsea_st_cluster(fsea_cptr p, int byte_off, float2 v) {
+#if defined(FSEA_EMU)
+    *(float2*)(p + byte_off) = v;
+#else
+    asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(p + (uint32_t)byte_off), "f"(v.x), "f"(v.y) : "memory");
+#endif
+}
+// asynchronous store into the shared memory of a block of the cluster; the bytes are counted in on `bar`, an mbarrier of
+// the SAME destination block (complete_tx): the consumer's wait on that barrier is the only synchronisation -- no
+// release fence (a release at cluster scope is a MEMBAR.ALL.GPU + ERRBAR per thread)
+__device__ __forceinline__ void fsea_st_async(fsea_cptr p, int byte_off, float v, fsea_cptr bar) {
+#if defined(FSEA_EMU)
+    *(float*)(p + byte_off) = v;
+    fsea_emu::mbar_complete_tx(bar, 4);
+#else
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0], %1, [%2];"
+                 ::"r"(p + (uint32_t)byte_off), "f"(v), "r"(bar) : "memory");
+#endif
+}
+__device__ __forceinline__ void fsea_st_async(fsea_cptr p, int byte_off, float2 v, fsea_cptr bar) {
+#if defined(FSEA_EMU)
+    *(float2*)(p + byte_off) = v;
+    fsea_emu::mbar_complete_tx(bar, 8);
+#else
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0], {%1, %2}, [%3];"
+                 ::"r"(p + (uint32_t)byte_off), "f"(v.x), "f"(v.y), "r"(bar) : "memory");
+#endif
+}
+// the same with a compile-time byte offset folded into the instruction's address (one base register for a whole row of stores)
+template <int OFF> __device__ __forceinline__ void fsea_st_async_at(fsea_cptr p, float v, fsea_cptr bar) {
+#if defined(FSEA_EMU)
+    *(float*)(p + OFF) = v;
+    fsea_emu::mbar_complete_tx(bar, 4);
+#else
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.f32 [%0+%3], %1, [%2];"
+                 ::"r"(p), "f"(v), "r"(bar), "n"(OFF) : "memory");
+#endif
+}
+template <int OFF> __device__ __forceinline__ void fsea_st_async_at(fsea_cptr p, float2 v, fsea_cptr bar) {
+#if defined(FSEA_EMU)
+    *(float2*)(p + OFF) = v;
+    fsea_emu::mbar_complete_tx(bar, 8);
+#else
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.f32 [%0+%4], {%1, %2}, [%3];"
+                 ::"r"(p), "f"(v.x), "f"(v.y), "r"(bar), "n"(OFF) : "memory");
+#endif
+}
+// plain stores into a block of the cluster with the byte offset as an immediate; made visible by fsea_fence_cluster()
+// + an arrive on the consumer's barrier
+template <int OFF> __device__ __forceinline__ void fsea_st_cluster_at(fsea_cptr p, float v) {
+#if defined(FSEA_EMU)
+    *(float*)(p + OFF) = v;
+#else
+    asm volatile("st.shared::cluster.f32 [%0+%2], %1;" ::"r"(p), "f"(v), "n"(OFF) : "memory");
+#endif
+}
+template <int OFF> __device__ __forceinline__ void fsea_st_cluster_at(fsea_cptr p, float2 v) {
+#if defined(FSEA_EMU)
+    *(float2*)(p + OFF) = v;
+#else
+    asm volatile("st.shared::cluster.v2.f32 [%0+%3], {%1, %2};" ::"r"(p), "f"(v.x), "f"(v.y), "n"(OFF) : "memory");
+#endif
+}
+__device__ __forceinline__ void fsea_fence_cluster() {
+#if !defined(FSEA_EMU)
+    asm volatile("fence.acq_rel.cluster;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void fsea_mbar_arrive_cluster_relaxed(fsea_cptr bar) {     // a signal that orders nothing but itself
+#if defined(FSEA_EMU)
+    fsea_emu::mbar_arrive(bar, 0);
+#else
+    asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+#endif
+}
+__device__ __forceinline__ void fsea_mbar_init(void* bar, unsigned count) {
+#if defined(FSEA_EMU)
+    fsea_emu::mbar_init(bar, count);
+#else
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+#endif
+}
+__device__ __forceinline__ void fsea_mbar_init_fence() {          // makes the inits visible to the other blocks of the cluster
+#if !defined(FSEA_EMU)
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#endif
+}
+__device__ __forceinline__ void fsea_mbar_arrive(void* bar) {     // this block's barrier
+#if defined(FSEA_EMU)
+    fsea_emu::mbar_arrive(bar, 0);
+#else
+    asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+#endif
+}
+__device__ __forceinline__ void fsea_mbar_arrive_cluster(fsea_cptr bar) {   // a barrier of any block of the cluster; releases this thread's (remote) stores
+#if defined(FSEA_EMU)
+    fsea_emu::mbar_arrive(bar, 0);
+#else
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+#endif
+}
+__device__ __forceinline__ void fsea_mbar_expect_tx(void* bar, unsigned bytes) {      // arrive + expect `bytes` of asynchronous copies
+#if defined(FSEA_EMU)
+    fsea_emu::mbar_arrive(bar, bytes);
+#else
+    asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+#endif
+}
+__device__ __forceinline__ void fsea_mbar_wait(void* bar, unsigned parity) {          // until the phase of that parity has completed
+#if defined(FSEA_EMU)
+    fsea_emu::mbar_wait(bar, parity);
+#else
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "FSEA_MBAR_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra FSEA_MBAR_DONE_%=;\n"
+        "bra FSEA_MBAR_WAIT_%=;\n"
+        "FSEA_MBAR_DONE_%=:\n"
+        "}\n" ::"r"(a), "r"(parity) : "memory");
+#endif
+}
+__device__ __forceinline__ void fsea_mbar_wait_cluster(void* bar, unsigned parity) {  // ... acquiring what the arriving threads of OTHER blocks released
+#if defined(FSEA_EMU)
+    fsea_emu::mbar_wait(bar, parity);
+#else
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "FSEA_MBARC_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra FSEA_MBARC_DONE_%=;\n"
+        "bra FSEA_MBARC_WAIT_%=;\n"
+        "FSEA_MBARC_DONE_%=:\n"
+        "}\n" ::"r"(a), "r"(parity) : "memory");
+#endif
+}
+// one box of a 3-d tensor (bytes) -> shared memory, completion counted on `bar` in bytes
+__device__ __forceinline__ void fsea_tma_load_3d(void* smem_dst, const fsea_tmap* tm, int c0, int c1, int c2, void* bar) {
+#if defined(FSEA_EMU)
+    fsea_emu::tma_load_3d((unsigned char*)smem_dst, tm, c0, c1, c2, bar);
+#else
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+                 ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(tm), "r"(c0), "r"(c1), "r"(c2),
+                   "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+#endif
+}
+__device__ __forceinline__ void fsea_cluster_sync_all() {
+    fsea_cluster_arrive_release();
+    fsea_cluster_wait_acquire();
+}

@@ -54,6 +54,7 @@ static inline uchar2 make_uchar2(unsigned char a, unsigned char b) { uchar2 r; r
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
+#define __grid_constant__
 #define __align__(n) __attribute__((aligned(n)))
 
 // ---- the fiber machine (tests/emu/emu.cpp) ------------------------------------------------
@@ -73,12 +74,20 @@ void sync_warp();                                     // __syncwarp (full mask)
 unsigned shfl_idx(unsigned v, int src_lane);          // shfl.sync.idx, full mask
 double shfl_down_f64(double v, int delta);
 void cluster_arrive();
+unsigned char* map_cluster(unsigned char* local_smem, unsigned cta_rank);   // mapa: the same offset in another block of the cluster
+void mbar_init(void* bar, unsigned count);
+void mbar_arrive(void* bar, unsigned expect_tx_bytes);
+void mbar_complete_tx(void* bar, unsigned bytes);
+void mbar_wait(void* bar, unsigned parity);
 void cluster_wait();
 void cp_async(void* smem_dst, const void* gsrc, int bytes);
 void cp_async_wait_all();
 void yield();
 void launch(dim3 grid, dim3 block, size_t smem, int cluster_size, const std::function<void()>& body);
 }  // namespace fsea_emu
+
+struct fsea_tmap;
+namespace fsea_emu { void tma_load_3d(unsigned char* dst, const fsea_tmap* tm, int c0, int c1, int c2, void* bar); }
 
 // threadIdx.x etc.: objects whose .x reads the running fiber's coordinates when converted
 namespace fsea_emu {
@@ -190,5 +199,5 @@ static inline cudaError_t cudaLaunchKernelExC(const cudaLaunchConfig_t* lc, cons
     int cs = 1;
     for (unsigned i = 0; i < lc->numAttrs; i++)
         if (lc->attrs[i].id == cudaLaunchAttributeClusterDimension) cs = (int)lc->attrs[i].val.clusterDim.x;
-    return fsea_emu_launch_kparams(fn, lc->gridDim, lc->blockDim, args, lc->dynamicSmemBytes, cs);
+    return fsea_emu_launch_kparams(fn, lc->gridDim, lc->blockDim, args, lc->dynamicSmemBytes, cs);       // (args[1], if the kernel takes one: a tensor map)
 }

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "../../frequensea_b200/csrc/fsea_kparams.h"
+struct fsea_tmap { const unsigned char* base; unsigned long long dim[3], stride[3]; unsigned box[3]; };
 
 namespace fsea_emu {
 
@@ -108,6 +109,56 @@ void cluster_wait() {
     Barrier& c = L->clusters[myblock().cluster];
     while (c.gen == me().cluster_gen) yield();
 }
+// ---- distributed shared memory / mbarriers / TMA (fsea_wsc.cuh) ---------------------------------------
+unsigned char* map_cluster(unsigned char* local_smem, unsigned cta_rank) {
+    Block& b = myblock();
+    const size_t off = (size_t)(local_smem - b.smem.data());
+    if (off >= b.smem.size()) { fprintf(stderr, "fsea_emu: mapa of an address outside dynamic shared memory\n"); abort(); }
+    const int cs = cur->cluster_size;
+    const int first = (int)(cur->bid.x / cs) * cs;
+    return L->blocks[first + (int)cta_rank].smem.data() + off;
+}
+struct MBar { unsigned count = 0, pending = 0; long tx = 0; unsigned phase = 0; };
+static std::map<void*, MBar> g_mbar;                     // keyed by the barrier's address (in some block's shared memory)
+static void mbar_try_complete(MBar& m) {
+    if (m.pending == 0 && m.tx == 0) { m.pending = m.count; m.phase ^= 1u; progress++; }
+}
+void mbar_init(void* bar, unsigned count) { MBar m; m.count = m.pending = count; g_mbar[bar] = m; }
+void mbar_arrive(void* bar, unsigned expect_tx_bytes) {
+    auto it = g_mbar.find(bar);
+    if (it == g_mbar.end()) { fprintf(stderr, "fsea_emu: arrive on an uninitialised mbarrier\n"); abort(); }
+    MBar& m = it->second;
+    if (m.pending == 0) { fprintf(stderr, "fsea_emu: more arrivals than the mbarrier's count\n"); abort(); }
+    m.tx += expect_tx_bytes;
+    m.pending--;
+    progress++;
+    mbar_try_complete(m);
+}
+void mbar_complete_tx(void* bar, unsigned bytes) {
+    MBar& m = g_mbar.at(bar);
+    m.tx -= bytes;
+    progress++;
+    mbar_try_complete(m);
+}
+void mbar_wait(void* bar, unsigned parity) {
+    auto it = g_mbar.find(bar);
+    if (it == g_mbar.end()) { fprintf(stderr, "fsea_emu: wait on an uninitialised mbarrier\n"); abort(); }
+    while (it->second.phase == (parity & 1u)) yield();     // the phase of that parity is still in progress
+}
+void tma_load_3d(unsigned char* dst, const fsea_tmap* tm, int c0, int c1, int c2, void* bar) {
+    // box[0] bytes x box[1] rows x box[2] planes, rows packed in shared memory; out-of-bounds elements read as zero
+    unsigned bytes = 0;
+    for (unsigned z = 0; z < tm->box[2]; z++)
+        for (unsigned y = 0; y < tm->box[1]; y++)
+            for (unsigned x = 0; x < tm->box[0]; x++, bytes++) {
+                const unsigned long long i0 = c0 + x, i1 = c1 + y, i2 = c2 + z;
+                unsigned char v = 0;
+                if (i0 < tm->dim[0] && i1 < tm->dim[1] && i2 < tm->dim[2]) v = tm->base[i0 + i1 * tm->stride[1] + i2 * tm->stride[2]];
+                dst[bytes] = v;
+            }
+    mbar_complete_tx(bar, bytes);
+}
+
 void cp_async(void* dst, const void* src, int bytes) { me().copies.push_back({dst, src, bytes}); }
 void cp_async_wait_all() {
     for (auto& c : me().copies) memcpy(c.dst, c.src, (size_t)c.bytes);
@@ -174,12 +225,20 @@ void launch(dim3 grid, dim3 block, size_t smem, int cluster_size, const std::fun
     }
     cur = nullptr;
     L = nullptr;
+    g_mbar.clear();
 }
 
 }  // namespace fsea_emu
 
 cudaError_t fsea_emu_launch_kparams(const void* fn, dim3 grid, dim3 block, void** args, size_t smem, int cluster) {
     const fsea_kparams kp = *(const fsea_kparams*)args[0];
+    if (kp.n2 >= 32 && kp.scratch == nullptr && cluster > 1) {
+        // fsea_wsc_kernel(kparams, tensor map): the cluster kernels without an L2 scratch take the input's tensor map too
+        const fsea_tmap tm = *(const fsea_tmap*)args[1];
+        void (*k2)(const fsea_kparams, const fsea_tmap) = (void (*)(const fsea_kparams, const fsea_tmap))fn;
+        fsea_emu::launch(grid, block, smem, cluster, [&] { k2(kp, tm); });
+        return cudaSuccess;
+    }
     void (*k)(const fsea_kparams) = (void (*)(const fsea_kparams))fn;
     fsea_emu::launch(grid, block, smem, cluster, [&] { k(kp); });
     return cudaSuccess;

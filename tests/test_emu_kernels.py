@@ -60,10 +60,11 @@ def test_emulated_alternative_arrangements(emu_lib):
 
 
 def test_emulated_four_step_sizes(emu_lib):
-    """N = 16384 .. 65536: the defaults -- the warp-specialised block-per-frame kernel (16384) and the
-    cluster kernel (sub-spectra, cluster barrier, comb) incl. slot reuse."""
+    """N = 16384 .. 65536: the defaults -- the warp-specialised block-per-frame kernel (16384), its cluster form with
+    the intermediate in distributed shared memory and TMA-fed tiles (32768), and the L2 cluster kernel (65536:
+    sub-spectra, cluster barrier, comb) incl. slot reuse."""
     res = run_check(emu_lib, [16384, 32768, 65536])
-    assert "ws4<" in res[0]["kernel"] and all("fft4<" in r["kernel"] for r in res[1:])
+    assert "ws4<" in res[0]["kernel"] and "wsc<" in res[1]["kernel"] and "fft4<" in res[2]["kernel"]
     verify(res)
 
 
@@ -71,11 +72,11 @@ def test_emulated_warp_specialised_and_cluster_alternatives(emu_lib):
     """fsea_ws4_kernel at every length it exists for (FSEA_WS=1: 4, 2 and 1 frames per block iteration; named
     barriers between transform and comb warps, register gathers, frames past the end of the batch), and
     the cluster kernel at 16384 (FSEA_FOUR_ALT=9), which the default no longer picks."""
-    res = run_check(emu_lib, [4096, 8192, 16384], FSEA_WS="1")
-    assert all("ws4<" in r["kernel"] for r in res)
+    res = run_check(emu_lib, [4096, 8192, 16384, 32768, 65536], FSEA_WS="1")
+    assert all("ws4<" in r["kernel"] for r in res[:3]) and all("wsc<" in r["kernel"] for r in res[3:])     # mbarriers, TMA boxes, stores into peer blocks
     verify(res)
-    res = run_check(emu_lib, [16384], FSEA_FOUR_ALT="9")
-    assert "fft4<" in res[0]["kernel"]
+    res = run_check(emu_lib, [16384, 32768], FSEA_FOUR_ALT="9")
+    assert all("fft4<" in r["kernel"] for r in res)
     verify(res)
 
 

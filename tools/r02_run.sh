@@ -1,19 +1,7 @@
-O=gpurun_out/r02e; mkdir -p $O
-timeout 1200 python -m pytest tests -m gpu -q -x > $O/pytest_gpu.txt 2>&1; tail -5 $O/pytest_gpu.txt
-timeout 900 python bench.py > $O/bench.json 2> $O/bench.err; tail -3 $O/bench.err; python - <<'PY'
-import json
-try:
-    d = json.loads(open("gpurun_out/r02e/bench.json").read().strip().splitlines()[-1])
-    print("value", d["value"]/1e6, "frac", d["roofline"]["frac"], "burst_frac", d["roofline"]["burst_frac"], "clocks", d["clocks"], "bench_s", d["bench_seconds"])
-    print("e2e", d["e2e"])
-    for k, v in d["secondary"].items():
-        if v is None: print(k, None); continue
-        if "error" in v or "skipped" in v: print(k, v); continue
-        if k == "sweep": print(k, json.dumps(v)[:1500]); continue
-        if k == "sustained": print(k, json.dumps(v)[:800]); continue
-        print(k, round(v["value"]/1e6, 2), "Mframes/s frac", round(v["roofline"]["frac"], 3), v["kernel"][:40], v["parity_gate"], v["clocks"])
-except Exception as e:
-    print("ERR", e)
-PY
-timeout 300 python tools/sweep_mgpu.py --gpus 1 --freqs 100 --rows 512 --mode gather > $O/mgpu_1gpu_gather.json 2> $O/mgpu.err; cat $O/mgpu_1gpu_gather.json; tail -3 $O/mgpu.err
-timeout 300 python tools/sweep_mgpu.py --gpus 1 --freqs 100 --rows 512 --mode p2p > $O/mgpu_1gpu_p2p.json 2>> $O/mgpu.err; cat $O/mgpu_1gpu_p2p.json
+O=gpurun_out/r02j; mkdir -p $O
+timeout 400 python tools/sweep.py n32768 n65536 cfg5 n32768::build_alt/libfsea_stas.so n65536::build_alt/libfsea_stas.so n32768:::FSEA_WS=0 n65536:::FSEA_WS=0 > $O/sweep.txt 2>&1; cat $O/sweep.txt
+SWEEP_STEPS=1 SWEEP_WARMUP=1 timeout 600 ncu --set full --clock-control none --import-source on -k regex:fsea_ -s 1 -c 1 -o $O/prof python tools/sweep.py n65536@2048 > $O/ncu.log 2>&1
+python tools/ncu_summary.py $O/prof.ncu-rep > $O/ncu_full.txt 2>&1; python tools/ncu_ops.py $O/prof.ncu-rep > $O/ncu_ops.txt 2>&1
+ncu -i $O/prof.ncu-rep --page source --csv 2>/dev/null | gzip > $O/ncu_source.csv.gz
+rm -f $O/prof.ncu-rep
+cat $O/ncu_full.txt
