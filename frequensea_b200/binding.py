@@ -42,6 +42,12 @@ class FseaSweepConfig(C.Structure):
                 ("own_raw", C.c_int), ("own_images", C.c_int), ("reserved", C.c_int * 4)]
 
 
+class FseaChainConfig(C.Structure):
+    _fields_ = [("fft_size", C.c_int), ("block_samples", C.c_int), ("shifter", C.c_int), ("freq_offset", C.c_int),
+                ("shifter_sample_rate", C.c_int), ("filter", C.c_int), ("taps", C.c_int), ("coefficients", C.POINTER(C.c_double)),
+                ("device", C.c_int), ("reserved", C.c_int * 4)]
+
+
 class FseaError(RuntimeError):
     def __init__(self, code: int, what: str, detail: str = ""):
         self.code = code
@@ -101,6 +107,12 @@ def lib() -> C.CDLL:
     L.fsea_exec_device_strided.argtypes = [vp, vp, vp, l, l, vp]; L.fsea_exec_device_strided.restype = i
     L.fsea_copy_only_host.argtypes = [vp, vp, vp, l]; L.fsea_copy_only_host.restype = i
     L.fsea_host_bind_near_device.argtypes = [i]; L.fsea_host_bind_near_device.restype = i
+    L.fsea_chain_create.argtypes = [C.POINTER(FseaChainConfig), C.POINTER(vp)]; L.fsea_chain_create.restype = i
+    L.fsea_chain_destroy.argtypes = [vp]; L.fsea_chain_destroy.restype = i
+    L.fsea_chain_process_u8.argtypes = [vp, vp, vp]; L.fsea_chain_process_u8.restype = i
+    L.fsea_chain_launch_count.argtypes = [vp]; L.fsea_chain_launch_count.restype = l
+    L.fsea_history_put_device.argtypes = [vp, i, vp, i, vp]; L.fsea_history_put_device.restype = i
+    L.fsea_history_shift_device.argtypes = [vp, vp, i, i, i, vp]; L.fsea_history_shift_device.restype = i
     L.fsea_ipc_alloc.argtypes = [i, C.c_size_t, C.POINTER(vp), C.c_char_p]; L.fsea_ipc_alloc.restype = i
     L.fsea_ipc_open.argtypes = [i, C.c_char_p, C.POINTER(vp)]; L.fsea_ipc_open.restype = i
     L.fsea_ipc_close.argtypes = [vp]; L.fsea_ipc_close.restype = i
@@ -367,6 +379,47 @@ class SharedDeviceBuffer:
         if self.ptr:
             (lib().fsea_ipc_free if self.owner else lib().fsea_ipc_close)(C.c_void_p(self.ptr))
             self.ptr = 0
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Chain:
+    """Device block -> [frequency shifter] -> [IQ low-pass] -> nrf_fft row, fused on the device (fsea_chain_*)."""
+
+    def __init__(self, fft_size: int, block_samples: int = 131072, shifter=None, fir_coefficients=None, device: int = 0):
+        """shifter: (freq_offset, sample_rate) or None; fir_coefficients: the taps (nrf_fir_get_low_pass_coefficients) or None"""
+        cfg = FseaChainConfig(fft_size=fft_size, block_samples=block_samples, device=device)
+        self._coef = None
+        if shifter is not None:
+            cfg.shifter, cfg.freq_offset, cfg.shifter_sample_rate = 1, int(shifter[0]), int(shifter[1])
+        if fir_coefficients is not None:
+            self._coef = np.ascontiguousarray(fir_coefficients, dtype=np.float64)
+            cfg.filter, cfg.taps = 1, int(self._coef.size)
+            cfg.coefficients = self._coef.ctypes.data_as(C.POINTER(C.c_double))
+        self.n, self.block_samples = fft_size, block_samples
+        self._h = C.c_void_p()
+        _check(lib().fsea_chain_create(C.byref(cfg), C.byref(self._h)), "fsea_chain_create")
+
+    def process(self, block_u8: np.ndarray) -> np.ndarray:
+        block_u8 = np.ascontiguousarray(block_u8, dtype=np.uint8).ravel()
+        if block_u8.size < 2 * self.block_samples:
+            raise ValueError("a device block holds 2 * block_samples bytes")
+        row = np.empty(self.n, dtype=np.float64)
+        _check(lib().fsea_chain_process_u8(self._h, block_u8.ctypes.data_as(C.c_void_p), row.ctypes.data_as(C.c_void_p)), "fsea_chain_process_u8")
+        return row
+
+    @property
+    def launches(self) -> int:
+        return int(lib().fsea_chain_launch_count(self._h))
+
+    def close(self) -> None:
+        if self._h:
+            lib().fsea_chain_destroy(self._h)
+            self._h = C.c_void_p()
 
     def __del__(self):
         try:

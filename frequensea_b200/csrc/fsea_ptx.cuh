@@ -54,6 +54,14 @@ __device__ __forceinline__ void fsea_st_stream(float2* p, float2 v) {
 #endif
 }
 
+__device__ __forceinline__ void fsea_st_stream(float4* p, float4 v) {
+#if defined(FSEA_EMU) || !FSEA_COMB_STREAM
+    *p = v;
+#else
+    asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+#endif
+}
+
 // ---- asynchronous global -> shared copies (LDGSTS) --------------------------------------
 __device__ __forceinline__ void fsea_cp_async16(void* smem_dst, const void* gsrc) {        // 16 bytes, L2 only
 #if defined(FSEA_EMU)

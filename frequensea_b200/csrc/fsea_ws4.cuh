@@ -58,6 +58,51 @@ __device__ __forceinline__ void fsea_ws_comb_load(const float* y, int k, f2* re,
     }
 }
 
+// ... and of FOUR neighbouring bins k .. k+3 (k a multiple of 4): one LDS.128 per sub-spectrum and plane; the two bin
+// pairs land in two packed register sets
+template <int N2>
+__device__ __forceinline__ void fsea_ws_comb_load4(const float* y, int k, f2* re0, f2* im0, f2* re1, f2* im1) {
+#pragma unroll
+    for (int j = 0; j < N2; j++) {
+        const float4 a = *(const float4*)(y + j * 1024 + k);
+        const float4 b = *(const float4*)(y + (N2 + j) * 1024 + k);
+        re0[j] = mk2(a.x, a.y); re1[j] = mk2(a.z, a.w);
+        im0[j] = mk2(b.x, b.y); im1[j] = mk2(b.z, b.w);
+    }
+}
+
+// radix-N2 + epilogue of four neighbouring bins: spectrum positions k .. k+3 of every row m leave as ONE 16-byte store
+// (float32) or ONE 4-byte store (u8 pixels: c/fft-batch.c:85-92 rows, four bins per store instead of one)
+template <int OUT, int N1, int N2>
+__device__ __forceinline__ void fsea_ws_comb_finish4(const fsea_kparams& kp, int k, uint8_t* row, bool dc_patch,
+                                                     f2* re0, f2* im0, f2* re1, f2* im1) {
+    constexpr int ESZ = (OUT == FSEA_OUT_PIX) ? 1 : 4;
+    fsea_dft<N2, f2>::run(re0, im0);
+    fsea_dft<N2, f2>::run(re1, im1);
+    if (kp.dc_term && k == 0) { re0[0].v.x += (float)(N2 / 2) * (float)N1; im0[0].v.x += (float)(N2 / 2) * (float)N1; }   // N/2 (1+i)
+#pragma unroll
+    for (int m = 0; m < N2; m++) {
+        const f2 p0 = vfma2(re0[m], re0[m], vmul(im0[m], im0[m]));
+        const f2 p1 = vfma2(re1[m], re1[m], vmul(im1[m], im1[m]));
+        uint8_t* dst = row + ((size_t)k + (size_t)N1 * (m ^ (N2 / 2))) * ESZ;
+        __align__(16) unsigned char tmp[16];
+        fsea_tile_put<OUT>(tmp, p0, kp.pix_scale, kp.lg);
+        fsea_tile_put<OUT>(tmp + 2 * ESZ, p1, kp.pix_scale, kp.lg);
+        if (m == 0 && dc_patch && k == 0) {                                  // bin 0 is not stored (src/nrf.c:621-622)
+            if (ESZ == 4) { ((float*)dst)[1] = ((const float*)tmp)[1]; ((float*)dst)[2] = ((const float*)tmp)[2]; ((float*)dst)[3] = ((const float*)tmp)[3]; }
+            else { dst[1] = tmp[1]; dst[2] = tmp[2]; dst[3] = tmp[3]; }
+        } else if (ESZ == 4) {
+            fsea_st_stream((float4*)dst, *(const float4*)tmp);
+        } else {
+            *(uchar4*)dst = *(const uchar4*)tmp;
+        }
+        if (m == N2 - 1 && dc_patch && k == N1 - 4) {                        // bin N-1 also fills the DC slot N/2
+            uint8_t* dc = row + (size_t)(N2 / 2) * N1 * ESZ;
+            if (ESZ == 4) ((float*)dc)[0] = ((const float*)tmp)[3]; else dc[0] = tmp[3];
+        }
+    }
+}
+
 template <int N2, int OUT, bool WIN>
 __global__ void __launch_bounds__(FSEA_WS_THREADS, 1)
 fsea_ws4_kernel(const fsea_kparams kp) {
@@ -185,14 +230,17 @@ fsea_ws4_kernel(const fsea_kparams kp) {
                 const long f = g * FPB + fi;
                 const float* yf = Y + (size_t)fi * (2 * N2 * 1024);
                 uint8_t* row = f < frames ? (uint8_t*)kp.out + fsea_out_row(kp, f) : (uint8_t*)kp.dump;
+                // a call works on U / 2 groups of FOUR neighbouring bins: 4 (p0 + v CPF) .. + 3
+                static_assert(U % 2 == 0, "bin pairs are combed two at a time");
                 f2 re[U][N2], im[U][N2];
 #pragma unroll
-                for (int uu = 0; uu < U; uu++) fsea_ws_comb_load<N2>(yf, 2 * (p0 + uu * CPF), re[uu], im[uu]);
+                for (int v = 0; v < U / 2; v++) fsea_ws_comb_load4<N2>(yf, 4 * (p0 + v * CPF), re[2 * v], im[2 * v], re[2 * v + 1], im[2 * v + 1]);
 #pragma unroll
-                for (int uu = 0; uu < U; uu++) COMB::twiddle(kp, 2 * (p0 + uu * CPF), re[uu], im[uu]);
+                for (int uu = 0; uu < U; uu++) COMB::twiddle(kp, 4 * (p0 + (uu / 2) * CPF) + 2 * (uu & 1), re[uu], im[uu]);
                 if (it == BIT - 1 && more) free_y();                   // Y has been read
 #pragma unroll
-                for (int uu = 0; uu < U; uu++) COMB::finish(kp, 2 * (p0 + uu * CPF), row, dc_patch, re[uu], im[uu]);
+                for (int v = 0; v < U / 2; v++)
+                    fsea_ws_comb_finish4<OUT, N1, N2>(kp, 4 * (p0 + v * CPF), row, dc_patch, re[2 * v], im[2 * v], re[2 * v + 1], im[2 * v + 1]);
             }
         }
     }

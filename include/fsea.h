@@ -212,6 +212,32 @@ const void *fsea_sweep_raw(fsea_sweep *s, int slot);   /* device pointer of the 
 void *fsea_sweep_stream(fsea_sweep *s);           /* the engine's cudaStream_t */
 long fsea_sweep_launch_count(const fsea_sweep *s);
 
+/* ---- the operators in front of the path, fused with it ----------------
+ * One device block (block_samples complex u8 samples, as nut buffers hold them) -> [nrf_freq_shifter, src/nrf.c:843-866]
+ * -> [nrf_iq_filter, src/nrf.c:738-768] -> nrf_fft's row (first fft_size samples, |X|, DC patch, float64) in ONE call on
+ * the device: no float64 nut_buffer of the whole block crosses the host between the operators, and the filter computes
+ * the fft_size outputs the transform reads instead of all block_samples.  Rotator phase and the filter's taps - 1
+ * carried-over samples persist from block to block as in the reference.  The filter's sums are bit-identical to the
+ * reference's (fsea_fir_iq_device); coefficients come from the caller (nrf_fir_get_low_pass_coefficients). */
+typedef struct fsea_chain fsea_chain;
+typedef struct {
+    int fft_size;                 /* N */
+    int block_samples;            /* complex samples per device block: NRF_SAMPLES_LENGTH = 131072 */
+    int shifter;                  /* 1: rotator in front */
+    int freq_offset;              /* nrf_freq_shifter_new(freq_offset, sample_rate) */
+    int shifter_sample_rate;
+    int filter;                   /* 1: FIR low-pass behind the rotator */
+    int taps;                     /* coefficients actually used (nrf_fir_filter::length) */
+    const double *coefficients;   /* taps doubles (copied) */
+    int device;
+    int reserved[4];
+} fsea_chain_config;
+int fsea_chain_create(const fsea_chain_config *cfg, fsea_chain **out);
+int fsea_chain_destroy(fsea_chain *chain);
+/* h_block: 2 * block_samples bytes (interleaved I, Q, offset-binary u8); h_row: fft_size doubles.  Synchronous. */
+int fsea_chain_process_u8(fsea_chain *chain, const uint8_t *h_block, double *h_row);
+long fsea_chain_launch_count(const fsea_chain *chain);
+
 /* ---- the history image on the device ----------------
  * nrf_fft's N x H image (src/nrf.c:617,633-635) as a ring of float64 rows in device memory: put = one new row
  * (a float32 or float64 spectrum row already on the device) written in place of the oldest; shift = the retune

@@ -619,6 +619,71 @@ def test_mgpu_driver_one_process(fbg):
             assert res["equals_one_gpu_job"]
 
 
+def test_chain_fused_front_operators(fbg, iq):
+    """fsea_chain_* (SURVEY 8(f) rank 3): device block -> frequency shifter / IQ low-pass -> nrf_fft row in one call on
+    the device, only the N samples the transform reads going through the filter.  Against the SAME operators called one
+    after the other through the reference's API (float64 nut_buffers of the whole block across the host, themselves
+    bit-identical to the compiled reference: test_iq_filter_bit_exact_and_chain, test_freq_shifter_host_...): the
+    filter's sums and the rotator's products are the same roundings, so the rows agree bit for bit, block after
+    block (carried FIR tail, carried rotator phase)."""
+    fb = fbg
+    nrf = fb.nrf
+    from frequensea_b200.binding import Chain
+    n = 1024
+    blocks = [orc.device_unpack(iq["rf200big4"][b * BLOCK:(b + 1) * BLOCK]) for b in range(4)]
+
+    def unfused(make_front, process_front, get_front, free_front):
+        fft = nrf.fft_new(n, 2)
+        front = make_front()
+        rows = []
+        for blk in blocks:
+            buf = nrf.nut_buffer_new_u8(131072, 2, blk)
+            process_front(front, buf)
+            nrf.fft_process(fft, get_front(front))
+            rows.append(nrf.fft_get_buffer(fft).numpy()[:n].copy())
+        free_front(front)
+        nrf.fft_free(fft)
+        return rows
+
+    # IQ low-pass (lua/iq-tex-filtered.lua:43-46: 200 kHz, 51 taps; an even tap count as well)
+    for taps, half in ((51, 200000), (50, 100000)):
+        ref = unfused(lambda: nrf.iq_filter_new(5000000, half, taps), nrf.iq_filter_process, nrf.iq_filter_get_buffer, nrf.iq_filter_free)
+        coef = nrf.fir_low_pass_coefficients(5000000, half, taps)[:taps]
+        ch = Chain(n, fir_coefficients=coef)
+        for blk, r in zip(blocks, ref):
+            assert np.array_equal(ch.process(blk), r), taps
+        assert ch.launches == 3 * len(blocks)                       # prepare + FIR + transform per block
+    # frequency shifter (lua/fft-shifted.lua:42-54, -10 kHz at 5 MS/s)
+    ref = unfused(lambda: nrf.freq_shifter_new(-10000, 5000000), nrf.freq_shifter_process, nrf.freq_shifter_get_buffer, nrf.freq_shifter_free)
+    ch = Chain(n, shifter=(-10000, 5000000))
+    for blk, r in zip(blocks, ref):
+        assert np.array_equal(ch.process(blk), r)
+    # both, against a float64 model of the intended composition (the reference's own shifter hands a buffer of twice
+    # the block's length to whatever follows, src/nrf.c:849-852: scripts never chain the two)
+    coef = nrf.fir_low_pass_coefficients(5000000, 200000, 51)[:51]
+    ch = Chain(n, shifter=(-10000, 5000000), fir_coefficients=coef)
+    step = 2 * np.pi * -10000 / 5000000.0
+    c, s = 1.0, 0.0
+    tail = np.zeros((50, 2))
+    for blk in blocks[:2]:
+        v = blk.astype(np.float64).reshape(-1, 2) / 256.0
+        ph = np.empty((131072, 2))
+        dc, ds = np.cos(step), np.sin(step)
+        for j in range(131072):
+            ph[j] = (c, s)
+            c, s = c * dc - s * ds, c * ds + s * dc
+        sh = np.stack([v[:, 0] * ph[:, 0] - v[:, 1] * ph[:, 1] + 0.5, v[:, 0] * ph[:, 1] + v[:, 1] * ph[:, 0] + 0.5], axis=1)
+        line = np.concatenate([tail, sh[:n]])
+        fi = np.array([np.dot(coef, line[i:i + 51, 0]) for i in range(n)])
+        fq = np.array([np.dot(coef, line[i:i + 51, 1]) for i in range(n)])
+        tail = sh[-50:]
+        x = np.empty(2 * n)
+        x[0::2], x[1::2] = fi, fq
+        want = orc.engine_frame(x, n, orc.IN_F64C, orc.WIN_NONE, orc.OUT_MAG, flags=orc.FLAG_DC_PATCH)
+        got = ch.process(blk)
+        assert np.max(np.abs(got - want)) < 1e-11 * np.sqrt(np.mean(want ** 2))
+
+
 def test_block_graph_filter_into_fft(fbg, iq):
     """nrf_block_connect / nrf_block_process (src/nrf.c:24-50): pushing a buffer into a filter block
     runs the filter, hands its result to the connected nrf_fft and frees it -- same history as calling
