@@ -958,8 +958,8 @@ template <int OUT, int N1, int N2> struct fsea_comb {
         f2 br[LG], bi[LG];                                                       // W^(2^r k), r < LG
 #pragma unroll
         for (int r = 0; r < LG; r++) {
-            const float2 wa = __ldg((const float2*)((const float*)kp.tw4 + (size_t)(2 * r) * N1 + k));       // re plane
-            const float2 wb = __ldg((const float2*)((const float*)kp.tw4 + (size_t)(2 * r + 1) * N1 + k));   // im plane
+            const float2 wa = fsea_ldg_stream((const float2*)((const float*)kp.tw4 + (size_t)(2 * r) * N1 + k));       // re plane
+            const float2 wb = fsea_ldg_stream((const float2*)((const float*)kp.tw4 + (size_t)(2 * r + 1) * N1 + k));   // im plane
             br[r] = mk2(wa.x, wa.y); bi[r] = mk2(wb.x, wb.y);
         }
         f2 wr[N2], wi[N2];                                                       // (only a chain of <= LG is live at a time)

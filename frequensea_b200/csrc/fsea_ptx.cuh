@@ -34,6 +34,25 @@ __device__ __forceinline__ void fsea_prefetch_l2(const void* p) {
 #endif
 }
 
+__device__ __forceinline__ void fsea_prefetch_l1(const void* p) {
+#if defined(FSEA_EMU)
+    (void)p;
+#else
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
+// read-only table loads that do not take L1 space (the comb's four-step twiddle rows: 32 KB per frame that would push
+// the raw IQ lines the transform warps are about to gather out of the ~50 KB of L1 left beside 206 KB of shared memory)
+__device__ __forceinline__ float2 fsea_ldg_stream(const float2* p) {
+#if defined(FSEA_EMU)
+    return *p;
+#else
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+#endif
+}
+
 // ---- streaming (evict-first) stores: spectra are written once and never read again by the
 // kernel, the four-step intermediate next to them in L2 is -- keep the spectra from pushing it out
 #ifndef FSEA_COMB_STREAM

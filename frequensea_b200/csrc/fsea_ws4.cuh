@@ -24,11 +24,16 @@
 //                    coalesced stores of the spectrum.
 //
 // A computes frames f+1 while B combs frames f: all 12 warps run at once, as in the 1024-point
-// kernel, and the only waits are named barriers (producer: bar.arrive, consumer: bar.sync):
-// Y_FULL (all A -> B) and one Y_FREE per transform warp (B -> that warp; a warp holds its finished
-// unit in registers until the comb has read the previous frames out of Y) -- per warp, so that
-// the transform warps never wait for EACH OTHER and drift apart into different phases (load /
-// arithmetic / exchange) the way the independent warps of the 1024-point kernel do.
+// kernel, and the only waits are mbarriers in shared memory.  The comb reads Y in PHASES (BIT
+// passes of its 128 threads over the block's bins: the lower and the upper half of the bins for
+// N2 = 16, one frame per phase for N2 <= 8), and each phase has its own pair
+//   full[p]  (the transform warps whose values the phase reads -> B)
+//   free[p]  (B -> those warps; a warp holds its finished unit in registers until the comb has
+//             read the previous frames' values of that phase out of Y)
+// so a transform warp stores the half the comb reads first while the comb is still busy with the
+// other half of the previous frame, and -- waiting on an mbarrier, not a bar.sync -- never waits
+// for its SIBLINGS: the transform warps drift apart into different phases (load / arithmetic /
+// exchange) the way the independent warps of the 1024-point kernel do.
 // Shared memory: 8 exchange planes (66 KB) + Y (128 KB) + the pass-1 twiddle table (8 KB): one
 // block per SM, 384 threads at 168 registers.
 //
@@ -36,15 +41,17 @@
 #pragma once
 #include "fsea_kernels.cuh"
 
+#ifndef FSEA_WS_EARLY
+#define FSEA_WS_EARLY 0   /* measured: 20.8 vs 24.0 M frames/s at 16384 -- the 32 extra live registers spill */
+#endif
 #define FSEA_WS_NA 8
 #define FSEA_WS_NB 4
 #define FSEA_WS_THREADS ((FSEA_WS_NA + FSEA_WS_NB) * 32)
 #define FSEA_WS_PLANE (1056 * 8)
 #define FSEA_WS_Y (2 * 16 * 1024 * 4)
 #define FSEA_WS_TW (31 * 32 * 8)
-#define FSEA_WS_SMEM (FSEA_WS_NA * FSEA_WS_PLANE + FSEA_WS_Y + FSEA_WS_TW)
+#define FSEA_WS_SMEM (FSEA_WS_NA * FSEA_WS_PLANE + FSEA_WS_Y + FSEA_WS_TW + 64)        /* + 8 mbarriers */
 
-enum { FSEA_WS_BAR_Y_FULL = 1, FSEA_WS_BAR_Y_FREE = 2 /* + transform warp: 2 .. 9 */ };
 
 
 // step B loads: one bin pair of all N2 sub-spectra from Y in shared memory (rows of 1024 floats)
@@ -128,7 +135,18 @@ fsea_ws4_kernel(const fsea_kparams kp) {
     const size_t frame_bytes = (size_t)kp.seq_stride * 2;
     const uint32_t x4 = kp.xor_mask | (kp.xor_mask << 16);
 
+    // phases of the comb: BIT passes; phase p reads the values of APP transform warps
+    constexpr int NPH = BIT;
+    constexpr int APP = (N2 == 16) ? FSEA_WS_NA : FSEA_WS_NA / NPH;          // transform warps whose values a phase reads
+    static_assert(N2 == 16 ? NPH == 2 : NPH == FPB, "one phase per frame of the group (N2 <= 8) or per half of the bins (N2 = 16)");
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(fsea_smem + FSEA_WS_NA * FSEA_WS_PLANE + FSEA_WS_Y + FSEA_WS_TW);
+    unsigned long long* full = bars;                        // [NPH]
+    unsigned long long* fre = bars + 4;                     // [NPH]
     for (int q = tid; q < 31 * 32; q += FSEA_WS_THREADS) stw[q] = ((const float2*)kp.tw1)[q];
+    if (tid == 0) {
+#pragma unroll
+        for (int p = 0; p < NPH; p++) { fsea_mbar_init(full + p, APP * 32); fsea_mbar_init(fre + p, TB); }
+    }
     __syncthreads();
 
     if (w < FSEA_WS_NA) {
@@ -142,12 +160,18 @@ fsea_ws4_kernel(const fsea_kparams kp) {
             if (f >= frames) f = frames - 1;
             return (const uint8_t*)kp.in + (size_t)f * frame_bytes + 4 * u;
         };
-        for (long g = blockIdx.x; g < groups; g += step) {
-            f2 re[32], im[32];
+        unsigned it = 0;
+        uint32_t raw[32];
+        auto gather = [&](long g) {
             const uint8_t* src = unit_src(g) + (size_t)t * (2 * N2);
-            uint32_t raw[32];
 #pragma unroll
             for (int j = 0; j < 32; j++) raw[j] = __ldg((const uint32_t*)(src + (size_t)j * (32 * 2 * N2)));
+        };
+        constexpr bool EARLY = (N2 == 16) && FSEA_WS_EARLY;  // the next frame's gathers are issued between the two halves of the Y store
+        if (EARLY && (long)blockIdx.x < groups) gather(blockIdx.x);
+        for (long g = blockIdx.x; g < groups; g += step, it++) {
+            f2 re[32], im[32];
+            if (!EARLY) gather(g);
             const float* wsrc = WIN ? kp.window + (size_t)N2 * t + 2 * u : nullptr;    // sample n = N2 n1 + 2u (+1), n1 = t + 32 j
 #pragma unroll
             for (int j = 0; j < 32; j++) {
@@ -187,27 +211,43 @@ fsea_ws4_kernel(const fsea_kparams kp) {
                 vcmul(re[j], im[j], tw.x, tw.y);
             }
             fsea_dft32<f2>(re, im);
-            fsea_named_sync(FSEA_WS_BAR_Y_FREE + w, 32 + FSEA_WS_NB * 32);   // the comb has read the previous frames
+            if constexpr (N2 == 16) {
+                // bins t + 32 m: m < 16 is the half the comb reads first
 #pragma unroll
-            for (int m = 0; m < 32; m++) {
-                yre[32 * m] = re[m].v.x;
-                yre[1024 + 32 * m] = re[m].v.y;
-                yim[32 * m] = im[m].v.x;
-                yim[1024 + 32 * m] = im[m].v.y;
+                for (int h = 0; h < 2; h++) {
+                    fsea_mbar_wait(fre + h, (it & 1) ^ 1);             // the comb has read this half of the previous frame
+#pragma unroll
+                    for (int m = 16 * h; m < 16 * h + 16; m++) {
+                        yre[32 * m] = re[m].v.x;
+                        yre[1024 + 32 * m] = re[m].v.y;
+                        yim[32 * m] = im[m].v.x;
+                        yim[1024 + 32 * m] = im[m].v.y;
+                    }
+                    fsea_mbar_arrive(full + h);
+                    // half of the result registers are free: the next frame's raw words start their trip now, behind the
+                    // wait for the comb and the second half of the stores, instead of at the top of the loop
+                    if (h == 0 && g + step < groups) gather(g + step);
+                }
+            } else {
+                fsea_mbar_wait(fre + fi, (it & 1) ^ 1);                // the comb has read this frame slot of the previous group
+#pragma unroll
+                for (int m = 0; m < 32; m++) {
+                    yre[32 * m] = re[m].v.x;
+                    yre[1024 + 32 * m] = re[m].v.y;
+                    yim[32 * m] = im[m].v.x;
+                    yim[1024 + 32 * m] = im[m].v.y;
+                }
+                fsea_mbar_arrive(full + fi);
             }
-            fsea_named_arrive(FSEA_WS_BAR_Y_FULL, FSEA_WS_THREADS);
         }
     } else {
         // ------------------------------------------------ B: comb warps
         const int bt = tid - FSEA_WS_NA * 32;
         const bool dc_patch = (kp.flags & FSEA_FLAG_DC_PATCH) != 0;
         long g = blockIdx.x;
-        auto free_y = [&]() {
-#pragma unroll
-            for (int a = 0; a < FSEA_WS_NA; a++) fsea_named_arrive(FSEA_WS_BAR_Y_FREE + a, 32 + FSEA_WS_NB * 32);
-        };
-        // the raw bytes of a group (FPB frames of 2 N bytes = 256 lines), pulled into L2 two iterations ahead
-        auto prefetch = [&](long gg) {
+        // the raw bytes of a group (FPB frames of 2 N bytes = 256 lines), pulled into L2 two iterations ahead (L1 is the
+        // 28 KB left beside 228 KB of shared memory: a frame does not fit)
+        auto prefetch_l2 = [&](long gg) {
             if (gg >= groups) return;
 #pragma unroll
             for (int q = 0; q < 2; q++) {
@@ -218,13 +258,12 @@ fsea_ws4_kernel(const fsea_kparams kp) {
                 fsea_prefetch_l2((const uint8_t*)kp.in + (size_t)f * frame_bytes + (size_t)pl * 128);
             }
         };
-        if (g < groups) { free_y(); prefetch(g + step); }                  // Y starts out free
-        for (; g < groups; g += step) {
-            const bool more = g + step < groups;
-            prefetch(g + 2 * step);
-            fsea_named_sync(FSEA_WS_BAR_Y_FULL, FSEA_WS_THREADS);      // the sub-spectra of this group are in Y
+        unsigned gi = 0;
+        for (; g < groups; g += step, gi++) {
+            prefetch_l2(g + 2 * step);
 #pragma unroll 1
             for (int it = 0; it < BIT; it++) {
+                fsea_mbar_wait(full + it, gi & 1);                     // the values this phase reads are in Y
                 const int c = it * TB + bt;                            // comb call: frame c / CPF, pairs (c % CPF) + uu CPF
                 const int fi = c / CPF, p0 = c - fi * CPF;
                 const long f = g * FPB + fi;
@@ -237,7 +276,7 @@ fsea_ws4_kernel(const fsea_kparams kp) {
                 for (int v = 0; v < U / 2; v++) fsea_ws_comb_load4<N2>(yf, 4 * (p0 + v * CPF), re[2 * v], im[2 * v], re[2 * v + 1], im[2 * v + 1]);
 #pragma unroll
                 for (int uu = 0; uu < U; uu++) COMB::twiddle(kp, 4 * (p0 + (uu / 2) * CPF) + 2 * (uu & 1), re[uu], im[uu]);
-                if (it == BIT - 1 && more) free_y();                   // Y has been read
+                fsea_mbar_arrive(fre + it);                            // this phase's part of Y has been read
 #pragma unroll
                 for (int v = 0; v < U / 2; v++)
                     fsea_ws_comb_finish4<OUT, N1, N2>(kp, 4 * (p0 + v * CPF), row, dc_patch, re[2 * v], im[2 * v], re[2 * v + 1], im[2 * v + 1]);
