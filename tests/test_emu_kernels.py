@@ -43,7 +43,7 @@ def verify(res):
         assert r["logmag_db"] < 2e-3, tag            # dB, bins >= 1e-3 rms
         assert r["dc_bin_db"] < 1e-3, tag            # the analytic N/2 (1+i) DC term of uncentred u8/256
         assert r["scope_err"] < 1.4e-3, tag          # 7 log10(): the 2e-3 dB bound scaled by 7/10
-        assert r["pix_max"] <= 1 and r["pix_frac"] < 5e-3, tag   # trunc() of a float: <= 1 LSB on < 0.5 % of pixels
+        assert r["pix_max"] <= 1 and r["pix_frac"] < 2e-4, tag   # trunc() of a float: <= 1 LSB on < 2e-4 of the pixels (measured <= 3e-5)
 
 
 def test_emulated_single_launch_sizes(emu_lib):

@@ -7,7 +7,7 @@ Tolerances (north star: spectra within 1e-5 relative of a float64 DFT):
           butterflies leave sigma ~ 1.1e-7 relative per bin at N = 8192 -- DESIGN.md 4 -- so a bin 52 x rms,
           as in the cfg3 generator, cannot be promised to 1e-5 * rms = 1.6 ulp; it is held to 1e-6 of itself.)
   LOGMAG  |dB - dB_ref| <= 2e-3 dB wherever |X_ref| >= 1e-3 * rms (log of a cancelling bin is ill-conditioned)
-  PIX     |pix - pix_ref| <= 1 and fewer than 0.5 % of pixels differ (trunc() of a float)
+  PIX     |pix - pix_ref| <= 1 and fewer than 2e-4 of the pixels differ (trunc() of a float; measured 8e-6 ... 3e-5)
   F64     max |y - y_ref| <= 1e-11 * rms
 """
 import os
@@ -21,6 +21,15 @@ from conftest import BLOCK, synth_s8, synth_u8
 pytestmark = pytest.mark.gpu
 
 MAG_TOL = 1e-5
+# u8 pixels are trunc() of a float: the fp32 spectrum's ~1e-6 relative error moves S * dB by ~4e-5 S / 10, so about that
+# fraction of pixels lands on the other side of an integer (measured on 10^8 pixels of the cfg4 job and in every test
+# here: 8e-6 ... 3e-5 differing, always by exactly 1).  Bound: 1 LSB and 2e-4 of the pixels (a handful in a small test).
+PIX_DIFF_FRAC = 2e-4
+
+
+def pix_close(d):
+    d = np.asarray(d)
+    return bool(d.max() <= 1 and (d > 0).sum() <= max(3, PIX_DIFF_FRAC * d.size))
 
 
 def rel_err(got, ref):
@@ -137,7 +146,7 @@ def test_frame_per_unit_variants(fbg, n, arith):
     got = plan.exec_host(data, frames)
     ref = oracle_rows(data, n, hop, frames, orc.IN_U8, orc.WIN_HANN, orc.OUT_PIX, 5.0, orc.FLAG_DC_PATCH)
     d = np.abs(got.astype(int) - ref.astype(int))
-    assert d.max() <= 1 and (d > 0).mean() < 0.005, plan.kernel_name
+    assert pix_close(d), plan.kernel_name
 
 
 @pytest.mark.parametrize("n", [16384, 32768, 65536])
@@ -166,7 +175,7 @@ def test_four_step_sizes(fbg, n):
     got = plan.exec_host(data, frames)
     ref = oracle_rows(data, n, hop, frames, orc.IN_U8, orc.WIN_HANN, orc.OUT_PIX, 5.0, orc.FLAG_DC_PATCH)
     d = np.abs(got.astype(int) - ref.astype(int))
-    assert d.max() <= 1 and (d > 0).mean() < 0.005
+    assert pix_close(d)
 
 
 def test_four_step_many_frames(fbg):
@@ -200,7 +209,7 @@ def test_sweep_pixels_match_reference_tools(fbg, iq, golden):
         got = plan.exec_host(raw, 4)                       # one row per 262144-byte block, as the tools do
         ref = golden[key]
         d = np.abs(got.astype(int) - ref.astype(int))
-        assert d.max() <= 1 and (d > 0).mean() < 0.005
+        assert pix_close(d)
         if n == 1024:
             assert got[0, 512] == 255                      # SURVEY golden: DC pixel saturates without the patch
         # all frames of block 0 against the oracle
@@ -209,7 +218,7 @@ def test_sweep_pixels_match_reference_tools(fbg, iq, golden):
         got = plan.exec_host(raw, frames)
         ref = oracle_rows(raw, n, n, frames, orc.IN_S8, orc.WIN_NONE, orc.OUT_PIX, scale, flags)
         d = np.abs(got.astype(int) - ref.astype(int))
-        assert d.max() <= 1 and (d > 0).mean() < 0.005
+        assert pix_close(d)
 
 
 @pytest.mark.parametrize("n", [512, 1024, 16384])
@@ -288,7 +297,7 @@ def test_fft_batch_all_blocks_of_the_big_capture(fbg):
     plan = fb.Plan(n, hop=n, in_format=fb.IN_S8, out_mode=fb.OUT_PIX, pix_scale=10.0)
     got = plan.exec_host(heads["heads"].reshape(-1), 100)                     # 100 blocks x first 1024 samples
     d = np.abs(got.astype(int) - heads["ref_pix"].astype(int))
-    assert d.max() <= 1 and (d > 0).mean() < 0.005
+    assert pix_close(d)
     assert got[0, 512] == 255 and int(heads["ref_pix"][0].sum()) == 23772       # SURVEY 8(c) goldens: block 0
     if not os.path.exists(big):
         return
@@ -303,7 +312,7 @@ def test_fft_batch_all_blocks_of_the_big_capture(fbg):
     pix = plan.exec_host(raw, frames)
     refp = orc.engine_batch(raw, n, n, frames, orc.IN_S8, orc.WIN_NONE, orc.OUT_PIX, 10.0)
     d = np.abs(pix.astype(int) - refp.astype(int))
-    assert d.max() <= 1 and (d > 0).mean() < 0.005
+    assert pix_close(d)
 
 
 def test_sweep_stitch(fbg, iq):
@@ -321,7 +330,7 @@ def test_sweep_stitch(fbg, iq):
     ref_images = np.stack([oracle_rows(raw[b * BLOCK:], n, n, rows, orc.IN_S8, orc.WIN_NONE, orc.OUT_PIX, 5.0, orc.FLAG_DC_PATCH)
                            for b in range(4)])
     d = np.abs(fb.stitch(images, 102).astype(int) - orc.stitch(ref_images, 102).astype(int))
-    assert d.max() <= 1 and (d > 0).mean() < 0.005
+    assert pix_close(d)
 
 
 def test_gate_mean(fbg, iq, golden):
@@ -564,7 +573,7 @@ def test_sweep_engine_device_resident(fbg):
             continue
         ref = orc.engine_batch(raws[f], n, n, rows, orc.IN_S8, orc.WIN_NONE, orc.OUT_PIX, 5.0, flags=orc.FLAG_DC_PATCH)
         d = np.abs(images[f].astype(int) - ref.astype(int))
-        assert d.max() <= 1 and (d > 0).mean() < 0.005
+        assert pix_close(d)
     # deterministic: a second engine fed the same bytes through submit_device / submit_host agrees bit for bit
     eng2 = Sweep(n, rows, nf, gate_rows=8, own_images=True)
     for f in range(nf):
@@ -590,7 +599,7 @@ def test_sweep_job_single_gpu(fbg):
     np.testing.assert_allclose(got["means"], ref["means"], rtol=1e-5)
     gi, ri = got["images"].cpu().numpy(), ref["images"].numpy()
     d = np.abs(gi.astype(int) - ri.astype(int))
-    assert d.max() <= 1 and (d > 0).mean() < 0.005
+    assert pix_close(d)
     assert np.array_equal(got["stitched"].cpu().numpy(), orc.stitch(gi, step))     # stitch itself is bit-exact
     assert tuple(got["stitched"].shape) == (rows, n + (n_freqs - 1) * step)
     # WIDTH_STEP = N (c/fft-stitch-broad.c with SAMPLE_RATE = FREQUENCY_STEP): canvas stores == gather + stitch

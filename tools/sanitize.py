@@ -28,3 +28,29 @@ for n, frames, kw in CASES:
     plan = fb.Plan(n, in_format=fb.IN_S8 if "window" not in kw else fb.IN_U8, **kw)
     out = plan.exec_host(data, frames)
     print(n, plan.kernel_name, out.shape, float(np.asarray(out, dtype=np.float64).sum()))
+
+# round 2: sweep engine (side streams, grouped output rows, device-drawn source), fused front chain, device history ring,
+# float frames above 8192 points, and the cluster form of the warp-specialised kernel at 65536 (TMA, mbarriers, DSMEM)
+from frequensea_b200.binding import Chain, Sweep  # noqa: E402
+eng = Sweep(4096, 12, 5, gate_rows=4, own_images=True)
+for f in range(5):
+    eng.submit_synth(f, f, 3)
+means, keep = eng.gate(5)
+eng.render(5)
+print("sweep", keep.tolist(), int(eng.read_images(0, 5).sum()))
+nrf = fb.nrf
+blk = synth_u8(131072, seed=3)
+coef = nrf.fir_low_pass_coefficients(5000000, 200000, 51)[:51]
+ch = Chain(1024, shifter=(-10000, 5000000), fir_coefficients=coef)
+print("chain", float(ch.process(blk).sum()), float(ch.process(blk).sum()))
+fft = nrf.fft_new(1024, 8)
+for _ in range(10):
+    nrf.fft_process(fft, nrf.nut_buffer_new_u8(131072, 2, blk))
+nrf.fft_shift(fft, 16.0)
+print("history", float(nrf.fft_get_buffer(fft).numpy().sum()))
+nrf.fft_free(fft)
+x = np.random.default_rng(1).normal(0, 1, 2 * 16384)
+print("bigf", float(fb.Plan(16384, in_format=fb.IN_F64C).exec_host(x, 1).sum()))
+os.environ["FSEA_WS"] = "1"
+plan = fb.Plan(65536, in_format=fb.IN_S8, out_mode=fb.OUT_LOGMAG)
+print(plan.kernel_name, float(plan.exec_host(synth_s8(3 * 65536, seed=9), 3).sum()))
