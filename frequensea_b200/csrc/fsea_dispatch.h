@@ -53,7 +53,7 @@ struct fsea_kernel_info4 {
     const void* fn;          // __global__ entry
     int cs;                  // blocks per cluster (1: plain launch, one block per frame)
     int ws;                  // > 0: warp-specialised kernel (no L2 intermediate, one block per SM), frames per block iteration
-    int tma;                 // 1: fsea_wsc_kernel -- takes a tensor map of the input as its second argument
+    int tma;                 // 1: the kernel reads a tensor map of the input (its second argument); 2: takes the argument, ignores it
     int threads;             // block size
     size_t smem;             // dynamic shared memory per block
     int n1, n2;              // sub-spectrum length, sub-sequences

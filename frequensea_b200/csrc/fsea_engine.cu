@@ -496,6 +496,7 @@ static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cu
     kp.out_stride = out_stride > 0 ? out_stride : (long)p->cfg.fft_size * p->out_elem_bytes;
     kp.out_group = out_group;
     kp.out_group_stride = out_group_stride;
+    kp.tmap_arg = 0;
     if (p->bigf) return fsea_bigf_launch(p->bigf, kp, n_frames, stream, &p->launches);
     if (p->four) {
         // one launch: a cluster per frame, the intermediate lives in the clusters' L2-resident slots
@@ -507,8 +508,10 @@ static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cu
         kp.ticket = nullptr;
         const long nc = p->k4.ws ? std::min<long>((n_frames + p->k4.ws - 1) / p->k4.ws, p->max_clusters) : std::min<long>(n_frames, p->max_clusters);
         fsea_tmap tmap;
+        memset(&tmap, 0, sizeof(tmap));
         void* af[] = {&kp, &tmap};
-        if (p->k4.tma) {
+        kp.tmap_arg = p->k4.tma ? 1 : 0;
+        if (p->k4.tma == 1) {
             const int trc = make_input_tmap(&tmap, d_in, p->k4.n2, p->hop, n_frames);
             if (trc != FSEA_OK) return trc;
         }

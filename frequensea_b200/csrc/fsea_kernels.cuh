@@ -954,14 +954,17 @@ template <int OUT, int N1, int N2> struct fsea_comb {
             re[j] = mk2(a.x, a.y); im[j] = mk2(b.x, b.y);
         }
     }
-    static __device__ __forceinline__ void twiddle(const fsea_kparams& kp, int k, f2* re, f2* im) {
-        f2 br[LG], bi[LG];                                                       // W^(2^r k), r < LG
+    // the log2 N2 table rows of a bin pair (loads only: can be issued long before the sub-spectra are there) ...
+    static __device__ __forceinline__ void twiddle_load(const fsea_kparams& kp, int k, f2* br, f2* bi) {
 #pragma unroll
         for (int r = 0; r < LG; r++) {
             const float2 wa = fsea_ldg_stream((const float2*)((const float*)kp.tw4 + (size_t)(2 * r) * N1 + k));       // re plane
             const float2 wb = fsea_ldg_stream((const float2*)((const float*)kp.tw4 + (size_t)(2 * r + 1) * N1 + k));   // im plane
             br[r] = mk2(wa.x, wa.y); bi[r] = mk2(wb.x, wb.y);
         }
+    }
+    // ... and the chain of products W^(n2 k) built from them, applied
+    static __device__ __forceinline__ void twiddle_apply(const f2* br, const f2* bi, f2* re, f2* im) {
         f2 wr[N2], wi[N2];                                                       // (only a chain of <= LG is live at a time)
 #pragma unroll
         for (int j = 1; j < N2; j++) {
@@ -977,6 +980,11 @@ template <int OUT, int N1, int N2> struct fsea_comb {
             im[j] = vfma2(re[j], wi[j], vmul(im[j], wr[j]));
             re[j] = a;
         }
+    }
+    static __device__ __forceinline__ void twiddle(const fsea_kparams& kp, int k, f2* re, f2* im) {
+        f2 br[LG], bi[LG];                                                       // W^(2^r k), r < LG
+        twiddle_load(kp, k, br, bi);
+        twiddle_apply(br, bi, re, im);
     }
     static __device__ __forceinline__ void finish(const fsea_kparams& kp, int k, uint8_t* row, bool dc_patch, f2* re, f2* im) {
         fsea_dft<N2, f2>::run(re, im);

@@ -34,6 +34,7 @@ struct fsea_kparams {
     uint32_t xor_mask;     // 0x8080 for two's-complement input (FSEA_IN_S8), else 0
     const void* twh;       // "half" kernels: W_2N^i, i < M (butterflies of the last pass), float2
     void* scratch;         // fused four-step: resident clusters x N float2 (the L2-resident intermediate)
+    int tmap_arg;          // 1: the kernel takes a second argument, the input's tensor map (fsea_ws4 / fsea_wsc kernels)
     long out_group;        // > 0: output rows come in groups of this many frames (a sweep frequency's image), group g starting
     long out_group_stride; //      g * out_group_stride bytes into `out` (images side by side in a stitched canvas); 0: one run of rows
     long out_stride;       // bytes between the starts of consecutive output rows (N x element size when rows are packed;

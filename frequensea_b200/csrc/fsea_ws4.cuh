@@ -50,7 +50,9 @@
 #define FSEA_WS_PLANE (1056 * 8)
 #define FSEA_WS_Y (2 * 16 * 1024 * 4)
 #define FSEA_WS_TW (31 * 32 * 8)
-#define FSEA_WS_SMEM (FSEA_WS_NA * FSEA_WS_PLANE + FSEA_WS_Y + FSEA_WS_TW + 64)        /* + 8 mbarriers */
+#define FSEA_WS_STAGE (2 * 1024 * 16)
+#define FSEA_WS_SMEM (FSEA_WS_NA * FSEA_WS_PLANE + FSEA_WS_Y + FSEA_WS_TW + 128)       /* + mbarriers */
+#define FSEA_WS_SMEM_TMA (FSEA_WS_NA * FSEA_WS_PLANE + FSEA_WS_Y + FSEA_WS_STAGE + 128)
 
 
 
@@ -110,9 +112,15 @@ __device__ __forceinline__ void fsea_ws_comb_finish4(const fsea_kparams& kp, int
     }
 }
 
-template <int N2, int OUT, bool WIN>
+// TMA (N2 = 16): the frame's raw IQ -- 1024 rows of 32 bytes -- is fetched by cp.async.bulk.tensor into a staging
+// buffer [16-byte chunk][n1] a whole iteration ahead (one elected thread, 8 boxes, bytes counted in on an mbarrier)
+// instead of being gathered by the transform warps: a 4-byte gather pays one L1 wavefront per 128-byte line it touches
+// (2048 per frame, 22 % of this kernel's L1 traffic; staged: 256 in + 1024 out with 4-way conflicts) and 32 loads +
+// their address arithmetic per thread.  The 32 KB come out of the pass-1 twiddle table's place (read through L1 instead).
+template <int N2, int OUT, bool WIN, bool TMA>
 __global__ void __launch_bounds__(FSEA_WS_THREADS, 1)
-fsea_ws4_kernel(const fsea_kparams kp) {
+fsea_ws4_kernel(const fsea_kparams kp, const __grid_constant__ fsea_tmap tm) {
+    static_assert(!TMA || N2 == 16, "the staged form exists for one frame per block");
     constexpr int N1 = 1024;
     constexpr int FPB = 16 / N2;                            // frames a block works on at a time
     constexpr int UPF = N2 / 2;                             // units (= transform warps) per frame
@@ -128,7 +136,8 @@ fsea_ws4_kernel(const fsea_kparams kp) {
     const int tid = threadIdx.x;
     const int w = tid >> 5, t = tid & 31;
     float* Y = reinterpret_cast<float*>(fsea_smem + FSEA_WS_NA * FSEA_WS_PLANE);       // [frame][re | im][n2][1024]
-    float2* stw = reinterpret_cast<float2*>(fsea_smem + FSEA_WS_NA * FSEA_WS_PLANE + FSEA_WS_Y);
+    float2* stw = reinterpret_cast<float2*>(fsea_smem + FSEA_WS_NA * FSEA_WS_PLANE + FSEA_WS_Y);      // (!TMA)
+    unsigned char* stage = fsea_smem + FSEA_WS_NA * FSEA_WS_PLANE + FSEA_WS_Y;                        // (TMA) 2 chunks x 1024 rows x 16 bytes
     const long frames = kp.n_seq;
     const long groups = (frames + FPB - 1) / FPB;           // block iterations in the batch
     const long step = gridDim.x;
@@ -139,15 +148,24 @@ fsea_ws4_kernel(const fsea_kparams kp) {
     constexpr int NPH = BIT;
     constexpr int APP = (N2 == 16) ? FSEA_WS_NA : FSEA_WS_NA / NPH;          // transform warps whose values a phase reads
     static_assert(N2 == 16 ? NPH == 2 : NPH == FPB, "one phase per frame of the group (N2 <= 8) or per half of the bins (N2 = 16)");
-    unsigned long long* bars = reinterpret_cast<unsigned long long*>(fsea_smem + FSEA_WS_NA * FSEA_WS_PLANE + FSEA_WS_Y + FSEA_WS_TW);
+    unsigned long long* bars = reinterpret_cast<unsigned long long*>(fsea_smem + FSEA_WS_NA * FSEA_WS_PLANE + FSEA_WS_Y + (TMA ? FSEA_WS_STAGE : FSEA_WS_TW));
     unsigned long long* full = bars;                        // [NPH]
     unsigned long long* fre = bars + 4;                     // [NPH]
-    for (int q = tid; q < 31 * 32; q += FSEA_WS_THREADS) stw[q] = ((const float2*)kp.tw1)[q];
+    unsigned long long *raw_full = bars + 8, *raw_empty = bars + 9;     // (TMA)
+    if (!TMA) for (int q = tid; q < 31 * 32; q += FSEA_WS_THREADS) stw[q] = ((const float2*)kp.tw1)[q];
     if (tid == 0) {
 #pragma unroll
         for (int p = 0; p < NPH; p++) { fsea_mbar_init(full + p, APP * 32); fsea_mbar_init(fre + p, TB); }
+        if (TMA) { fsea_mbar_init(raw_full, 1); fsea_mbar_init(raw_empty, FSEA_WS_NA); }
     }
     __syncthreads();
+    auto fetch = [&](long f) {                              // one thread: the raw tile of frame f
+        fsea_mbar_expect_tx(raw_full, FSEA_WS_STAGE);
+#pragma unroll
+        for (int h = 0; h < 2; h++)
+#pragma unroll
+            for (int q = 0; q < 4; q++) fsea_tma_load_3d(stage + h * 16384 + q * 4096, &tm, 16 * h, 256 * q, (int)f, raw_full);
+    };
 
     if (w < FSEA_WS_NA) {
         // ------------------------------------------------ A: transform warps
@@ -161,17 +179,32 @@ fsea_ws4_kernel(const fsea_kparams kp) {
             return (const uint8_t*)kp.in + (size_t)f * frame_bytes + 4 * u;
         };
         unsigned it = 0;
+        const uint32_t* words = reinterpret_cast<const uint32_t*>(stage + (u >> 2) * 16384) + (u & 3);   // (TMA) word of row n1 at [4 n1]
+        const float2* tw1g = (const float2*)kp.tw1;
+        if (TMA && w == 0 && t == 0 && (long)blockIdx.x < groups) fetch(blockIdx.x);
         uint32_t raw[32];
         auto gather = [&](long g) {
             const uint8_t* src = unit_src(g) + (size_t)t * (2 * N2);
 #pragma unroll
             for (int j = 0; j < 32; j++) raw[j] = __ldg((const uint32_t*)(src + (size_t)j * (32 * 2 * N2)));
         };
-        constexpr bool EARLY = (N2 == 16) && FSEA_WS_EARLY;  // the next frame's gathers are issued between the two halves of the Y store
+        constexpr bool EARLY = (N2 == 16) && FSEA_WS_EARLY && !TMA;  // the next frame's gathers are issued between the two halves of the Y store
         if (EARLY && (long)blockIdx.x < groups) gather(blockIdx.x);
+        (void)words; (void)tw1g;
         for (long g = blockIdx.x; g < groups; g += step, it++) {
             f2 re[32], im[32];
-            if (!EARLY) gather(g);
+            if constexpr (TMA) {
+                fsea_mbar_wait(raw_full, it & 1);
+#pragma unroll
+                for (int j = 0; j < 32; j++) raw[j] = words[4 * (t + 32 * j)];
+                __syncwarp();
+                if (t == 0) fsea_mbar_arrive(raw_empty);               // this warp has taken its words
+                if (w == 0 && t == 0 && g + step < groups) {           // the next frame's tile, a whole iteration ahead
+                    fsea_mbar_wait(raw_empty, it & 1);
+                    fetch(g + step);
+                }
+                __syncwarp();
+            } else if (!EARLY) gather(g);
             const float* wsrc = WIN ? kp.window + (size_t)N2 * t + 2 * u : nullptr;    // sample n = N2 n1 + 2u (+1), n1 = t + 32 j
 #pragma unroll
             for (int j = 0; j < 32; j++) {
@@ -207,7 +240,7 @@ fsea_ws4_kernel(const fsea_kparams kp) {
             im[0] = vmuls(im[0], 1.0f / 256.0f);
 #pragma unroll
             for (int j = 1; j < 32; j++) {
-                const float2 tw = stw[(j - 1) * 32 + t];
+                const float2 tw = TMA ? __ldg(tw1g + (j - 1) * 32 + t) : stw[(j - 1) * 32 + t];
                 vcmul(re[j], im[j], tw.x, tw.y);
             }
             fsea_dft32<f2>(re, im);
@@ -226,7 +259,7 @@ fsea_ws4_kernel(const fsea_kparams kp) {
                     fsea_mbar_arrive(full + h);
                     // half of the result registers are free: the next frame's raw words start their trip now, behind the
                     // wait for the comb and the second half of the stores, instead of at the top of the loop
-                    if (h == 0 && g + step < groups) gather(g + step);
+                    if (!TMA && h == 0 && g + step < groups) gather(g + step);
                 }
             } else {
                 fsea_mbar_wait(fre + fi, (it & 1) ^ 1);                // the comb has read this frame slot of the previous group
@@ -260,10 +293,9 @@ fsea_ws4_kernel(const fsea_kparams kp) {
         };
         unsigned gi = 0;
         for (; g < groups; g += step, gi++) {
-            prefetch_l2(g + 2 * step);
+            if (!TMA) prefetch_l2(g + 2 * step);
 #pragma unroll 1
             for (int it = 0; it < BIT; it++) {
-                fsea_mbar_wait(full + it, gi & 1);                     // the values this phase reads are in Y
                 const int c = it * TB + bt;                            // comb call: frame c / CPF, pairs (c % CPF) + uu CPF
                 const int fi = c / CPF, p0 = c - fi * CPF;
                 const long f = g * FPB + fi;
@@ -271,9 +303,12 @@ fsea_ws4_kernel(const fsea_kparams kp) {
                 uint8_t* row = f < frames ? (uint8_t*)kp.out + fsea_out_row(kp, f) : (uint8_t*)kp.dump;
                 // a call works on U / 2 groups of FOUR neighbouring bins: 4 (p0 + v CPF) .. + 3
                 static_assert(U % 2 == 0, "bin pairs are combed two at a time");
+                fsea_mbar_wait(full + it, gi & 1);                     // the values this phase reads are in Y
                 f2 re[U][N2], im[U][N2];
 #pragma unroll
                 for (int v = 0; v < U / 2; v++) fsea_ws_comb_load4<N2>(yf, 4 * (p0 + v * CPF), re[2 * v], im[2 * v], re[2 * v + 1], im[2 * v + 1]);
+                // (issuing the twiddle rows' loads BEFORE the wait -- they do not depend on Y -- was measured: 24.4 vs 25.7 M
+                // frames/s; the 32 extra live registers cost more than the L2 latency they hide)
 #pragma unroll
                 for (int uu = 0; uu < U; uu++) COMB::twiddle(kp, 4 * (p0 + (uu / 2) * CPF) + 2 * (uu & 1), re[uu], im[uu]);
                 fsea_mbar_arrive(fre + it);                            // this phase's part of Y has been read

@@ -232,8 +232,8 @@ void launch(dim3 grid, dim3 block, size_t smem, int cluster_size, const std::fun
 
 cudaError_t fsea_emu_launch_kparams(const void* fn, dim3 grid, dim3 block, void** args, size_t smem, int cluster) {
     const fsea_kparams kp = *(const fsea_kparams*)args[0];
-    if (kp.n2 >= 32 && kp.scratch == nullptr && cluster > 1) {
-        // fsea_wsc_kernel(kparams, tensor map): the cluster kernels without an L2 scratch take the input's tensor map too
+    if (kp.tmap_arg) {
+        // kernel(kparams, tensor map)
         const fsea_tmap tm = *(const fsea_tmap*)args[1];
         void (*k2)(const fsea_kparams, const fsea_tmap) = (void (*)(const fsea_kparams, const fsea_tmap))fn;
         fsea_emu::launch(grid, block, smem, cluster, [&] { k2(kp, tm); });
