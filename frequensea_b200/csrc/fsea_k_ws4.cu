@@ -27,7 +27,10 @@ static bool fill_ws(fsea_kernel_info4* o, bool window, int out_mode, const char*
 bool fsea_get_kernel_ws4(int n, bool window, int out_mode, fsea_kernel_info4* o) {
     switch (n) {
         case 4096: return fill_ws<4, false>(o, window, out_mode, "ws4<4096=1024x4: 8 transform + 4 comb warps, 4 frames per block, intermediate in shared memory, f32x2>");
-        case 8192: return fill_ws<8, false>(o, window, out_mode, "ws4<8192=1024x8: 8 transform + 4 comb warps, 2 frames per block, intermediate in shared memory, f32x2>");
+        case 8192:
+            // (TMA tiles measured at this length too: 50.3 vs 58.5 M frames/s -- rows of 16 bytes make the gathers cheap, 4 lines per
+            //  load, and the staged form pays 4-way conflicts and loses the twiddle table's place in shared memory)
+            return fill_ws<8, false>(o, window, out_mode, "ws4<8192=1024x8: 8 transform + 4 comb warps, 2 frames per block, intermediate in shared memory, f32x2>");
         case 16384:
             // measured (profiles/r02_ws4/sweep_tma_ab.txt): float32 spectra 25.7 vs 23.8 M frames/s with TMA tiles; u8 pixels,
             // where the comb warps' heavier epilogue is the critical path, 23.9 vs 24.7: the gathered form stays there

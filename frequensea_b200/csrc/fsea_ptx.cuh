@@ -34,6 +34,12 @@ __device__ __forceinline__ void fsea_prefetch_l2(const void* p) {
 #endif
 }
 
+// hides a value's provenance from the optimiser (keeps loop-invariant arithmetic INSIDE a loop whose registers are all spoken for)
+__device__ __forceinline__ void fsea_opaque(float& x) {
+#if !defined(FSEA_EMU)
+    asm volatile("" : "+f"(x));
+#endif
+}
 __device__ __forceinline__ void fsea_prefetch_l1(const void* p) {
 #if defined(FSEA_EMU)
     (void)p;

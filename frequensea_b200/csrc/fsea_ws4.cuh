@@ -112,6 +112,46 @@ __device__ __forceinline__ void fsea_ws_comb_finish4(const fsea_kparams& kp, int
     }
 }
 
+// cos / sin(2 pi j / 32), j a compile-time constant after unrolling (folded into FFMA immediates)
+__device__ __forceinline__ float fsea_cos32(int j) {
+    switch (j & 31) {
+        case 0: return 1.0f;
+        case 1: return 0.98078528040323043f;
+        case 2: return 0.92387953251128674f;
+        case 3: return 0.83146961230254524f;
+        case 4: return 0.70710678118654757f;
+        case 5: return 0.55557023301960229f;
+        case 6: return 0.38268343236508984f;
+        case 7: return 0.19509032201612833f;
+        case 8: return 6.123233995736766e-17f;
+        case 9: return -0.19509032201612819f;
+        case 10: return -0.38268343236508973f;
+        case 11: return -0.55557023301960196f;
+        case 12: return -0.70710678118654746f;
+        case 13: return -0.83146961230254535f;
+        case 14: return -0.92387953251128674f;
+        case 15: return -0.98078528040323043f;
+        case 16: return -1.0f;
+        case 17: return -0.98078528040323043f;
+        case 18: return -0.92387953251128685f;
+        case 19: return -0.83146961230254546f;
+        case 20: return -0.70710678118654768f;
+        case 21: return -0.55557023301960218f;
+        case 22: return -0.38268343236509034f;
+        case 23: return -0.19509032201612866f;
+        case 24: return -1.8369701987210297e-16f;
+        case 25: return 0.1950903220161283f;
+        case 26: return 0.38268343236509f;
+        case 27: return 0.55557023301960184f;
+        case 28: return 0.70710678118654735f;
+        case 29: return 0.83146961230254524f;
+        case 30: return 0.92387953251128652f;
+        case 31: return 0.98078528040323032f;
+    }
+    return 1.0f;
+}
+__device__ __forceinline__ float fsea_sin32(int j) { return fsea_cos32(j + 24); }      // sin x = cos(x - pi/2) = cos(x + 3 pi/2)
+
 // TMA (N2 = 16): the frame's raw IQ -- 1024 rows of 32 bytes -- is fetched by cp.async.bulk.tensor into a staging
 // buffer [16-byte chunk][n1] a whole iteration ahead (one elected thread, 8 boxes, bytes counted in on an mbarrier)
 // instead of being gathered by the transform warps: a 4-byte gather pays one L1 wavefront per 128-byte line it touches
@@ -120,7 +160,8 @@ __device__ __forceinline__ void fsea_ws_comb_finish4(const fsea_kparams& kp, int
 template <int N2, int OUT, bool WIN, bool TMA>
 __global__ void __launch_bounds__(FSEA_WS_THREADS, 1)
 fsea_ws4_kernel(const fsea_kparams kp, const __grid_constant__ fsea_tmap tm) {
-    static_assert(!TMA || N2 == 16, "the staged form exists for one frame per block");
+    static_assert(!TMA || N2 >= 8, "a TMA box is at least 16 bytes wide: rows of 2 N2 bytes");
+    constexpr int CH = (2 * N2) / 16 > 0 ? (2 * N2) / 16 : 1;     // (TMA) 16-byte chunks per row of the frame
     constexpr int N1 = 1024;
     constexpr int FPB = 16 / N2;                            // frames a block works on at a time
     constexpr int UPF = N2 / 2;                             // units (= transform warps) per frame
@@ -137,7 +178,7 @@ fsea_ws4_kernel(const fsea_kparams kp, const __grid_constant__ fsea_tmap tm) {
     const int w = tid >> 5, t = tid & 31;
     float* Y = reinterpret_cast<float*>(fsea_smem + FSEA_WS_NA * FSEA_WS_PLANE);       // [frame][re | im][n2][1024]
     float2* stw = reinterpret_cast<float2*>(fsea_smem + FSEA_WS_NA * FSEA_WS_PLANE + FSEA_WS_Y);      // (!TMA)
-    unsigned char* stage = fsea_smem + FSEA_WS_NA * FSEA_WS_PLANE + FSEA_WS_Y;                        // (TMA) 2 chunks x 1024 rows x 16 bytes
+    unsigned char* stage = fsea_smem + FSEA_WS_NA * FSEA_WS_PLANE + FSEA_WS_Y;                        // (TMA) [frame of the group][chunk][n1][16 bytes] = 32 KB
     const long frames = kp.n_seq;
     const long groups = (frames + FPB - 1) / FPB;           // block iterations in the batch
     const long step = gridDim.x;
@@ -159,12 +200,15 @@ fsea_ws4_kernel(const fsea_kparams kp, const __grid_constant__ fsea_tmap tm) {
         if (TMA) { fsea_mbar_init(raw_full, 1); fsea_mbar_init(raw_empty, FSEA_WS_NA); }
     }
     __syncthreads();
-    auto fetch = [&](long f) {                              // one thread: the raw tile of frame f
+    auto fetch = [&](long g) {                              // one thread: the raw bytes of group g (frames past the end of the batch read as zeros)
         fsea_mbar_expect_tx(raw_full, FSEA_WS_STAGE);
 #pragma unroll
-        for (int h = 0; h < 2; h++)
+        for (int ff = 0; ff < FPB; ff++)
 #pragma unroll
-            for (int q = 0; q < 4; q++) fsea_tma_load_3d(stage + h * 16384 + q * 4096, &tm, 16 * h, 256 * q, (int)f, raw_full);
+            for (int h = 0; h < CH; h++)
+#pragma unroll
+                for (int q = 0; q < 4; q++)
+                    fsea_tma_load_3d(stage + ((ff * CH + h) * 4 + q) * 4096, &tm, 16 * h, 256 * q, (int)(g * FPB + ff), raw_full);
     };
 
     if (w < FSEA_WS_NA) {
@@ -179,8 +223,15 @@ fsea_ws4_kernel(const fsea_kparams kp, const __grid_constant__ fsea_tmap tm) {
             return (const uint8_t*)kp.in + (size_t)f * frame_bytes + 4 * u;
         };
         unsigned it = 0;
-        const uint32_t* words = reinterpret_cast<const uint32_t*>(stage + (u >> 2) * 16384) + (u & 3);   // (TMA) word of row n1 at [4 n1]
+        const uint32_t* words = reinterpret_cast<const uint32_t*>(stage + (fi * CH + (u >> 2)) * 16384) + (u & 3);   // (TMA) word of row n1 at [4 n1]
         const float2* tw1g = (const float2*)kp.tw1;
+        f2 hc = mk2(1.0f, 1.0f), hs = mk2(0.0f, 0.0f);     // (WIN) cos / sin of 2 pi n0 / N for the thread's first sample pair n0 = N2 t + 2u (+1)
+        if (WIN) {
+            float c0, s0, c1, s1;
+            sincospif(2.0f * (float)(N2 * t + 2 * u) / (float)(N1 * N2), &s0, &c0);
+            sincospif(2.0f * (float)(N2 * t + 2 * u + 1) / (float)(N1 * N2), &s1, &c1);
+            hc = mk2(c0, c1); hs = mk2(s0, s1);
+        }
         if (TMA && w == 0 && t == 0 && (long)blockIdx.x < groups) fetch(blockIdx.x);
         uint32_t raw[32];
         auto gather = [&](long g) {
@@ -205,15 +256,20 @@ fsea_ws4_kernel(const fsea_kparams kp, const __grid_constant__ fsea_tmap tm) {
                 }
                 __syncwarp();
             } else if (!EARLY) gather(g);
-            const float* wsrc = WIN ? kp.window + (size_t)N2 * t + 2 * u : nullptr;    // sample n = N2 n1 + 2u (+1), n1 = t + 32 j
+            if (WIN) {      // the 32 window values of a thread are the same for every frame: recompute them here rather than keep 64 registers
+                fsea_opaque(hc.v.x); fsea_opaque(hc.v.y); fsea_opaque(hs.v.x); fsea_opaque(hs.v.y);
+            }
 #pragma unroll
             for (int j = 0; j < 32; j++) {
                 const uint32_t v = raw[j] ^ x4;
                 re[j] = mk2(__uint_as_float(__byte_perm(v, 0x47000000u, 0x7504)), __uint_as_float(__byte_perm(v, 0x47000000u, 0x7524)));
                 im[j] = mk2(__uint_as_float(__byte_perm(v, 0x47000000u, 0x7514)), __uint_as_float(__byte_perm(v, 0x47000000u, 0x7534)));
                 if (WIN) {
-                    const float2 wv = __ldg((const float2*)(wsrc + (size_t)N2 * 32 * j));
-                    const f2 w2 = mk2(wv.x, wv.y), off = mk2(32896.0f, 32896.0f);
+                    // Hann without a table: sample n = N2 (t + 32 j) + 2u (+1), so 2 pi n / N = a + 2 pi j / 32 with a of this thread's
+                    // first sample pair: w = 1/2 - 1/2 (cos a cos(2 pi j/32) - sin a sin(2 pi j/32)), the j-part as immediates
+                    const f2 cw = vfnma(hs, fsea_sin32(j), vmuls(hc, fsea_cos32(j)));      // cos(a + 2 pi j / 32)
+                    const f2 w2 = vfnma(cw, 0.5f, mk2(0.5f, 0.5f));
+                    const f2 off = mk2(32896.0f, 32896.0f);
                     re[j] = vmul(vsub(re[j], off), w2);
                     im[j] = vmul(vsub(im[j], off), w2);
                 }

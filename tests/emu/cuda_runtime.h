@@ -120,6 +120,7 @@ static inline unsigned __byte_perm(unsigned a, unsigned b, unsigned s) {
 static inline unsigned __float_as_uint(float f) { unsigned u; memcpy(&u, &f, 4); return u; }
 static inline float __uint_as_float(unsigned u) { float f; memcpy(&f, &u, 4); return f; }
 #define __log2f(x) log2f(x)
+static inline void sincospif(float x, float* s, float* c) { *s = (float)sin(3.14159265358979323846 * (double)x); *c = (float)cos(3.14159265358979323846 * (double)x); }
 static inline int __float2int_rz(float x) { return (int)x; }
 static inline size_t __cvta_generic_to_shared(const void* p) { return (size_t)p; }
 static inline int max(int a, int b) { return a > b ? a : b; }
