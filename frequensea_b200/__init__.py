@@ -15,7 +15,7 @@ from .binding import (  # noqa: F401
     FseaError, Plan, build, device_count, lib, lib_path, stitch,
     IN_U8, IN_S8, IN_F32C, IN_F64C, WIN_NONE, WIN_HANN,
     OUT_MAG, OUT_LOGMAG, OUT_PIX, FLAG_DC_PATCH,
-    ARITH_AUTO, ARITH_F32, ARITH_F32X2, ARITH_F32X2_FRAME,
+    ARITH_AUTO, ARITH_F32, ARITH_F32X2, ARITH_F32X2_FRAME, ARITH_F32X2_RADIX64, ARITH_F64,
 )
 from . import nrf  # noqa: F401
 from . import shard, sweep  # noqa: F401

@@ -23,7 +23,7 @@ IN_U8, IN_S8, IN_F32C, IN_F64C = 0, 1, 2, 3
 WIN_NONE, WIN_HANN = 0, 1
 OUT_MAG, OUT_LOGMAG, OUT_PIX = 0, 1, 2
 FLAG_DC_PATCH = 1
-ARITH_AUTO, ARITH_F32, ARITH_F32X2, ARITH_F32X2_FRAME, ARITH_F32X2_RADIX64 = 0, 1, 2, 3, 4
+ARITH_AUTO, ARITH_F32, ARITH_F32X2, ARITH_F32X2_FRAME, ARITH_F32X2_RADIX64, ARITH_F64 = 0, 1, 2, 3, 4, 5
 
 OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_NO_DEVICE, ERR_CUDA, ERR_NOMEM = 0, -1, -2, -3, -4, -5
 
@@ -180,7 +180,7 @@ class Plan:
         self.cfg = cfg
         self.n = fft_size
         self.hop = cfg.hop
-        self.in_format, self.out_mode = in_format, out_mode
+        self.in_format, self.out_mode, self.arith = in_format, out_mode, arith
         self._h = C.c_void_p()
         _check(L.fsea_plan_create(C.byref(cfg), C.byref(self._h)), "fsea_plan_create")
 
@@ -198,7 +198,7 @@ class Plan:
     def out_dtype(self):
         if self.out_mode == OUT_PIX:
             return np.uint8
-        return np.float64 if self.in_format == IN_F64C else np.float32
+        return np.float64 if (self.in_format == IN_F64C or self.arith == ARITH_F64) else np.float32
 
     @property
     def kernel_name(self) -> str:

@@ -1,4 +1,5 @@
-// fsea_bigf.cu -- float-sample frames longer than 8192 points (FSEA_IN_F32C / FSEA_IN_F64C, N = 16384 .. 65536).
+// fsea_bigf.cu -- float-sample frames longer than 8192 points (FSEA_IN_F32C / FSEA_IN_F64C, N = 16384 .. 65536);
+// also what FSEA_ARITH_F64 runs above 8192 points once fsea_engine.cu has widened the 8-bit samples.
 //
 // The reference's float64 branch (src/nrf.c:607-609: raw doubles from a frequency shifter or an IQ filter)
 // has no length limit below its 131072-sample block.  The fast kernels of this engine take 8-bit IQ above
@@ -28,6 +29,9 @@ struct fsea_bigf {
     long chunk = 1;                     // frames per pass through the work buffers
     double2* d_tw = nullptr;            // exp(-2 pi i j / N), j < N/2
     double2* d_work[2] = {nullptr, nullptr};
+    cudaEvent_t done = nullptr;         // the work buffers are shared: launches on different streams are ordered by this event
+    cudaStream_t last = nullptr;
+    bool used = false;
 };
 
 // x[n] = w[n] * sample[n]  (src/nrf.c:607-612; the (-1)^n is the output rotation of the last launch)
@@ -89,6 +93,7 @@ int fsea_bigf_destroy(fsea_bigf* b) {
     if (b->d_tw) cudaFree(b->d_tw);
     if (b->d_work[0]) cudaFree(b->d_work[0]);
     if (b->d_work[1]) cudaFree(b->d_work[1]);
+    if (b->done) cudaEventDestroy(b->done);
     delete b;
     return FSEA_OK;
 }
@@ -108,7 +113,8 @@ int fsea_bigf_create(int n, int in_format, fsea_bigf** out) {
     if ((e = cudaMalloc(&b->d_tw, tw.size() * sizeof(double2))) != cudaSuccess ||
         (e = cudaMemcpy(b->d_tw, tw.data(), tw.size() * sizeof(double2), cudaMemcpyHostToDevice)) != cudaSuccess ||
         (e = cudaMalloc(&b->d_work[0], (size_t)b->chunk * n * sizeof(double2))) != cudaSuccess ||
-        (e = cudaMalloc(&b->d_work[1], (size_t)b->chunk * n * sizeof(double2))) != cudaSuccess) {
+        (e = cudaMalloc(&b->d_work[1], (size_t)b->chunk * n * sizeof(double2))) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&b->done, cudaEventDisableTiming)) != cudaSuccess) {
         fsea_bigf_destroy(b);
         return fsea_fail_cuda_internal(e, "float-frame work buffers");
     }
@@ -121,6 +127,7 @@ int fsea_bigf_launch(fsea_bigf* b, const fsea_kparams& kp, long n_frames, cudaSt
     const int n = b->n;
     const int f32 = b->in_format == FSEA_IN_F32C;
     const int gx = std::min(n / 2 / 256, 32);
+    if (b->used && b->last != stream) CU(cudaStreamWaitEvent(stream, b->done, 0));
     for (long f0 = 0; f0 < n_frames; f0 += b->chunk) {
         const long nf = std::min(b->chunk, n_frames - f0);
         const void* in = f32 ? (const void*)((const float2*)kp.in + f0 * kp.seq_stride) : (const void*)((const double2*)kp.in + f0 * kp.seq_stride);
@@ -135,5 +142,8 @@ int fsea_bigf_launch(fsea_bigf* b, const fsea_kparams& kp, long n_frames, cudaSt
         (*launches) += 2;
         CU(cudaGetLastError());
     }
+    CU(cudaEventRecord(b->done, stream));
+    b->last = stream;
+    b->used = true;
     return FSEA_OK;
 }

@@ -109,6 +109,16 @@ struct fsea_plan {
     // gate (fsea_gate_mean_host): grow-only device buffers, no allocation per call
     void* d_gate_in = nullptr; size_t gate_in_bytes = 0;
     void* d_gate_out = nullptr; size_t gate_out_bytes = 0;
+    // FSEA_ARITH_F64 on 8-bit input: samples widened to double (window applied in double) into `d_wide`, chunk by
+    // chunk, and transformed by a float64 plan -- the arithmetic of the reference itself (src/nrf.c:599-615)
+    fsea_plan* wide = nullptr;
+    void* d_wide = nullptr;
+    long wide_frames = 0;                        // frames per chunk
+    double* d_window64 = nullptr;
+    cudaEvent_t wide_done = nullptr;             // launches on different streams share d_wide: ordered by this event
+    cudaStream_t wide_stream = nullptr;
+    bool wide_used = false;
+    char name_store[160] = "";
 };
 
 static fsea_get_kernel_fn size_table(int n) {
@@ -191,6 +201,10 @@ extern "C" int fsea_plan_destroy(fsea_plan* p) {
     }
     if (p->d_gate_in) cudaFree(p->d_gate_in);
     if (p->d_gate_out) cudaFree(p->d_gate_out);
+    if (p->wide) fsea_plan_destroy(p->wide);
+    if (p->d_wide) cudaFree(p->d_wide);
+    if (p->d_window64) cudaFree(p->d_window64);
+    if (p->wide_done) cudaEventDestroy(p->wide_done);
     delete p;
     return FSEA_OK;
 }
@@ -227,14 +241,72 @@ static int upload_twiddles(const fsea_kernel_info& ki, void** d1, void** d2, flo
     return FSEA_OK;
 }
 
+// ------------------------------------------------------------------ FSEA_ARITH_F64 on 8-bit input
+// x[n] = w[n] * sample[n] exactly as the reference forms it in double (src/nrf.c:599-612, c/fft-batch.c:61-66):
+// b / 256 (after the HackRF byte flip) without a window, w (b - 128) / 256 with one; dense frames of N double2.
+__global__ void fsea_widen_kernel(const uint8_t* __restrict__ in, long hop, int n, unsigned flip, const double* __restrict__ win,
+                                  double2* __restrict__ out, long total) {
+    for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long f = idx / n;
+        const int i = (int)(idx - f * n);
+        const uchar2 b = ((const uchar2*)in)[f * hop + i];
+        const int vi = (int)(b.x ^ flip), vq = (int)(b.y ^ flip);            // (v + 128) % 256 == v ^ 0x80
+        double re, im;
+        if (win) { const double w = win[i]; re = w * ((double)(vi - 128) / 256.0); im = w * ((double)(vq - 128) / 256.0); }
+        else { re = (double)vi / 256.0; im = (double)vq / 256.0; }
+        out[idx] = make_double2(re, im);
+    }
+}
+
+static int create_wide_plan(const fsea_config* cfg, fsea_plan** out) {
+    const int n = cfg->fft_size;
+    if (n < 16 || n > 65536 || (n & (n - 1))) return FSEA_ERR_UNSUPPORTED;
+    if (cfg->window != FSEA_WIN_NONE && cfg->window != FSEA_WIN_HANN) return FSEA_ERR_INVALID;
+    if (cfg->hop < 0 || (cfg->hop % 8) != 0) return FSEA_ERR_INVALID;
+    fsea_config sub = *cfg;
+    sub.in_format = FSEA_IN_F64C; sub.window = FSEA_WIN_NONE; sub.hop = n; sub.arith = FSEA_ARITH_AUTO;
+    fsea_plan* inner = nullptr;
+    int rc = fsea_plan_create(&sub, &inner);
+    if (rc != FSEA_OK) return rc;
+    fsea_plan* p = new (std::nothrow) fsea_plan();
+    if (!p) { fsea_plan_destroy(inner); return FSEA_ERR_NOMEM; }
+    p->cfg = *cfg;
+    p->hop = cfg->hop > 0 ? cfg->hop : n;
+    p->variant = FSEA_VAR_F64;
+    p->sample_bytes = 2;
+    p->out_elem_bytes = inner->out_elem_bytes;
+    p->wide = inner;
+    memset(&p->ki, 0, sizeof(p->ki));
+    p->ki.n = n; p->ki.lanes = 1; p->ki.groups = 1; p->ki.threads = 256; p->ki.scalar_bytes = 8;
+    snprintf(p->name_store, sizeof(p->name_store), "f64 <- 8-bit (widened in double): %s", inner->ki.name);
+    p->ki.name = p->name_store;
+    p->wide_frames = std::max<long>(2, (64L << 20) / ((long)n * 16));
+    cudaError_t e;
+    if ((e = cudaMalloc(&p->d_wide, (size_t)p->wide_frames * n * sizeof(double2))) != cudaSuccess ||
+        (e = cudaEventCreateWithFlags(&p->wide_done, cudaEventDisableTiming)) != cudaSuccess) {
+        rc = cuda_fail(e, "float64 sample buffer");
+    }
+    if (rc == FSEA_OK && cfg->window == FSEA_WIN_HANN) {
+        std::vector<double> w(n);
+        const long double PI2 = 6.283185307179586476925286766559005768L;
+        for (int i = 0; i < n; i++) w[i] = (double)(0.5L * (1.0L - cosl(PI2 * i / n)));
+        if ((e = cudaMalloc(&p->d_window64, n * sizeof(double))) != cudaSuccess ||
+            (e = cudaMemcpy(p->d_window64, w.data(), n * sizeof(double), cudaMemcpyHostToDevice)) != cudaSuccess) rc = cuda_fail(e, "float64 window");
+    }
+    if (rc != FSEA_OK) { fsea_plan_destroy(p); return rc; }
+    *out = p;
+    return FSEA_OK;
+}
+
 extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
     if (!cfg || !out) return FSEA_ERR_INVALID;
     *out = nullptr;
     const int n = cfg->fft_size;
     if (n < 16 || n > 65536 || (n & (n - 1))) return FSEA_ERR_UNSUPPORTED;
+    const bool eight = cfg->in_format == FSEA_IN_U8 || cfg->in_format == FSEA_IN_S8;
+    if (cfg->arith == FSEA_ARITH_F64) return eight ? create_wide_plan(cfg, out) : FSEA_ERR_INVALID;   // (float64 samples are always transformed in fp64)
     fsea_get_kernel_fn get = size_table(n);
     fsea_kernel_info4 k4;
-    const bool eight = cfg->in_format == FSEA_IN_U8 || cfg->in_format == FSEA_IN_S8;
     int alt = 0;
     if (const char* ev = getenv("FSEA_FOUR_ALT")) alt = atoi(ev);                 // A/B runs
     // N >= 16384 always runs four-step; N = 8192 can (FSEA_8192_FOUR, A/B runs: measured slower
@@ -468,6 +540,29 @@ static int make_input_tmap(fsea_tmap* tm, const void* d_in, int n2, long hop, lo
 static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cudaStream_t stream, int slot = 0, long out_stride = 0,
                   long out_group = 0, long out_group_stride = 0) {
     if (n_frames <= 0) return FSEA_OK;
+    if (p->wide) {
+        if (out_group != 0) return FSEA_ERR_INVALID;
+        const int n = p->cfg.fft_size;
+        const long ostride = out_stride > 0 ? out_stride : (long)n * p->out_elem_bytes;
+        if (p->wide_used && p->wide_stream != stream) CU(cudaStreamWaitEvent(stream, p->wide_done, 0));
+        for (long f0 = 0; f0 < n_frames; f0 += p->wide_frames) {
+            const long nf = std::min(p->wide_frames, n_frames - f0);
+            const long total = nf * n;
+            const unsigned blocks = (unsigned)std::min<long>((total + 255) / 256, 148L * 16);
+            FSEA_LAUNCH(fsea_widen_kernel, blocks, 256, stream, (const uint8_t*)d_in + (size_t)f0 * p->hop * 2, (long)p->hop, n,
+                        p->cfg.in_format == FSEA_IN_S8 ? 0x80u : 0u, (const double*)p->d_window64, (double2*)p->d_wide, total);
+            CU(cudaGetLastError());
+            p->launches++;
+            const long before = p->wide->launches;
+            const int rc = launch(p->wide, p->d_wide, (uint8_t*)d_out + (size_t)f0 * ostride, nf, stream, slot, ostride);
+            if (rc != FSEA_OK) return rc;
+            p->launches += p->wide->launches - before;
+        }
+        CU(cudaEventRecord(p->wide_done, stream));
+        p->wide_stream = stream;
+        p->wide_used = true;
+        return FSEA_OK;
+    }
     fsea_kparams kp;
     kp.in = d_in;
     kp.out = d_out;

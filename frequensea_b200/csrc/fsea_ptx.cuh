@@ -370,19 +370,36 @@ __device__ __forceinline__ void fsea_mbar_wait(void* bar, unsigned parity) {    
         "}\n" ::"r"(a), "r"(parity) : "memory");
 #endif
 }
+#ifndef FSEA_MBARC_MODE
+#define FSEA_MBARC_MODE 1
+#endif
 __device__ __forceinline__ void fsea_mbar_wait_cluster(void* bar, unsigned parity) {  // ... acquiring what the arriving threads of OTHER blocks released
 #if defined(FSEA_EMU)
     fsea_emu::mbar_wait(bar, parity);
+#elif FSEA_MBARC_MODE == 0
+    const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "FSEA_MBARC_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"      // (invalidates L1 on EVERY poll)
+        "@p bra FSEA_MBARC_DONE_%=;\n"
+        "bra FSEA_MBARC_WAIT_%=;\n"
+        "FSEA_MBARC_DONE_%=:\n"
+        "}\n" ::"r"(a), "r"(parity) : "memory");
 #else
     const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
         "FSEA_MBARC_WAIT_%=:\n"
-        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 p, [%0], %1;\n"      // spin relaxed, acquire once
         "@p bra FSEA_MBARC_DONE_%=;\n"
         "bra FSEA_MBARC_WAIT_%=;\n"
         "FSEA_MBARC_DONE_%=:\n"
+#if FSEA_MBARC_MODE == 1
+        "fence.acq_rel.cluster;\n"
+#endif
         "}\n" ::"r"(a), "r"(parity) : "memory");
 #endif
 }

@@ -34,35 +34,60 @@
 #define FSEA_WSC_STAGE (2 * 1024 * 16)                       // [chunk][n1][16 bytes]
 #define FSEA_WSC_SMEM (FSEA_WS_NA * FSEA_WS_PLANE + FSEA_WS_Y + FSEA_WSC_STAGE + 64)
 
-// a transform thread's 32 bins of both sub-spectra -> Y of the blocks that comb them (compile-time recursion over m:
-// every byte offset is an immediate)
-template <int N2, int CS, int KL, bool PAIRED, int M>
-__device__ __forceinline__ void fsea_ws_store_y(const fsea_cptr* ybase, const fsea_cptr* bar, const f2* re, const f2* im) {
-    if constexpr (M < 32) {
-        constexpr int MPB = 32 / CS;                                   // values of m per destination block
-        constexpr int C = M / MPB, KOFF = 32 * (M % MPB);              // destination block, local bin offset from t
+// a transform thread's 32 bins of both sub-spectra -> Y of the blocks that comb them.  Bins t + 32 m, m in [C MPB, (C+1) MPB),
+// belong to block C: ordinary shared-memory stores where that is this block, stores into the peer's shared memory
+// otherwise (compile-time recursion over m: every byte offset is an immediate).
+template <int N2, int CS, int KL, bool PAIRED, bool LOCAL, int C, int MM>
+__device__ __forceinline__ void fsea_ws_store_y_block(fsea_cptr ybase, float* ylocal, fsea_cptr bar, const f2* re, const f2* im) {
+    constexpr int MPB = 32 / CS;                                       // values of m per destination block
+    if constexpr (MM < MPB) {
+        constexpr int M = C * MPB + MM, KOFF = 32 * MM;                // local bin offset from t
+        if constexpr (LOCAL) {
+            if constexpr (PAIRED) {
+                ((float2*)ylocal)[KOFF] = make_float2(re[M].v.x, re[M].v.y);
+                ((float2*)ylocal)[(N2 / 2) * KL + KOFF] = make_float2(im[M].v.x, im[M].v.y);
+            } else {
+                ylocal[KOFF] = re[M].v.x;
+                ylocal[KL + KOFF] = re[M].v.y;
+                ylocal[N2 * KL + KOFF] = im[M].v.x;
+                ylocal[(N2 + 1) * KL + KOFF] = im[M].v.y;
+            }
+        } else {
 #if FSEA_WSC_STAS
-        if constexpr (PAIRED) {
-            fsea_st_async_at<KOFF * 8>(ybase[C], make_float2(re[M].v.x, re[M].v.y), bar[C]);
-            fsea_st_async_at<((N2 / 2) * KL + KOFF) * 8>(ybase[C], make_float2(im[M].v.x, im[M].v.y), bar[C]);
-        } else {
-            fsea_st_async_at<KOFF * 4>(ybase[C], re[M].v.x, bar[C]);
-            fsea_st_async_at<(KL + KOFF) * 4>(ybase[C], re[M].v.y, bar[C]);
-            fsea_st_async_at<(N2 * KL + KOFF) * 4>(ybase[C], im[M].v.x, bar[C]);
-            fsea_st_async_at<((N2 + 1) * KL + KOFF) * 4>(ybase[C], im[M].v.y, bar[C]);
-        }
+            if constexpr (PAIRED) {
+                fsea_st_async_at<KOFF * 8>(ybase, make_float2(re[M].v.x, re[M].v.y), bar);
+                fsea_st_async_at<((N2 / 2) * KL + KOFF) * 8>(ybase, make_float2(im[M].v.x, im[M].v.y), bar);
+            } else {
+                fsea_st_async_at<KOFF * 4>(ybase, re[M].v.x, bar);
+                fsea_st_async_at<(KL + KOFF) * 4>(ybase, re[M].v.y, bar);
+                fsea_st_async_at<(N2 * KL + KOFF) * 4>(ybase, im[M].v.x, bar);
+                fsea_st_async_at<((N2 + 1) * KL + KOFF) * 4>(ybase, im[M].v.y, bar);
+            }
 #else
-        if constexpr (PAIRED) {
-            fsea_st_cluster_at<KOFF * 8>(ybase[C], make_float2(re[M].v.x, re[M].v.y));
-            fsea_st_cluster_at<((N2 / 2) * KL + KOFF) * 8>(ybase[C], make_float2(im[M].v.x, im[M].v.y));
-        } else {
-            fsea_st_cluster_at<KOFF * 4>(ybase[C], re[M].v.x);
-            fsea_st_cluster_at<(KL + KOFF) * 4>(ybase[C], re[M].v.y);
-            fsea_st_cluster_at<(N2 * KL + KOFF) * 4>(ybase[C], im[M].v.x);
-            fsea_st_cluster_at<((N2 + 1) * KL + KOFF) * 4>(ybase[C], im[M].v.y);
-        }
+            if constexpr (PAIRED) {
+                fsea_st_cluster_at<KOFF * 8>(ybase, make_float2(re[M].v.x, re[M].v.y));
+                fsea_st_cluster_at<((N2 / 2) * KL + KOFF) * 8>(ybase, make_float2(im[M].v.x, im[M].v.y));
+            } else {
+                fsea_st_cluster_at<KOFF * 4>(ybase, re[M].v.x);
+                fsea_st_cluster_at<(KL + KOFF) * 4>(ybase, re[M].v.y);
+                fsea_st_cluster_at<(N2 * KL + KOFF) * 4>(ybase, im[M].v.x);
+                fsea_st_cluster_at<((N2 + 1) * KL + KOFF) * 4>(ybase, im[M].v.y);
+            }
 #endif
-        fsea_ws_store_y<N2, CS, KL, PAIRED, M + 1>(ybase, bar, re, im);
+        }
+        fsea_ws_store_y_block<N2, CS, KL, PAIRED, LOCAL, C, MM + 1>(ybase, ylocal, bar, re, im);
+    }
+}
+template <int N2, int CS, int KL, bool PAIRED, int C>
+__device__ __forceinline__ void fsea_ws_store_y(const fsea_cptr* ybase, float* ylocal, const fsea_cptr* bar, unsigned crank, const f2* re, const f2* im) {
+    if constexpr (C < CS) {
+#if FSEA_WSC_STAS
+        fsea_ws_store_y_block<N2, CS, KL, PAIRED, false, C, 0>(ybase[C], ylocal, bar[C], re, im);      // (every byte is counted in: local ones too)
+#else
+        if (crank == (unsigned)C) fsea_ws_store_y_block<N2, CS, KL, PAIRED, true, C, 0>(ybase[C], ylocal, bar[C], re, im);
+        else fsea_ws_store_y_block<N2, CS, KL, PAIRED, false, C, 0>(ybase[C], ylocal, bar[C], re, im);
+#endif
+        fsea_ws_store_y<N2, CS, KL, PAIRED, C + 1>(ybase, ylocal, bar, crank, re, im);
     }
 }
 
@@ -126,6 +151,7 @@ fsea_wsc_kernel(const fsea_kparams kp, const __grid_constant__ fsea_tmap tm) {
         fsea_cptr ybase[CS];
 #pragma unroll
         for (int c = 0; c < CS; c++) ybase[c] = fsea_mapa(Y, (unsigned)c) + (PAIRED ? ((gu * KL + t) * 2) * 4 : ((2 * gu) * KL + t) * 4);
+        float* ylocal = Y + (PAIRED ? (gu * KL + t) * 2 : (2 * gu) * KL + t);     // the same element in this block's own Y
         fsea_cptr full_dst[CS];
 #pragma unroll
         for (int c = 0; c < CS; c++) full_dst[c] = fsea_mapa(y_full, (unsigned)c);
@@ -180,7 +206,7 @@ fsea_wsc_kernel(const fsea_kparams kp, const __grid_constant__ fsea_tmap tm) {
             }
             fsea_dft32<f2>(re, im);
             fsea_mbar_wait(y_free, (it & 1) ^ 1);                      // every comb warp of the cluster has read the previous frame
-            fsea_ws_store_y<N2, CS, KL, PAIRED, 0>(ybase, full_dst, re, im);
+            fsea_ws_store_y<N2, CS, KL, PAIRED, 0>(ybase, ylocal, full_dst, crank, re, im);
 #if !FSEA_WSC_STAS
             fsea_fence_cluster();                                      // ONE release for all of this thread's stores ...
 #pragma unroll

@@ -35,7 +35,10 @@
  *          = clamp_u8(trunc(pix_scale * 10 log10(|X[k]|^2 + 1e-20)))   FSEA_OUT_PIX (c/fft-batch.c:89-92)
  *   FSEA_FLAG_DC_PATCH:  out[N/2] = out[N/2-1]   (src/nrf.c:621-622, c/fft-batch-broad.c:115-117)
  * Output element type: float32 (MAG/LOGMAG), uint8 (PIX), float64 for
- * FSEA_IN_F64C (computed in fp64).  Output row f holds N bins.
+ * FSEA_IN_F64C and for FSEA_ARITH_F64 (computed in fp64).  Output row f holds N bins.
+ * The fp32 kernels reproduce the reference's float64 spectrum to ~1e-6 of the row's rms; a pixel whose
+ * scaled dB value lies that close to an integer can therefore come out 1 LSB off (measured: < 2e-4 of all
+ * pixels, tests/test_gpu_parity.py).  FSEA_ARITH_F64 is the mode without that caveat.
  */
 #ifndef FSEA_H
 #define FSEA_H
@@ -56,7 +59,10 @@ enum { FSEA_FLAG_DC_PATCH = 1 };
 /* arithmetic variant of the fp32 kernels (results agree to fp32 rounding) */
 enum { FSEA_ARITH_AUTO = 0, FSEA_ARITH_F32 = 1, FSEA_ARITH_F32X2 = 2,
        FSEA_ARITH_F32X2_FRAME = 3 /* packed lanes = even / odd samples of ONE frame (N = 2048, 4096, 8192; 8-bit input) */,
-       FSEA_ARITH_F32X2_RADIX64 = 4 /* N = 4096 = 64 x 64, 64 points per thread, one exchange (8-bit input, no window) */ };
+       FSEA_ARITH_F32X2_RADIX64 = 4 /* N = 4096 = 64 x 64, 64 points per thread, one exchange (8-bit input, no window) */,
+       FSEA_ARITH_F64 = 5 /* 8-bit input transformed in float64 like the reference (src/nrf.c:599-615): samples widened
+                             (and windowed) in double on the device, MAG / LOGMAG rows are float64, FSEA_OUT_PIX pixels
+                             equal the reference's byte for byte.  Any N; several times slower than the fp32 kernels. */ };
 
 enum {
     FSEA_OK = 0,

@@ -221,6 +221,46 @@ def test_sweep_pixels_match_reference_tools(fbg, iq, golden):
         assert pix_close(d)
 
 
+@pytest.mark.parametrize("n", [16, 256, 1024, 8192, 16384, 65536])
+def test_float64_arithmetic_pixels_exact(fbg, n):
+    """FSEA_ARITH_F64: 8-bit samples widened and windowed in double on the device, transformed in fp64 -- the
+    arithmetic of the reference (src/nrf.c:599-615, c/fft-batch.c:61-92).  Pixels are the oracle's BYTE FOR BYTE
+    (both tools' scales, with and without the Hann window / overlap), float rows agree to 1e-11 of the rms."""
+    fb = fbg
+    frames = 5 if n <= 8192 else 3
+    data = synth_s8(n * frames, seed=n + 41)
+    for scale, flags in ((10.0, 0), (5.0, fb.FLAG_DC_PATCH)):                 # c/fft-batch.c, c/fft-batch-broad.c
+        plan = fb.Plan(n, in_format=fb.IN_S8, out_mode=fb.OUT_PIX, pix_scale=scale, flags=flags, arith=fb.ARITH_F64)
+        got = plan.exec_host(data, frames)
+        ref = oracle_rows(data, n, n, frames, orc.IN_S8, orc.WIN_NONE, orc.OUT_PIX, scale, orc.FLAG_DC_PATCH if flags else 0)
+        assert got.dtype == np.uint8 and np.array_equal(got, ref), plan.kernel_name
+    hop = n // 2
+    data = synth_u8((frames - 1) * hop + n, seed=n + 42)
+    plan = fb.Plan(n, hop=hop, in_format=fb.IN_U8, window=fb.WIN_HANN, out_mode=fb.OUT_PIX, pix_scale=5.0,
+                   flags=fb.FLAG_DC_PATCH, arith=fb.ARITH_F64)
+    got = plan.exec_host(data, frames)
+    ref = oracle_rows(data, n, hop, frames, orc.IN_U8, orc.WIN_HANN, orc.OUT_PIX, 5.0, orc.FLAG_DC_PATCH)
+    assert np.array_equal(got, ref), plan.kernel_name
+    plan = fb.Plan(n, hop=hop, in_format=fb.IN_U8, window=fb.WIN_HANN, out_mode=fb.OUT_MAG, arith=fb.ARITH_F64)
+    got = plan.exec_host(data, frames)
+    ref = oracle_rows(data, n, hop, frames, orc.IN_U8, orc.WIN_HANN, orc.OUT_MAG)
+    assert got.dtype == np.float64
+    assert np.max(np.abs(got - ref)) <= 1e-11 * np.sqrt(np.mean(ref ** 2))
+    with pytest.raises(fb.FseaError):
+        fb.Plan(n, in_format=fb.IN_F32C, arith=fb.ARITH_F64)                 # float samples pick their arithmetic themselves
+
+
+def test_float64_arithmetic_reference_tool_rows(fbg, iq, golden):
+    """The rows c/fft-batch.c and c/fft-batch-broad.c write for the committed capture blocks (golden: computed by
+    the compiled reference), byte for byte."""
+    fb = fbg
+    raw = iq["rf200big4"]
+    for n, scale, flags, key in ((1024, 10.0, 0, "np_pix_batch_n1024"), (256, 5.0, fb.FLAG_DC_PATCH, "np_pix_broad_n256")):
+        plan = fb.Plan(n, hop=BLOCK // 2, in_format=fb.IN_S8, out_mode=fb.OUT_PIX, pix_scale=scale, flags=flags, arith=fb.ARITH_F64)
+        got = plan.exec_host(raw, 4)
+        assert np.array_equal(got, golden[key]), key
+
+
 @pytest.mark.parametrize("n", [512, 1024, 16384])
 def test_scope_row_matches_c_fft(fbg, iq, n):
     """c/fft.c:45-56,181-197 (the 512-point scope): raw bytes / 255 with no offset conversion,

@@ -62,7 +62,7 @@ def run(item, steps=int(os.environ.get("SWEEP_STEPS", "5")), warmup=int(os.envir
     cfg.out_mode = {"mag": B.OUT_MAG, "logmag": B.OUT_LOGMAG, "pix": B.OUT_PIX}[w["out"]]
     cfg.flags = B.FLAG_DC_PATCH if w["patch"] else 0
     cfg.pix_scale = w.get("scale", 10.0)
-    cfg.arith = {"auto": 0, "f32": 1, "f32x2": 2, "f32x2h": 3, "r64": 4}[arith]
+    cfg.arith = {"auto": 0, "f32": 1, "f32x2": 2, "f32x2h": 3, "r64": 4, "f64": 5}[arith]
     h = C.c_void_p()
     rc = L.fsea_plan_create(C.byref(cfg), C.byref(h))
     if rc:
@@ -73,7 +73,7 @@ def run(item, steps=int(os.environ.get("SWEEP_STEPS", "5")), warmup=int(os.envir
     nbytes = L.fsea_input_bytes(h, frames)
     d_in = torch.randint(0, 256, (nbytes,), dtype=torch.uint8, device=dev, generator=g)
     pix = cfg.out_mode == B.OUT_PIX
-    d_out = torch.zeros((frames, n), dtype=torch.uint8 if pix else torch.float32, device=dev)
+    d_out = torch.zeros((frames, n), dtype=torch.uint8 if pix else (torch.float64 if arith == "f64" else torch.float32), device=dev)
     s = torch.cuda.current_stream().cuda_stream
 
     def go():
