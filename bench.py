@@ -650,6 +650,17 @@ def main():
                 secondary[name] = measure_workload(ctx, fb, name)
             except Exception as e:
                 secondary[name] = {"error": str(e)[:300]}
+        if world == 1 and ctx.elapsed() <= args.budget_s:
+            # cfg4's rows in the reference's own arithmetic (FSEA_ARITH_F64): the pixels must EQUAL the oracle's
+            try:
+                ex = measure_workload(ctx, fb, "cfg4", frames_override=512, min_region_s=0.2, arith=fb.ARITH_F64)
+                ex["note"] = ("FSEA_ARITH_F64: samples widened in double on the device, fp64 transform; the mode whose pixels are the "
+                              "reference's byte for byte (roofline fraction is not the point of this entry)")
+                if ex["parity_gate"]["max_pixel_diff"] != 0:
+                    raise RuntimeError(f"fp64 pixels differ from the oracle: {ex['parity_gate']}")
+                secondary["cfg4_pixels_f64"] = ex
+            except Exception as e:
+                secondary["cfg4_pixels_f64"] = {"error": str(e)[:300]}
         if ctx.max_over_ranks(ctx.elapsed())[0] <= args.budget_s:
             try:
                 sustained = sustained_cfg5(ctx, fb, seconds=5.0)

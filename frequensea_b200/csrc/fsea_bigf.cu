@@ -4,7 +4,7 @@
 // The reference's float64 branch (src/nrf.c:607-609: raw doubles from a frequency shifter or an IQ filter)
 // has no length limit below its 131072-sample block.  The fast kernels of this engine take 8-bit IQ above
 // 8192 points; a float frame that long is one spectrum row per device block for a script such as
-// lua/fft-shifted.lua, not a throughput case -- it gets a plain, exact path: a radix-2 Stockham autosort
+// lua/fft-shifted.lua, not a throughput case -- it gets a plain, exact path: a radix-16 Stockham autosort
 // transform in fp64, one launch per stage through two work buffers in global memory (L2-resident for the
 // one-frame use), samples widened on load, |X| / log / pixel and the fftshift rotation in a last launch.
 #include <cuda_runtime.h>
@@ -27,7 +27,7 @@
 struct fsea_bigf {
     int n = 0, in_format = 0, out_mode = 0, flags = 0;
     long chunk = 1;                     // frames per pass through the work buffers
-    double2* d_tw = nullptr;            // exp(-2 pi i j / N), j < N/2
+    double2* d_tw = nullptr;            // exp(-2 pi i j / N), j < N
     double2* d_work[2] = {nullptr, nullptr};
     cudaEvent_t done = nullptr;         // the work buffers are shared: launches on different streams are ordered by this event
     cudaStream_t last = nullptr;
@@ -47,19 +47,64 @@ __global__ void fsea_bigf_load_kernel(const void* __restrict__ in, int f32, long
     }
 }
 
-// one radix-2 Stockham stage: ns = 1, 2, 4 .. N/2 sub-transform length going in
+// One radix-R Stockham autosort stage (R = 2, 4, 8, 16), ns = product of the radices already done: item j < N/R takes
+// in[j + t N/R], t < R, turns input t by W_{ns R}^{t k} (k = j mod ns), transforms the R values in registers and writes
+// out[(j - k) R + k + m ns], m < R.  tw[q] = exp(-2 pi i q / N), q < N.
+__constant__ double2 fsea_bigf_w16[8] = {
+    {1.0, -0.0},
+    {0.92387953251128675613, -0.38268343236508977173},
+    {0.70710678118654752440, -0.70710678118654752440},
+    {0.38268343236508977173, -0.92387953251128675613},
+    {0.0, -1.0},
+    {-0.38268343236508977173, -0.92387953251128675613},
+    {-0.70710678118654752440, -0.70710678118654752440},
+    {-0.92387953251128675613, -0.38268343236508977173}};
+
+template <int R> __device__ __forceinline__ void fsea_bigf_dft(double2* v) {       // in place, natural order in and out
+    constexpr int LG = (R == 2) ? 1 : (R == 4) ? 2 : (R == 8) ? 3 : 4;
+#pragma unroll
+    for (int i = 0; i < R; i++) {                                                    // bit reversal
+        int r = 0;
+#pragma unroll
+        for (int b = 0; b < LG; b++) r |= ((i >> b) & 1) << (LG - 1 - b);
+        if (r > i) { const double2 x = v[i]; v[i] = v[r]; v[r] = x; }
+    }
+#pragma unroll
+    for (int len = 2; len <= R; len <<= 1) {
+#pragma unroll
+        for (int base = 0; base < R; base += len) {
+#pragma unroll
+            for (int q = 0; q < len / 2; q++) {
+                const double2 w = fsea_bigf_w16[q * (16 / len)];                    // W_len^q
+                const double2 a = v[base + q], b0 = v[base + q + len / 2];
+                const double2 b = (q == 0) ? b0 : make_double2(b0.x * w.x - b0.y * w.y, b0.x * w.y + b0.y * w.x);
+                v[base + q] = make_double2(a.x + b.x, a.y + b.y);
+                v[base + q + len / 2] = make_double2(a.x - b.x, a.y - b.y);
+            }
+        }
+    }
+}
+
+template <int R>
 __global__ void fsea_bigf_stage_kernel(const double2* __restrict__ in, double2* __restrict__ out, const double2* __restrict__ tw,
                                        int n, int ns, int gx) {
     const long f = blockIdx.x / gx;
-    const int half = n >> 1;
-    for (int j = (blockIdx.x % gx) * blockDim.x + threadIdx.x; j < half; j += gx * blockDim.x) {
+    const int items = n / R;
+    const int tstep = n / (ns * R);                                     // table stride of W_{ns R}
+    for (int j = (blockIdx.x % gx) * blockDim.x + threadIdx.x; j < items; j += gx * blockDim.x) {
         const int k = j & (ns - 1);
-        const double2 w = tw[(size_t)k * (half / ns)];                 // exp(-2 pi i k / (2 ns))
-        const double2 a = in[f * n + j], b0 = in[f * n + j + half];
-        const double2 b = make_double2(b0.x * w.x - b0.y * w.y, b0.x * w.y + b0.y * w.x);
-        const size_t o = (size_t)f * n + (size_t)(j - k) * 2 + k;
-        out[o] = make_double2(a.x + b.x, a.y + b.y);
-        out[o + ns] = make_double2(a.x - b.x, a.y - b.y);
+        double2 v[R];
+#pragma unroll
+        for (int t = 0; t < R; t++) {
+            const double2 x = in[f * n + j + (size_t)t * items];
+            if (t == 0 || ns == 1) { v[t] = x; continue; }
+            const double2 w = tw[(size_t)t * k * tstep];
+            v[t] = make_double2(x.x * w.x - x.y * w.y, x.x * w.y + x.y * w.x);
+        }
+        fsea_bigf_dft<R>(v);
+        const size_t o = (size_t)f * n + (size_t)(j - k) * R + k;
+#pragma unroll
+        for (int m = 0; m < R; m++) out[o + (size_t)m * ns] = v[m];
     }
 }
 
@@ -103,9 +148,9 @@ int fsea_bigf_create(int n, int in_format, fsea_bigf** out) {
     b->n = n;
     b->in_format = in_format;
     b->chunk = std::max<long>(1, (1L << 21) / n);
-    std::vector<double2> tw((size_t)n / 2);
+    std::vector<double2> tw((size_t)n);
     const long double PI2 = 6.283185307179586476925286766559005768L;
-    for (int j = 0; j < n / 2; j++) {
+    for (int j = 0; j < n; j++) {
         const long double a = -PI2 * (long double)j / (long double)n;
         tw[j].x = (double)cosl(a); tw[j].y = (double)sinl(a);
     }
@@ -133,9 +178,19 @@ int fsea_bigf_launch(fsea_bigf* b, const fsea_kparams& kp, long n_frames, cudaSt
         const void* in = f32 ? (const void*)((const float2*)kp.in + f0 * kp.seq_stride) : (const void*)((const double2*)kp.in + f0 * kp.seq_stride);
         FSEA_LAUNCH(fsea_bigf_load_kernel, (unsigned)(gx * nf), 256, stream, in, f32, kp.seq_stride, n, kp.window, b->d_work[0], gx);
         int cur = 0;
-        for (int ns = 1; ns < n; ns <<= 1) {
-            FSEA_LAUNCH(fsea_bigf_stage_kernel, (unsigned)(gx * nf), 256, stream, (const double2*)b->d_work[cur], b->d_work[cur ^ 1], (const double2*)b->d_tw, n, ns, gx);
+        for (int ns = 1; ns < n;) {                                      // radix 16 while it divides what is left, then the rest
+            const int left = n / ns;
+            const int r = left >= 16 ? 16 : left;
+            const double2* src = b->d_work[cur];
+            double2* dst = b->d_work[cur ^ 1];
+            const int gs = std::max(1, std::min(n / r / 128, 32));     // blocks per frame
+            const unsigned grid = (unsigned)(gs * nf);
+            if (r == 16) FSEA_LAUNCH(fsea_bigf_stage_kernel<16>, grid, 128, stream, src, dst, (const double2*)b->d_tw, n, ns, gs);
+            else if (r == 8) FSEA_LAUNCH(fsea_bigf_stage_kernel<8>, grid, 128, stream, src, dst, (const double2*)b->d_tw, n, ns, gs);
+            else if (r == 4) FSEA_LAUNCH(fsea_bigf_stage_kernel<4>, grid, 128, stream, src, dst, (const double2*)b->d_tw, n, ns, gs);
+            else FSEA_LAUNCH(fsea_bigf_stage_kernel<2>, grid, 128, stream, src, dst, (const double2*)b->d_tw, n, ns, gs);
             cur ^= 1;
+            ns *= r;
             (*launches)++;
         }
         FSEA_LAUNCH(fsea_bigf_finish_kernel, (unsigned)(gx * nf), 256, stream, (const double2*)b->d_work[cur], n, kp, f32 ? 0 : 1, f0, gx);

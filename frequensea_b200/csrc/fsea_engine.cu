@@ -361,7 +361,7 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
         memset(&p->ki, 0, sizeof(p->ki));
         p->ki.n = n; p->ki.lanes = 1; p->ki.groups = 1; p->ki.threads = 256;
         p->ki.scalar_bytes = cfg->in_format == FSEA_IN_F64C ? 8 : 4;
-        p->ki.name = cfg->in_format == FSEA_IN_F64C ? "bigf<radix-2 Stockham, fp64, one launch per stage, f64 samples>" : "bigf<radix-2 Stockham, fp64, one launch per stage, f32 samples>";
+        p->ki.name = cfg->in_format == FSEA_IN_F64C ? "bigf<radix-16 Stockham, fp64, one launch per stage, f64 samples>" : "bigf<radix-16 Stockham, fp64, one launch per stage, f32 samples>";
     } else if (four) {
         p->four = true;
         p->k4 = k4;

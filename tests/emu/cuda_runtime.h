@@ -51,6 +51,7 @@ static inline uchar2 make_uchar2(unsigned char a, unsigned char b) { uchar2 r; r
 // ---- function / variable qualifiers -----------------------------------------------------
 #define __global__
 #define __device__
+#define __constant__ static const
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
