@@ -39,7 +39,7 @@ class FseaConfig(C.Structure):
 class FseaSweepConfig(C.Structure):
     _fields_ = [("fft_size", C.c_int), ("rows", C.c_int), ("gate_rows", C.c_int), ("gate_threshold", C.c_double),
                 ("pix_scale", C.c_float), ("in_format", C.c_int), ("device", C.c_int), ("capacity", C.c_int),
-                ("own_raw", C.c_int), ("own_images", C.c_int), ("reserved", C.c_int * 4)]
+                ("own_raw", C.c_int), ("own_images", C.c_int), ("pixel_arith", C.c_int), ("reserved", C.c_int * 3)]
 
 
 class FseaChainConfig(C.Structure):
@@ -283,10 +283,11 @@ class Sweep:
     -> gate decisions -> u8 pixel rows, nothing crossing the host in between (c/fft-batch-broad.c:56-129)."""
 
     def __init__(self, fft_size: int, rows: int, capacity: int, gate_rows: int = 100, gate_threshold: float = 1.1,
-                 pix_scale: float = 5.0, in_format: int = IN_S8, device: int = 0, own_raw: bool = True, own_images: bool = False):
+                 pix_scale: float = 5.0, in_format: int = IN_S8, device: int = 0, own_raw: bool = True, own_images: bool = False,
+                 pixel_arith: int = ARITH_AUTO):
         cfg = FseaSweepConfig(fft_size=fft_size, rows=rows, gate_rows=gate_rows, gate_threshold=gate_threshold,
                               pix_scale=pix_scale, in_format=in_format, device=device, capacity=capacity,
-                              own_raw=int(own_raw), own_images=int(own_images))
+                              own_raw=int(own_raw), own_images=int(own_images), pixel_arith=pixel_arith)
         self.n, self.rows, self.capacity, self.device = fft_size, rows, capacity, device
         self._h = C.c_void_p()
         _check(lib().fsea_sweep_create(C.byref(cfg), C.byref(self._h)), "fsea_sweep_create")

@@ -541,22 +541,27 @@ static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cu
                   long out_group = 0, long out_group_stride = 0) {
     if (n_frames <= 0) return FSEA_OK;
     if (p->wide) {
-        if (out_group != 0) return FSEA_ERR_INVALID;
         const int n = p->cfg.fft_size;
         const long ostride = out_stride > 0 ? out_stride : (long)n * p->out_elem_bytes;
         if (p->wide_used && p->wide_stream != stream) CU(cudaStreamWaitEvent(stream, p->wide_done, 0));
-        for (long f0 = 0; f0 < n_frames; f0 += p->wide_frames) {
-            const long nf = std::min(p->wide_frames, n_frames - f0);
-            const long total = nf * n;
-            const unsigned blocks = (unsigned)std::min<long>((total + 255) / 256, 148L * 16);
-            FSEA_LAUNCH(fsea_widen_kernel, blocks, 256, stream, (const uint8_t*)d_in + (size_t)f0 * p->hop * 2, (long)p->hop, n,
-                        p->cfg.in_format == FSEA_IN_S8 ? 0x80u : 0u, (const double*)p->d_window64, (double2*)p->d_wide, total);
-            CU(cudaGetLastError());
-            p->launches++;
-            const long before = p->wide->launches;
-            const int rc = launch(p->wide, p->d_wide, (uint8_t*)d_out + (size_t)f0 * ostride, nf, stream, slot, ostride);
-            if (rc != FSEA_OK) return rc;
-            p->launches += p->wide->launches - before;
+        // (rows in groups, fsea_out_row(): a chunk never straddles two groups, so the inner launch sees plain rows)
+        const long group = out_group > 0 ? out_group : n_frames;
+        for (long g0 = 0; g0 < n_frames; g0 += group) {
+            const long ng = std::min(group, n_frames - g0);
+            uint8_t* gout = (uint8_t*)d_out + (out_group > 0 ? (size_t)(g0 / group) * out_group_stride : 0);
+            for (long f0 = 0; f0 < ng; f0 += p->wide_frames) {
+                const long nf = std::min(p->wide_frames, ng - f0);
+                const long total = nf * n;
+                const unsigned blocks = (unsigned)std::min<long>((total + 255) / 256, 148L * 16);
+                FSEA_LAUNCH(fsea_widen_kernel, blocks, 256, stream, (const uint8_t*)d_in + (size_t)(g0 + f0) * p->hop * 2, (long)p->hop, n,
+                            p->cfg.in_format == FSEA_IN_S8 ? 0x80u : 0u, (const double*)p->d_window64, (double2*)p->d_wide, total);
+                CU(cudaGetLastError());
+                p->launches++;
+                const long before = p->wide->launches;
+                const int rc = launch(p->wide, p->d_wide, gout + (size_t)f0 * ostride, nf, stream, slot, ostride);
+                if (rc != FSEA_OK) return rc;
+                p->launches += p->wide->launches - before;
+            }
         }
         CU(cudaEventRecord(p->wide_done, stream));
         p->wide_stream = stream;

@@ -130,6 +130,7 @@ static int sweep_setup(fsea_sweep* s) {
     int rc = fsea_plan_create(&pc, &s->mag);
     if (rc != FSEA_OK) return rc;
     pc.out_mode = FSEA_OUT_PIX;
+    pc.arith = (c.pixel_arith == FSEA_ARITH_F64) ? FSEA_ARITH_F64 : FSEA_ARITH_AUTO;
     pc.flags = FSEA_FLAG_DC_PATCH;
     pc.pix_scale = c.pix_scale;
     if ((rc = fsea_plan_create(&pc, &s->pix)) != FSEA_OK) return rc;

@@ -61,14 +61,14 @@ class DeviceEngine:
     """This rank's GPU: fsea_sweep (raw -> gate -> pixel rows, device-resident) + stitch."""
 
     def __init__(self, n: int, rows: int, capacity: int, device: int = 0, gate_rows: int = GATE_ROWS,
-                 gate_threshold: float = GATE_THRESHOLD, pix_scale: float = PIX_SCALE):
+                 gate_threshold: float = GATE_THRESHOLD, pix_scale: float = PIX_SCALE, pixel_arith: int = 0):
         import torch
         from . import binding as B
         self._B, self._torch = B, torch
         self.n, self.rows, self.capacity, self.device = n, rows, capacity, device
         self.tdev = torch.device("cuda", device)
         self.eng = B.Sweep(n, rows, capacity, gate_rows=gate_rows, gate_threshold=gate_threshold, pix_scale=pix_scale,
-                           in_format=B.IN_S8, device=device, own_raw=True, own_images=False)
+                           in_format=B.IN_S8, device=device, own_raw=True, own_images=False, pixel_arith=pixel_arith)
 
     def submit(self, slot: int, freq_idx: int, raw: Optional[np.ndarray] = None, quiet_every: int = 10) -> None:
         """raw IQ of a frequency: host bytes (uploaded once) or, with raw=None, the 8(d) source drawn on the device"""

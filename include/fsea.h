@@ -190,7 +190,9 @@ typedef struct {
     int capacity;          /* frequencies held at once */
     int own_raw;           /* 1: the engine keeps the raw IQ (needed by submit_host / submit_synth) */
     int own_images;        /* 1: the engine keeps images [capacity][rows][N] */
-    int reserved[4];
+    int pixel_arith;       /* arithmetic of the pixel pass: FSEA_ARITH_AUTO (fp32 kernels; < 2e-4 of the pixels 1 LSB off the
+                              reference's) or FSEA_ARITH_F64 (the reference's picture byte for byte, ~10 x slower) */
+    int reserved[3];
 } fsea_sweep_config;
 int fsea_sweep_create(const fsea_sweep_config *cfg, fsea_sweep **out);
 int fsea_sweep_destroy(fsea_sweep *s);

@@ -221,7 +221,7 @@ def test_sweep_pixels_match_reference_tools(fbg, iq, golden):
         assert pix_close(d)
 
 
-@pytest.mark.parametrize("n", [16, 256, 1024, 8192, 16384, 65536])
+@pytest.mark.parametrize("n", [16, 256, 1024, 8192, 16384, 32768, 65536])
 def test_float64_arithmetic_pixels_exact(fbg, n):
     """FSEA_ARITH_F64: 8-bit samples widened and windowed in double on the device, transformed in fp64 -- the
     arithmetic of the reference (src/nrf.c:599-615, c/fft-batch.c:61-92).  Pixels are the oracle's BYTE FOR BYTE
@@ -614,6 +614,17 @@ def test_sweep_engine_device_resident(fbg):
         ref = orc.engine_batch(raws[f], n, n, rows, orc.IN_S8, orc.WIN_NONE, orc.OUT_PIX, 5.0, flags=orc.FLAG_DC_PATCH)
         d = np.abs(images[f].astype(int) - ref.astype(int))
         assert pix_close(d)
+    # the pixel pass in the reference's arithmetic: the oracle's pictures byte for byte (kept slots in runs: rows in groups)
+    eng3 = Sweep(n, rows, nf, gate_rows=8, own_images=True, pixel_arith=fb.ARITH_F64)
+    for f in range(nf):
+        eng3.submit_host(f, raws[f])
+    means3, keep3 = eng3.gate(nf)
+    assert np.array_equal(keep3, keep)
+    eng3.render(nf)
+    images3 = eng3.read_images(0, nf)
+    for f in range(nf):
+        ref = orc.engine_batch(raws[f], n, n, rows, orc.IN_S8, orc.WIN_NONE, orc.OUT_PIX, 5.0, flags=orc.FLAG_DC_PATCH)
+        assert np.array_equal(images3[f], ref if keep[f] else np.zeros_like(ref)), f
     # deterministic: a second engine fed the same bytes through submit_device / submit_host agrees bit for bit
     eng2 = Sweep(n, rows, nf, gate_rows=8, own_images=True)
     for f in range(nf):
