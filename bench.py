@@ -400,7 +400,13 @@ def sweep_job(ctx, fb, n_freqs=1000, rows=512, n=16384):
     eng.eng.sync()
     modes = {}
     resident = _Resident(eng, len(mine))
-    for mode in ("gather", "p2p"):
+    def column_checksums(pic, count):
+        """one int64 per frequency: position-weighted sum of every 64th row of its N columns"""
+        v = pic[::64].reshape(-1, count, n).to(torch.int64)
+        w = torch.arange(1, n + 1, dtype=torch.int64, device=pic.device)
+        return (v * w).sum(dim=(0, 2))
+    full_sums = None
+    for mode in ("gather", "p2p") + (("stripes",) if ctx.world > 1 else ()):
         try:
             canvas = sweep.prepare_canvas(eng, n_freqs, n, rows, ctx.rank, ctx.world) if (mode == "p2p" and ctx.world > 1) else None
             # set-up run (connections, allocator), then the timed one
@@ -413,10 +419,27 @@ def sweep_job(ctx, fb, n_freqs=1000, rows=512, n=16384):
             torch.cuda.synchronize()
             dt = ctx.max_over_ranks(time.perf_counter() - t0)[0]
             launches = eng.launches - l0
+            if mode == "stripes":
+                import torch.distributed as dist
+                mine_sums = column_checksums(res["stripe"], per)
+                all_sums = [torch.empty_like(mine_sums) for _ in range(ctx.world)]
+                dist.all_gather(all_sums, mine_sums)
+                if ctx.rank == 0:
+                    kept = int(res["keep"].sum())
+                    got = torch.stack(all_sums, dim=1).reshape(-1)[:n_freqs]          # frequency f = j world + r
+                    modes[mode] = {"seconds": dt, "rows_per_s": kept * rows / dt, "kept": kept, "gated_off": n_freqs - kept,
+                                   "stripe_shape": list(res["stripe"].shape), "gpu_launches_rank0": launches,
+                                   "exchange": "none: every rank keeps the pixel rows of its frequencies (SURVEY 8(e) (i): results stay where they are produced)",
+                                   "same_pixels_as_p2p": bool(full_sums is not None and torch.equal(got.cpu(), full_sums.cpu()))}
+                del res
+                torch.cuda.empty_cache()
+                continue
             if ctx.rank == 0:
                 kept = int(res["keep"].sum())
                 import hashlib
                 pic = res["stitched"]
+                if mode == "p2p" and ctx.world > 1:
+                    full_sums = column_checksums(pic, n_freqs)
                 # a cheap fingerprint of the 8 GB picture: column sums of every 64th row
                 fp = hashlib.sha256(pic[::64].to(torch.int64).sum(dim=0).cpu().numpy().tobytes()).hexdigest()[:16]
                 modes[mode] = {"seconds": dt, "rows_per_s": kept * rows / dt, "kept": kept, "gated_off": n_freqs - kept,
@@ -436,7 +459,8 @@ def sweep_job(ctx, fb, n_freqs=1000, rows=512, n=16384):
         except Exception as e:                                    # never lose the bench line over this leg
             modes[mode] = {"error": str(e)[:300]}
     out["modes"] = modes
-    best = max((m for m in modes.values() if "rows_per_s" in m), key=lambda m: m["rows_per_s"], default=None)
+    # the job's value is a COMPLETE picture on one GPU; the stripes leg is reported beside it
+    best = max((m for k, m in modes.items() if "rows_per_s" in m and k != "stripes"), key=lambda m: m["rows_per_s"], default=None)
     if best:
         out["value"] = best["rows_per_s"]
         out["unit"] = "rows/s"

@@ -18,6 +18,10 @@ owns the stitched picture is the job's only exchange, in one of two ways:
                  over CUDA IPC and every rank's transform kernel stores its pixel rows straight
                  into it -- the kernel's stores ARE the gather (NVLink peer writes), there is no
                  collective and no stitch pass.
+  mode="stripes" no exchange at all: every rank keeps the pixel rows of ITS frequencies as a stripe canvas
+                 [rows, per N] in its own memory (frequency j world + rank at column j N) -- SURVEY.md 8(e)'s
+                 "spectra left where they are produced"; a consumer reads the stripes in parallel (8 PCIe
+                 links instead of one).  Every rank gets {"stripe": ...} back.
 
 `engine` is DeviceEngine in the product; the CPU test-suite passes a stand-in with the same methods.
 """
@@ -92,6 +96,13 @@ class DeviceEngine:
     def render_into(self, n_slots: int, ptr: int, stride: int, col0: int, col_step: int) -> None:
         self.eng.render(n_slots, ptr, stride, col0, col_step)
         self.eng.sync()
+
+    def render_stripe(self, n_slots: int, per: int):
+        """[rows, per N] u8 on the device: slot j's image at column j N (gated-off and unused slots zero)"""
+        stripe = self.new_canvas(self.rows, per * self.n)
+        self._torch.cuda.current_stream(self.tdev).synchronize()
+        self.render_into(n_slots, stripe.data_ptr(), per * self.n, 0, self.n)
+        return stripe
 
     def new_canvas(self, rows: int, width: int):
         return self._torch.zeros((rows, width), dtype=self._torch.uint8, device=self.tdev)
@@ -180,7 +191,12 @@ def sweep(engine, n_freqs: int, n: int, rows: int, width_step: int,
     dist.gather(t_k, gk, dst=dst, group=group)
 
     res = None
-    if mode == "p2p" and width_step == n and nccl:
+    if mode == "stripes":
+        stripe = engine.render_stripe(len(mine), per)                             # slot j at column j N of this rank's stripe
+        res = {"stripe": stripe, "frequencies": list(mine)}
+        if rank != dst:
+            return res
+    elif mode == "p2p" and width_step == n and nccl:
         own = canvas is None
         cv, ptr, alive = _share_canvas(engine, rows, out_width, rank, dst, group) if own else canvas
         engine.render_into(len(mine), ptr, out_width, rank * n, world * n)        # frequency j * world + rank at column (j world + rank) N

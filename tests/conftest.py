@@ -125,6 +125,10 @@ class OracleEngine:
                                           flags=orc.FLAG_DC_PATCH)
         return torch.from_numpy(img)
 
+    def render_stripe(self, n_slots, per):
+        img = self.render_images(n_slots, per)                       # [per, rows, n] -> [rows, per n]
+        return img.permute(1, 0, 2).reshape(self.rows, per * self.n).contiguous()
+
     def stitch(self, gathered, n_freqs, world, per, width_step):
         import torch
         from oracle import orc

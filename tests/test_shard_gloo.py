@@ -72,9 +72,18 @@ def _sweep_worker(rank, world, port, n_freqs, n, rows, step, q):
     stream = lambda f: sweep.synth_frequency(f, n, rows, quiet_every=4)
     per = (n_freqs + world - 1) // world
     res = sweep.sweep(OracleEngine(n, rows, per, gate_rows=8), n_freqs, n, rows, step, source=stream, rank=rank, world=world)
+    # mode="stripes": nothing travels but the gate decisions; every rank keeps the images of its frequencies side by side
+    st = sweep.sweep(OracleEngine(n, rows, per, gate_rows=8), n_freqs, n, rows, n, source=stream, rank=rank, world=world, mode="stripes")
+    stripes = [None] * world
+    dist.all_gather_object(stripes, (st["frequencies"], np.asarray(st["stripe"])))
     if rank == 0:
         one = sweep.sweep(OracleEngine(n, rows, n_freqs, gate_rows=8), n_freqs, n, rows, step, source=stream)   # the same job on one rank
         same = all(np.array_equal(np.asarray(res[k]), np.asarray(one[k])) for k in ("means", "keep", "images", "stitched"))
+        same = same and np.array_equal(st["keep"], one["keep"]) and np.array_equal(st["means"], one["means"])
+        for freqs, stripe in stripes:
+            assert stripe.shape == (rows, per * n)
+            for j, f in enumerate(freqs):
+                same = same and np.array_equal(stripe[:, j * n:(j + 1) * n], np.asarray(one["images"][f]))
         q.put((bool(same), res["keep"].tolist(), tuple(res["stitched"].shape)))
     dist.barrier()
     dist.destroy_process_group()
