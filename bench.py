@@ -409,6 +409,9 @@ def sweep_job(ctx, fb, n_freqs=1000, rows=512, n=16384):
     for mode in ("gather", "p2p") + (("stripes",) if ctx.world > 1 else ()):
         try:
             canvas = sweep.prepare_canvas(eng, n_freqs, n, rows, ctx.rank, ctx.world) if (mode == "p2p" and ctx.world > 1) else None
+            if mode == "stripes":                                 # like the shared canvas: allocated and cleared once, outside the job
+                canvas = eng.new_canvas(rows, per * n)
+                torch.cuda.synchronize()
             # set-up run (connections, allocator), then the timed one
             res = sweep.sweep(resident, n_freqs, n, rows, n, rank=ctx.rank, world=ctx.world, mode=mode, keep_images=False, canvas=canvas)
             del res
@@ -432,6 +435,7 @@ def sweep_job(ctx, fb, n_freqs=1000, rows=512, n=16384):
                                    "exchange": "none: every rank keeps the pixel rows of its frequencies (SURVEY 8(e) (i): results stay where they are produced)",
                                    "same_pixels_as_p2p": bool(full_sums is not None and torch.equal(got.cpu(), full_sums.cpu()))}
                 del res
+                canvas = None
                 torch.cuda.empty_cache()
                 continue
             if ctx.rank == 0:
@@ -452,7 +456,7 @@ def sweep_job(ctx, fb, n_freqs=1000, rows=512, n=16384):
                 if "parity" not in out:
                     out["parity"] = _sweep_parity(eng, res, mine, n, rows)
             del res
-            if canvas is not None:
+            if canvas is not None and mode == "p2p":
                 canvas[2].close()
             canvas = None
             torch.cuda.empty_cache()

@@ -192,7 +192,11 @@ def sweep(engine, n_freqs: int, n: int, rows: int, width_step: int,
 
     res = None
     if mode == "stripes":
-        stripe = engine.render_stripe(len(mine), per)                             # slot j at column j N of this rank's stripe
+        if canvas is None:
+            stripe = engine.render_stripe(len(mine), per)                         # slot j at column j N of this rank's stripe
+        else:                                                                     # a stripe canvas the caller keeps between sweeps
+            stripe = canvas
+            engine.render_into(len(mine), stripe.data_ptr(), per * n, 0, n)
         res = {"stripe": stripe, "frequencies": list(mine)}
         if rank != dst:
             return res
