@@ -538,9 +538,11 @@ static int make_input_tmap(fsea_tmap* tm, const void* d_in, int n2, long hop, lo
 }
 
 static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cudaStream_t stream, int slot = 0, long out_stride = 0,
-                  long out_group = 0, long out_group_stride = 0) {
+                  long out_group = 0, long out_group_stride = 0, long hop = 0) {
     if (n_frames <= 0) return FSEA_OK;
+    if (hop <= 0) hop = p->hop;                          // (hop > 0: this launch's frames lie `hop` samples apart, whatever the plan says)
     if (p->wide) {
+        if (hop != p->hop) return FSEA_ERR_INVALID;
         const int n = p->cfg.fft_size;
         const long ostride = out_stride > 0 ? out_stride : (long)n * p->out_elem_bytes;
         if (p->wide_used && p->wide_stream != stream) CU(cudaStreamWaitEvent(stream, p->wide_done, 0));
@@ -572,7 +574,7 @@ static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cu
     kp.in = d_in;
     kp.out = d_out;
     kp.n_seq = n_frames;
-    kp.seq_stride = p->hop;
+    kp.seq_stride = hop;
     kp.tw1 = p->d_tw1;
     kp.tw2 = p->d_tw2;
     kp.window = p->d_window;
@@ -612,7 +614,7 @@ static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cu
         void* af[] = {&kp, &tmap};
         kp.tmap_arg = p->k4.tma ? 1 : 0;
         if (p->k4.tma == 1) {
-            const int trc = make_input_tmap(&tmap, d_in, p->k4.n2, p->hop, n_frames);
+            const int trc = make_input_tmap(&tmap, d_in, p->k4.n2, hop, n_frames);
             if (trc != FSEA_OK) return trc;
         }
         if (p->k4.cs > 1) {
@@ -664,8 +666,8 @@ extern "C" int fsea_exec_device_strided(fsea_plan* p, const void* d_in, void* d_
 
 // the sweep engine (fsea_sweep.cu) launches plans on its own stream
 int fsea_launch_internal(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cudaStream_t stream, long out_stride, int scratch_slot,
-                         long out_group, long out_group_stride) {
-    return launch(p, d_in, d_out, n_frames, stream, scratch_slot, out_stride, out_group, out_group_stride);
+                         long out_group, long out_group_stride, long hop) {
+    return launch(p, d_in, d_out, n_frames, stream, scratch_slot, out_stride, out_group, out_group_stride, hop);
 }
 int fsea_fail_cuda_internal(cudaError_t e, const char* what) { return cuda_fail(e, what); }
 int fsea_plan_elem_bytes_internal(const fsea_plan* p) { return p->out_elem_bytes; }

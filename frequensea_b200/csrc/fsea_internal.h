@@ -15,7 +15,8 @@
 // output rows (0: packed); scratch_slot < 4: which L2 intermediate a four-step plan uses (launches that
 // share a slot on different streams are serialised)
 int fsea_launch_internal(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cudaStream_t stream, long out_stride, int scratch_slot = 0,
-                         long out_group = 0, long out_group_stride = 0);   // out_group > 0: rows in groups (fsea_kparams.h)
+                         long out_group = 0, long out_group_stride = 0,    // out_group > 0: rows in groups (fsea_kparams.h)
+                         long hop = 0);                                     // hop > 0: samples between this launch's frames (0: the plan's)
 int fsea_fail_cuda_internal(cudaError_t e, const char* what);      // records the text for fsea_last_cuda_error(), returns FSEA_ERR_CUDA
 int fsea_plan_elem_bytes_internal(const fsea_plan* p);
 void fsea_count_launch_internal(fsea_plan* p);

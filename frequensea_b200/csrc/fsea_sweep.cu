@@ -41,6 +41,7 @@ struct fsea_sweep {
     uint8_t* d_raw = nullptr;                   // [capacity][raw_bytes]   (own_raw)
     std::vector<const void*> raw_ptr;           // where each slot's raw IQ lives
     float* d_gate_mag = nullptr;                // NS x gate_rows x N
+    float* d_gate_rowmag = nullptr;             // NS x capacity x N: |X| of ONE gate row of every slot (own_raw, sweep_gate_by_rows)
     double* d_partials = nullptr;               // [capacity][FSEA_SUM_BLOCKS]
     double* d_means = nullptr;
     uint8_t* d_keep = nullptr;
@@ -104,6 +105,7 @@ extern "C" int fsea_sweep_destroy(fsea_sweep* s) {
     fsea_plan_destroy(s->pix);
     if (s->d_raw) cudaFree(s->d_raw);
     if (s->d_gate_mag) cudaFree(s->d_gate_mag);
+    if (s->d_gate_rowmag) cudaFree(s->d_gate_rowmag);
     if (s->d_partials) cudaFree(s->d_partials);
     if (s->d_means) cudaFree(s->d_means);
     if (s->d_keep) cudaFree(s->d_keep);
@@ -146,6 +148,7 @@ static int sweep_setup(fsea_sweep* s) {
     if (c.own_raw) CU(cudaMalloc(&s->d_raw, s->raw_bytes * c.capacity));
     if (c.own_images) CU(cudaMalloc(&s->d_images, s->img_bytes * c.capacity));
     CU(cudaMalloc(&s->d_gate_mag, sizeof(float) * fsea_sweep::NS * (size_t)c.gate_rows * c.fft_size));
+    if (c.own_raw && c.gate_rows <= FSEA_SUM_BLOCKS) CU(cudaMalloc(&s->d_gate_rowmag, sizeof(float) * fsea_sweep::NS * (size_t)c.capacity * c.fft_size));
     CU(cudaMalloc(&s->d_partials, sizeof(double) * FSEA_SUM_BLOCKS * (size_t)c.capacity));
     CU(cudaMalloc(&s->d_means, sizeof(double) * c.capacity));
     CU(cudaMalloc(&s->d_keep, (size_t)c.capacity));
@@ -197,6 +200,48 @@ static int sweep_gate_rows(fsea_sweep* s, int slot) {
     return FSEA_OK;
 }
 
+// The same sums, taken ROW by row over all slots at once when the raw IQ lies in the engine's own store: gate row r of
+// slots 0 .. n_slots-1 are frames rows * N samples apart, so one launch transforms row r of every slot (n_slots frames:
+// a full grid, where a slot's gate_rows frames fill two thirds of one wave) and one block per slot sums its N magnitudes.
+// partials[slot][r] = that row's sum (block order = row order: the same bits wherever the slot sits and however many
+// slots there are), entries r >= gate_rows zero; fsea_gate_decide_kernel adds them as before.
+__global__ void fsea_rowsum_kernel(const float* __restrict__ x, int n, double* __restrict__ partials, int r) {
+    FSEA_STATIC_SMEM(double, warp_sum, 8);
+    const float* row = x + (size_t)blockIdx.x * n;
+    double s = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s += (double)row[i];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) warp_sum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int w = 0; w < 8; w++) t += warp_sum[w];
+        partials[(size_t)blockIdx.x * FSEA_SUM_BLOCKS + r] = t;
+    }
+}
+
+static bool sweep_in_own_store(const fsea_sweep* s, int n_slots) {
+    if (!s->d_raw || !s->d_gate_rowmag) return false;
+    for (int j = 0; j < n_slots; j++) if (s->raw_ptr[j] != s->d_raw + (size_t)j * s->raw_bytes) return false;
+    return true;
+}
+
+static int sweep_gate_by_rows(fsea_sweep* s, int n_slots) {          // (between sweep_fork and sweep_join)
+    const int n = s->cfg.fft_size;
+    CU(cudaMemsetAsync(s->d_partials, 0, sizeof(double) * FSEA_SUM_BLOCKS * (size_t)n_slots, s->stream));
+    int rc = sweep_fork(s);
+    for (int r = 0; r < s->cfg.gate_rows && rc == FSEA_OK; r++) {
+        const int k = r % fsea_sweep::NS;
+        float* mag = s->d_gate_rowmag + (size_t)k * s->cfg.capacity * n;
+        rc = fsea_launch_internal(s->mag, s->d_raw + (size_t)r * n * 2, mag, n_slots, s->side[k], 0, k, 0, 0, (long)s->cfg.rows * n);
+        if (rc != FSEA_OK) break;
+        FSEA_LAUNCH(fsea_rowsum_kernel, n_slots, 256, s->side[k], (const float*)mag, n, s->d_partials, r);
+        CU(cudaGetLastError());
+        s->launches += 2;
+    }
+    return rc;
+}
+
 extern "C" int fsea_sweep_submit_host(fsea_sweep* s, int slot, const void* h_raw) {
     if (!s || !h_raw || slot < 0 || slot >= s->cfg.capacity || !s->d_raw) return FSEA_ERR_INVALID;
     CU(cudaSetDevice(s->cfg.device));
@@ -234,8 +279,13 @@ extern "C" int fsea_sweep_gate_begin(fsea_sweep* s, int n_slots) {
     if (!s || n_slots <= 0 || n_slots > s->cfg.capacity) return FSEA_ERR_INVALID;
     for (int j = 0; j < n_slots; j++) if (!s->raw_ptr[j]) return FSEA_ERR_INVALID;
     CU(cudaSetDevice(s->cfg.device));
-    int rc = sweep_fork(s);
-    for (int j = 0; j < n_slots && rc == FSEA_OK; j++) rc = sweep_gate_rows(s, j);
+    int rc;
+    if (sweep_in_own_store(s, n_slots)) {
+        rc = sweep_gate_by_rows(s, n_slots);
+    } else {
+        rc = sweep_fork(s);
+        for (int j = 0; j < n_slots && rc == FSEA_OK; j++) rc = sweep_gate_rows(s, j);
+    }
     if (rc == FSEA_OK) rc = sweep_join(s);
     if (rc != FSEA_OK) return rc;
     const double count = (double)s->cfg.gate_rows * (double)s->cfg.fft_size;
