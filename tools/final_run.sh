@@ -32,6 +32,7 @@ for w in n2048@65536 n4096@32768 n8192@16384 cfg3@16384 n16384@8192 cfg4@8192 n3
   python tools/ncu_summary.py $O/prof_$tag.ncu-rep > $O/ncu_full_$tag.txt 2>&1
   rm -f $O/prof_$tag.ncu-rep
 done
+python tools/sweep.py cfg2@65536:f64 n8192@8192:f64 cfg4@2048:f64 n65536@256:f64 2>&1 | cut -c1-200 > $O/f64_mode.txt
 python tools/bench_fir.py --taps 51 > $O/bench_fir_51.json 2> $O/bench_fir_51.err
 python tools/bench_fir.py --taps 97 > $O/bench_fir_97.json 2> $O/bench_fir_97.err
 python tools/bench_operator.py > $O/bench_operator_per_draw.json 2> $O/bench_operator.err
