@@ -408,7 +408,7 @@ def sweep_job(ctx, fb, n_freqs=1000, rows=512, n=16384):
     full_sums = None
     for mode in ("gather", "p2p") + (("stripes",) if ctx.world > 1 else ()):
         try:
-            canvas = sweep.prepare_canvas(eng, n_freqs, n, rows, ctx.rank, ctx.world) if (mode == "p2p" and ctx.world > 1) else None
+            canvas = sweep.prepare_canvas(eng, n_freqs, n, rows, ctx.rank, ctx.world) if mode == "p2p" else None
             if mode == "stripes":                                 # like the shared canvas: allocated and cleared once, outside the job
                 canvas = eng.new_canvas(rows, per * n)
                 torch.cuda.synchronize()
@@ -456,7 +456,7 @@ def sweep_job(ctx, fb, n_freqs=1000, rows=512, n=16384):
                 if "parity" not in out:
                     out["parity"] = _sweep_parity(eng, res, mine, n, rows)
             del res
-            if canvas is not None and mode == "p2p":
+            if canvas is not None and mode == "p2p" and canvas[2] is not None:
                 canvas[2].close()
             canvas = None
             torch.cuda.empty_cache()

@@ -51,6 +51,7 @@ FSEA_DECL_SIZE(8192)
 // combs the sub-spectra; the intermediate stays in L2.
 struct fsea_kernel_info4 {
     const void* fn;          // __global__ entry
+    const void* fn_sums;     // the same kernel leaving per-frame sums of |X| instead of spectra (fsea_kparams::frame_sums), or null
     int cs;                  // blocks per cluster (1: plain launch, one block per frame)
     int ws;                  // > 0: warp-specialised kernel (no L2 intermediate, one block per SM), frames per block iteration
     int tma;                 // 1: the kernel reads a tensor map of the input (its second argument); 2: takes the argument, ignores it

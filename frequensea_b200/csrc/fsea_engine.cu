@@ -383,6 +383,8 @@ extern "C" int fsea_plan_create(const fsea_config* cfg, fsea_plan** out) {
             if ((rc = fsea_bigf_create(n, cfg->in_format, &p->bigf)) != FSEA_OK) break;
         } else {
         if ((rc = setup_kernel(p->ki, cfg->device, &p->max_blocks)) != FSEA_OK) break;
+        if (p->four && p->k4.fn_sums &&
+            (e = cudaFuncSetAttribute(p->k4.fn_sums, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->k4.smem)) != cudaSuccess) { rc = cuda_fail(e, "sums kernel setup"); break; }
         // staged 8-bit kernels transform integer-scaled samples (b - 128): the 1/256 of
         // src/nrf.c:605-606 rides on the pass-1 twiddles
         const bool staged = p->four || ((p->variant == FSEA_VAR_F32 || p->variant == FSEA_VAR_F32X2 ||
@@ -538,8 +540,10 @@ static int make_input_tmap(fsea_tmap* tm, const void* d_in, int n2, long hop, lo
 }
 
 static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cudaStream_t stream, int slot = 0, long out_stride = 0,
-                  long out_group = 0, long out_group_stride = 0, long hop = 0) {
+                  long out_group = 0, long out_group_stride = 0, long hop = 0, double* sums = nullptr, long sums_stride = 0,
+                  long sums_offset = 0) {
     if (n_frames <= 0) return FSEA_OK;
+    if (sums && !(p->four && p->k4.fn_sums)) return FSEA_ERR_UNSUPPORTED;     // (sums: fsea_kparams::frame_sums, no spectra stored)
     if (hop <= 0) hop = p->hop;                          // (hop > 0: this launch's frames lie `hop` samples apart, whatever the plan says)
     if (p->wide) {
         if (hop != p->hop) return FSEA_ERR_INVALID;
@@ -599,6 +603,7 @@ static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cu
     kp.out_group = out_group;
     kp.out_group_stride = out_group_stride;
     kp.tmap_arg = 0;
+    kp.frame_sums = sums; kp.sums_stride = sums_stride; kp.sums_offset = sums_offset;
     if (p->bigf) return fsea_bigf_launch(p->bigf, kp, n_frames, stream, &p->launches);
     if (p->four) {
         // one launch: a cluster per frame, the intermediate lives in the clusters' L2-resident slots
@@ -627,7 +632,7 @@ static int launch(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cu
             lc.dynamicSmemBytes = p->k4.smem; lc.stream = stream; lc.attrs = at; lc.numAttrs = 1;
             CU(cudaLaunchKernelExC(&lc, p->k4.fn, af));
         } else {
-            CU(cudaLaunchKernel(p->k4.fn, dim3((unsigned)nc), dim3((unsigned)p->k4.threads), af, p->k4.smem, stream));
+            CU(cudaLaunchKernel(sums ? p->k4.fn_sums : p->k4.fn, dim3((unsigned)nc), dim3((unsigned)p->k4.threads), af, p->k4.smem, stream));
         }
         if (!p->k4.ws) {
             CU(cudaEventRecord(p->scratch_done[slot], stream));
@@ -668,6 +673,11 @@ extern "C" int fsea_exec_device_strided(fsea_plan* p, const void* d_in, void* d_
 int fsea_launch_internal(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cudaStream_t stream, long out_stride, int scratch_slot,
                          long out_group, long out_group_stride, long hop) {
     return launch(p, d_in, d_out, n_frames, stream, scratch_slot, out_stride, out_group, out_group_stride, hop);
+}
+bool fsea_plan_has_sums_internal(const fsea_plan* p) { return p->four && p->k4.fn_sums != nullptr && p->k4.cs == 1; }
+int fsea_launch_sums_internal(fsea_plan* p, const void* d_in, long n_frames, cudaStream_t stream, long hop, double* sums, long sums_stride,
+                              long sums_offset) {
+    return launch(p, d_in, p->d_dump, n_frames, stream, 0, 0, 0, 0, hop, sums, sums_stride, sums_offset);
 }
 int fsea_fail_cuda_internal(cudaError_t e, const char* what) { return cuda_fail(e, what); }
 int fsea_plan_elem_bytes_internal(const fsea_plan* p) { return p->out_elem_bytes; }

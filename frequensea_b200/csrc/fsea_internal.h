@@ -17,6 +17,11 @@
 int fsea_launch_internal(fsea_plan* p, const void* d_in, void* d_out, long n_frames, cudaStream_t stream, long out_stride, int scratch_slot = 0,
                          long out_group = 0, long out_group_stride = 0,    // out_group > 0: rows in groups (fsea_kparams.h)
                          long hop = 0);                                     // hop > 0: samples between this launch's frames (0: the plan's)
+// per-frame sums of |X| instead of spectra (plans whose kernel has the SUMS form: N = 16384, 8-bit, float32 magnitudes):
+// comb warp w of frame f adds into sums[f * sums_stride + sums_offset + w], w < 4
+bool fsea_plan_has_sums_internal(const fsea_plan* p);
+int fsea_launch_sums_internal(fsea_plan* p, const void* d_in, long n_frames, cudaStream_t stream, long hop, double* sums, long sums_stride,
+                              long sums_offset);
 int fsea_fail_cuda_internal(cudaError_t e, const char* what);      // records the text for fsea_last_cuda_error(), returns FSEA_ERR_CUDA
 int fsea_plan_elem_bytes_internal(const fsea_plan* p);
 void fsea_count_launch_internal(fsea_plan* p);

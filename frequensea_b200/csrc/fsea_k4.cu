@@ -14,6 +14,7 @@ static bool fill_fused(fsea_kernel_info4* o, bool window, int out_mode, const ch
     o->fn = window ? (out_mode == FSEA_OUT_MAG ? FSEA_FUSED(true, FSEA_OUT_MAG) : out_mode == FSEA_OUT_LOGMAG ? FSEA_FUSED(true, FSEA_OUT_LOGMAG) : FSEA_FUSED(true, FSEA_OUT_PIX))
                    : (out_mode == FSEA_OUT_MAG ? FSEA_FUSED(false, FSEA_OUT_MAG) : out_mode == FSEA_OUT_LOGMAG ? FSEA_FUSED(false, FSEA_OUT_LOGMAG) : FSEA_FUSED(false, FSEA_OUT_PIX));
 #undef FSEA_FUSED
+    o->fn_sums = nullptr;
     o->cs = CS;
     o->ws = 0;
     o->tma = 0;

@@ -12,6 +12,8 @@ static bool fill_ws(fsea_kernel_info4* o, bool window, int out_mode, const char*
     o->fn = window ? (out_mode == FSEA_OUT_MAG ? FSEA_WS(true, FSEA_OUT_MAG) : out_mode == FSEA_OUT_LOGMAG ? FSEA_WS(true, FSEA_OUT_LOGMAG) : FSEA_WS(true, FSEA_OUT_PIX))
                    : (out_mode == FSEA_OUT_MAG ? FSEA_WS(false, FSEA_OUT_MAG) : out_mode == FSEA_OUT_LOGMAG ? FSEA_WS(false, FSEA_OUT_LOGMAG) : FSEA_WS(false, FSEA_OUT_PIX));
 #undef FSEA_WS
+    o->fn_sums = nullptr;
+    if constexpr (N2 == 16) { if (!window && out_mode == FSEA_OUT_MAG) o->fn_sums = (const void*)&fsea_ws4_kernel<N2, FSEA_OUT_MAG, false, TMA, true>; }
     o->cs = 1;
     o->ws = 16 / N2;                       // frames per block iteration
     o->tma = TMA ? 1 : 2;                  // (2: the kernel takes a tensor-map argument it does not read)
@@ -46,6 +48,7 @@ static bool fill_wsc(fsea_kernel_info4* o, bool window, int out_mode, const char
     o->fn = window ? (out_mode == FSEA_OUT_MAG ? FSEA_WSC(true, FSEA_OUT_MAG) : out_mode == FSEA_OUT_LOGMAG ? FSEA_WSC(true, FSEA_OUT_LOGMAG) : FSEA_WSC(true, FSEA_OUT_PIX))
                    : (out_mode == FSEA_OUT_MAG ? FSEA_WSC(false, FSEA_OUT_MAG) : out_mode == FSEA_OUT_LOGMAG ? FSEA_WSC(false, FSEA_OUT_LOGMAG) : FSEA_WSC(false, FSEA_OUT_PIX));
 #undef FSEA_WSC
+    o->fn_sums = nullptr;
     o->cs = N2 / 16;
     o->ws = 1;
     o->tma = 1;

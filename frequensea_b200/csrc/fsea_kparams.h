@@ -39,6 +39,9 @@ struct fsea_kparams {
     long out_group_stride; //      g * out_group_stride bytes into `out` (images side by side in a stitched canvas); 0: one run of rows
     long out_stride;       // bytes between the starts of consecutive output rows (N x element size when rows are packed;
                            // larger when the rows land inside a wider picture, e.g. a sweep's stitched canvas)
+    double* frame_sums;    // kernels built with SUMS (fsea_ws4.cuh): no spectrum is stored; comb warp w of frame f leaves the sum of
+    long sums_stride;      //   the |X| it computed at frame_sums[f * sums_stride + sums_offset + w] (the sweep gate,
+    long sums_offset;      //   c/fft-batch-broad.c:80-98, without a magnitude row ever reaching memory)
 };
 
 FSEA_KP_HD size_t fsea_out_row(const fsea_kparams& kp, long f) {

@@ -43,6 +43,8 @@ struct fsea_sweep {
     float* d_gate_mag = nullptr;                // NS x gate_rows x N
     float* d_gate_rowmag = nullptr;             // NS x capacity x N: |X| of ONE gate row of every slot (own_raw, sweep_gate_by_rows)
     double* d_partials = nullptr;               // [capacity][FSEA_SUM_BLOCKS]
+    double* d_warpsums = nullptr;               // [capacity][gate_rows][4]: the SUMS kernel's per-warp sums (N = 16384, own_raw)
+    bool by_sums = false;                       // the last gate used them
     double* d_means = nullptr;
     uint8_t* d_keep = nullptr;
     double* h_means = nullptr;                  // pinned
@@ -55,12 +57,12 @@ struct fsea_sweep {
 
 // mean over the gate rows from the FSEA_SUM_BLOCKS partial sums of a slot, added in block order as
 // fsea_gate_mean_host does on the host (same bits), and the "interesting?" decision (:93-97)
-__global__ void fsea_gate_decide_kernel(const double* __restrict__ partials, int n_slots, double count, double threshold,
+__global__ void fsea_gate_decide_kernel(const double* __restrict__ partials, int entries, int n_slots, double count, double threshold,
                                         double* __restrict__ means, uint8_t* __restrict__ keep) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_slots) return;
     double total = 0.0;
-    for (int b = 0; b < FSEA_SUM_BLOCKS; b++) total += partials[(size_t)s * FSEA_SUM_BLOCKS + b];
+    for (int b = 0; b < entries; b++) total += partials[(size_t)s * entries + b];
     const double m = total / count;
     means[s] = m;
     keep[s] = (m < threshold) ? 0 : 1;
@@ -107,6 +109,7 @@ extern "C" int fsea_sweep_destroy(fsea_sweep* s) {
     if (s->d_gate_mag) cudaFree(s->d_gate_mag);
     if (s->d_gate_rowmag) cudaFree(s->d_gate_rowmag);
     if (s->d_partials) cudaFree(s->d_partials);
+    if (s->d_warpsums) cudaFree(s->d_warpsums);
     if (s->d_means) cudaFree(s->d_means);
     if (s->d_keep) cudaFree(s->d_keep);
     if (s->h_means) cudaFreeHost(s->h_means);
@@ -148,8 +151,9 @@ static int sweep_setup(fsea_sweep* s) {
     if (c.own_raw) CU(cudaMalloc(&s->d_raw, s->raw_bytes * c.capacity));
     if (c.own_images) CU(cudaMalloc(&s->d_images, s->img_bytes * c.capacity));
     CU(cudaMalloc(&s->d_gate_mag, sizeof(float) * fsea_sweep::NS * (size_t)c.gate_rows * c.fft_size));
-    if (c.own_raw && c.gate_rows <= FSEA_SUM_BLOCKS) CU(cudaMalloc(&s->d_gate_rowmag, sizeof(float) * fsea_sweep::NS * (size_t)c.capacity * c.fft_size));
+    if (c.own_raw && c.gate_rows <= FSEA_SUM_BLOCKS && !fsea_plan_has_sums_internal(s->mag)) CU(cudaMalloc(&s->d_gate_rowmag, sizeof(float) * fsea_sweep::NS * (size_t)c.capacity * c.fft_size));
     CU(cudaMalloc(&s->d_partials, sizeof(double) * FSEA_SUM_BLOCKS * (size_t)c.capacity));
+    if (c.own_raw && fsea_plan_has_sums_internal(s->mag)) CU(cudaMalloc(&s->d_warpsums, sizeof(double) * 4 * (size_t)c.gate_rows * c.capacity));
     CU(cudaMalloc(&s->d_means, sizeof(double) * c.capacity));
     CU(cudaMalloc(&s->d_keep, (size_t)c.capacity));
     CU(cudaMallocHost((void**)&s->h_means, sizeof(double) * c.capacity));
@@ -221,13 +225,25 @@ __global__ void fsea_rowsum_kernel(const float* __restrict__ x, int n, double* _
 }
 
 static bool sweep_in_own_store(const fsea_sweep* s, int n_slots) {
-    if (!s->d_raw || !s->d_gate_rowmag) return false;
+    if (!s->d_raw || (!s->d_gate_rowmag && !s->d_warpsums)) return false;
     for (int j = 0; j < n_slots; j++) if (s->raw_ptr[j] != s->d_raw + (size_t)j * s->raw_bytes) return false;
     return true;
 }
 
 static int sweep_gate_by_rows(fsea_sweep* s, int n_slots) {          // (between sweep_fork and sweep_join)
     const int n = s->cfg.fft_size;
+    s->by_sums = s->d_warpsums != nullptr;
+    if (s->by_sums) {
+        // the kernel's SUMS form: no magnitude row is written at all, comb warp w of (slot, row r) leaves its share at
+        // warpsums[slot][r][w]; the decision kernel adds a slot's 4 gate_rows values in that order
+        int rc = sweep_fork(s);
+        for (int r = 0; r < s->cfg.gate_rows && rc == FSEA_OK; r++) {
+            rc = fsea_launch_sums_internal(s->mag, s->d_raw + (size_t)r * n * 2, n_slots, s->side[r % fsea_sweep::NS], (long)s->cfg.rows * n,
+                                           s->d_warpsums, 4L * s->cfg.gate_rows, 4L * r);
+            s->launches++;
+        }
+        return rc;
+    }
     CU(cudaMemsetAsync(s->d_partials, 0, sizeof(double) * FSEA_SUM_BLOCKS * (size_t)n_slots, s->stream));
     int rc = sweep_fork(s);
     for (int r = 0; r < s->cfg.gate_rows && rc == FSEA_OK; r++) {
@@ -280,6 +296,7 @@ extern "C" int fsea_sweep_gate_begin(fsea_sweep* s, int n_slots) {
     for (int j = 0; j < n_slots; j++) if (!s->raw_ptr[j]) return FSEA_ERR_INVALID;
     CU(cudaSetDevice(s->cfg.device));
     int rc;
+    s->by_sums = false;
     if (sweep_in_own_store(s, n_slots)) {
         rc = sweep_gate_by_rows(s, n_slots);
     } else {
@@ -289,8 +306,8 @@ extern "C" int fsea_sweep_gate_begin(fsea_sweep* s, int n_slots) {
     if (rc == FSEA_OK) rc = sweep_join(s);
     if (rc != FSEA_OK) return rc;
     const double count = (double)s->cfg.gate_rows * (double)s->cfg.fft_size;
-    FSEA_LAUNCH(fsea_gate_decide_kernel, (n_slots + 127) / 128, 128, s->stream, (const double*)s->d_partials, n_slots, count,
-                s->cfg.gate_threshold, s->d_means, s->d_keep);
+    FSEA_LAUNCH(fsea_gate_decide_kernel, (n_slots + 127) / 128, 128, s->stream, (const double*)(s->by_sums ? s->d_warpsums : s->d_partials),
+                s->by_sums ? 4 * s->cfg.gate_rows : FSEA_SUM_BLOCKS, n_slots, count, s->cfg.gate_threshold, s->d_means, s->d_keep);
     CU(cudaGetLastError());
     s->launches++;
     CU(cudaMemcpyAsync(s->h_means, s->d_means, sizeof(double) * n_slots, cudaMemcpyDeviceToHost, s->stream));

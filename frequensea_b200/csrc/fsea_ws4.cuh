@@ -82,9 +82,10 @@ __device__ __forceinline__ void fsea_ws_comb_load4(const float* y, int k, f2* re
 
 // radix-N2 + epilogue of four neighbouring bins: spectrum positions k .. k+3 of every row m leave as ONE 16-byte store
 // (float32) or ONE 4-byte store (u8 pixels: c/fft-batch.c:85-92 rows, four bins per store instead of one)
-template <int OUT, int N1, int N2>
+// SUMS (float32 magnitudes only): nothing is stored, the 4 N2 magnitudes are added into `acc` instead
+template <int OUT, int N1, int N2, bool SUMS = false>
 __device__ __forceinline__ void fsea_ws_comb_finish4(const fsea_kparams& kp, int k, uint8_t* row, bool dc_patch,
-                                                     f2* re0, f2* im0, f2* re1, f2* im1) {
+                                                     f2* re0, f2* im0, f2* re1, f2* im1, float* acc = nullptr) {
     constexpr int ESZ = (OUT == FSEA_OUT_PIX) ? 1 : 4;
     fsea_dft<N2, f2>::run(re0, im0);
     fsea_dft<N2, f2>::run(re1, im1);
@@ -97,6 +98,11 @@ __device__ __forceinline__ void fsea_ws_comb_finish4(const fsea_kparams& kp, int
         __align__(16) unsigned char tmp[16];
         fsea_tile_put<OUT>(tmp, p0, kp.pix_scale, kp.lg);
         fsea_tile_put<OUT>(tmp + 2 * ESZ, p1, kp.pix_scale, kp.lg);
+        if constexpr (SUMS) {
+            static_assert(!SUMS || OUT == FSEA_OUT_MAG, "sums are sums of magnitudes");
+            *acc += (((const float*)tmp)[0] + ((const float*)tmp)[1]) + (((const float*)tmp)[2] + ((const float*)tmp)[3]);
+            continue;
+        }
         if (m == 0 && dc_patch && k == 0) {                                  // bin 0 is not stored (src/nrf.c:621-622)
             if (ESZ == 4) { ((float*)dst)[1] = ((const float*)tmp)[1]; ((float*)dst)[2] = ((const float*)tmp)[2]; ((float*)dst)[3] = ((const float*)tmp)[3]; }
             else { dst[1] = tmp[1]; dst[2] = tmp[2]; dst[3] = tmp[3]; }
@@ -157,10 +163,11 @@ __device__ __forceinline__ float fsea_sin32(int j) { return fsea_cos32(j + 24); 
 // instead of being gathered by the transform warps: a 4-byte gather pays one L1 wavefront per 128-byte line it touches
 // (2048 per frame, 22 % of this kernel's L1 traffic; staged: 256 in + 1024 out with 4-way conflicts) and 32 loads +
 // their address arithmetic per thread.  The 32 KB come out of the pass-1 twiddle table's place (read through L1 instead).
-template <int N2, int OUT, bool WIN, bool TMA>
+template <int N2, int OUT, bool WIN, bool TMA, bool SUMS = false>
 __global__ void __launch_bounds__(FSEA_WS_THREADS, 1)
 fsea_ws4_kernel(const fsea_kparams kp, const __grid_constant__ fsea_tmap tm) {
     static_assert(!TMA || N2 >= 8, "a TMA box is at least 16 bytes wide: rows of 2 N2 bytes");
+    static_assert(!SUMS || (N2 == 16 && OUT == FSEA_OUT_MAG), "per-frame magnitude sums: one frame per block iteration");
     constexpr int CH = (2 * N2) / 16 > 0 ? (2 * N2) / 16 : 1;     // (TMA) 16-byte chunks per row of the frame
     constexpr int N1 = 1024;
     constexpr int FPB = 16 / N2;                            // frames a block works on at a time
@@ -350,6 +357,7 @@ fsea_ws4_kernel(const fsea_kparams kp, const __grid_constant__ fsea_tmap tm) {
         unsigned gi = 0;
         for (; g < groups; g += step, gi++) {
             if (!TMA) prefetch_l2(g + 2 * step);
+            double fsum = 0.0;                                         // (SUMS) this thread's share of sum |X| of frame g
 #pragma unroll 1
             for (int it = 0; it < BIT; it++) {
                 const int c = it * TB + bt;                            // comb call: frame c / CPF, pairs (c % CPF) + uu CPF
@@ -368,9 +376,15 @@ fsea_ws4_kernel(const fsea_kparams kp, const __grid_constant__ fsea_tmap tm) {
 #pragma unroll
                 for (int uu = 0; uu < U; uu++) COMB::twiddle(kp, 4 * (p0 + (uu / 2) * CPF) + 2 * (uu & 1), re[uu], im[uu]);
                 fsea_mbar_arrive(fre + it);                            // this phase's part of Y has been read
+                float acc = 0.0f;
 #pragma unroll
                 for (int v = 0; v < U / 2; v++)
-                    fsea_ws_comb_finish4<OUT, N1, N2>(kp, 4 * (p0 + v * CPF), row, dc_patch, re[2 * v], im[2 * v], re[2 * v + 1], im[2 * v + 1]);
+                    fsea_ws_comb_finish4<OUT, N1, N2, SUMS>(kp, 4 * (p0 + v * CPF), row, dc_patch, re[2 * v], im[2 * v], re[2 * v + 1], im[2 * v + 1], &acc);
+                if (SUMS) fsum += (double)acc;                         // (float over one call's 4 N2 U/2 magnitudes, double beyond)
+            }
+            if (SUMS) {                                                // lanes by shuffle in a fixed order, one value per comb warp
+                for (int o = 16; o > 0; o >>= 1) fsum += __shfl_down_sync(0xffffffffu, fsum, o);
+                if ((bt & 31) == 0 && g < frames) kp.frame_sums[(size_t)g * kp.sums_stride + kp.sums_offset + (bt >> 5)] = fsum;
             }
         }
     }

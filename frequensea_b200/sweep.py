@@ -148,6 +148,9 @@ def _share_canvas(engine, rows: int, width: int, rank: int, dst: int, group):
 def prepare_canvas(engine, n_freqs: int, n: int, rows: int, rank: int = 0, world: int = 1, dst: int = 0, group=None):
     """mode="p2p" across ranks: allocate the destination's canvas and share it ONCE (the allocation, the clear and the
     handle exchange are set-up, not part of a sweep); pass the result to sweep(canvas=...) as often as wanted."""
+    if world == 1:
+        cv = engine.new_canvas(rows, n * n_freqs)
+        return cv, cv.data_ptr(), None
     return _share_canvas(engine, rows, n * n_freqs, rank, dst, group)
 
 
@@ -170,10 +173,13 @@ def sweep(engine, n_freqs: int, n: int, rows: int, width_step: int,
     if world == 1:
         all_means, all_keep = means, np.asarray(keep, dtype=bool)
         if mode == "p2p" and width_step == n:
-            canvas = engine.new_canvas(rows, out_width)
-            torch.cuda.synchronize()
-            engine.render_into(len(mine), canvas.data_ptr(), out_width, 0, n)
-            return {"means": all_means, "keep": all_keep, "stitched": canvas}
+            if canvas is None:
+                cv = engine.new_canvas(rows, out_width)
+                torch.cuda.synchronize()
+            else:
+                cv = canvas[0]                                     # prepare_canvas(): allocated and cleared once, kept between sweeps
+            engine.render_into(len(mine), cv.data_ptr(), out_width, 0, n)
+            return {"means": all_means, "keep": all_keep, "stitched": cv}
         img = engine.render_images(len(mine), per)
         res = {"means": all_means, "keep": all_keep, "stitched": engine.stitch(img, n_freqs, 1, per, width_step)}
         if keep_images:
