@@ -51,6 +51,17 @@ print("history", float(nrf.fft_get_buffer(fft).numpy().sum()))
 nrf.fft_free(fft)
 x = np.random.default_rng(1).normal(0, 1, 2 * 16384)
 print("bigf", float(fb.Plan(16384, in_format=fb.IN_F64C).exec_host(x, 1).sum()))
+# float64 arithmetic on 8-bit input (widen kernel + fp64 register kernel / radix-16 global passes) and the sweep gate at
+# N = 16384 (per-launch hop through the tensor map, SUMS form of the warp-specialised kernel), pixel pass in fp64
+for n in (1024, 32768):
+    pl = fb.Plan(n, hop=n // 2, in_format=fb.IN_U8, window=fb.WIN_HANN, out_mode=fb.OUT_PIX, pix_scale=5.0, flags=fb.FLAG_DC_PATCH, arith=fb.ARITH_F64)
+    print(pl.kernel_name, int(pl.exec_host(synth_u8(2 * n, seed=n + 1), 3).sum()))
+eng = Sweep(16384, 6, 4, gate_rows=3, own_images=True, pixel_arith=fb.ARITH_F64)
+for f in range(4):
+    eng.submit_synth(f, f, 3)
+means, keep = eng.gate(4)
+eng.render(4)
+print("sweep 16384 (sums gate, f64 pixels)", keep.tolist(), [round(float(m), 4) for m in means], int(eng.read_images(0, 4).sum()))
 os.environ["FSEA_WS"] = "1"
 plan = fb.Plan(65536, in_format=fb.IN_S8, out_mode=fb.OUT_LOGMAG)
 print(plan.kernel_name, float(plan.exec_host(synth_s8(3 * 65536, seed=9), 3).sum()))
