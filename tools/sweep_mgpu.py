@@ -68,11 +68,12 @@ def main():
     ap.add_argument("--mode", default="gather", choices=sorted(MODES))
     ap.add_argument("--step", type=int, default=0, help="WIDTH_STEP (0: N, the c/fft-stitch-broad.c convention)")
     ap.add_argument("--check", action="store_true")
+    ap.add_argument("--out", default="", help="write the stitched picture as a binary PGM (P5): what c/fft-stitch-broad.c hands to its PNG writer")
     ap.add_argument("--f32-gather-mib", type=int, default=1024, help="SURVEY 8(e) (iii): MiB each GPU sends to the root (0: skip)")
     a = ap.parse_args()
     L = load()
     step = a.step or a.n
-    picture = a.check
+    picture = a.check or bool(a.out)
     means, keep, pic, t = run(L, a.gpus, a.n, a.rows, a.freqs, a.mode, step, picture)
     out = {"workload": "cfg4 sweep job (one process, ncclCommInitAll)", "n_gpus": a.gpus, "freqs": a.freqs, "rows": a.rows,
            "fft_size": a.n, "mode": a.mode, "width_step": step, "kept": int(t.kept), "rows_rendered": int(t.rows_rendered),
@@ -95,6 +96,11 @@ def main():
             total = (a.gpus - 1) * (a.f32_gather_mib << 20)
             out["f32_gather_to_root"] = {"bytes": total, "seconds": sec.value, "gbs_into_root": total / sec.value / 1e9,
                                          "note": "SURVEY 8(e) (iii): float32 spectra gathered on one root are bound by its NVLink ingest"}
+    if a.out and pic is not None:
+        with open(a.out, "wb") as fh:                      # rows x width u8, row-major: a PGM is the header plus exactly these bytes
+            fh.write(b"P5\n%d %d\n255\n" % (pic.shape[1], pic.shape[0]))
+            fh.write(np.ascontiguousarray(pic).tobytes())
+        out["picture_file"] = {"path": a.out, "width": int(pic.shape[1]), "height": int(pic.shape[0])}
     print(json.dumps(out))
     if a.check and a.gpus > 1:
         assert out["equals_one_gpu_job"]
