@@ -385,6 +385,38 @@ def sustained_cfg5(ctx, fb, seconds=5.0):
     return out
 
 
+def file_ingest(ctx, fb, frames=768, repeats=4):
+    """a capture FILE (raw interleaved int8 as c/reader.c / c/rfcap.c write it) through
+    fsea_exec_file -- pread() into pinned slots, H2D, the cfg5 transform, D2H -- against the 20 MS/s a HackRF delivers."""
+    import tempfile
+    torch = ctx.torch
+    w = WORKLOADS["cfg5"]
+    n = w["n"]
+    rng = np.random.default_rng(11)
+    raw = rng.integers(0, 256, size=2 * n * frames, dtype=np.uint8)
+    d = "/dev/shm" if os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK) else None
+    with tempfile.NamedTemporaryFile(prefix="fsea_capture_", suffix=".raw", dir=d, delete=False) as fh:
+        fh.write(raw.tobytes())
+        path = fh.name
+    try:
+        plan = make_plan(fb, w, ctx.local)
+        out = torch.empty((frames, n), dtype=torch.float32, pin_memory=True).numpy()
+        plan.exec_file(path, frames, out=out)                       # warm: page cache, staging slots
+        ref = plan.exec_host(raw, frames)
+        same = bool(np.array_equal(out, ref))                       # the same bytes through the same kernel
+        l0 = plan.launches
+        t0 = time.perf_counter()
+        for _ in range(repeats):
+            plan.exec_file(path, frames, out=out)
+        dt = (time.perf_counter() - t0) / repeats
+        return {"workload": f"capture file of {frames} x {n}-pt frames ({raw.nbytes >> 20} MiB, int8 IQ) -> fsea_exec_file -> f32 log-magnitude rows on the host",
+                "value": frames / dt, "unit": UNIT, "iq_gsps": frames * n / dt / 1e9, "x_real_time_at_20MSps": frames * n / dt / 20e6,
+                "file_gbs": raw.nbytes / dt / 1e9, "equals_exec_host": same, "gpu_launches": plan.launches - l0,
+                "where": "tmpfs" if d else "temp dir (page cache)"}
+    finally:
+        os.unlink(path)
+
+
 def sweep_job(ctx, fb, n_freqs=1000, rows=512, n=16384):
     """The cfg4 JOB (c/fft-batch-broad.c:56-129,189-209 + c/fft-stitch-broad.c:66-88): 1000 centre frequencies x 512
     rows x 16384 points, frequency f -> rank f mod N, raw IQ resident per rank (drawn on the device, untimed), then
@@ -692,6 +724,11 @@ def main():
                 secondary["cfg4_pixels_f64"] = ex
             except Exception as e:
                 secondary["cfg4_pixels_f64"] = {"error": str(e)[:300]}
+        if world == 1 and ctx.elapsed() <= args.budget_s:
+            try:
+                secondary["file_ingest"] = file_ingest(ctx, fb)
+            except Exception as e:
+                secondary["file_ingest"] = {"error": str(e)[:300]}
         if ctx.max_over_ranks(ctx.elapsed())[0] <= args.budget_s:
             try:
                 sustained = sustained_cfg5(ctx, fb, seconds=5.0)
